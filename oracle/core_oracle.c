@@ -1,0 +1,257 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY — never linked into the product library.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this.
+ *
+ * Independent CPU restatement ("port") of the reference C core codec:
+ *   rade_core_encoder   /root/reference/src/rade_enc.c:55-114   (state: src/rade_enc.h:35-47)
+ *   rade_core_decoder   /root/reference/src/rade_dec.c:50-102   (state: src/rade_dec.h:34-46)
+ * on top of the opus DNN primitives restated in oracle/nnet_shim/nnet_shim.c (see that
+ * file's header for the third-party dependency, its pinned commit and the parity status:
+ * "parity unpinned" at the opus boundary, layouts pinned against the PyTorch reference).
+ *
+ * Differences in FORM (not in results) from the _ref build, so that the two check each other:
+ *   - weights come from this repo's RDW container (row-major int8 [out][in], radae_b200/rdw.py),
+ *     not from the 8x4-blocked tables;
+ *   - the int8 dot products accumulate in int32 (exact) instead of integer-valued floats — equal
+ *     whenever |acc| < 2^24, which oracle/_ref's instrumentation confirms (max seen ~4e5);
+ *   - conv memories are a FIFO of `dilation` past input frames, oldest first.
+ * Every float operation is a separately rounded binary32 op in the reference's order
+ * (compile with -ffp-contract=off); tests require this file == oracle/_ref bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+
+#define ENC_IN 84
+#define ENC_CAT 864
+#define ENC_Z 80
+#define DEC_IN 80
+#define DEC_CAT 736
+#define DEC_OUT 84
+#define MAXK 1536
+
+typedef struct { const int8_t *w8; const float *scale; const float *bias; const float *wf; int nin, nout; } layer_t;
+
+typedef struct {
+  unsigned char *blob;
+  layer_t enc_dense1, enc_zdense, enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
+  layer_t dec_dense1, dec_output, dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
+} model_t;
+
+static const int ENC_DIL[5] = {1, 2, 2, 2, 2};     /* radae/radae_base.py:239-247, src/rade_enc.c:76-104 */
+
+/* state layouts (floats) */
+#define ENC_GRU_N 64
+#define ENC_CONV_N 96
+#define DEC_GRU_N 96
+#define DEC_CONV_N 32
+API int oracle_enc_state_floats(void) { return 5*64 + 128 + 2*(288+448+608+768); }   /* 4672 */
+API int oracle_dec_state_floats(void) { return 5*96 + (192+320+448+576+704); }        /* 2720 */
+
+/* ---------- RDW reader ---------- */
+typedef struct { char name[48]; uint32_t dtype, rows, cols, rsv; uint64_t off, nbytes; } rdw_entry;
+
+static const void *find(const model_t *m, const char *name, uint32_t *rows, uint32_t *cols)
+{
+  uint32_t n = *(const uint32_t*)(m->blob + 12), i;
+  for (i=0;i<n;i++) {
+    const rdw_entry *e = (const rdw_entry*)(m->blob + 64 + 80*(size_t)i);
+    if (strncmp(e->name, name, 48) == 0) { if (rows) *rows = e->rows; if (cols) *cols = e->cols; return m->blob + e->off; }
+  }
+  return NULL;
+}
+
+static int load_layer(const model_t *m, layer_t *l, const char *name, int nin, int nout, int is_float)
+{
+  char key[64]; uint32_t r, c;
+  memset(l, 0, sizeof(*l)); l->nin = nin; l->nout = nout;
+  snprintf(key, sizeof key, "%s.bias", name);
+  if (!(l->bias = (const float*)find(m, key, &r, &c)) || (int)c != nout) return 1;
+  if (is_float) {
+    snprintf(key, sizeof key, "%s.wf", name);
+    if (!(l->wf = (const float*)find(m, key, &r, &c)) || (int)r != nin || (int)c != nout) return 1;
+  } else {
+    snprintf(key, sizeof key, "%s.w8", name);
+    if (!(l->w8 = (const int8_t*)find(m, key, &r, &c)) || (int)r != nout || (int)c != nin) return 1;
+    snprintf(key, sizeof key, "%s.scale", name);
+    if (!(l->scale = (const float*)find(m, key, &r, &c)) || (int)c != nout) return 1;
+  }
+  return 0;
+}
+
+API void *oracle_core_open(const char *rdw_path)
+{
+  static const int enc_k[5] = {64, 224, 384, 544, 704}, enc_ck[5] = {256, 576, 896, 1216, 1536};
+  static const int dec_k[5] = {96, 224, 352, 480, 608}, dec_ck[5] = {384, 640, 896, 1152, 1408};
+  FILE *f = fopen(rdw_path, "rb"); long len; model_t *m; int i, bad = 0; char nm[64];
+  if (!f) { fprintf(stderr, "oracle_core_open: cannot open %s\n", rdw_path); return NULL; }
+  fseek(f, 0, SEEK_END); len = ftell(f); fseek(f, 0, SEEK_SET);
+  m = (model_t*)calloc(1, sizeof(*m));
+  m->blob = (unsigned char*)malloc(len);
+  if (fread(m->blob, 1, len, f) != (size_t)len || memcmp(m->blob, "RADEB200", 8) != 0) { fclose(f); return NULL; }
+  fclose(f);
+  bad |= load_layer(m, &m->enc_dense1, "enc_dense1", ENC_IN, 64, 1);
+  bad |= load_layer(m, &m->enc_zdense, "enc_zdense", ENC_CAT, ENC_Z, 1);
+  bad |= load_layer(m, &m->dec_dense1, "dec_dense1", DEC_IN, 96, 1);
+  bad |= load_layer(m, &m->dec_output, "dec_output", DEC_CAT, DEC_OUT, 1);
+  for (i=0;i<5;i++) {
+    snprintf(nm, sizeof nm, "enc_gru%d_input", i+1);     bad |= load_layer(m, &m->enc_gru_in[i], nm, enc_k[i], 192, 0);
+    snprintf(nm, sizeof nm, "enc_gru%d_recurrent", i+1); bad |= load_layer(m, &m->enc_gru_rec[i], nm, 64, 192, 0);
+    snprintf(nm, sizeof nm, "enc_conv%d", i+1);          bad |= load_layer(m, &m->enc_conv[i], nm, enc_ck[i], 96, 0);
+    snprintf(nm, sizeof nm, "dec_gru%d_input", i+1);     bad |= load_layer(m, &m->dec_gru_in[i], nm, dec_k[i], 288, 0);
+    snprintf(nm, sizeof nm, "dec_gru%d_recurrent", i+1); bad |= load_layer(m, &m->dec_gru_rec[i], nm, 96, 288, 0);
+    snprintf(nm, sizeof nm, "dec_glu%d", i+1);           bad |= load_layer(m, &m->dec_glu[i], nm, 96, 96, 0);
+    snprintf(nm, sizeof nm, "dec_conv%d", i+1);          bad |= load_layer(m, &m->dec_conv[i], nm, dec_ck[i], 32, 0);
+  }
+  if (bad) { fprintf(stderr, "oracle_core_open: missing/mis-shaped arrays in %s\n", rdw_path); return NULL; }
+  return m;
+}
+
+API void oracle_core_close(void *h) { model_t *m = (model_t*)h; if (m) { free(m->blob); free(m); } }
+
+/* ---------- primitives (restating nnet_shim.c with unblocked weights) ---------- */
+
+static float tanh_rational(float x)
+{
+  const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
+  const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
+  float x2 = x*x;
+  float num = (N2*x2 + N1)*x2 + N0;
+  float den = (D2*x2 + D1)*x2 + D0;
+  float y = num*x/den;
+  if (y > 1.f) y = 1.f;
+  if (y < -1.f) y = -1.f;
+  return y;
+}
+static float sigmoid_rational(float x) { return .5f + .5f*tanh_rational(.5f*x); }
+
+static void quantise(int8_t *q, const float *x, int n)
+{
+  int i;
+  for (i=0;i<n;i++) q[i] = (int8_t)(int)floor(.5 + 127*(double)x[i]);
+}
+
+/* out = (W8 xq)*scale + bias */
+static void linear_i8(const layer_t *l, float *out, const int8_t *xq)
+{
+  int i, j;
+  for (i=0;i<l->nout;i++) {
+    const int8_t *w = l->w8 + (size_t)i*l->nin;
+    int32_t acc = 0;
+    for (j=0;j<l->nin;j++) acc += (int32_t)w[j]*(int32_t)xq[j];
+    out[i] = (float)acc*l->scale[i] + l->bias[i];
+  }
+}
+
+/* out[i] = (((0 + W[0][i] x0) + W[1][i] x1) + ...) + bias[i] */
+static void linear_f32(const layer_t *l, float *out, const float *x)
+{
+  int i, j;
+  for (i=0;i<l->nout;i++) {
+    float acc = 0;
+    for (j=0;j<l->nin;j++) acc += l->wf[(size_t)j*l->nout + i]*x[j];
+    out[i] = acc + l->bias[i];
+  }
+}
+
+static void gru_step(const layer_t *wi, const layer_t *wr, float *state, const float *in)
+{
+  int8_t xq[MAXK], hq[128];
+  float gi[3*96], gr[3*96];
+  const int N = wr->nin; int i;
+  quantise(xq, in, wi->nin);
+  quantise(hq, state, N);
+  linear_i8(wi, gi, xq);
+  linear_i8(wr, gr, hq);
+  for (i=0;i<N;i++) {
+    float z = sigmoid_rational(gi[i] + gr[i]);
+    float r = sigmoid_rational(gi[N+i] + gr[N+i]);
+    float n = tanh_rational(gi[2*N+i] + gr[2*N+i]*r);
+    state[i] = z*state[i] + (1-z)*n;
+  }
+}
+
+/* k=2 causal conv over the concat prefix [0,in_size): taps at t-dilation and t */
+static void conv_step(const layer_t *l, float *out, float *fifo, const float *in, int in_size, int dilation)
+{
+  float tmp[MAXK]; int8_t q[MAXK]; float y[96]; int i;
+  memcpy(tmp, fifo, in_size*sizeof(float));                      /* oldest frame */
+  memcpy(tmp + in_size, in, in_size*sizeof(float));
+  quantise(q, tmp, 2*in_size);
+  linear_i8(l, y, q);
+  for (i=0;i<l->nout;i++) out[i] = tanh_rational(y[i]);
+  memmove(fifo, fifo + in_size, (size_t)(dilation-1)*in_size*sizeof(float));
+  memcpy(fifo + (size_t)(dilation-1)*in_size, in, in_size*sizeof(float));
+}
+
+static void enc_step(const model_t *m, float *st, const float *feat, float *z, float *cat_out)
+{
+  float cat[ENC_CAT], y[96]; int i, off = 0;
+  float *gru = st, *conv = st + 5*64;
+  linear_f32(&m->enc_dense1, y, feat);
+  for (i=0;i<64;i++) cat[i] = tanh_rational(y[i]);
+  off = 64;
+  for (i=0;i<5;i++) {
+    gru_step(&m->enc_gru_in[i], &m->enc_gru_rec[i], gru + 64*i, cat);
+    memcpy(cat + off, gru + 64*i, 64*sizeof(float)); off += 64;
+    conv_step(&m->enc_conv[i], cat + off, conv, cat, off, ENC_DIL[i]);
+    conv += ENC_DIL[i]*off; off += 96;
+  }
+  linear_f32(&m->enc_zdense, z, cat);                            /* bottleneck 3: linear (src/rade_enc.c:107-113) */
+  if (cat_out) memcpy(cat_out, cat, sizeof cat);
+}
+
+static void dec_step(const model_t *m, float *st, const float *z, float *feat, float *cat_out)
+{
+  float cat[DEC_CAT], y[96], g[96]; int8_t hq[96]; int i, k, off = 0;
+  float *gru = st, *conv = st + 5*96;
+  linear_f32(&m->dec_dense1, y, z);
+  for (i=0;i<96;i++) cat[i] = tanh_rational(y[i]);
+  off = 96;
+  for (i=0;i<5;i++) {
+    float *h = gru + 96*i;
+    gru_step(&m->dec_gru_in[i], &m->dec_gru_rec[i], h, cat);
+    quantise(hq, h, 96);                                         /* GLU on the un-gated state (src/rade_dec.c:66-67) */
+    linear_i8(&m->dec_glu[i], g, hq);
+    for (k=0;k<96;k++) cat[off+k] = h[k]*sigmoid_rational(g[k]);
+    off += 96;
+    conv_step(&m->dec_conv[i], cat + off, conv, cat, off, 1);
+    conv += off; off += 32;
+  }
+  linear_f32(&m->dec_output, feat, cat);
+  if (cat_out) memcpy(cat_out, cat, sizeof cat);
+}
+
+/* features [n][steps][84] -> z [n][steps][80];  states [n][4672] (zero = rade_init_encoder);
+ * cat (optional) [n][steps][864] = the concat buffer after each step, for layer-level debugging */
+API void oracle_core_encode(void *h, float *states, int n_streams, int n_steps,
+                            const float *features, float *z, float *cat, int nthreads)
+{
+  const model_t *m = (const model_t*)h; int s;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+  for (s=0;s<n_streams;s++) {
+    int t;
+    for (t=0;t<n_steps;t++) {
+      size_t k = (size_t)s*n_steps + t;
+      enc_step(m, states + (size_t)s*oracle_enc_state_floats(), features + k*ENC_IN, z + k*ENC_Z, cat ? cat + k*ENC_CAT : NULL);
+    }
+  }
+}
+
+API void oracle_core_decode(void *h, float *states, int n_streams, int n_steps,
+                            const float *z, float *features, float *cat, int nthreads)
+{
+  const model_t *m = (const model_t*)h; int s;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+  for (s=0;s<n_streams;s++) {
+    int t;
+    for (t=0;t<n_steps;t++) {
+      size_t k = (size_t)s*n_steps + t;
+      dec_step(m, states + (size_t)s*oracle_dec_state_floats(), z + k*DEC_IN, features + k*DEC_OUT, cat ? cat + k*DEC_CAT : NULL);
+    }
+  }
+}
