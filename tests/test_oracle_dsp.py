@@ -1,0 +1,76 @@
+"""CPU tests: the numpy DSP oracle against golden vectors produced by the Python reference
+(radae_txe.radae_tx, radae_rxe.radae_rx, radae.complex_bpf — see tools/make_golden.py)."""
+import numpy as np
+import pytest
+from oracle import dsp as od
+from oracle.core import CoreOraclePort
+
+SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus"]
+
+
+def relrms(a, b):
+    return float(np.sqrt(np.mean(np.abs(a - b) ** 2)) / np.sqrt(np.mean(np.abs(b) ** 2)))
+
+
+def test_constants():
+    c = od.consts()
+    assert (od.NMF, od.NEOO, od.NIN_MAX, od.RXBUF, od.N_FEATURES, od.N_EOO_BITS) == (960, 1152, 1120, 2112, 432, 180)
+    assert abs(c.pilot_gain - 23.2038) < 1e-3
+    assert abs(float(c.bpf_centre) - 1475.0) < 0.01 and abs(float(c.bpf_bw) - 1740.0) < 0.01
+    assert c.fcoarse[0] == -50.0 and c.fcoarse[-1] == 47.5 and len(c.fcoarse) == 40
+
+
+def test_transmitter_vs_reference(golden):
+    g = golden("tx")
+    tx = np.array([od.transmitter_one(z) for z in g["z"]])
+    assert relrms(tx, g["tx"]) < 1e-5
+    assert relrms(od.eoo_frame(), g["eoo_nobits"]) < 1e-5
+    assert relrms(od.eoo_frame(g["eoo_bits"]), g["eoo_withbits"]) < 1e-5
+    # size-independent properties: cyclic prefix is the tail copy, PA limiter bounds |tx| < 1
+    fr = tx[0].reshape(5, 192)
+    assert np.allclose(fr[:, :32], fr[:, -32:])
+    assert np.abs(tx).max() < 1.0
+
+
+def test_bpf_chunked_vs_reference_including_memory_quirk(golden):
+    g = golden("bpf")
+    f = od.ComplexBPF()
+    o = 0; ys = []
+    for n in g["chunks"]:
+        ys.append(f.bpf(g["x"][o:o + n])); o += n
+    assert relrms(np.concatenate(ys), g["y"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_streaming_receiver_vs_reference(golden, name):
+    g = golden("rx_" + name)
+    rx = od.RadaeRx(CoreOraclePort(n_streams=1))
+    o = 0
+    tr = {k: [] for k in ("nin", "ret", "state", "tmax", "fmax", "snr", "uw_errors")}
+    zs, fs, eo = [], [], []
+    while o + rx.nin <= len(g["rx_in"]):
+        nin = rx.nin
+        ret, feat, eoo = rx.do_radae_rx(g["rx_in"][o:o + nin]); o += nin
+        for k, v in (("nin", nin), ("ret", ret), ("state", rx.state), ("tmax", rx.tmax), ("fmax", rx.fmax),
+                     ("snr", rx.receiver.snrdB_3k_est), ("uw_errors", rx.uw_errors)):
+            tr[k].append(v)
+        if ret & 1:
+            zs.append(rx.z_hat.reshape(-1)); fs.append(feat)
+        if ret & 2:
+            eo.append(eoo)
+    for k in ("nin", "ret", "state", "tmax", "uw_errors"):            # framing / state machine: bit exact
+        assert np.array_equal(np.array(tr[k]), g[k]), k
+    assert np.max(np.abs(np.array(tr["fmax"]) - g["fmax"])) < 1e-6
+    assert np.max(np.abs(np.array(tr["snr"]) - g["snr"])) < 1e-3
+    assert relrms(np.array(zs).reshape(-1, 240), g["z_hat"]) < 1e-5     # PSK symbols: 1e-5 relative rms
+    if len(eo):
+        assert np.max(np.abs(np.array(eo) - g["eoo"])) < 1e-3
+
+
+def test_arange_restatement_matches_numpy():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        f = float(rng.uniform(-60, 60))
+        assert np.array_equal(od.arange_like_numpy(f - 1, f + 1, 0.1), np.arange(f - 1, f + 1, 0.1))
+    for f in np.arange(-50, 50, 2.5):
+        assert np.array_equal(od.arange_like_numpy(f - 10, f + 10, 0.25), np.arange(f - 10, f + 10, 0.25))
