@@ -1,0 +1,99 @@
+/* rade_b200.h — batched multi-stream extension of the rade_api.h C ABI (libradae_b200).
+ *
+ * The reference API is "single context only" (src/rade_api.h:87); one B200 carries thousands of independent
+ * streams, so this header adds a context that owns S streams on one CUDA device.  Semantics per stream are
+ * exactly those of rade_tx / rade_rx / rade_nin / ... (src/rade_api.c:403-555), arrays simply gain a leading
+ * stream dimension.  Plain pointers and sizes only; `_dev` entry points take DEVICE pointers and enqueue work
+ * on the context's CUDA stream without synchronising, the others take HOST pointers, copy in/out and synchronise.
+ * All functions return 0 (or a count) on success and a negative value on error, after printing the CUDA error.
+ */
+#ifndef RADE_B200_H
+#define RADE_B200_H
+#include <stddef.h>
+#include "rade_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rade_batch rade_batch;
+
+/* weights: NULL/0 -> the RDW blob embedded in the library; else an RDW v1 or DNNw blob in host memory
+ * (what a caller receives from the one-off ncclBroadcast at start-up).  device < 0 -> current device. */
+RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, const void *weights, size_t weights_len);
+RADE_EXPORT void rade_b200_close(rade_batch *b);
+RADE_EXPORT int rade_b200_n_streams(rade_batch *b);
+RADE_EXPORT void *rade_b200_cuda_stream(rade_batch *b);                 /* cudaStream_t */
+RADE_EXPORT int rade_b200_synchronize(rade_batch *b);
+RADE_EXPORT long long rade_b200_launch_count(rade_batch *b);            /* kernels launched so far by this context */
+RADE_EXPORT const void *rade_b200_default_weights_blob(size_t *len);    /* the embedded RDW blob (host memory) */
+RADE_EXPORT int rade_b200_reset(rade_batch *b);                         /* all streams back to the rade_open() state */
+
+/* --- core codec only (rade_core_encoder / rade_core_decoder, src/rade_core.h:42-49), n_steps 40 ms steps ---
+ * features [S][n_steps][84] (4 x (20 features + aux)), z [S][n_steps][80] */
+RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float *d_features, int n_steps);
+RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, const float *d_z, int n_steps);
+RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *features, int n_steps);
+RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const float *z, int n_steps);
+
+/* --- transmitter: rade_tx / rade_tx_set_eoo_bits / rade_tx_eoo per stream ---
+ * features_in [S][432], tx_out [S][960], eoo_bits [S][180] (+-1), tx_eoo_out [S][1152] */
+RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_features_in);
+RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *features_in);
+RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits);
+RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out);
+/* OFDM modulator alone (transmitter_one, radae/dsp.py:340-378): z [S][3][80] -> tx [S][960] */
+RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z);
+
+/* --- receiver: rade_nin / rade_rx / rade_sync / rade_snrdB_3k_est per stream ---
+ * rx_in [S][1120]: row s holds nin[s] fresh samples (800 | 960 | 1120);  features_out [S][432];
+ * ret [S] = valid | eoo << 1 (radae_rxe.py:330);  eoo_out [S][180];  active [S] (optional, NULL = all):
+ * streams with active == 0 are not advanced at all. */
+RADE_EXPORT int rade_b200_nin(rade_batch *b, int *nin);
+RADE_EXPORT int rade_b200_rx(rade_batch *b, float *features_out, int *ret, float *eoo_out, const RADE_COMP *rx_in,
+                             const unsigned char *active);
+RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out,
+                                 const RADE_COMP *d_rx_in, const unsigned char *d_active);
+RADE_EXPORT const int *rade_b200_nin_dev(rade_batch *b);                /* device array [S], valid after rx_dev */
+
+typedef struct {              /* one per stream; what the reference prints per frame at -v 2 (radae_rxe.py:239-246) */
+  int state;                  /* 0 search, 1 candidate, 2 sync */
+  int nin, tmax, valid_count, uw_errors, synced_count;
+  int snrdB_3k_est;           /* int(), like get_snrdB_3k_est (radae_rxe.py:162-163) */
+  float snrdB_3k_est_f;
+  double fmax;
+  float Dthresh, Dtmax12, Dtmax12_eoo;
+} rade_b200_rx_status;
+RADE_EXPORT int rade_b200_rx_get_status(rade_batch *b, rade_b200_rx_status *status /* [S] host */);
+/* z_hat of the last rade_b200_rx call, [S][240] (what bypass_dec hands to the C decoder, radae_rxe.py:318) */
+RADE_EXPORT int rade_b200_rx_get_z_hat(rade_batch *b, float *z_hat);
+
+/* --- channel simulator: rate-Fs branch of RADAE.forward (radae/radae.py:529-599), per stream ---
+ * explicit form (parity tests): rx = gain*(mp_gain*(tx*G1 + delay_d(tx*G2))*exp(j(phase0+2*pi*f*(n+1)/Fs)) + sigma*noise)
+ * all arrays [S][n] complex64 on the device. */
+RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx, const RADE_COMP *d_G1,
+                                            const RADE_COMP *d_G2, const RADE_COMP *d_noise, int n, int delay,
+                                            float mp_gain, float freq_offset_hz, float phase0, float sigma, float gain);
+typedef struct {
+  float EbNodB;               /* sigma = sqrt(Fs/(EbNo*Rb)), Rb = 2000 (radae.py:570-574) */
+  float freq_offset_hz;       /* per stream: freq_offset_hz + U(-1,1)*freq_offset_spread_hz */
+  float freq_offset_spread_hz;
+  float doppler_spread_hz;    /* 0 = AWGN only (G1 = 1, G2 = 0); MPP = 1.0 */
+  int delay_samples;          /* 16 = 2 ms (MPP) */
+  float gain;
+  unsigned long long seed;
+} rade_b200_channel_cfg;
+/* streaming generator form: consumes tx [S][960] (one modem frame per stream), Philox AWGN + two-path Watterson
+ * fading with Gaussian Doppler spectrum generated in-kernel; keeps per-stream phase / delay-line / time state */
+RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_cfg *cfg);
+RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx);
+
+/* --- loop-back link between channel output and receiver input (per-stream sample FIFO on the device): the
+ * receiver consumes nin[s] in {800, 960, 1120} samples per call while the transmitter produces 960 --- */
+RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples /* [S][960] */);
+RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

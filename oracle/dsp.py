@@ -80,7 +80,8 @@ class Consts:
                           [1, np.exp(-1j * np.float64(self.w[cm]) * a)],
                           [1, np.exp(-1j * np.float64(self.w[cm + 1]) * a)]]).astype(np.complex64)
             self.Pmat[c] = (np.linalg.inv((A.T @ A).astype(np.complex64)) @ A.T).astype(np.complex64)
-        self.eq_rot = np.exp(-1j * self.w.astype(np.float64) * a).astype(np.complex64)         # exp(-j w_c a), dsp.py:433
+        # torch.exp(-1j*self.w[c]*a) on a complex64 scalar: the angle w_c*a is a float32 product (dsp.py:433)
+        self.eq_rot = np.exp(-1j * (self.w * f32(a)).astype(f32).astype(np.float64)).astype(np.complex64)
         # BPF (radae_rxe.py:104-109): `w = np.array(model.w)` is float32, so bandwidth and centre are evaluated in
         # float32 scalar arithmetic (NEP 50: Python literals adopt float32), left to right
         f32 = np.float32

@@ -1,0 +1,156 @@
+"""Host-side (Python) face of the batched C ABI: S independent RADE streams on one B200.
+
+Thin by design — sizes, pointer plumbing and error checks only; all arithmetic happens in libradae_b200.so.
+numpy arrays are passed as host pointers (the library copies H2D/D2H itself); torch CUDA tensors, when the
+caller has them, go through the `_dev` methods as raw device pointers.
+"""
+import ctypes as C
+import numpy as np
+from . import _capi as capi
+from ._capi import NMF, NEOO, NIN_MAX, NFEAT, NEOO_BITS
+
+
+def _np(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data
+
+
+def _check(rc, what):
+    if rc is None or rc < 0:
+        raise RuntimeError(f"libradae_b200: {what} failed (see stderr for the CUDA error)")
+    return rc
+
+
+class RadeBatch:
+    def __init__(self, n_streams, device=-1, flags=capi.RADE_USE_C_ENCODER | capi.RADE_USE_C_DECODER | capi.RADE_VERBOSE_0,
+                 weights=None):
+        self.lib = capi.lib()
+        self.S = int(n_streams)
+        buf, n = (None, 0)
+        if weights is not None:
+            self._w = bytes(weights); buf, n = C.c_char_p(self._w), len(self._w)
+        self.h = self.lib.rade_b200_open(self.S, device, flags, buf, n)
+        if not self.h:
+            raise RuntimeError("rade_b200_open failed: no usable sm_100 CUDA device or bad weights (no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rade_b200_close(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing
+    @property
+    def cuda_stream(self):
+        return self.lib.rade_b200_cuda_stream(self.h)
+
+    def synchronize(self):
+        _check(self.lib.rade_b200_synchronize(self.h), "synchronize")
+
+    def launch_count(self):
+        return int(self.lib.rade_b200_launch_count(self.h))
+
+    def reset(self):
+        _check(self.lib.rade_b200_reset(self.h), "reset")
+
+    # ---- core codec (host arrays)
+    def core_encode(self, features):
+        f, pf = _np(features, np.float32)
+        S, T, K = f.shape
+        assert S == self.S and K == 84
+        z = np.empty((S, T, 80), np.float32)
+        _check(self.lib.rade_b200_core_encode(self.h, z.ctypes.data, pf, T), "core_encode")
+        return z
+
+    def core_decode(self, z):
+        zz, pz = _np(z, np.float32)
+        S, T, K = zz.shape
+        assert S == self.S and K == 80
+        f = np.empty((S, T, 84), np.float32)
+        _check(self.lib.rade_b200_core_decode(self.h, f.ctypes.data, pz, T), "core_decode")
+        return f
+
+    # ---- transmitter
+    def tx(self, features_in):
+        f, pf = _np(features_in, np.float32)
+        assert f.size == self.S * NFEAT
+        out = np.empty((self.S, NMF), np.complex64)
+        _check(self.lib.rade_b200_tx(self.h, out.ctypes.data, pf), "tx")
+        return out
+
+    def tx_set_eoo_bits(self, bits):
+        b, pb = _np(bits, np.float32)
+        assert b.size == self.S * NEOO_BITS
+        _check(self.lib.rade_b200_tx_set_eoo_bits(self.h, pb), "tx_set_eoo_bits")
+
+    def tx_eoo(self):
+        out = np.empty((self.S, NEOO), np.complex64)
+        _check(self.lib.rade_b200_tx_eoo(self.h, out.ctypes.data), "tx_eoo")
+        return out
+
+    # ---- receiver
+    def nin(self):
+        n = np.empty(self.S, np.int32)
+        _check(self.lib.rade_b200_nin(self.h, n.ctypes.data), "nin")
+        return n
+
+    def rx(self, rx_in, active=None):
+        """rx_in [S][1120] complex64 (row s: nin[s] fresh samples) -> (features [S][432], ret [S], eoo [S][180])"""
+        x, px = _np(rx_in, np.complex64)
+        assert x.shape == (self.S, NIN_MAX)
+        feats = np.zeros((self.S, NFEAT), np.float32)
+        ret = np.zeros(self.S, np.int32)
+        eoo = np.zeros((self.S, NEOO_BITS), np.float32)
+        pa = None
+        if active is not None:
+            a, pa = _np(active, np.uint8)
+        _check(self.lib.rade_b200_rx(self.h, feats.ctypes.data, ret.ctypes.data, eoo.ctypes.data, px, pa), "rx")
+        return feats, ret, eoo
+
+    def rx_status(self):
+        arr = (capi.RxStatus * self.S)()
+        _check(self.lib.rade_b200_rx_get_status(self.h, arr), "rx_get_status")
+        return list(arr)
+
+    def rx_z_hat(self):
+        z = np.empty((self.S, 240), np.float32)
+        _check(self.lib.rade_b200_rx_get_z_hat(self.h, z.ctypes.data), "rx_get_z_hat")
+        return z
+
+    # ---- raw device-pointer entry points (ints = CUDA device addresses)
+    def core_encode_dev(self, d_z, d_features, n_steps):
+        _check(self.lib.rade_b200_core_encode_dev(self.h, d_z, d_features, n_steps), "core_encode_dev")
+
+    def core_decode_dev(self, d_features, d_z, n_steps):
+        _check(self.lib.rade_b200_core_decode_dev(self.h, d_features, d_z, n_steps), "core_decode_dev")
+
+    def tx_dev(self, d_tx_out, d_features_in):
+        _check(self.lib.rade_b200_tx_dev(self.h, d_tx_out, d_features_in), "tx_dev")
+
+    def ofdm_mod_dev(self, d_tx_out, d_z):
+        _check(self.lib.rade_b200_ofdm_mod_dev(self.h, d_tx_out, d_z), "ofdm_mod_dev")
+
+    def rx_dev(self, d_features_out, d_ret, d_eoo_out, d_rx_in, d_active=None):
+        _check(self.lib.rade_b200_rx_dev(self.h, d_features_out, d_ret, d_eoo_out, d_rx_in, d_active), "rx_dev")
+
+    def channel_config(self, EbNodB=100.0, freq_offset_hz=0.0, freq_offset_spread_hz=0.0, doppler_spread_hz=0.0,
+                       delay_samples=16, gain=1.0, seed=1):
+        cfg = capi.ChannelCfg(EbNodB, freq_offset_hz, freq_offset_spread_hz, doppler_spread_hz, delay_samples, gain, seed)
+        _check(self.lib.rade_b200_channel_config(self.h, C.byref(cfg)), "channel_config")
+
+    def channel_dev(self, d_rx, d_tx):
+        _check(self.lib.rade_b200_channel_dev(self.h, d_rx, d_tx), "channel_dev")
+
+    def channel_apply_dev(self, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq, phase0, sigma, gain):
+        _check(self.lib.rade_b200_channel_apply_dev(self.h, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq,
+                                                    phase0, sigma, gain), "channel_apply_dev")
+
+    def link_push_dev(self, d_samples):
+        _check(self.lib.rade_b200_link_push_dev(self.h, d_samples), "link_push_dev")
+
+    def link_pop_dev(self, d_rx_in, d_active):
+        _check(self.lib.rade_b200_link_pop_dev(self.h, d_rx_in, d_active), "link_pop_dev")

@@ -1,0 +1,439 @@
+// C ABI of libradae_b200: the batched context (include/rade_b200.h) and, on top of a 1-stream batch, the
+// reference's single-stream surface (include/rade_api.h <-> /root/reference/src/rade_api.h:71-129, rade_api.c).
+#include <cstring>
+#include <vector>
+#include <string>
+#include "rade_common.h"
+#include "rade_host.h"
+#include "rade_b200.h"
+
+#define LINK_CAP 4096
+
+struct rade_batch {
+  int S, device, flags;
+  cudaStream_t stream;
+  long long launches;
+  CoreWeightsHolder weights;
+  std::vector<void *> allocs;
+  DspTables tables;
+  // state
+  EncStreamState *enc_state;
+  RxBuffers rx;
+  ChanState *chan_state;
+  rade_b200_channel_cfg chan_cfg;
+  float2 *link_ring; long long *link_wr, *link_rd;
+  // transmitter
+  float *z_tx;                // [S][240]
+  float *eoo_bits; int *has_eoo_bits;
+  // device staging for the host-pointer API
+  float *d_feat_in, *d_feat_out, *d_z, *d_core_in, *d_core_out; size_t core_cap;
+  float2 *d_tx, *d_tx_eoo, *d_rx_in;
+  int *d_ret; unsigned char *d_active;
+  // pinned host staging
+  float *h_feat; float2 *h_cplx; int *h_int;
+};
+
+namespace {
+
+template <typename T> int dalloc(rade_batch *b, T **p, size_t n) {
+  void *d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, n * sizeof(T)));
+  CUDA_CHECK(cudaMemset(d, 0, n * sizeof(T)));
+  b->allocs.push_back(d);
+  *p = (T *)d;
+  return 0;
+}
+
+int reset_state(rade_batch *b) {
+  const int S = b->S;
+  CUDA_CHECK(cudaMemsetAsync(b->enc_state, 0, sizeof(EncStreamState) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.dec_state, 0, sizeof(DecStreamState) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.ring, 0, sizeof(float2) * RADE_RXBUF * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.bpf_mem, 0, sizeof(float2) * RADE_BPF_MEM * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.rowsum, 0, sizeof(float) * 2 * RADE_NMF * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.z_hat, 0, sizeof(float) * 240 * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.eoo, 0, sizeof(float) * RADE_NEOO_BITS * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.dec_active, 0, S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->link_wr, 0, sizeof(long long) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->link_rd, 0, sizeof(long long) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->has_eoo_bits, 0, sizeof(int) * S, b->stream));
+  const double foff_err = (b->flags & RADE_FOFF_TEST) ? 10.0 : 0.0;     // src/rade_api.c:263-264
+  if (rx_init_launch(b->rx.ctl, b->rx.uw_errors, S, foff_err, b->stream) < 0) return -1;
+  std::vector<int> nin(S, RADE_NMF);
+  CUDA_CHECK(cudaMemcpyAsync(b->rx.nin, nin.data(), sizeof(int) * S, cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  b->launches += 1;
+  return 0;
+}
+
+int ensure_core_staging(rade_batch *b, size_t floats) {
+  if (floats <= b->core_cap) return 0;
+  if (b->d_core_in) { cudaFree(b->d_core_in); cudaFree(b->d_core_out); }
+  CUDA_CHECK(cudaMalloc((void **)&b->d_core_in, floats * sizeof(float)));
+  CUDA_CHECK(cudaMalloc((void **)&b->d_core_out, floats * sizeof(float)));
+  b->core_cap = floats;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+RADE_EXPORT const void *rade_b200_default_weights_blob(size_t *len) {
+  if (len) *len = (size_t)(rade_b200_default_weights_end - rade_b200_default_weights);
+  return rade_b200_default_weights;
+}
+
+RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, const void *weights, size_t weights_len) {
+  if (n_streams <= 0) { fprintf(stderr, "libradae_b200: n_streams must be positive\n"); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "libradae_b200: no CUDA device available (%s) — this library has no CPU fallback\n", cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { fprintf(stderr, "libradae_b200: cannot select device %d\n", device); return nullptr; }
+  if (device < 0) cudaGetDevice(&device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    fprintf(stderr, "libradae_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+    return nullptr;
+  }
+  rade_batch *b = new rade_batch();
+  b->S = n_streams; b->device = device; b->flags = flags; b->launches = 0; b->core_cap = 0;
+  b->d_core_in = b->d_core_out = nullptr;
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
+  if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
+  if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
+  DspTablesHost th; dsp_tables_host(th);
+  if (dsp_tables_upload(th, &b->tables, b->allocs) < 0) { delete b; return nullptr; }
+  const size_t S = n_streams;
+  int bad = 0;
+  bad |= dalloc(b, &b->enc_state, S);
+  bad |= dalloc(b, &b->rx.dec_state, S);
+  bad |= dalloc(b, &b->rx.ctl, S);
+  bad |= dalloc(b, &b->rx.ring, S * RADE_RXBUF);
+  bad |= dalloc(b, &b->rx.bpf_mem, S * RADE_BPF_MEM);
+  bad |= dalloc(b, &b->rx.rowsum, S * 2 * RADE_NMF);
+  bad |= dalloc(b, &b->rx.uw_errors, S);
+  bad |= dalloc(b, &b->rx.z_hat, S * 240);
+  bad |= dalloc(b, &b->rx.eoo, S * RADE_NEOO_BITS);
+  bad |= dalloc(b, &b->rx.dec_active, S);
+  bad |= dalloc(b, &b->rx.nin, S);
+  bad |= dalloc(b, &b->chan_state, S);
+  bad |= dalloc(b, &b->link_ring, S * LINK_CAP);
+  bad |= dalloc(b, &b->link_wr, S);
+  bad |= dalloc(b, &b->link_rd, S);
+  bad |= dalloc(b, &b->z_tx, S * 240);
+  bad |= dalloc(b, &b->eoo_bits, S * RADE_NEOO_BITS);
+  bad |= dalloc(b, &b->has_eoo_bits, S);
+  bad |= dalloc(b, &b->d_feat_in, S * RADE_NFEAT);
+  bad |= dalloc(b, &b->d_feat_out, S * RADE_NFEAT);
+  bad |= dalloc(b, &b->d_z, S * 240);
+  bad |= dalloc(b, &b->d_tx, S * RADE_NMF);
+  bad |= dalloc(b, &b->d_tx_eoo, S * RADE_NEOO);
+  bad |= dalloc(b, &b->d_rx_in, S * RADE_NIN_MAX);
+  bad |= dalloc(b, &b->d_ret, S);
+  bad |= dalloc(b, &b->d_active, S);
+  if (bad) { rade_b200_close(b); return nullptr; }
+  if (cudaMallocHost((void **)&b->h_feat, S * RADE_NFEAT * sizeof(float)) != cudaSuccess ||
+      cudaMallocHost((void **)&b->h_cplx, S * RADE_NEOO * sizeof(float2)) != cudaSuccess ||
+      cudaMallocHost((void **)&b->h_int, S * 4 * sizeof(int)) != cudaSuccess) { rade_b200_close(b); return nullptr; }
+  memset(&b->chan_cfg, 0, sizeof(b->chan_cfg));
+  b->chan_cfg.EbNodB = 100.f; b->chan_cfg.gain = 1.f; b->chan_cfg.delay_samples = 16; b->chan_cfg.seed = 1;
+  if (reset_state(b) < 0) { rade_b200_close(b); return nullptr; }
+  return b;
+}
+
+RADE_EXPORT void rade_b200_close(rade_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  for (void *p : b->allocs) cudaFree(p);
+  core_weights_free(&b->weights);
+  if (b->d_core_in) { cudaFree(b->d_core_in); cudaFree(b->d_core_out); }
+  if (b->h_feat) cudaFreeHost(b->h_feat);
+  if (b->h_cplx) cudaFreeHost(b->h_cplx);
+  if (b->h_int) cudaFreeHost(b->h_int);
+  cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+RADE_EXPORT int rade_b200_n_streams(rade_batch *b) { return b->S; }
+RADE_EXPORT void *rade_b200_cuda_stream(rade_batch *b) { return (void *)b->stream; }
+RADE_EXPORT int rade_b200_synchronize(rade_batch *b) { CUDA_CHECK(cudaStreamSynchronize(b->stream)); return 0; }
+RADE_EXPORT long long rade_b200_launch_count(rade_batch *b) { return b->launches; }
+RADE_EXPORT int rade_b200_reset(rade_batch *b) { return reset_state(b); }
+
+// ------------------------------------------------------------------ core codec
+RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float *d_features, int n_steps) {
+  if (core_encoder_launch(b->weights.dev, b->enc_state, d_features, 0, d_z, nullptr, b->S, n_steps, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, const float *d_z, int n_steps) {
+  if (core_decoder_launch(b->weights.dev, b->rx.dec_state, d_z, d_features, 0, nullptr, nullptr, b->S, n_steps, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *features, int n_steps) {
+  const size_t nin = (size_t)b->S * n_steps * ENC_IN, nout = (size_t)b->S * n_steps * RADE_LATENT;
+  if (ensure_core_staging(b, nin) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, features, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_core_encode_dev(b, b->d_core_out, b->d_core_in, n_steps) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(z, b->d_core_out, nout * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const float *z, int n_steps) {
+  const size_t nin = (size_t)b->S * n_steps * RADE_LATENT, nout = (size_t)b->S * n_steps * DEC_OUT;
+  if (ensure_core_staging(b, nout) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, z, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_core_decode_dev(b, b->d_core_out, b->d_core_in, n_steps) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(features, b->d_core_out, nout * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ transmitter
+RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z) {
+  if (ofdm_mod_launch(b->tables, d_z, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_features_in) {
+  // 3 core-encoder steps on the API feature layout (src/rade_api.c:411-434) then transmitter_one (radae_txe.py:127)
+  if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, b->stream) < 0) return -1;
+  if (ofdm_mod_launch(b->tables, b->z_tx, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  b->launches += 2;
+  return RADE_NMF;
+}
+RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *features_in) {
+  const size_t S = b->S;
+  memcpy(b->h_feat, features_in, S * RADE_NFEAT * sizeof(float));
+  CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, b->h_feat, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(b->h_cplx, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  memcpy(tx_out, b->h_cplx, S * RADE_NMF * sizeof(float2));
+  return RADE_NMF;
+}
+RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits) {
+  const size_t S = b->S;
+  std::vector<int> ones(S, 1);
+  CUDA_CHECK(cudaMemcpyAsync(b->eoo_bits, eoo_bits, S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->has_eoo_bits, ones.data(), S * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
+  const size_t S = b->S;
+  if (eoo_launch(b->tables, b->eoo_bits, b->has_eoo_bits, b->d_tx_eoo, b->S, b->stream) < 0) return -1;
+  b->launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(b->h_cplx, b->d_tx_eoo, S * RADE_NEOO * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  memcpy(tx_eoo_out, b->h_cplx, S * RADE_NEOO * sizeof(float2));
+  return RADE_NEOO;
+}
+
+// ------------------------------------------------------------------ receiver
+RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out, const RADE_COMP *d_rx_in,
+                                 const unsigned char *d_active) {
+  const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
+  int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, b->S, 1, reset_dec, d_ret, b->stream);
+  if (n < 0) return -1;
+  // decoder last, only for streams with valid output; counts aux-symbol errors (src/rade_api.c:494-513)
+  if (core_decoder_launch(b->weights.dev, b->rx.dec_state, b->rx.z_hat, d_features_out, 1, b->rx.uw_errors, b->rx.dec_active,
+                          b->S, RADE_NZMF, b->stream) < 0) return -1;
+  b->launches += n + 1;
+  if (d_eoo_out && d_eoo_out != b->rx.eoo) {
+    CUDA_CHECK(cudaMemcpyAsync(d_eoo_out, b->rx.eoo, (size_t)b->S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
+  }
+  return 0;
+}
+RADE_EXPORT const int *rade_b200_nin_dev(rade_batch *b) { return b->rx.nin; }
+RADE_EXPORT int rade_b200_nin(rade_batch *b, int *nin) {
+  CUDA_CHECK(cudaMemcpyAsync(nin, b->rx.nin, sizeof(int) * b->S, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+RADE_EXPORT int rade_b200_rx(rade_batch *b, float *features_out, int *ret, float *eoo_out, const RADE_COMP *rx_in,
+                             const unsigned char *active) {
+  const size_t S = b->S;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, rx_in, S * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+  if (active) CUDA_CHECK(cudaMemcpyAsync(b->d_active, active, S, cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)b->d_rx_in, active ? b->d_active : nullptr) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(features_out, b->d_feat_out, S * RADE_NFEAT * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(ret, b->d_ret, S * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (eoo_out) CUDA_CHECK(cudaMemcpyAsync(eoo_out, b->rx.eoo, S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+RADE_EXPORT int rade_b200_rx_get_status(rade_batch *b, rade_b200_rx_status *status) {
+  std::vector<RxCtl> ctl(b->S); std::vector<int> uw(b->S);
+  CUDA_CHECK(cudaMemcpyAsync(ctl.data(), b->rx.ctl, sizeof(RxCtl) * b->S, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(uw.data(), b->rx.uw_errors, sizeof(int) * b->S, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  for (int s = 0; s < b->S; s++) {
+    const RxCtl &c = ctl[s]; rade_b200_rx_status &o = status[s];
+    o.state = c.state; o.nin = c.nin; o.tmax = c.tmax; o.valid_count = c.valid_count; o.uw_errors = uw[s];
+    o.synced_count = c.synced_count; o.snrdB_3k_est = (int)c.snr_est; o.snrdB_3k_est_f = (float)c.snr_est;
+    o.fmax = c.fmax; o.Dthresh = c.Dthresh; o.Dtmax12 = c.Dtmax12; o.Dtmax12_eoo = c.Dtmax12_eoo;
+  }
+  return 0;
+}
+RADE_EXPORT int rade_b200_rx_get_z_hat(rade_batch *b, float *z_hat) {
+  CUDA_CHECK(cudaMemcpyAsync(z_hat, b->rx.z_hat, (size_t)b->S * 240 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ channel + link
+RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx, const RADE_COMP *d_G1,
+                                            const RADE_COMP *d_G2, const RADE_COMP *d_noise, int n, int delay,
+                                            float mp_gain, float freq_offset_hz, float phase0, float sigma, float gain) {
+  if (channel_apply_launch((float2 *)d_rx, (const float2 *)d_tx, (const float2 *)d_G1, (const float2 *)d_G2, (const float2 *)d_noise,
+                           b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_cfg *cfg) {
+  if (cfg->delay_samples < 0 || cfg->delay_samples > 64) return -1;
+  b->chan_cfg = *cfg;
+  CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * b->S, b->stream));
+  return 0;
+}
+RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx) {
+  const rade_b200_channel_cfg &c = b->chan_cfg;
+  const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));       // radae.py:570-574, Rb = 80/0.04
+  if (channel_stream_launch((float2 *)d_rx, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz,
+                            c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {
+  if (link_push_launch(b->link_ring, b->link_wr, (const float2 *)d_samples, b->S, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsigned char *d_active) {
+  if (link_pop_launch(b->link_ring, b->link_wr, b->link_rd, b->rx.ctl, (float2 *)d_rx_in, d_active, b->S, b->stream) < 0) return -1;
+  b->launches += 1;
+  return 0;
+}
+
+// debug/test hook: DSP tables as built on the host (no device needed) — lets the CPU test-suite compare them with
+// the oracle's.  which: 0 Winv, 1 Wfwd, 2 p, 3 pend, 4 p_w, 5 Pmat, 6 eq_rot, 7 bpf_exp, 8 eoo_base (complex64);
+// 16 bpf_h, 17 fcoarse, 18 {pilot_gain, bpf_bw, bpf_centre, bpf_alpha} (float32).  Returns element count.
+RADE_EXPORT int rade_b200_debug_tables(int which, float *out, int cap_floats) {
+  DspTablesHost T; dsp_tables_host(T);
+  const std::vector<std::complex<float>> *cv = nullptr; std::vector<float> fv;
+  switch (which) {
+    case 0: cv = &T.Winv; break; case 1: cv = &T.Wfwd; break; case 2: cv = &T.p; break; case 3: cv = &T.pend; break;
+    case 4: cv = &T.p_w; break; case 5: cv = &T.Pmat; break; case 6: cv = &T.eq_rot; break; case 7: cv = &T.bpf_exp; break;
+    case 8: cv = &T.eoo_base; break;
+    case 16: fv = T.bpf_h; break; case 17: fv = T.fcoarse; break;
+    case 18: fv = {(float)T.pilot_gain, T.bpf_bw, T.bpf_centre, T.bpf_alpha}; break;
+    default: return -1;
+  }
+  if (cv) {
+    if ((int)cv->size() * 2 > cap_floats) return -1;
+    memcpy(out, cv->data(), cv->size() * sizeof(std::complex<float>));
+    return (int)cv->size();
+  }
+  if ((int)fv.size() > cap_floats) return -1;
+  memcpy(out, fv.data(), fv.size() * sizeof(float));
+  return (int)fv.size();
+}
+
+// ================================================================== rade_api.h: the reference's single-stream surface
+struct rade {
+  rade_batch *b;
+  int flags;
+  int nin, sync, snr;
+  float freq_offset;
+};
+
+RADE_EXPORT void rade_initialize(void) {}      /* reference: starts CPython (src/rade_api.c:329-332); nothing to start here */
+RADE_EXPORT void rade_finalize(void) {}
+
+RADE_EXPORT struct rade *rade_open(char model_file[], int flags) {
+  struct rade *r = new rade();
+  r->flags = flags;
+  std::vector<unsigned char> blob;
+  if (model_file) {                             // honoured when it is a readable RDW / DNNw file, else embedded weights
+    FILE *f = fopen(model_file, "rb");
+    if (f) {
+      fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+      if (n > 8) { blob.resize(n); if (fread(blob.data(), 1, n, f) != (size_t)n) blob.clear(); }
+      fclose(f);
+      if (blob.size() > 8 && memcmp(blob.data(), "RADEB200", 8) != 0 && memcmp(blob.data(), "DNNw", 4) != 0) blob.clear();
+    }
+  }
+  if (!(flags & RADE_VERBOSE_0))
+    fprintf(stderr, "libradae_b200: model: %s\n", blob.empty() ? "embedded model19_check3" : model_file);
+  r->b = rade_b200_open(1, -1, flags, blob.empty() ? nullptr : blob.data(), blob.size());
+  if (!r->b) {
+    fprintf(stderr, "Error: libradae_b200 could not create a CUDA context; there is no CPU fallback\n");
+    exit(1);                                    // same contract as the reference's check_error (src/rade_api.c:93-102)
+  }
+  r->nin = RADE_NMF; r->sync = 0; r->snr = 0; r->freq_offset = 0.f;
+  return r;
+}
+
+RADE_EXPORT void rade_close(struct rade *r) {
+  if (!r) return;
+  rade_b200_close(r->b);
+  delete r;
+}
+
+RADE_EXPORT int rade_version(void) { return 1; }                                      /* src/rade_api.c:37 */
+RADE_EXPORT int rade_n_tx_out(struct rade *r) { (void)r; return RADE_NMF; }
+RADE_EXPORT int rade_n_tx_eoo_out(struct rade *r) { (void)r; return RADE_NEOO; }
+RADE_EXPORT int rade_nin_max(struct rade *r) { (void)r; return RADE_NIN_MAX; }
+RADE_EXPORT int rade_n_features_in_out(struct rade *r) { (void)r; return RADE_NFEAT; }
+RADE_EXPORT int rade_n_eoo_bits(struct rade *r) { (void)r; return RADE_NEOO_BITS; }
+
+RADE_EXPORT int rade_tx(struct rade *r, RADE_COMP tx_out[], float features_in[]) {
+  if (!r || !tx_out || !features_in) { fprintf(stderr, "rade_tx: NULL argument\n"); abort(); }   /* assert()s in the reference */
+  if (rade_b200_tx(r->b, tx_out, features_in) < 0) { fprintf(stderr, "Error: rade_tx failed on the device\n"); exit(1); }
+  return RADE_NMF;
+}
+RADE_EXPORT void rade_tx_set_eoo_bits(struct rade *r, float eoo_bits[]) {
+  if (!r || !eoo_bits) { fprintf(stderr, "rade_tx_set_eoo_bits: NULL argument\n"); abort(); }
+  if (rade_b200_tx_set_eoo_bits(r->b, eoo_bits) < 0) exit(1);
+}
+RADE_EXPORT int rade_tx_eoo(struct rade *r, RADE_COMP tx_eoo_out[]) {
+  if (!r || !tx_eoo_out) { fprintf(stderr, "rade_tx_eoo: NULL argument\n"); abort(); }
+  if (rade_b200_tx_eoo(r->b, tx_eoo_out) < 0) exit(1);
+  return RADE_NEOO;
+}
+RADE_EXPORT int rade_nin(struct rade *r) { return r->nin; }
+
+RADE_EXPORT int rade_rx(struct rade *r, float features_out[], int *has_eoo_out, float eoo_out[], RADE_COMP rx_in[]) {
+  if (!r || !features_out || !rx_in) { fprintf(stderr, "rade_rx: NULL argument\n"); abort(); }
+  rade_batch *b = r->b;
+  // only nin samples are valid in the caller's array (src/rade_api.c:472)
+  CUDA_CHECK_FATAL(cudaMemcpyAsync(b->d_rx_in, rx_in, (size_t)r->nin * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)b->d_rx_in, nullptr) < 0) exit(1);
+  int ret = 0; RxCtl c;
+  CUDA_CHECK_FATAL(cudaMemcpyAsync(&ret, b->d_ret, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK_FATAL(cudaMemcpyAsync(&c, b->rx.ctl, sizeof(RxCtl), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK_FATAL(cudaStreamSynchronize(b->stream));
+  const int valid = ret & 1, eoo = ret & 2;
+  if (valid) CUDA_CHECK_FATAL(cudaMemcpy(features_out, b->d_feat_out, RADE_NFEAT * sizeof(float), cudaMemcpyDeviceToHost));
+  if (has_eoo_out) *has_eoo_out = 0;
+  if (eoo) {
+    if (eoo_out) CUDA_CHECK_FATAL(cudaMemcpy(eoo_out, b->rx.eoo, RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToHost));
+    if (has_eoo_out) *has_eoo_out = 1;
+  }
+  r->nin = c.nin; r->sync = (c.state == 2); r->snr = (int)c.snr_est; r->freq_offset = (float)c.fmax;   /* src/rade_api.c:528-530 */
+  return valid ? RADE_NFEAT : 0;
+}
+RADE_EXPORT int rade_sync(struct rade *r) { return r->sync; }
+/* the reference returns 0 here ("TODO: we need a float getter", src/rade_api.c:547-550); we return the tracked offset */
+RADE_EXPORT float rade_freq_offset(struct rade *r) { return r->freq_offset; }
+RADE_EXPORT int rade_snrdB_3k_est(struct rade *r) { return r->snr; }
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+// HF channel simulator + loop-back sample link.
+//
+// Replaces the rate-Fs channel branch of RADAE.forward (radae/radae.py:529-599): two-path multipath
+// tx*G1 + delay_d(tx*G2) (:530-534), frequency/phase offset exp(j*cumsum(omega)) (:542-553), AWGN with
+// sigma = sqrt(Fs/(EbNo*Rb)) (:570-578) and gain (:589).  Deviation, stated in DESIGN.md: the reference
+// normalises multipath power over the WHOLE batch tensor (:536-539); here normalisation is per stream and by
+// expectation (E|G1|^2 + E|G2|^2 = 1, which is what multipath_samples.m:27-31's hf_gain achieves on its files).
+// The Watterson gains (Gaussian Doppler spectrum, doppler_spread.m:11-41) are synthesised in-kernel as a sum of
+// sinusoids with Gaussian-distributed Doppler shifts, evaluated at frame edges and interpolated linearly, the
+// way the reference interpolates its 10 Hz gain samples up to Fs.  Noise: Philox4x32-10 counter RNG keyed by
+// (seed, stream), counter = absolute sample index, Box-Muller.
+#include "rade_common.h"
+#include "rade_host.h"
+
+namespace {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// unit-variance circular complex normal for (seed, stream, sample index, salt)
+__device__ __forceinline__ float2 cnormal(unsigned long long seed, uint32_t stream, unsigned long long idx, uint32_t salt) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), stream, salt};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float r = sqrtf(-logf(u01(c[0])));          // |n|^2 ~ Exp(1): variance 1 in total (torch.randn on a complex tensor)
+  float sn, cs;
+  sincospif(2.f * u01(c[1]), &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
+// explicit form used by the parity tests: every random quantity supplied by the caller
+__global__ void channel_apply_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, const float2 *__restrict__ G1,
+                                     const float2 *__restrict__ G2, const float2 *__restrict__ noise, int S, int n, int d,
+                                     float mp_gain, float freq, float phase0, float sigma, float gain) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)S * n) return;
+  const int k = (int)(i % n);
+  float2 mp = cmul(tx[i], G1[i]);
+  if (k >= d) { float2 e = cmul(tx[i - d], G2[i - d]); mp.x += e.x; mp.y += e.y; }
+  double sn, cs;
+  sincos((double)phase0 + 2.0 * M_PI * (double)freq / RADE_FS * (double)(k + 1), &sn, &cs);
+  float2 v = cmul(make_float2(mp_gain * mp.x, mp_gain * mp.y), make_float2((float)cs, (float)sn));
+  rx[i] = make_float2(gain * (v.x + sigma * noise[i].x), gain * (v.y + sigma * noise[i].y));
+}
+
+constexpr int NSIN = 16;
+
+// path gain at absolute time t (samples): (1/sqrt(2*NSIN)) * sum_i exp(j(2*pi*f_i*t/Fs + phi_i)), f_i ~ N(0, (spread/2)^2)
+__device__ float2 path_gain(unsigned long long seed, uint32_t stream, uint32_t path, double t, float spread) {
+  float re = 0.f, im = 0.f;
+  for (int i = 0; i < NSIN; i++) {
+    uint32_t c[4] = {(uint32_t)i, path, stream, 0x5EEDu};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float rr = sqrtf(-2.f * logf(u01(c[0])));
+    float s1, c1; sincospif(2.f * u01(c[1]), &s1, &c1);
+    const double f = 0.5 * (double)spread * (double)(rr * c1);           // Gaussian Doppler: sigma_f = spread/2
+    double sn, cs;
+    sincos(2.0 * M_PI * (f * t / RADE_FS + (double)u01(c[2])), &sn, &cs);
+    re += (float)cs; im += (float)sn;
+  }
+  const float a = rsqrtf(2.f * NSIN);
+  return make_float2(a * re, a * im);
+}
+
+// streaming generator form: one CTA per stream, one modem frame (960 samples) per call
+__global__ void __launch_bounds__(256)
+channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, ChanState *__restrict__ st, int S,
+                      float sigma, float freq0, float freq_spread, float doppler, int d, float gain, unsigned long long seed) {
+  __shared__ float2 stx[64 + RADE_NMF];
+  __shared__ float2 g[4];                       // G1(t0), G1(t0+960), G2(t0), G2(t0+960)
+  const int s = blockIdx.x, tid = threadIdx.x;
+  ChanState &cs_ = st[s];
+  const long long t0 = cs_.t;
+  const double ph0 = cs_.phase;
+  const float2 *txs = tx + (size_t)s * RADE_NMF;
+  for (int i = tid; i < 64; i += blockDim.x) stx[i] = cs_.delay[i];
+  for (int i = tid; i < RADE_NMF; i += blockDim.x) stx[64 + i] = txs[i];
+  if (tid < 4) {
+    if (doppler > 0.f) g[tid] = path_gain(seed, s, tid >> 1, (double)(t0 + (tid & 1) * RADE_NMF), doppler);
+    else g[tid] = (tid < 2) ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f);
+  }
+  // per-stream frequency offset: freq0 + U(-1,1)*freq_spread, fixed for the life of the stream
+  uint32_t c[4] = {0u, 0u, (uint32_t)s, 0xF0FFu};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double f = (double)freq0 + (double)freq_spread * (2.0 * (double)u01(c[0]) - 1.0);
+  const double dphi = 2.0 * M_PI * f / RADE_FS;
+  __syncthreads();
+  float2 *out = rx + (size_t)s * RADE_NMF;
+  for (int i = tid; i < RADE_NMF; i += blockDim.x) {
+    const float a = (float)i * (1.f / RADE_NMF);
+    const float2 g1 = make_float2(g[0].x + a * (g[1].x - g[0].x), g[0].y + a * (g[1].y - g[0].y));
+    const float2 g2 = make_float2(g[2].x + a * (g[3].x - g[2].x), g[2].y + a * (g[3].y - g[2].y));
+    float2 mp = cmul(stx[64 + i], g1);
+    const float2 e = cmul(stx[64 + i - d], g2);   // g2 of the current instant: gains vary by <1e-3 over the 2 ms delay
+    mp.x += e.x; mp.y += e.y;
+    double sn, cs;
+    sincos(ph0 + dphi * (double)(i + 1), &sn, &cs);
+    const float2 v = cmul(mp, make_float2((float)cs, (float)sn));
+    const float2 nz = cnormal(seed, s, (unsigned long long)(t0 + i), 0xA11CEu);
+    out[i] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
+  }
+  __syncthreads();
+  for (int i = tid; i < 64; i += blockDim.x) cs_.delay[i] = stx[RADE_NMF + i];
+  if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); }
+}
+
+// ---------------------------------------------------------------- loop-back link (per-stream FIFO)
+constexpr int LINK_CAP = 4096;
+
+__global__ void link_push_kernel(float2 *__restrict__ ring, long long *__restrict__ wr, const float2 *__restrict__ in, int S) {
+  const int s = blockIdx.x;
+  const long long w = wr[s];
+  for (int i = threadIdx.x; i < RADE_NMF; i += blockDim.x)
+    ring[(size_t)s * LINK_CAP + ((w + i) & (LINK_CAP - 1))] = in[(size_t)s * RADE_NMF + i];
+  __syncthreads();
+  if (threadIdx.x == 0) wr[s] = w + RADE_NMF;
+}
+
+__global__ void link_pop_kernel(const float2 *__restrict__ ring, const long long *__restrict__ wr, long long *__restrict__ rd,
+                                const RxCtl *__restrict__ ctl, float2 *__restrict__ out, unsigned char *__restrict__ active, int S) {
+  const int s = blockIdx.x;
+  const int nin = ctl[s].nin;
+  const long long r = rd[s];
+  const bool ok = wr[s] - r >= nin;
+  if (ok)
+    for (int i = threadIdx.x; i < nin; i += blockDim.x)
+      out[(size_t)s * RADE_NIN_MAX + i] = ring[(size_t)s * LINK_CAP + ((r + i) & (LINK_CAP - 1))];
+  __syncthreads();
+  if (threadIdx.x == 0) { active[s] = ok ? 1 : 0; if (ok) rd[s] = r + nin; }
+}
+
+}  // namespace
+
+int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
+                         int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream) {
+  const size_t total = (size_t)S * n;
+  channel_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(rx, tx, G1, G2, noise, S, n, d, mp_gain, freq, phase0, sigma, gain);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
+                          float doppler, int d, float gain, unsigned long long seed, cudaStream_t stream) {
+  if (d < 0 || d > 64) return -1;
+  channel_stream_kernel<<<S, 256, 0, stream>>>(rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream) {
+  link_push_kernel<<<S, 256, 0, stream>>>(ring, wr, in, S);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, const RxCtl *ctl, float2 *out,
+                    unsigned char *active, int S, cudaStream_t stream) {
+  link_pop_kernel<<<S, 256, 0, stream>>>(ring, wr, rd, ctl, out, active, S);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,576 @@
+// Streaming receiver DSP for S independent streams: band-pass filter, pilot acquisition (coarse grid search,
+// fine refinement, sync check), frequency correction, OFDM demodulation, least-squares pilot equalisation,
+// SNR estimate, end-of-over detection and the search/candidate/sync state machine.
+//
+// Replaces, per stream and per call of radae_rx.do_radae_rx (radae_rxe.py:171-330):
+//   complex_bpf.bpf                 radae/dsp.py:63-102   (incl. the Ntap+1 memory quirk, dsp.py:96)
+//   acquisition.detect_pilots       radae/dsp.py:178-231
+//   acquisition.refine              radae/dsp.py:233-270  (complex128 correlations -> csingle, f outer / t inner, strict >)
+//   acquisition.check_pilots        radae/dsp.py:273-320  (deterministic row schedule instead of np.random)
+//   receiver_one.receiver_one       radae/dsp.py:487-526  (+ est_pilots :418-435, update_snr_est :438-456, do_pilot_eq_one :459-484)
+//   the state machine               radae_rxe.py:248-297
+//
+// Data layout per stream in HBM: rx_buf as a 2112-sample RING (no 17 KB shift per call, only the nin new samples
+// are written), 102-sample BPF history, two 960-entry row-sum vectors sum_f|Dt1|, sum_f|Dt2| (all the reference
+// ever reads back from its two 960x40 complex grids = 614 KB/stream), a 128-byte control block.
+// Kernels (one launch each per rade_rx call, every stream handled by its own CTA(s), branching on its state):
+//   rx_bpf -> rx_detect (search/candidate streams) -> rx_track (sync streams) -> rx_demod (sync streams) -> rx_finish
+#include "rade_common.h"
+#include "rade_host.h"
+
+namespace {
+
+enum { ST_SEARCH = 0, ST_CANDIDATE = 1, ST_SYNC = 2 };
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ double2 dcmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ int ring_idx(int head, int i) { int k = head + i; return k >= RADE_RXBUF ? k - RADE_RXBUF : k; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum, result valid in every thread; scratch: >= 32 floats of shared memory
+__device__ float block_sum(float v, float *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.f;
+  if (w == 0) { t = warp_sum(t); if (lane == 0) scratch[0] = t; }
+  __syncthreads();
+  return scratch[0];
+}
+
+// ================================================================= band-pass filter + ring append
+__global__ void __launch_bounds__(256)
+rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, float2 *__restrict__ bpf_mem,
+              const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en) {
+  __shared__ float2 X[RADE_BPF_MEM + RADE_NIN_MAX];
+  __shared__ float h[RADE_BPF_NTAP];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (active && !active[s]) return;
+  RxCtl &c = ctl[s];
+  const int nin = c.nin, head = c.ring_head;
+  const float2 *xin = rx_in + (size_t)s * RADE_NIN_MAX;
+  float2 *rg = ring + (size_t)s * RADE_RXBUF;
+  if (bpf_en) {
+    const float2 ph = c.bpf_phase;
+    const int off = c.bpf_first ? 2 : 0;
+    float2 *mem = bpf_mem + (size_t)s * RADE_BPF_MEM;
+    if (tid < RADE_BPF_NTAP) h[tid] = T.bpf_h[tid];
+    for (int i = tid; i < RADE_BPF_MEM; i += blockDim.x) X[i] = mem[i];
+    for (int i = tid; i < nin; i += blockDim.x) X[RADE_BPF_MEM + i] = cmul(xin[i], cmul(ph, T.bpf_exp[i]));   // mix down
+    __syncthreads();
+    for (int i = tid; i < nin; i += blockDim.x) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int k = 0; k < RADE_BPF_NTAP; k++) {
+        const float2 v = X[i + k + off];
+        acc.x += h[k] * v.x; acc.y += h[k] * v.y;
+      }
+      rg[ring_idx(head, i)] = cmul(acc, cconj(cmul(ph, T.bpf_exp[i])));                                         // mix up
+    }
+    __syncthreads();
+    for (int i = tid; i < RADE_BPF_MEM; i += blockDim.x) mem[i] = X[nin + i];
+    if (tid == 0) { c.bpf_phase = cmul(ph, T.bpf_exp[nin - 1]); c.bpf_first = 0; }
+  } else {
+    for (int i = tid; i < nin; i += blockDim.x) rg[ring_idx(head, i)] = xin[i];
+  }
+  if (tid == 0) {
+    int nh = head + nin; if (nh >= RADE_RXBUF) nh -= RADE_RXBUF;
+    c.ring_head = nh;                      // logical sample 0 of rx_buf now lives at ring[nh]
+    c.detect_key = 0ull;
+    c.candidate = 0; c.endofover = 0; c.valid_output = 0; c.uw_fail = 0; c.ran_sync = 0; c.ret = 0;
+  }
+}
+
+// ================================================================= coarse pilot search (search / candidate streams)
+// grid (15, S): CTA = 64 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations
+constexpr int DET_TB = 64;
+struct DetectSmem {
+  float2 pw[RADE_M][RADE_NFCOARSE];
+  float2 r1[DET_TB + RADE_M];
+  float2 r2[DET_TB + RADE_M];
+  float part[2][4][DET_TB];
+  unsigned long long best[8];
+};
+
+__global__ void __launch_bounds__(256)
+rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
+                 const unsigned char *__restrict__ active) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DetectSmem &sm = *reinterpret_cast<DetectSmem *>(smem_raw);
+  const int s = blockIdx.y, tid = threadIdx.x;
+  if (active && !active[s]) return;
+  RxCtl &c = ctl[s];
+  if (c.state == ST_SYNC) return;
+  const int head = c.ring_head, t0 = blockIdx.x * DET_TB;
+  const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+  for (int i = tid; i < RADE_M * RADE_NFCOARSE; i += blockDim.x) (&sm.pw[0][0])[i] = T.p_w[i];
+  for (int i = tid; i < DET_TB + RADE_M; i += blockDim.x) {
+    sm.r1[i] = cconj(rg[ring_idx(head, t0 + i)]);
+    sm.r2[i] = cconj(rg[ring_idx(head, t0 + RADE_NMF + i)]);
+  }
+  __syncthreads();
+  const int tl = tid & (DET_TB - 1), fg = tid >> 6;
+  float2 a1[10], a2[10];
+#pragma unroll
+  for (int j = 0; j < 10; j++) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
+  for (int n = 0; n < RADE_M; n++) {
+    const float2 x1 = sm.r1[tl + n], x2 = sm.r2[tl + n];
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+      const float2 w = sm.pw[n][fg * 10 + j];
+      a1[j].x += x1.x * w.x - x1.y * w.y; a1[j].y += x1.x * w.y + x1.y * w.x;
+      a2[j].x += x2.x * w.x - x2.y * w.y; a2[j].y += x2.x * w.y + x2.y * w.x;
+    }
+  }
+  float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = 0;
+#pragma unroll
+  for (int j = 0; j < 10; j++) {
+    const float m1 = hypotf(a1[j].x, a1[j].y), m2 = hypotf(a2[j].x, a2[j].y);
+    s1 += m1; s2 += m2;
+    const float d = m1 + m2;
+    if (d > best) { best = d; bestf = fg * 10 + j; }
+  }
+  sm.part[0][fg][tl] = s1; sm.part[1][fg][tl] = s2;
+  // arg-max with "first (t, f) wins": larger key = larger value, then smaller flat index
+  unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (0xFFFFFFFFu - (unsigned)((t0 + tl) * RADE_NFCOARSE + bestf));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
+  if ((tid & 31) == 0) sm.best[tid >> 5] = key;
+  __syncthreads();
+  if (tid < 2 * DET_TB) {
+    const int half = tid >> 6, t = tid & (DET_TB - 1);
+    rowsum[((size_t)s * 2 + half) * RADE_NMF + t0 + t] = ((sm.part[half][0][t] + sm.part[half][1][t]) + sm.part[half][2][t]) + sm.part[half][3][t];
+  }
+  if (tid == 0) {
+    unsigned long long k = sm.best[0];
+    for (int i = 1; i < 8; i++) k = sm.best[i] > k ? sm.best[i] : k;
+    atomicMax(&c.detect_key, k);
+  }
+}
+
+// ================================================================= fine timing / frequency refinement (shared by track & finish)
+constexpr int REF_CH = 21;        // frequencies per chunk
+constexpr int REF_NT = 16;        // max timing offsets
+struct RefineSmem {
+  double2 vtab[REF_CH][RADE_M];   // conj(p[n]) * exp(-j w n)
+  float2 ra[REF_NT + RADE_M];     // rx[t_lo ...]
+  float2 rb[REF_NT + RADE_M];     // rx[t_lo + Nmf ...]
+  float2 d1[REF_CH][REF_NT];
+  float2 d2[REF_CH][REF_NT];
+  float red_mag[8]; int red_ord[8];
+  float best_mag; int best_t; int best_found; double best_f;
+};
+
+// values of np.arange(start, stop, step) for float64: v[i] = start + i*((start+step)-start), len = ceil((stop-start)/step)
+__device__ __forceinline__ int arange_len(double start, double stop, double step) { return (int)ceil((stop - start) / step); }
+
+// searches t in [t_lo, t_lo+nt) x f in arange(f_start, f_stop, f_step); result in sm.best_* (best_found == 0: nothing beat 0)
+__device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *rg, int head, int t_lo, int nt,
+                             double f_start, double f_stop, double f_step) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int nf = arange_len(f_start, f_stop, f_step);
+  const double delta = (f_start + f_step) - f_start;
+  if (tid == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
+  for (int i = tid; i < nt + RADE_M; i += nthr) {
+    sm.ra[i] = rg[ring_idx(head, t_lo + i)];
+    sm.rb[i] = rg[ring_idx(head, t_lo + RADE_NMF + i)];
+  }
+  for (int c0 = 0; c0 < nf; c0 += REF_CH) {
+    const int nfc = min(REF_CH, nf - c0);
+    __syncthreads();
+    for (int idx = tid; idx < nfc * RADE_M; idx += nthr) {
+      const int fi = idx / RADE_M, n = idx % RADE_M;
+      const double f = f_start + (double)(c0 + fi) * delta;
+      const double w = 2.0 * M_PI * f / RADE_FS;
+      double sn, cs; sincos(w * (double)n, &sn, &cs);
+      const float2 pn = T.p[n];
+      sm.vtab[fi][n] = dcmul(make_double2(cs, -sn), make_double2((double)pn.x, -(double)pn.y));
+    }
+    __syncthreads();
+    for (int item = tid; item < nfc * nt * 2; item += nthr) {
+      const int half = item & 1, ti = (item >> 1) % nt, fi = (item >> 1) / nt;
+      const float2 *r = half ? sm.rb : sm.ra;
+      double ax = 0.0, ay = 0.0;
+      for (int n = 0; n < RADE_M; n++) {
+        const double2 v = sm.vtab[fi][n];
+        const double rx = (double)r[ti + n].x, ry = (double)r[ti + n].y;
+        ax += rx * v.x - ry * v.y; ay += rx * v.y + ry * v.x;
+      }
+      if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
+        const double f = f_start + (double)(c0 + fi) * delta;
+        double sn, cs; sincos(2.0 * M_PI * f / RADE_FS * (double)RADE_NMF, &sn, &cs);
+        const double2 e = dcmul(make_double2(ax, ay), make_double2(cs, -sn));
+        sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y);
+      } else sm.d1[fi][ti] = make_float2((float)ax, (float)ay);
+    }
+    __syncthreads();
+    float bm = -1.f; int bo = 0x7fffffff;
+    for (int k = tid; k < nfc * nt; k += nthr) {
+      const int fi = k / nt, ti = k % nt;
+      const float2 a = sm.d1[fi][ti], b = sm.d2[fi][ti];
+      const float m = hypotf(a.x + b.x, a.y + b.y);
+      const int ord = (c0 + fi) * nt + ti;          // f outer loop, t inner loop
+      if (m > bm || (m == bm && ord < bo)) { bm = m; bo = ord; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
+      if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
+    }
+    if ((tid & 31) == 0) { sm.red_mag[tid >> 5] = bm; sm.red_ord[tid >> 5] = bo; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < (nthr >> 5); i++)
+        if (sm.red_mag[i] > bm || (sm.red_mag[i] == bm && sm.red_ord[i] < bo)) { bm = sm.red_mag[i]; bo = sm.red_ord[i]; }
+      if (bm > sm.best_mag) {     // strict >, chunks are visited in increasing f
+        sm.best_mag = bm; sm.best_found = 1;
+        sm.best_t = t_lo + bo % nt;
+        sm.best_f = f_start + (double)(bo / nt) * delta;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// sigma_r = (mean|Dt1| + mean|Dt2|) / (2*sqrt(pi/2)) from the row sums, float32 like the reference's np.mean
+__device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scratch) {
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < RADE_NMF; i += blockDim.x) { a += rs[i]; b += rs[RADE_NMF + i]; }
+  const float sa = block_sum(a, scratch), sb = block_sum(b, scratch);
+  const float k = 1.2533141373155001f;              // (pi/2)**0.5 as float32
+  const float s1 = (sa / (float)(RADE_NMF * RADE_NFCOARSE)) / k, s2 = (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / k;
+  return (s1 + s2) / 2.0f;
+}
+
+// ================================================================= sync-state tracking: refine + check_pilots + slips
+struct TrackSmem {
+  RefineSmem ref;
+  float absd[RADE_NUPDATE * 2 * RADE_NFCOARSE];
+  float scratch[32];
+  double spot[4];
+};
+
+__global__ void __launch_bounds__(256)
+rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
+                int *__restrict__ uw_errors, const unsigned char *__restrict__ active) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (active && !active[s]) return;
+  RxCtl &c = ctl[s];
+  if (c.state != ST_SYNC) return;
+  const int head = c.ring_head;
+  const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+  float *rs = rowsum + (size_t)s * 2 * RADE_NMF;
+
+  // ---- refine: t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, 0.1)   (radae_rxe.py:202-205)
+  const int tmax0 = c.tmax; const double fmax0 = c.fmax;
+  const int t_lo = max(0, tmax0 - 8);
+  refine_block(sm.ref, T, rg, head, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1);
+  int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
+  const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
+  const double fmax = 0.9 * fmax0 + 0.1 * fhat;
+
+  // ---- check_pilots: refresh 48 rows of the |Dt| row sums (deterministic schedule), thresholds, spot correlations
+  const int rot = c.n_check % 20;
+  for (int item = tid; item < RADE_NUPDATE * 2 * RADE_NFCOARSE; item += blockDim.x) {
+    const int f = item % RADE_NFCOARSE, half = (item / RADE_NFCOARSE) & 1, i = item / (2 * RADE_NFCOARSE);
+    const int t = 20 * i + rot + half * RADE_NMF;
+    float ax = 0.f, ay = 0.f;
+    for (int n = 0; n < RADE_M; n++) {
+      const float2 x = rg[ring_idx(head, t + n)];
+      const float2 w = T.p_w[n * RADE_NFCOARSE + f];
+      ax += x.x * w.x + x.y * w.y; ay += x.x * w.y - x.y * w.x;        // conj(x) * w
+    }
+    sm.absd[item] = hypotf(ax, ay);
+  }
+  __syncthreads();
+  if (tid < RADE_NUPDATE * 2) {
+    const int half = tid & 1, i = tid >> 1;
+    const float *a = &sm.absd[(i * 2 + half) * RADE_NFCOARSE];
+    float sum = 0.f;
+    for (int f = 0; f < RADE_NFCOARSE; f++) sum += a[f];
+    rs[half * RADE_NMF + 20 * i + rot] = sum;
+  }
+  __syncthreads();
+  const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);
+  // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
+  {
+    const int wp = tid >> 5, lane = tid & 31;
+    if (wp < 4) {
+      const int o = tmax + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
+      const float2 *q = (wp < 2) ? T.p : T.pend;
+      const double w = 2.0 * M_PI * fmax / RADE_FS;
+      double ax = 0.0, ay = 0.0;
+      for (int n = lane; n < RADE_M; n += 32) {
+        double sn, cs; sincos(w * (double)n, &sn, &cs);
+        const float2 x = rg[ring_idx(head, o + n)];
+        const double2 v = dcmul(make_double2(cs, -sn), make_double2((double)x.x, (double)x.y));     // w_vec * rx
+        const double2 r = dcmul(make_double2(v.x, -v.y), make_double2((double)q[n].x, (double)q[n].y));
+        ax += r.x; ay += r.y;
+      }
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, k); ay += __shfl_xor_sync(0xffffffffu, ay, k); }
+      if (lane == 0) sm.spot[wp] = hypot(ax, ay);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-4 / 5.0));
+    const double Dthresh_eoo = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
+    const double D = sm.spot[0] + sm.spot[1], De = sm.spot[2] + sm.spot[3];
+    const int valid = D > Dthresh, endofover = De > Dthresh_eoo;
+    c.Dthresh = (float)Dthresh; c.Dtmax12 = (float)D; c.Dtmax12_eoo = (float)De;
+    // timing slips (radae_rxe.py:208-218): the adjusted tmax is used for this call's extraction too
+    int nin = RADE_NMF;
+    if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
+    if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
+    c.nin = nin; c.tmax = tmax; c.fmax = fmax; c.n_check += 1;
+    c.synced_count += 1;
+    int uw_fail = 0;
+    if (c.synced_count % RADE_SYNCED_ONE_SEC == 0) {
+      if (uw_errors[s] > RADE_UW_THRESH) uw_fail = 1;
+      uw_errors[s] = 0;
+    }
+    c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = !endofover; c.ran_sync = 1;
+  }
+}
+
+// ================================================================= frequency correction + OFDM demod + pilot EQ
+struct DemodSmem {
+  float2 xs[RADE_NS + 2][RADE_M];
+  float2 sym[RADE_NS + 2][RADE_NC];
+  float2 pil[2][RADE_NC];
+  float2 rotc[RADE_NC];
+  float scratch[32];
+  float mag;
+};
+
+__global__ void __launch_bounds__(192)
+rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ z_hat,
+                float *__restrict__ eoo_out, const unsigned char *__restrict__ active) {
+  __shared__ DemodSmem sm;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (active && !active[s]) return;
+  RxCtl &c = ctl[s];
+  if (!c.ran_sync) return;
+  const int head = c.ring_head, tmax = c.tmax, endofover = c.endofover;
+  const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+  const double w = 2.0 * M_PI * c.fmax / RADE_FS;
+  const double2 P0 = make_double2(c.rx_phase_re, c.rx_phase_im);
+  // rx_phase_vec[n] = rx_phase * exp(-j w (n+1)) (closed form of the recursion radae_rxe.py:227-231), stored csingle;
+  // keep only the M samples of each symbol after Ncp + time_offset = 16
+  for (int idx = tid; idx < (RADE_NS + 2) * RADE_M; idx += blockDim.x) {
+    const int r = idx / RADE_M, k = idx % RADE_M;
+    const int n = r * RADE_SYM + RADE_NCP + RADE_TIME_OFFSET + k;
+    double sn, cs; sincos(w * (double)(n + 1), &sn, &cs);
+    const double2 v = dcmul(P0, make_double2(cs, -sn));
+    sm.xs[r][k] = cmul(rg[ring_idx(head, tmax - RADE_NCP + n)], make_float2((float)v.x, (float)v.y));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double sn, cs; sincos(w * (double)RADE_NEOO, &sn, &cs);
+    const double2 v = dcmul(P0, make_double2(cs, -sn));
+    c.rx_phase_re = v.x; c.rx_phase_im = v.y;
+  }
+  if (tid < (RADE_NS + 2) * RADE_NC) {              // 180 DFT outputs, 160-point each
+    const int r = tid / RADE_NC, cc = tid % RADE_NC;
+    float ax = 0.f, ay = 0.f;
+    for (int k = 0; k < RADE_M; k++) {
+      const float2 x = sm.xs[r][k], wv = T.Wfwd[k * RADE_NC + cc];
+      ax += x.x * wv.x - x.y * wv.y; ay += x.x * wv.y + x.y * wv.x;
+    }
+    sm.sym[r][cc] = make_float2(ax, ay);
+  }
+  __syncthreads();
+  if (!endofover) {
+    // 3-pilot least-squares fit per carrier on the two pilot rows (dsp.py:418-435)
+    if (tid < 2 * RADE_NC) {
+      const int i = tid / RADE_NC, cc = tid % RADE_NC, row = i ? RADE_NS + 1 : 0;
+      const int cm = min(max(cc, 1), RADE_NC - 2);
+      float2 g0 = make_float2(0.f, 0.f), g1 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float pk = T.P[cm - 1 + k].x;
+        const float2 hk = make_float2(sm.sym[row][cm - 1 + k].x / pk, sm.sym[row][cm - 1 + k].y / pk);
+        const float2 a = cmul(T.Pmat[cc * 6 + k], hk), b = cmul(T.Pmat[cc * 6 + 3 + k], hk);
+        g0.x += a.x; g0.y += a.y; g1.x += b.x; g1.y += b.y;
+      }
+      const float2 e = cmul(g1, T.eq_rot[cc]);
+      sm.pil[i][cc] = make_float2(g0.x + e.x, g0.y + e.y);
+    }
+    __syncthreads();
+    // SNR estimate from pilot row 0 (dsp.py:438-456) and coarse magnitude (dsp.py:477-482)
+    float s1 = 0.f, s2 = 0.f, pw = 0.f;
+    if (tid < RADE_NC) {
+      const float2 pc = sm.sym[0][tid], pl = sm.pil[0][tid];
+      s1 = pc.x * pc.x + pc.y * pc.y;
+      const float m = hypotf(pl.x, pl.y);
+      const float im = (m > 0.f) ? (pc.y * pl.x - pc.x * pl.y) / m : pc.y;          // imag(Pcn * exp(-j angle(pilot)))
+      s2 = im * im;
+    }
+    if (tid < 2 * RADE_NC) { const float2 pl = sm.pil[tid / RADE_NC][tid % RADE_NC]; pw = pl.x * pl.x + pl.y * pl.y; }
+    const float S1 = block_sum(s1, sm.scratch), S2 = block_sum(s2, sm.scratch), PW = block_sum(pw, sm.scratch);
+    if (tid == 0) {
+      double snr = (double)S1 / (2.0 * ((double)S2 + 1e-12)) - 1.0;
+      if (snr <= 0.0) snr = 0.1;
+      const double snrdB = (10.0 * log10(snr) - 2.513) / 0.8070;
+      const double Rs = (double)RADE_FS / RADE_M;
+      const double snr3k = snrdB + 10.0 * log10(Rs * RADE_NC / 3000.0) + 10.0 * log10((double)(RADE_M + RADE_NCP) / RADE_M);
+      c.snr_est = 0.9 * c.snr_est + 0.1 * snr3k;
+      float mag = sqrtf(PW / (float)(2 * RADE_NC)) + 1e-6f;
+      sm.mag = mag * T.p0_abs / T.pilot_gain;
+    }
+    __syncthreads();
+    // phase-only EQ with the channel linearly interpolated between the two pilot rows, then demap (dsp.py:466-474, :507-512)
+    if (tid < RADE_NS * RADE_NC) {
+      const int r = 1 + tid / RADE_NC, cc = tid % RADE_NC;
+      const float2 p0 = sm.pil[0][cc], p1 = sm.pil[1][cc];
+      const float2 slope = make_float2((p1.x - p0.x) / (float)(RADE_NS + 1), (p1.y - p0.y) / (float)(RADE_NS + 1));
+      const float2 ch = make_float2(slope.x * (float)r + p0.x, slope.y * (float)r + p0.y);
+      const float m = hypotf(ch.x, ch.y);
+      const float2 rotv = (m > 0.f) ? make_float2(ch.x / m, -ch.y / m) : make_float2(1.f, 0.f);
+      const float2 v = cmul(sm.sym[r][cc], rotv);
+      float *z = z_hat + (size_t)s * RADE_NZMF * RADE_LATENT;
+      z[2 * tid] = v.x / sm.mag; z[2 * tid + 1] = v.y / sm.mag;
+    }
+  } else {
+    // end of over: common phase from P, E, E (dsp.py:513-524); rows 2..4 carry 90 data symbols
+    if (tid < RADE_NC) {
+      const float2 a = sm.sym[0][tid], b = sm.sym[1][tid], d = sm.sym[RADE_NS + 1][tid];
+      const float p = T.P[tid].x, pe = T.Pend[tid].x;
+      const float2 acc = make_float2(a.x / p + b.x / pe + d.x / pe, a.y / p + b.y / pe + d.y / pe);
+      const float m = hypotf(acc.x, acc.y);
+      sm.rotc[tid] = (m > 0.f) ? make_float2(acc.x / m, -acc.y / m) : make_float2(1.f, 0.f);
+    }
+    __syncthreads();
+    if (tid < (RADE_NS - 1) * RADE_NC) {
+      const int r = 2 + tid / RADE_NC, cc = tid % RADE_NC;
+      const float2 v = cmul(sm.sym[r][cc], sm.rotc[cc]);
+      float *e = eoo_out + (size_t)s * RADE_NEOO_BITS;
+      e[2 * tid] = v.x; e[2 * tid + 1] = v.y;
+    }
+  }
+}
+
+// ================================================================= coarse-search post-processing + state machine
+struct FinishSmem {
+  RefineSmem ref;
+  float scratch[32];
+  int do_refine, to_sync;
+};
+
+__global__ void __launch_bounds__(256)
+rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, const float *__restrict__ rowsum,
+                 int *__restrict__ uw_errors, DecStreamState *__restrict__ dec_state, int reset_dec_on_sync,
+                 int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out,
+                 const unsigned char *__restrict__ active) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FinishSmem &sm = *reinterpret_cast<FinishSmem *>(smem_raw);
+  const int s = blockIdx.x, tid = threadIdx.x;
+  if (active && !active[s]) { if (tid == 0) { ret_out[s] = 0; dec_active[s] = 0; nin_out[s] = ctl[s].nin; } return; }
+  RxCtl &c = ctl[s];
+  const int state = c.state;
+  if (state != ST_SYNC) {
+    // detect_pilots epilogue (radae/dsp.py:217-231)
+    const float sigma_r = sigma_r_from_rowsums(rowsum + (size_t)s * 2 * RADE_NMF, sm.scratch);
+    if (tid == 0) {
+      const unsigned long long key = c.detect_key;
+      const float val = __uint_as_float((unsigned)(key >> 32));
+      const unsigned idx = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+      if (val > 0.f) { c.tmax = (int)(idx / RADE_NFCOARSE); c.fmax = (double)T.fcoarse[idx % RADE_NFCOARSE]; }
+      else { c.tmax = 0; c.fmax = 0.0; }
+      const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
+      c.Dthresh = (float)Dthresh; c.Dtmax12 = val;
+      c.candidate = ((double)val > Dthresh) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // state machine on the state held at entry (radae_rxe.py:248-293)
+    int next = state, do_refine = 0;
+    if (state == ST_SEARCH) {
+      if (c.candidate) { next = ST_CANDIDATE; c.tmax_candidate = c.tmax; c.valid_count = 1; }
+    } else if (state == ST_CANDIDATE) {
+      if (c.candidate && abs(c.tmax - c.tmax_candidate) < RADE_NCP) {
+        c.valid_count += 1;
+        if (c.valid_count > 3) {
+          next = ST_SYNC; do_refine = 1;
+          c.synced_count = 0; c.uw_fail = 0; uw_errors[s] = 0; c.valid_count = RADE_NMF_UNSYNC;
+        }
+      } else next = ST_SEARCH;
+    } else {
+      if (c.candidate) c.valid_count = RADE_NMF_UNSYNC;
+      else { c.valid_count -= 1; if (c.valid_count == 0) next = ST_SEARCH; }
+      if (c.endofover || c.uw_fail) next = ST_SEARCH;
+    }
+    c.state = next;
+    sm.do_refine = do_refine; sm.to_sync = do_refine;
+  }
+  __syncthreads();
+  if (sm.do_refine) {
+    // first fix after acquisition: t in [max(0,tmax-1), tmax+2), f in arange(fmax-10, fmax+10, 0.25)  (radae_rxe.py:267-273)
+    const int tm = c.tmax; const double fm = c.fmax;
+    const int t_lo = max(0, tm - 1);
+    refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25);
+    if (tid == 0) {
+      if (sm.ref.best_found) { c.tmax = sm.ref.best_t; c.fmax = sm.ref.best_f; }
+      c.fmax += c.foff_err; c.foff_err = 0.0;
+    }
+    if (reset_dec_on_sync) {        // model.core_decoder_statefull.module.reset() (radae_rxe.py:263)
+      uint32_t *d = reinterpret_cast<uint32_t *>(dec_state + s);
+      for (int i = tid; i < (int)(sizeof(DecStreamState) / 4); i += blockDim.x) d[i] = 0u;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (c.state == ST_SEARCH) c.nin = RADE_NMF;      // radae_rxe.py:294-296
+    c.ret = c.valid_output | (c.endofover << 1);
+    ret_out[s] = c.ret; dec_active[s] = (unsigned char)c.valid_output; nin_out[s] = c.nin;
+  }
+}
+
+__global__ void rx_init_kernel(RxCtl *ctl, int *uw_errors, int S, double foff_err) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  RxCtl c;
+  memset(&c, 0, sizeof(c));
+  c.nin = RADE_NMF; c.state = ST_SEARCH; c.rx_phase_re = 1.0; c.bpf_phase = make_float2(1.f, 0.f); c.bpf_first = 1;
+  c.foff_err = foff_err;
+  ctl[s] = c;
+  uw_errors[s] = 0;
+}
+
+}  // namespace
+
+int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream) {
+  rx_init_kernel<<<(S + 127) / 128, 128, 0, stream>>>(ctl, uw_errors, S, foff_err);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(rx_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetectSmem)));
+    CUDA_CHECK(cudaFuncSetAttribute(rx_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
+    CUDA_CHECK(cudaFuncSetAttribute(rx_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinishSmem)));
+    attr_set = true;
+  }
+  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en);
+  rx_detect_kernel<<<dim3(RADE_NMF / DET_TB, S), 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, active);
+  rx_track_kernel<<<S, 256, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
+  rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
+  rx_finish_kernel<<<S, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
+                                                           reset_dec_on_sync, ret_out, B.dec_active, B.nin, active);
+  CUDA_CHECK(cudaGetLastError());
+  return 5;
+}

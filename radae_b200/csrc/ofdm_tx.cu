@@ -1,0 +1,101 @@
+// OFDM modulator for one 120 ms modem frame per stream.
+//
+// Replaces transmitter_one.transmitter_one (radae/dsp.py:340-378; batch twin RADAE.forward radae/radae.py:482-527)
+// and the EOO frame of RADAE.__init__ / set_eoo_bits (radae/radae.py:208-219, :441-455) as used by
+// radae_tx.do_radae_tx / do_eoo (radae_txe.py:108-144).
+//
+// One CTA per stream, one thread per time sample of an OFDM symbol: z[3][80] -> 120 QPSK-like symbols laid out
+// row-major over [Ns=4][Nc=30] (symbol k -> row 1+k/30, carrier k%30), pilot row = pilot_gain*P, pruned 30->160
+// IDFT against the reference's own Winv table (L1/L2 resident, read coalesced), cyclic prefix = tail copy,
+// PA model tanh(|x|)*x/|x|.  HBM traffic: 960 B in, 7680 B out per stream-frame, nothing else.
+#include "rade_common.h"
+
+namespace {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// tanh(|x|) * exp(j angle(x)) == x * tanh(|x|)/|x|
+__device__ __forceinline__ float2 pa_limit(float2 x) {
+  float mag = hypotf(x.x, x.y);
+  if (mag == 0.f) return make_float2(0.f, 0.f);
+  float s = tanhf(mag) / mag;
+  return make_float2(x.x * s, x.y * s);
+}
+
+__global__ void __launch_bounds__(RADE_M)
+ofdm_mod_kernel(DspTables T, const float *__restrict__ z, float2 *__restrict__ tx, int S) {
+  __shared__ float2 sym[RADE_NS + 1][RADE_NC];
+  const int s = blockIdx.x, n = threadIdx.x;
+  if (n < RADE_NC) sym[0][n] = make_float2(T.pilot_gain * T.P[n].x, T.pilot_gain * T.P[n].y);
+  if (n < RADE_NS * RADE_NC) {
+    const float *zs = z + (size_t)s * RADE_NZMF * RADE_LATENT;
+    sym[1 + n / RADE_NC][n % RADE_NC] = make_float2(zs[2 * n], zs[2 * n + 1]);
+  }
+  __syncthreads();
+  float2 acc[RADE_NS + 1];
+#pragma unroll
+  for (int r = 0; r <= RADE_NS; r++) acc[r] = make_float2(0.f, 0.f);
+  for (int c = 0; c < RADE_NC; c++) {
+    const float2 w = T.Winv[c * RADE_M + n];
+#pragma unroll
+    for (int r = 0; r <= RADE_NS; r++) {
+      float2 v = cmul(sym[r][c], w);
+      acc[r].x += v.x; acc[r].y += v.y;
+    }
+  }
+  float2 *out = tx + (size_t)s * RADE_NMF;
+#pragma unroll
+  for (int r = 0; r <= RADE_NS; r++) {
+    float2 y = pa_limit(acc[r]);
+    out[r * RADE_SYM + RADE_NCP + n] = y;
+    if (n >= RADE_M - RADE_NCP) out[r * RADE_SYM + n - (RADE_M - RADE_NCP)] = y;
+  }
+}
+
+// EOO frame: skeleton (P E . . . E) + optionally 3 data symbols from 180 +-1 bits
+__global__ void __launch_bounds__(RADE_M)
+eoo_kernel(DspTables T, const float *__restrict__ bits, const int *__restrict__ has_bits, float2 *__restrict__ tx, int S) {
+  __shared__ float2 sym[RADE_NS - 1][RADE_NC];
+  const int s = blockIdx.x, n = threadIdx.x;
+  float2 *out = tx + (size_t)s * RADE_NEOO;
+  const bool data = has_bits[s] != 0;
+  for (int i = n; i < RADE_NEOO; i += RADE_M)
+    if (!data || i < 2 * RADE_SYM || i >= RADE_NMF) out[i] = T.eoo_base[i];     // data rows 2..4 are written below
+  if (!data) return;
+  if (n < (RADE_NS - 1) * RADE_NC) {
+    const float *b = bits + (size_t)s * RADE_NEOO_BITS;
+    sym[n / RADE_NC][n % RADE_NC] = make_float2(b[2 * n], b[2 * n + 1]);
+  }
+  __syncthreads();
+  float2 acc[RADE_NS - 1];
+#pragma unroll
+  for (int r = 0; r < RADE_NS - 1; r++) acc[r] = make_float2(0.f, 0.f);
+  for (int c = 0; c < RADE_NC; c++) {
+    const float2 w = T.Winv[c * RADE_M + n];
+#pragma unroll
+    for (int r = 0; r < RADE_NS - 1; r++) {
+      float2 v = cmul(sym[r][c], w);
+      acc[r].x += v.x; acc[r].y += v.y;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RADE_NS - 1; r++) {
+    float2 y = pa_limit(make_float2(acc[r].x * T.pilot_gain, acc[r].y * T.pilot_gain));
+    out[(2 + r) * RADE_SYM + RADE_NCP + n] = y;
+    if (n >= RADE_M - RADE_NCP) out[(2 + r) * RADE_SYM + n - (RADE_M - RADE_NCP)] = y;
+  }
+}
+
+}  // namespace
+
+int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream) {
+  ofdm_mod_kernel<<<S, RADE_M, 0, stream>>>(T, z, tx, S);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float2 *tx, int S, cudaStream_t stream) {
+  eoo_kernel<<<S, RADE_M, 0, stream>>>(T, bits, has_bits, tx, S);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,112 @@
+// Shared definitions for libradae_b200 (sm_100a only; there is no CPU fallback anywhere in this library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+// ---- waveform / model constants for model19_check3 (reference: radae/radae.py:128-232) ----
+#define RADE_FS 8000
+#define RADE_M 160
+#define RADE_NCP 32
+#define RADE_NC 30
+#define RADE_NS 4
+#define RADE_NZMF 3
+#define RADE_LATENT 80
+#define RADE_SYM (RADE_M + RADE_NCP)          // 192
+#define RADE_NMF 960
+#define RADE_NEOO 1152
+#define RADE_NIN_MAX 1120
+#define RADE_RXBUF 2112
+#define RADE_NFEAT 432                        // 12 x 36 floats per modem frame at the API
+#define RADE_NB_TOTAL_FEATURES 36
+#define RADE_NUM_USED_FEATURES 20
+#define RADE_NEOO_BITS 180
+#define RADE_NFCOARSE 40
+#define RADE_NUPDATE 48
+#define RADE_NMF_UNSYNC 25
+#define RADE_SYNCED_ONE_SEC 8
+#define RADE_UW_THRESH 7
+#define RADE_BPF_NTAP 101
+#define RADE_BPF_MEM 102                      // the reference keeps Ntap+1 samples (radae/dsp.py:96)
+#define RADE_TIME_OFFSET (-16)
+
+// ---- core codec dimensions (reference: src/rade_enc_data.h, src/rade_dec_data.h) ----
+#define ENC_IN 84
+#define ENC_CAT 864
+#define ENC_GRU 64
+#define ENC_CONV 96
+#define DEC_IN 80
+#define DEC_CAT 736
+#define DEC_GRU 96
+#define DEC_CONV 32
+#define DEC_OUT 84
+
+#define CORE_TS 16                            // streams per CTA tile (one m16 MMA tile)
+#define ENC_LDA 880                           // smem/global row stride of the int8 concat buffer (bank-conflict-free A fragments)
+#define DEC_LDA 752
+
+// per-stream persistent state in HBM
+struct __align__(16) EncStreamState {
+  float h[5 * ENC_GRU];                       // GRU hidden states, fp32 (src/rade_enc.h:37-41)
+  int8_t cat1[ENC_LDA];                       // quantised concat buffer of step t-1: conv taps (dilation 1) + recurrent GEMM input
+  int8_t cat2[ENC_LDA];                       // step t-2: dilation-2 conv taps (src/rade_enc.h:43-46 as int8)
+};
+struct __align__(16) DecStreamState {
+  float h[5 * DEC_GRU];                       // src/rade_dec.h:36-40
+  int8_t cat1[DEC_LDA];                       // step t-1 concat (all five convs have dilation 1, src/rade_dec.c:68-95)
+};
+
+struct I8LayerDev { const uint2 *wt; const float *scale; const float *bias; int K; int N; };
+struct F32LayerDev { const float *wf; const float *bias; int K; int N; };
+struct CoreWeightsDev {
+  F32LayerDev enc_dense1, enc_zdense, dec_dense1, dec_output;
+  I8LayerDev enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
+  I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
+};
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "libradae_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  return -1; } } while (0)
+#define CUDA_CHECK_FATAL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "libradae_b200: fatal CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  exit(1); } } while (0)
+
+// ---- DSP constant tables (device pointers), built on the host exactly the way RADAE.__init__ / acquisition.__init__ /
+//      receiver_one.__init__ / complex_bpf.__init__ derive them (radae/radae.py:172-219, radae/dsp.py:40-61,153-176,401-412)
+struct DspTables {
+  const float2 *Winv;      // [30][160]  exp(+j n w_c)/M
+  const float2 *Wfwd;      // [160][30]  exp(-j n w_c)
+  const float2 *P;         // [30] pilots (freq domain), Pend [30]
+  const float2 *Pend;
+  const float2 *p;         // [160] time-domain pilot symbol, pend [160]
+  const float2 *pend;
+  const float2 *p_w;       // [160][40] coarse-frequency-shifted pilots
+  const float2 *Pmat;      // [30][2][3] LS projectors
+  const float2 *eq_rot;    // [30] exp(-j w_c a)
+  const float *bpf_h;      // [101]
+  const float2 *bpf_exp;   // [1120] exp(-j alpha (i+1)), float32 argument
+  const float2 *eoo_base;  // [1152] P E 0 0 0 E frame after the PA limiter
+  const float *fcoarse;    // [40]
+  float pilot_gain;
+  float p0_abs;            // |P[0]|
+};
+
+// per-stream receiver control block (everything radae_rx keeps between calls, radae_rxe.py:128-142)
+struct __align__(16) RxCtl {
+  double fmax, foff_err, snr_est, rx_phase_re, rx_phase_im;
+  unsigned long long detect_key;
+  float2 bpf_phase;
+  float Dthresh, Dtmax12, Dtmax12_eoo, pad0;
+  int state, nin, tmax, tmax_candidate;
+  int valid_count, synced_count, n_check, bpf_first;
+  int ring_head, candidate, endofover, valid_output;
+  int uw_fail, ret, ran_sync, pad1;
+};
+
+// per-stream channel-simulator state
+struct __align__(16) ChanState {
+  double phase;            // carrier phase accumulated so far (radians)
+  long long t;             // samples processed
+  float2 delay[64];        // last tx samples (two-path delay line)
+};

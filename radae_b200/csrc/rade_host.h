@@ -1,0 +1,58 @@
+// Host-side internal interfaces of libradae_b200 (not part of the C ABI).
+#pragma once
+#include <vector>
+#include <stddef.h>
+#include "rade_common.h"
+
+struct CoreWeightsHolder {
+  CoreWeightsDev dev;
+  std::vector<void *> allocs;
+  size_t weight_bytes = 0;
+};
+int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h);
+void core_weights_free(CoreWeightsHolder *h);
+
+int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
+                        const uint8_t *active, int S, int T, cudaStream_t stream);
+int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
+                        int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream);
+
+extern "C" const unsigned char rade_b200_default_weights[];
+extern "C" const unsigned char rade_b200_default_weights_end[];
+
+#include <complex>
+struct DspTablesHost {
+  std::vector<float> w, bpf_h, fcoarse;
+  std::vector<std::complex<float>> Winv, Wfwd, P, Pend, p, pend, p_w, Pmat, eq_rot, bpf_exp, eoo_base;
+  double pilot_gain;
+  float bpf_bw, bpf_centre, bpf_alpha;
+};
+void dsp_tables_host(DspTablesHost &T);
+int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> &allocs);
+
+// device buffers of the receiver (all [S] leading dimension)
+struct RxBuffers {
+  RxCtl *ctl;
+  float2 *ring;            // [S][2112]
+  float2 *bpf_mem;         // [S][102]
+  float *rowsum;           // [S][2][960]
+  int *uw_errors;          // [S]
+  float *z_hat;            // [S][240]
+  float *eoo;              // [S][180]
+  DecStreamState *dec_state;
+  unsigned char *dec_active;  // [S] valid_output of the last call
+  int *nin;                // [S]
+};
+
+int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
+int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float2 *tx, int S, cudaStream_t stream);
+int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
+                         int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
+int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
+                          float doppler, int d, float gain, unsigned long long seed, cudaStream_t stream);
+int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream);
+int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, const RxCtl *ctl, float2 *out,
+                    unsigned char *active, int S, cudaStream_t stream);
+int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream);
+int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream);

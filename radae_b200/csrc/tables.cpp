@@ -1,0 +1,134 @@
+// Host-side construction of the DSP constant tables, mirroring the reference's own derivations INCLUDING the
+// precision each step is evaluated in (float32 torch tensors, float32 numpy scalars under NEP 50, complex128 numpy):
+//   RADAE.__init__           radae/radae.py:172-219   w, Winv, Wfwd, P, Pend, p, pend, pilot_gain, EOO frame
+//   acquisition.__init__     radae/dsp.py:153-176     fcoarse, p_w
+//   receiver_one.__init__    radae/dsp.py:401-412     Pmat (plain transpose, not conjugate), exp(-j w_c a)
+//   complex_bpf.__init__     radae/dsp.py:40-61 with the float32 arguments radae_rxe.py:104-109 passes
+// Checked against oracle/dsp.py (itself pinned against the reference) by tests/test_tables.py through
+// rade_b200_debug_tables().
+#include <cmath>
+#include <complex>
+#include <vector>
+#include "rade_common.h"
+#include "rade_host.h"
+
+typedef std::complex<double> cd;
+typedef std::complex<float> cf;
+
+static float2 f2(cf v) { return make_float2(v.real(), v.imag()); }
+// exp(j*ang) for a float32 angle, rounded to complex64 (torch.exp / np.exp on a complex64 argument)
+static cf cexp32(float ang) { return cf((float)std::cos((double)ang), (float)std::sin((double)ang)); }
+
+static cf pa_limit(cf x) {            // tanh(|x|)*exp(j*angle(x)), float32 (radae/dsp.py:376-377)
+  float mag = std::hypot(x.real(), x.imag());
+  float ang = std::atan2(x.imag(), x.real());
+  float t = std::tanh(mag);
+  cf e = cexp32(ang);
+  return cf(t * e.real(), t * e.imag());
+}
+
+void dsp_tables_host(DspTablesHost &T) {
+  const int M = RADE_M, NC = RADE_NC;
+  static const float barker13[13] = {1, 1, 1, 1, 1, -1, -1, 1, 1, -1, 1, -1, 1};
+  const float two_pi_f = (float)(2.0 * M_PI);
+  T.w.resize(NC);
+  for (int c = 0; c < NC; c++) T.w[c] = (two_pi_f * (float)(15 + c)) / (float)M;           // radae.py:174 (float32 tensor)
+  T.Winv.resize(NC * M); T.Wfwd.resize(M * NC);
+  for (int c = 0; c < NC; c++)
+    for (int n = 0; n < M; n++) {
+      float ang = (float)n * T.w[c];                                                       // float32 product (radae.py:178-179)
+      cf e = cexp32(ang);
+      T.Winv[c * M + n] = cf(e.real() / (float)M, e.imag() / (float)M);
+      T.Wfwd[n * NC + c] = std::conj(e);
+    }
+  T.P.resize(NC); T.Pend.resize(NC);
+  const float sqrt2f = (float)std::sqrt(2.0);
+  for (int c = 0; c < NC; c++) {
+    T.P[c] = cf(sqrt2f * barker13[c % 13], 0.f);                                           // radae.py:48-56, :182
+    T.Pend[c] = (c & 1) ? -T.P[c] : T.P[c];                                                // radae.py:184-185
+  }
+  T.p.assign(M, cf(0, 0)); T.pend.assign(M, cf(0, 0));
+  for (int n = 0; n < M; n++) {
+    cf a(0, 0), b(0, 0);
+    for (int c = 0; c < NC; c++) { a += T.P[c] * T.Winv[c * M + n]; b += T.Pend[c] * T.Winv[c * M + n]; }
+    T.p[n] = a; T.pend[n] = b;                                                             // radae.py:183, :186
+  }
+  T.pilot_gain = std::pow(10.0, -2.0 / 20.0) * M / std::sqrt((double)NC);                  // radae.py:195-199
+  // coarse frequency grid and shifted pilots (radae/dsp.py:163-173), complex128 product stored as csingle
+  T.fcoarse.resize(RADE_NFCOARSE); T.p_w.resize(M * RADE_NFCOARSE);
+  for (int i = 0; i < RADE_NFCOARSE; i++) {
+    double f = -50.0 + 2.5 * i;
+    T.fcoarse[i] = (float)f;
+    double w = 2 * M_PI * f / RADE_FS;
+    for (int n = 0; n < M; n++) {
+      cd v = std::exp(cd(0, w * n)) * cd(T.p[n].real(), T.p[n].imag());
+      T.p_w[n * RADE_NFCOARSE + i] = cf((float)v.real(), (float)v.imag());
+    }
+  }
+  // LS projectors: Pmat[c] = inv(A^T A) A^T, A = [[1, e^{-j w_{m-1} a}], [1, e^{-j w_m a}], [1, e^{-j w_{m+1} a}]]
+  const double a = 0.0025 * RADE_FS;
+  T.Pmat.resize(NC * 6); T.eq_rot.resize(NC);
+  for (int c = 0; c < NC; c++) {
+    int m = c < 1 ? 1 : (c > NC - 2 ? NC - 2 : c);
+    cd A[3][2];
+    for (int k = 0; k < 3; k++) { A[k][0] = 1.0; A[k][1] = std::exp(cd(0, -(double)T.w[m - 1 + k] * a)); }
+    cd G[2][2] = {{0, 0}, {0, 0}};
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 3; k++) G[i][j] += A[k][i] * A[k][j];
+    cd det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
+    cd Gi[2][2] = {{G[1][1] / det, -G[0][1] / det}, {-G[1][0] / det, G[0][0] / det}};
+    for (int i = 0; i < 2; i++) for (int k = 0; k < 3; k++) {
+      cd v = Gi[i][0] * A[k][0] + Gi[i][1] * A[k][1];
+      T.Pmat[c * 6 + i * 3 + k] = cf((float)v.real(), (float)v.imag());
+    }
+    T.eq_rot[c] = cexp32(-(T.w[c] * (float)a));                                            // dsp.py:433 (complex64)
+  }
+  // band-pass filter: float32 scalar arithmetic, left to right (radae_rxe.py:106-107, dsp.py:42-49)
+  const float w0 = T.w[0], w29 = T.w[NC - 1];
+  const float bw = ((1.2f * (w29 - w0)) * (float)RADE_FS) / two_pi_f;
+  const float centre = (((w29 + w0) * (float)RADE_FS) / two_pi_f) / 2.f;
+  const float B = bw / (float)RADE_FS;
+  const float alpha = (two_pi_f * centre) / (float)RADE_FS;
+  T.bpf_bw = bw; T.bpf_centre = centre; T.bpf_alpha = alpha;
+  T.bpf_h.resize(RADE_BPF_NTAP);
+  for (int i = 0; i < RADE_BPF_NTAP; i++) {
+    float n = (float)(i - (RADE_BPF_NTAP - 1) / 2);
+    float x = n * B;
+    float y = (float)M_PI * (x == 0.f ? 1.0e-20f : x);
+    float s = (float)std::sin((double)y) / y;                                              // np.sinc on float32
+    T.bpf_h[i] = B * s;
+  }
+  T.bpf_exp.resize(RADE_NIN_MAX);
+  for (int i = 0; i < RADE_NIN_MAX; i++) {
+    float arg = (float)(-((double)alpha * (double)(i + 1)));                               // argument rounded to float32 (dsp.py:61)
+    T.bpf_exp[i] = cexp32(arg);
+  }
+  // EOO frame skeleton P E 0 0 0 E (radae.py:208-219)
+  T.eoo_base.assign(RADE_NEOO, cf(0, 0));
+  const float pg = (float)T.pilot_gain;
+  for (int i = 0; i < RADE_SYM; i++) {
+    int src = (i < RADE_NCP) ? (M - RADE_NCP + i) : (i - RADE_NCP);
+    T.eoo_base[i] = T.p[src];
+    T.eoo_base[RADE_SYM + i] = T.pend[src];
+    T.eoo_base[RADE_NMF + i] = T.pend[src];
+  }
+  for (auto &v : T.eoo_base) v = pa_limit(cf(v.real() * pg, v.imag() * pg));
+}
+
+int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> &allocs) {
+  auto up = [&](const void *src, size_t bytes) -> void * {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    return d;
+  };
+#define UPC(field, vec) if (!(D->field = (const float2 *)up(vec.data(), vec.size() * sizeof(cf)))) return -1;
+  UPC(Winv, T.Winv) UPC(Wfwd, T.Wfwd) UPC(P, T.P) UPC(Pend, T.Pend) UPC(p, T.p) UPC(pend, T.pend)
+  UPC(p_w, T.p_w) UPC(Pmat, T.Pmat) UPC(eq_rot, T.eq_rot) UPC(bpf_exp, T.bpf_exp) UPC(eoo_base, T.eoo_base)
+#undef UPC
+  if (!(D->bpf_h = (const float *)up(T.bpf_h.data(), T.bpf_h.size() * 4))) return -1;
+  if (!(D->fcoarse = (const float *)up(T.fcoarse.data(), T.fcoarse.size() * 4))) return -1;
+  D->pilot_gain = (float)T.pilot_gain;
+  D->p0_abs = std::abs(T.P[0]);
+  return 0;
+}

@@ -1,0 +1,185 @@
+// Weight ingest for libradae_b200: RDW container (this repo's format, radae_b200/rdw.py) or the reference's DNNw
+// blob (src/write_rade_weights.c:51-74; int8 matrices in 8x4 blocks, weight-exchange/wexchange/c_export/common.py:59-67,
+// optional block index lists :156-170) -> host row-major matrices -> device layouts.
+// Device layout of an int8 layer: MMA B-fragment order, Wt[(nt*KB + kb)*32 + lane] = {b0, b1} with
+//   b0 = W[nt*8 + lane/4][kb*32 + (lane%4)*4 .. +3],  b1 = same row, columns +16   (m16n8k32 .col B operand).
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include "rade_common.h"
+#include "rade_host.h"
+
+namespace {
+
+struct HostArray { int dtype; int rows, cols; std::vector<unsigned char> data; };
+typedef std::map<std::string, HostArray> ArrayMap;
+
+bool parse_rdw(const unsigned char *buf, size_t len, ArrayMap &out) {
+  if (len < 64 || memcmp(buf, "RADEB200", 8) != 0) return false;
+  uint32_t version, n;
+  memcpy(&version, buf + 8, 4); memcpy(&n, buf + 12, 4);
+  if (version != 1 || 64 + 80 * (size_t)n > len) return false;
+  for (uint32_t i = 0; i < n; i++) {
+    const unsigned char *e = buf + 64 + 80 * (size_t)i;
+    char name[49]; memcpy(name, e, 48); name[48] = 0;
+    uint32_t dtype, rows, cols; uint64_t off, nbytes;
+    memcpy(&dtype, e + 48, 4); memcpy(&rows, e + 52, 4); memcpy(&cols, e + 56, 4);
+    memcpy(&off, e + 64, 8); memcpy(&nbytes, e + 72, 8);
+    if (off + nbytes > len) return false;
+    HostArray a; a.dtype = (int)dtype; a.rows = (int)rows; a.cols = (int)cols;
+    a.data.assign(buf + off, buf + off + nbytes);
+    out[name] = a;
+  }
+  return true;
+}
+
+struct LayerSpec { const char *name; int nin, nout; int kind; };   // kind 0 f32, 1 int8 dense, 2 int8 block-indexed
+
+void layer_specs(std::vector<LayerSpec> &v, std::vector<std::string> &names) {
+  static const int enc_k[5] = {64, 224, 384, 544, 704}, enc_ck[5] = {256, 576, 896, 1216, 1536};
+  static const int dec_k[5] = {96, 224, 352, 480, 608}, dec_ck[5] = {384, 640, 896, 1152, 1408};
+  names.reserve(64);
+  auto add = [&](const std::string &n, int a, int b, int k) { names.push_back(n); v.push_back({nullptr, a, b, k}); };
+  add("enc_dense1", 84, 64, 0); add("enc_zdense", 864, 80, 0); add("dec_dense1", 80, 96, 0); add("dec_output", 736, 84, 0);
+  for (int i = 0; i < 5; i++) {
+    std::string n = std::to_string(i + 1);
+    add("enc_gru" + n + "_input", enc_k[i], 192, 2); add("enc_gru" + n + "_recurrent", 64, 192, 1); add("enc_conv" + n, enc_ck[i], 96, 1);
+    add("dec_gru" + n + "_input", dec_k[i], 288, 2); add("dec_gru" + n + "_recurrent", 96, 288, 1);
+    add("dec_glu" + n, 96, 96, 1); add("dec_conv" + n, dec_ck[i], 32, 1);
+  }
+  for (size_t i = 0; i < v.size(); i++) v[i].name = names[i].c_str();
+}
+
+// DNNw blob -> the same flat map RDW gives (unblocking the 8x4 tiles)
+bool parse_dnnw(const unsigned char *buf, size_t len, ArrayMap &out) {
+  struct Raw { int type; const unsigned char *p; int size; };
+  std::map<std::string, Raw> raw;
+  size_t off = 0;
+  while (off + 64 <= len) {
+    if (memcmp(buf + off, "DNNw", 4) != 0) return false;
+    int version, type, size, block;
+    memcpy(&version, buf + off + 4, 4); memcpy(&type, buf + off + 8, 4);
+    memcpy(&size, buf + off + 12, 4); memcpy(&block, buf + off + 16, 4);
+    if (version != 0 || size <= 0 || block < size || off + 64 + (size_t)block > len) return false;
+    char name[45]; memcpy(name, buf + off + 20, 44); name[44] = 0;
+    raw[name] = {type, buf + off + 64, size};
+    off += 64 + (size_t)block;
+  }
+  std::vector<LayerSpec> specs; std::vector<std::string> names;
+  layer_specs(specs, names);
+  for (auto &L : specs) {
+    std::string n = L.name;
+    auto need = [&](const std::string &k, size_t bytes) -> const unsigned char * {
+      auto it = raw.find(k);
+      return (it != raw.end() && (size_t)it->second.size == bytes) ? it->second.p : nullptr;
+    };
+    const unsigned char *b = need(n + "_bias", 4 * (size_t)L.nout);
+    if (!b) return false;
+    HostArray bias; bias.dtype = 0; bias.rows = 1; bias.cols = L.nout; bias.data.assign(b, b + 4 * (size_t)L.nout);
+    out[n + ".bias"] = bias;
+    if (L.kind == 0) {
+      const unsigned char *w = need(n + "_weights_float", 4 * (size_t)L.nin * L.nout);
+      if (!w) return false;
+      HostArray a; a.dtype = 0; a.rows = L.nin; a.cols = L.nout; a.data.assign(w, w + 4 * (size_t)L.nin * L.nout);
+      out[n + ".wf"] = a;
+    } else {
+      const unsigned char *sc = need(n + "_scale", 4 * (size_t)L.nout);
+      auto itw = raw.find(n + "_weights_int8");
+      if (!sc || itw == raw.end()) return false;
+      const int8_t *wb = (const int8_t *)itw->second.p;
+      const int *idx = nullptr;
+      if (L.kind == 2) { auto ii = raw.find(n + "_weights_idx"); if (ii == raw.end()) return false; idx = (const int *)ii->second.p; }
+      HostArray a; a.dtype = 1; a.rows = L.nout; a.cols = L.nin; a.data.assign((size_t)L.nin * L.nout, 0);
+      size_t p = 0;
+      for (int ob = 0; ob < L.nout / 8; ob++) {
+        int nblk = idx ? *idx++ : L.nin / 4;
+        for (int j = 0; j < nblk; j++) {
+          int pos = idx ? *idx++ : 4 * j;
+          if (pos < 0 || pos + 3 >= L.nin || p + 32 > (size_t)itw->second.size) return false;
+          for (int k = 0; k < 8; k++) for (int c = 0; c < 4; c++)
+            a.data[(size_t)(ob * 8 + k) * L.nin + pos + c] = (unsigned char)wb[p + 4 * k + c];
+          p += 32;
+        }
+      }
+      out[n + ".w8"] = a;
+      HostArray s; s.dtype = 0; s.rows = 1; s.cols = L.nout; s.data.assign(sc, sc + 4 * (size_t)L.nout);
+      out[n + ".scale"] = s;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+void core_weights_free(CoreWeightsHolder *h) {
+  if (!h) return;
+  for (void *p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+}
+
+int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h) {
+  ArrayMap arrays;
+  if (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays)) {
+    fprintf(stderr, "libradae_b200: weight blob is neither RDW v1 nor a DNNw blob (%zu bytes)\n", len);
+    return -1;
+  }
+  std::vector<LayerSpec> specs; std::vector<std::string> names;
+  layer_specs(specs, names);
+  auto dev_copy = [&](const void *src, size_t bytes) -> void * {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    h->allocs.push_back(d);
+    return d;
+  };
+  std::map<std::string, I8LayerDev> i8; std::map<std::string, F32LayerDev> f32;
+  h->weight_bytes = 0;
+  for (auto &L : specs) {
+    std::string n = L.name;
+    auto get = [&](const std::string &k, int dtype, int rows, int cols) -> const HostArray * {
+      auto it = arrays.find(k);
+      if (it == arrays.end() || it->second.dtype != dtype || it->second.rows != rows || it->second.cols != cols) return nullptr;
+      return &it->second;
+    };
+    const HostArray *b = get(n + ".bias", 0, 1, L.nout);
+    if (!b) { fprintf(stderr, "libradae_b200: missing %s.bias\n", L.name); return -1; }
+    const float *dbias = (const float *)dev_copy(b->data.data(), b->data.size());
+    if (!dbias) return -1;
+    if (L.kind == 0) {
+      const HostArray *w = get(n + ".wf", 0, L.nin, L.nout);
+      if (!w) { fprintf(stderr, "libradae_b200: missing %s.wf\n", L.name); return -1; }
+      const float *dw = (const float *)dev_copy(w->data.data(), w->data.size());
+      if (!dw) return -1;
+      f32[n] = {dw, dbias, L.nin, L.nout};
+      h->weight_bytes += w->data.size();
+    } else {
+      const HostArray *w = get(n + ".w8", 1, L.nout, L.nin), *s = get(n + ".scale", 0, 1, L.nout);
+      if (!w || !s || (L.nin % 32) || (L.nout % 8)) { fprintf(stderr, "libradae_b200: missing/misshaped %s\n", L.name); return -1; }
+      const int KB = L.nin / 32, NTL = L.nout / 8;
+      std::vector<uint32_t> tiled((size_t)NTL * KB * 32 * 2);
+      const int8_t *W8 = (const int8_t *)w->data.data();
+      for (int nt = 0; nt < NTL; nt++) for (int kb = 0; kb < KB; kb++) for (int lane = 0; lane < 32; lane++) {
+        const int g = lane >> 2, tig = lane & 3;
+        const int8_t *row = W8 + (size_t)(nt * 8 + g) * L.nin + kb * 32 + tig * 4;
+        uint32_t b0, b1; memcpy(&b0, row, 4); memcpy(&b1, row + 16, 4);
+        size_t o = (((size_t)nt * KB + kb) * 32 + lane) * 2;
+        tiled[o] = b0; tiled[o + 1] = b1;
+      }
+      const uint2 *dw = (const uint2 *)dev_copy(tiled.data(), tiled.size() * 4);
+      const float *ds = (const float *)dev_copy(s->data.data(), s->data.size());
+      if (!dw || !ds) return -1;
+      i8[n] = {dw, ds, dbias, L.nin, L.nout};
+      h->weight_bytes += w->data.size();
+    }
+  }
+  CoreWeightsDev &W = h->dev;
+  W.enc_dense1 = f32["enc_dense1"]; W.enc_zdense = f32["enc_zdense"]; W.dec_dense1 = f32["dec_dense1"]; W.dec_output = f32["dec_output"];
+  for (int i = 0; i < 5; i++) {
+    std::string n = std::to_string(i + 1);
+    W.enc_gru_in[i] = i8["enc_gru" + n + "_input"]; W.enc_gru_rec[i] = i8["enc_gru" + n + "_recurrent"]; W.enc_conv[i] = i8["enc_conv" + n];
+    W.dec_gru_in[i] = i8["dec_gru" + n + "_input"]; W.dec_gru_rec[i] = i8["dec_gru" + n + "_recurrent"];
+    W.dec_glu[i] = i8["dec_glu" + n]; W.dec_conv[i] = i8["dec_conv" + n];
+  }
+  return 0;
+}
