@@ -93,6 +93,15 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples /* [S][960] */);
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
 
+/* --- per-kernel device timing (CUDA events on the context's stream; used by bench.py for the roofline line) --- */
+RADE_EXPORT int rade_b200_profile_enable(rade_batch *b, int enable);
+RADE_EXPORT int rade_b200_profile_n_kernels(void);
+RADE_EXPORT const char *rade_b200_profile_kernel_name(int k);
+RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts);
+
+/* --- host-buffer channel call (for end-to-end measurements through host memory): tx, rx [S][960] --- */
+RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,7 +132,8 @@ static float sigmoid_rational(float x) { return .5f + .5f*tanh_rational(.5f*x); 
 static void quantise(int8_t *q, const float *x, int n)
 {
   int i;
-  for (i=0;i<n;i++) q[i] = (int8_t)(int)floor(.5 + 127*(double)x[i]);
+  /* C semantics of `(int)floor(.5+127*x[i])`: 127*x is a FLOAT product (rounded), the sum with .5 is double */
+  for (i=0;i<n;i++) q[i] = (int8_t)(int)floor(.5 + 127*x[i]);
 }
 
 /* out = (W8 xq)*scale + bias */

@@ -101,7 +101,8 @@ static void apply_activation(float *y, const float *x, int n, int activation)
 static void quantise_input(opus_int8 *xq, const float *x, int n)
 {
   int i;
-  /* `.5+127*x` is evaluated in double (the literal .5 promotes), then floor */
+  /* C semantics: 127*x[i] is a FLOAT product (int promoted to float, result rounded to binary32); the literal .5
+   * then promotes the SUM to double; floor; truncate to int8 */
   for (i=0;i<n;i++) xq[i] = (opus_int8)(int)floor(.5 + 127*x[i]);
 }
 

@@ -154,3 +154,21 @@ class RadeBatch:
 
     def link_pop_dev(self, d_rx_in, d_active):
         _check(self.lib.rade_b200_link_pop_dev(self.h, d_rx_in, d_active), "link_pop_dev")
+
+    def channel(self, tx):
+        """host-buffer channel call: tx [S][960] complex64 -> rx [S][960]"""
+        t, pt = _np(tx, np.complex64)
+        assert t.shape == (self.S, NMF)
+        out = np.empty((self.S, NMF), np.complex64)
+        _check(self.lib.rade_b200_channel(self.h, out.ctypes.data, pt), "channel")
+        return out
+
+    # ---- per-kernel device timing
+    def profile_enable(self, on=True):
+        _check(self.lib.rade_b200_profile_enable(self.h, int(on)), "profile_enable")
+
+    def profile_read(self):
+        n = self.lib.rade_b200_profile_n_kernels()
+        ms = np.zeros(n, np.float32); cnt = np.zeros(n, np.int32)
+        _check(self.lib.rade_b200_profile_read(self.h, ms.ctypes.data, cnt.ctypes.data), "profile_read")
+        return {self.lib.rade_b200_profile_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}

@@ -13,6 +13,7 @@ struct rade_batch {
   int S, device, flags;
   cudaStream_t stream;
   long long launches;
+  Profiler prof;
   CoreWeightsHolder weights;
   std::vector<void *> allocs;
   DspTables tables;
@@ -104,6 +105,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   b->S = n_streams; b->device = device; b->flags = flags; b->launches = 0; b->core_cap = 0;
   b->d_core_in = b->d_core_out = nullptr;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
+  b->prof.stream = b->stream;
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   DspTablesHost th; dsp_tables_host(th);
@@ -168,12 +170,16 @@ RADE_EXPORT int rade_b200_reset(rade_batch *b) { return reset_state(b); }
 
 // ------------------------------------------------------------------ core codec
 RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float *d_features, int n_steps) {
+  b->prof.begin(K_CORE_ENC);
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features, 0, d_z, nullptr, b->S, n_steps, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_ENC);
   b->launches += 1;
   return 0;
 }
 RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, const float *d_z, int n_steps) {
+  b->prof.begin(K_CORE_DEC);
   if (core_decoder_launch(b->weights.dev, b->rx.dec_state, d_z, d_features, 0, nullptr, nullptr, b->S, n_steps, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_DEC);
   b->launches += 1;
   return 0;
 }
@@ -198,14 +204,19 @@ RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const floa
 
 // ------------------------------------------------------------------ transmitter
 RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z) {
+  b->prof.begin(K_OFDM_MOD);
   if (ofdm_mod_launch(b->tables, d_z, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_OFDM_MOD);
   b->launches += 1;
   return 0;
 }
 RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_features_in) {
   // 3 core-encoder steps on the API feature layout (src/rade_api.c:411-434) then transmitter_one (radae_txe.py:127)
+  b->prof.begin(K_CORE_ENC);
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_ENC); b->prof.begin(K_OFDM_MOD);
   if (ofdm_mod_launch(b->tables, b->z_tx, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_OFDM_MOD);
   b->launches += 2;
   return RADE_NMF;
 }
@@ -229,7 +240,9 @@ RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits) 
 }
 RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
   const size_t S = b->S;
+  b->prof.begin(K_EOO);
   if (eoo_launch(b->tables, b->eoo_bits, b->has_eoo_bits, b->d_tx_eoo, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_EOO);
   b->launches += 1;
   CUDA_CHECK(cudaMemcpyAsync(b->h_cplx, b->d_tx_eoo, S * RADE_NEOO * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -241,11 +254,13 @@ RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
 RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out, const RADE_COMP *d_rx_in,
                                  const unsigned char *d_active) {
   const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
-  int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, b->S, 1, reset_dec, d_ret, b->stream);
+  int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, b->S, 1, reset_dec, d_ret, b->stream, &b->prof);
   if (n < 0) return -1;
+  b->prof.begin(K_CORE_DEC);
   // decoder last, only for streams with valid output; counts aux-symbol errors (src/rade_api.c:494-513)
   if (core_decoder_launch(b->weights.dev, b->rx.dec_state, b->rx.z_hat, d_features_out, 1, b->rx.uw_errors, b->rx.dec_active,
                           b->S, RADE_NZMF, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_DEC);
   b->launches += n + 1;
   if (d_eoo_out && d_eoo_out != b->rx.eoo) {
     CUDA_CHECK(cudaMemcpyAsync(d_eoo_out, b->rx.eoo, (size_t)b->S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
@@ -307,20 +322,61 @@ RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_
 RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx) {
   const rade_b200_channel_cfg &c = b->chan_cfg;
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));       // radae.py:570-574, Rb = 80/0.04
+  b->prof.begin(K_CHANNEL);
   if (channel_stream_launch((float2 *)d_rx, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz,
                             c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->stream) < 0) return -1;
+  b->prof.end(K_CHANNEL);
   b->launches += 1;
   return 0;
 }
+RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx) {
+  const size_t S = b->S;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_channel_dev(b, (RADE_COMP *)b->d_rx_in, (const RADE_COMP *)b->d_tx) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(rx, b->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {
+  b->prof.begin(K_LINK_PUSH);
   if (link_push_launch(b->link_ring, b->link_wr, (const float2 *)d_samples, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_LINK_PUSH);
   b->launches += 1;
   return 0;
 }
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsigned char *d_active) {
+  b->prof.begin(K_LINK_POP);
   if (link_pop_launch(b->link_ring, b->link_wr, b->link_rd, b->rx.ctl, (float2 *)d_rx_in, d_active, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_LINK_POP);
   b->launches += 1;
   return 0;
+}
+
+// ---- per-kernel timing (CUDA events on the context's stream).  enable=1 starts recording an event pair around every
+// kernel launch; rade_b200_profile_read synchronises, returns per-kernel-class total milliseconds and launch counts
+// (arrays of rade_b200_profile_n_kernels() entries, names via rade_b200_profile_kernel_name) and clears the record.
+RADE_EXPORT int rade_b200_profile_enable(rade_batch *b, int enable) { b->prof.on = enable != 0; return 0; }
+RADE_EXPORT int rade_b200_profile_n_kernels(void) { return K_COUNT; }
+RADE_EXPORT const char *rade_b200_profile_kernel_name(int k) {
+  static const char *names[K_COUNT] = {"core_encoder_kernel", "ofdm_mod_kernel", "eoo_kernel", "channel_stream_kernel",
+                                       "link_push_kernel", "link_pop_kernel", "rx_bpf_kernel", "rx_detect_kernel",
+                                       "rx_track_kernel", "rx_demod_kernel", "rx_finish_kernel", "core_decoder_kernel"};
+  return (k >= 0 && k < K_COUNT) ? names[k] : "";
+}
+RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts) {
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  for (int k = 0; k < K_COUNT; k++) {
+    float tot = 0.f; int n = 0;
+    std::vector<cudaEvent_t> &v = b->prof.ev[k];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) { tot += ms; n++; }
+    }
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+    total_ms[k] = tot; counts[k] = n;
+  }
+  return K_COUNT;
 }
 
 // debug/test hook: DSP tables as built on the host (no device needed) — lets the CPU test-suite compare them with

@@ -40,9 +40,9 @@ __device__ __forceinline__ float tanh_r(float x) {
 __device__ __forceinline__ float sigmoid_r(float x) {
   return __fadd_rn(.5f, __fmul_rn(.5f, tanh_r(__fmul_rn(.5f, x))));
 }
-// (int)floor(.5 + 127*x) evaluated in double like the C expression
+// C semantics of `(int)floor(.5+127*x)`: 127*x is a float product (rounded to binary32), the sum with .5 is double
 __device__ __forceinline__ int8_t quant8(float x) {
-  return (int8_t)__double2int_rd(fma(127.0, (double)x, 0.5));
+  return (int8_t)__double2int_rd((double)__fmul_rn(127.f, x) + 0.5);
 }
 __device__ __forceinline__ float lin(int acc, float scale, float bias) {
   return __fadd_rn(__fmul_rn((float)acc, scale), bias);

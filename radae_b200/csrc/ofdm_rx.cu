@@ -557,7 +557,7 @@ int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStrea
 }
 
 int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
-                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream) {
+                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(rx_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetectSmem)));
@@ -565,12 +565,18 @@ int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, c
     CUDA_CHECK(cudaFuncSetAttribute(rx_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinishSmem)));
     attr_set = true;
   }
+  prof->begin(K_RX_BPF);
   rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en);
+  prof->end(K_RX_BPF); prof->begin(K_RX_DETECT);
   rx_detect_kernel<<<dim3(RADE_NMF / DET_TB, S), 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, active);
+  prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
   rx_track_kernel<<<S, 256, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
+  prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
+  prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
   rx_finish_kernel<<<S, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
                                                            reset_dec_on_sync, ret_out, B.dec_active, B.nin, active);
+  prof->end(K_RX_FINISH);
   CUDA_CHECK(cudaGetLastError());
   return 5;
 }

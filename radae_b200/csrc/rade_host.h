@@ -54,5 +54,18 @@ int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaS
 int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, const RxCtl *ctl, float2 *out,
                     unsigned char *active, int S, cudaStream_t stream);
 int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream);
+struct Profiler;
 int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
-                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream);
+                  int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof);
+
+// ---- optional per-kernel timing with CUDA events on the context's stream (rade_b200_profile_*)
+enum KernelId { K_CORE_ENC = 0, K_OFDM_MOD, K_EOO, K_CHANNEL, K_LINK_PUSH, K_LINK_POP, K_RX_BPF, K_RX_DETECT, K_RX_TRACK,
+                K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_COUNT };
+struct Profiler {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> ev[K_COUNT];       // start,end pairs
+  void begin(int k) { if (on) rec(k); }
+  void end(int k) { if (on) rec(k); }
+  void rec(int k) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); ev[k].push_back(e); }
+};

@@ -38,9 +38,9 @@ def test_float_variant_pins_layouts_against_pytorch(golden):
 
 
 @pytest.mark.skipif(not CoreOracleRef.available("int8"), reason="oracle/_ref not built (needs /root/reference)")
-def test_port_equals_ref_build_on_fresh_inputs():
-    S, T = 3, 30
-    x = pack_enc_input(synth_features(S, 4 * T, seed=99))
+@pytest.mark.parametrize("S,T,seed", [(3, 30, 99), (48, 12, 11), (64, 40, 2024)])
+def test_port_equals_ref_build_on_fresh_inputs(S, T, seed):
+    x = pack_enc_input(synth_features(S, 4 * T, seed=seed))
     p, r = CoreOraclePort(n_streams=S), CoreOracleRef("int8", S)
     zp, zr = p.encode(x, nthreads=2), r.encode(x, nthreads=2)
     assert np.array_equal(zp, zr)
