@@ -67,8 +67,22 @@ __device__ __forceinline__ void gemm_i8(int (&acc)[NT][4], const int8_t *A, int 
   const uint2 *w[NT];
 #pragma unroll
   for (int i = 0; i < NT; i++) w[i] = Wt + ((size_t)nt[i] * KBtot + kb0) * 32 + lane;
-#pragma unroll 2
-  for (int kb = 0; kb < KB; kb++) {
+  constexpr int U = 4;                        // k-blocks of B fragments in flight per warp
+  int kb = 0;
+  for (; kb + U <= KB; kb += U) {
+    uint2 b[U][NT];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int i = 0; i < NT; i++) b[u][i] = __ldg(w[i] + (kb + u) * 32);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      uint32_t a0 = r0[(kb + u) * 8], a1 = r1[(kb + u) * 8], a2 = r0[(kb + u) * 8 + 4], a3 = r1[(kb + u) * 8 + 4];
+#pragma unroll
+      for (int i = 0; i < NT; i++) mma_s8(acc[i], a0, a1, a2, a3, b[u][i].x, b[u][i].y);
+    }
+  }
+  for (; kb < KB; kb++) {
     uint32_t a0 = r0[kb * 8], a1 = r1[kb * 8], a2 = r0[kb * 8 + 4], a3 = r1[kb * 8 + 4];
 #pragma unroll
     for (int i = 0; i < NT; i++) {
@@ -82,8 +96,25 @@ __device__ __forceinline__ void gemm_i8(int (&acc)[NT][4], const int8_t *A, int 
 // thread (s = tid&15, grp = tid>>4) owns outputs o = grp + 8*i of stream s
 template <int NOUT, int NACC>
 __device__ __forceinline__ void dense_acc(float (&acc)[NACC], const float *xrow, int K, const float *__restrict__ wf, int grp) {
-  for (int j = 0; j < K; j++) {
-    float x = xrow[j];
+  constexpr int U = 8;                        // rows of W in flight per thread: hides the L2 latency of the weight fetch
+  int j = 0;
+  for (; j + U <= K; j += U) {
+    float w[U][NACC];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int i = 0; i < NACC; i++)
+        w[u][i] = (grp + 8 * i < NOUT) ? __ldg(wf + (size_t)(j + u) * NOUT + grp + 8 * i) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const float x = xrow[j + u];
+#pragma unroll
+      for (int i = 0; i < NACC; i++)
+        if (grp + 8 * i < NOUT) acc[i] = __fadd_rn(acc[i], __fmul_rn(w[u][i], x));
+    }
+  }
+  for (; j < K; j++) {
+    const float x = xrow[j];
     const float *wj = wf + (size_t)j * NOUT + grp;
 #pragma unroll
     for (int i = 0; i < NACC; i++)

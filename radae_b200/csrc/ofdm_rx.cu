@@ -250,9 +250,14 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 }
 
 // ================================================================= sync-state tracking: refine + check_pilots + slips
+constexpr int CHK_SPAN = 20 * (RADE_NUPDATE - 1) + RADE_M + 20;     // samples covered by the 48 refreshed rows of one half (1120)
+struct CheckSmem {                 // aliases RefineSmem once the refine is done
+  float2 pw[RADE_M][RADE_NFCOARSE];
+  float2 rx[2][CHK_SPAN];
+};
 struct TrackSmem {
-  RefineSmem ref;
-  float absd[RADE_NUPDATE * 2 * RADE_NFCOARSE];
+  union { RefineSmem ref; CheckSmem chk; };
+  float part[2][RADE_NUPDATE * 2];
   float scratch[32];
   double spot[4];
 };
@@ -279,25 +284,41 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   const double fmax = 0.9 * fmax0 + 0.1 * fhat;
 
   // ---- check_pilots: refresh 48 rows of the |Dt| row sums (deterministic schedule), thresholds, spot correlations
+  // rows t_i = 20 i + rot (both pilot positions): 96 (row, half) x 40 frequencies x 160-tap complex correlations, staged
+  // through shared memory (p_w table + the 1120-sample span the rows cover) and register-tiled 1 x 20 per thread
   const int rot = c.n_check % 20;
-  for (int item = tid; item < RADE_NUPDATE * 2 * RADE_NFCOARSE; item += blockDim.x) {
-    const int f = item % RADE_NFCOARSE, half = (item / RADE_NFCOARSE) & 1, i = item / (2 * RADE_NFCOARSE);
-    const int t = 20 * i + rot + half * RADE_NMF;
-    float ax = 0.f, ay = 0.f;
+  __syncthreads();                                   // everyone is done with sm.ref before it is overwritten
+  for (int i = tid; i < RADE_M * RADE_NFCOARSE; i += blockDim.x) (&sm.chk.pw[0][0])[i] = T.p_w[i];
+  for (int i = tid; i < 2 * CHK_SPAN; i += blockDim.x) {
+    const int half = i / CHK_SPAN, k = i % CHK_SPAN;
+    const int li = rot + k + half * RADE_NMF;
+    sm.chk.rx[half][k] = (li < RADE_RXBUF) ? cconj(rg[ring_idx(head, li)]) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  if (tid < RADE_NUPDATE * 2 * 2) {
+    const int rh = tid % (RADE_NUPDATE * 2), fg = tid / (RADE_NUPDATE * 2);
+    const int i = rh >> 1, half = rh & 1;
+    const float2 *x = &sm.chk.rx[half][20 * i];
+    float2 a[20];
+#pragma unroll
+    for (int j = 0; j < 20; j++) a[j] = make_float2(0.f, 0.f);
     for (int n = 0; n < RADE_M; n++) {
-      const float2 x = rg[ring_idx(head, t + n)];
-      const float2 w = T.p_w[n * RADE_NFCOARSE + f];
-      ax += x.x * w.x + x.y * w.y; ay += x.x * w.y - x.y * w.x;        // conj(x) * w
+      const float2 xv = x[n];
+#pragma unroll
+      for (int j = 0; j < 20; j++) {
+        const float2 w = sm.chk.pw[n][fg * 20 + j];
+        a[j].x += xv.x * w.x - xv.y * w.y; a[j].y += xv.x * w.y + xv.y * w.x;
+      }
     }
-    sm.absd[item] = hypotf(ax, ay);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 20; j++) sum += hypotf(a[j].x, a[j].y);
+    sm.part[fg][rh] = sum;
   }
   __syncthreads();
   if (tid < RADE_NUPDATE * 2) {
-    const int half = tid & 1, i = tid >> 1;
-    const float *a = &sm.absd[(i * 2 + half) * RADE_NFCOARSE];
-    float sum = 0.f;
-    for (int f = 0; f < RADE_NFCOARSE; f++) sum += a[f];
-    rs[half * RADE_NMF + 20 * i + rot] = sum;
+    const int i = tid >> 1, half = tid & 1;
+    rs[half * RADE_NMF + 20 * i + rot] = sm.part[0][tid] + sm.part[1][tid];
   }
   __syncthreads();
   const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);

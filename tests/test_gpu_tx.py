@@ -45,7 +45,7 @@ def test_batched_tx_vs_oracle_many_streams():
         assert relrms(tx, ref) < 1e-5
         fr = tx.reshape(S, 5, 192)
         assert np.array_equal(fr[:, :, :32], fr[:, :, -32:])      # cyclic prefix is a copy of the tail
-        assert np.abs(tx).max() < 1.0                              # PA model
+        assert np.abs(tx).max() <= 1.0 + 1e-6                      # PA model: tanh(|x|) saturates at 1
     bits = np.sign(np.random.default_rng(1).random((S, 180)) - 0.5).astype(np.float32)
     b.tx_set_eoo_bits(bits)
     eoo = b.tx_eoo()
