@@ -57,12 +57,22 @@ struct __align__(16) DecStreamState {
   int8_t cat1[DEC_LDA];                       // step t-1 concat (all five convs have dilation 1, src/rade_dec.c:68-95)
 };
 
-struct I8LayerDev { const uint2 *wt; const float *scale; const float *bias; int K; int N; };
-struct F32LayerDev { const float *wf; const float *bias; int K; int N; };
+// ---- weight streaming (core_codec.cu): all weights of one 40 ms step, laid out as a sequence of chunks in the exact
+// order the layer walk consumes them; a producer warp TMA-bulk-copies chunk after chunk into a shared-memory ring.
+#define CORE_STAGE_BYTES 32768
+#define CORE_NSTAGES 4
+#define ENC_NCW 8                             // consumer warps (encoder): 8 GRU unit tiles -> one per warp
+#define DEC_NCW 12                            // consumer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
+
+struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
+struct F32LayerDev { const float *bias; int K; int N; };
+struct ChunkDesc { unsigned int offset; unsigned int bytes; };
+struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; int n_chunks; };
 struct CoreWeightsDev {
   F32LayerDev enc_dense1, enc_zdense, dec_dense1, dec_output;
   I8LayerDev enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
+  CodecStreamDev enc_stream, dec_stream;
 };
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

@@ -8,7 +8,10 @@ struct CoreWeightsHolder {
   CoreWeightsDev dev;
   std::vector<void *> allocs;
   size_t weight_bytes = 0;
+  int enc_chunks_per_step = 0, dec_chunks_per_step = 0;
 };
+// k-blocks (32 inputs each) of an int8 layer with NTL n-tiles (8 outputs each) that fit one pipeline stage
+static inline __host__ __device__ int core_kbc(int NTL) { int k = CORE_STAGE_BYTES / (NTL * 256); return k < 1 ? 1 : k; }
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h);
 void core_weights_free(CoreWeightsHolder *h);
 

@@ -1,8 +1,12 @@
 // Weight ingest for libradae_b200: RDW container (this repo's format, radae_b200/rdw.py) or the reference's DNNw
 // blob (src/write_rade_weights.c:51-74; int8 matrices in 8x4 blocks, weight-exchange/wexchange/c_export/common.py:59-67,
 // optional block index lists :156-170) -> host row-major matrices -> device layouts.
-// Device layout of an int8 layer: MMA B-fragment order, Wt[(nt*KB + kb)*32 + lane] = {b0, b1} with
-//   b0 = W[nt*8 + lane/4][kb*32 + (lane%4)*4 .. +3],  b1 = same row, columns +16   (m16n8k32 .col B operand).
+// Device layout: ONE byte stream per codec holding every weight of a 40 ms step as a sequence of <= 32 KB chunks in the
+// order the kernel's layer walk consumes them (core_codec.cu); the kernel's producer warp TMA-bulk-copies chunk after
+// chunk into a shared-memory ring.  int8 layers are stored in MMA B-fragment order [kb][nt][lane] = {b0, b1} with
+//   b0 = W[nt*8 + lane/4][kb*32 + (lane%4)*4 .. +3],  b1 = same row, columns +16   (m16n8k32 .col B operand);
+// float layers as the rows [j][out] of the concat segment a chunk covers.
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -118,6 +122,41 @@ void core_weights_free(CoreWeightsHolder *h) {
   h->allocs.clear();
 }
 
+namespace {
+
+struct StreamBuilder {
+  std::vector<unsigned char> bytes;
+  std::vector<ChunkDesc> chunks;
+  bool ok = true;
+  void add(const void *p, size_t n) {
+    if (n == 0 || n > CORE_STAGE_BYTES || (n & 15)) { ok = false; return; }
+    ChunkDesc d; d.offset = (unsigned)bytes.size(); d.bytes = (unsigned)n;
+    const unsigned char *b = (const unsigned char *)p;
+    bytes.insert(bytes.end(), b, b + n);
+    chunks.push_back(d);
+  }
+  // k-blocks [kb_lo, kb_hi) of an int8 [N][K] matrix in fragment order, chunked kbc k-blocks at a time
+  void add_i8(const int8_t *W8, int N, int K, int kb_lo, int kb_hi) {
+    const int NTL = N / 8;
+    const int kbc = core_kbc(NTL);
+    for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += kbc) {
+      const int nk = std::min(kbc, kb_hi - kb0);
+      std::vector<uint32_t> t((size_t)nk * NTL * 64);
+      for (int kb = 0; kb < nk; kb++) for (int nt = 0; nt < NTL; nt++) for (int lane = 0; lane < 32; lane++) {
+        const int g = lane >> 2, tig = lane & 3;
+        const int8_t *row = W8 + (size_t)(nt * 8 + g) * K + (kb0 + kb) * 32 + tig * 4;
+        uint32_t b0, b1; memcpy(&b0, row, 4); memcpy(&b1, row + 16, 4);
+        const size_t o = (((size_t)kb * NTL + nt) * 32 + lane) * 2;
+        t[o] = b0; t[o + 1] = b1;
+      }
+      add(t.data(), t.size() * 4);
+    }
+  }
+  void add_f32_rows(const float *Wf, int NOUT, int j0, int nrows) { add(Wf + (size_t)j0 * NOUT, (size_t)nrows * NOUT * 4); }
+};
+
+}  // namespace
+
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h) {
   ArrayMap arrays;
   if (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays)) {
@@ -134,6 +173,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     return d;
   };
   std::map<std::string, I8LayerDev> i8; std::map<std::string, F32LayerDev> f32;
+  std::map<std::string, const HostArray *> w8, wf;
   h->weight_bytes = 0;
   for (auto &L : specs) {
     std::string n = L.name;
@@ -149,27 +189,16 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     if (L.kind == 0) {
       const HostArray *w = get(n + ".wf", 0, L.nin, L.nout);
       if (!w) { fprintf(stderr, "libradae_b200: missing %s.wf\n", L.name); return -1; }
-      const float *dw = (const float *)dev_copy(w->data.data(), w->data.size());
-      if (!dw) return -1;
-      f32[n] = {dw, dbias, L.nin, L.nout};
+      wf[n] = w;
+      f32[n] = {dbias, L.nin, L.nout};
       h->weight_bytes += w->data.size();
     } else {
       const HostArray *w = get(n + ".w8", 1, L.nout, L.nin), *s = get(n + ".scale", 0, 1, L.nout);
       if (!w || !s || (L.nin % 32) || (L.nout % 8)) { fprintf(stderr, "libradae_b200: missing/misshaped %s\n", L.name); return -1; }
-      const int KB = L.nin / 32, NTL = L.nout / 8;
-      std::vector<uint32_t> tiled((size_t)NTL * KB * 32 * 2);
-      const int8_t *W8 = (const int8_t *)w->data.data();
-      for (int nt = 0; nt < NTL; nt++) for (int kb = 0; kb < KB; kb++) for (int lane = 0; lane < 32; lane++) {
-        const int g = lane >> 2, tig = lane & 3;
-        const int8_t *row = W8 + (size_t)(nt * 8 + g) * L.nin + kb * 32 + tig * 4;
-        uint32_t b0, b1; memcpy(&b0, row, 4); memcpy(&b1, row + 16, 4);
-        size_t o = (((size_t)nt * KB + kb) * 32 + lane) * 2;
-        tiled[o] = b0; tiled[o + 1] = b1;
-      }
-      const uint2 *dw = (const uint2 *)dev_copy(tiled.data(), tiled.size() * 4);
       const float *ds = (const float *)dev_copy(s->data.data(), s->data.size());
-      if (!dw || !ds) return -1;
-      i8[n] = {dw, ds, dbias, L.nin, L.nout};
+      if (!ds) return -1;
+      w8[n] = w;
+      i8[n] = {ds, dbias, L.nin, L.nout};
       h->weight_bytes += w->data.size();
     }
   }
@@ -181,5 +210,51 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     W.dec_gru_in[i] = i8["dec_gru" + n + "_input"]; W.dec_gru_rec[i] = i8["dec_gru" + n + "_recurrent"];
     W.dec_glu[i] = i8["dec_glu" + n]; W.dec_conv[i] = i8["dec_conv" + n];
   }
+  // ---- per-step weight streams, in the kernels' consumption order (keep in lock-step with core_codec.cu)
+  auto I8 = [&](const std::string &n) { return (const int8_t *)w8[n]->data.data(); };
+  auto F = [&](const std::string &n) { return (const float *)wf[n]->data.data(); };
+  StreamBuilder e, d;
+  {
+    e.add_f32_rows(F("enc_dense1"), 64, 0, ENC_IN);
+    e.add_f32_rows(F("enc_zdense"), RADE_LATENT, 0, 64);
+    int off = 64;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      e.add_i8(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32);
+      e.add_i8(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2);
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, off, ENC_GRU);
+      off += ENC_GRU;
+      e.add_i8(I8("enc_conv" + n), 96, 2 * off, 0, off / 32);                    // tap 0 (oldest frame)
+      e.add_i8(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32);         // tap 1 (current frame)
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, off, ENC_CONV);
+      off += ENC_CONV;
+    }
+  }
+  {
+    d.add_f32_rows(F("dec_dense1"), 96, 0, DEC_IN);
+    d.add_f32_rows(F("dec_output"), DEC_OUT, 0, 96);
+    int off = 96;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      d.add_i8(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32);
+      d.add_i8(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3);
+      d.add_i8(I8("dec_glu" + n), 96, 96, 0, 3);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, off, DEC_GRU);
+      off += DEC_GRU;
+      d.add_i8(I8("dec_conv" + n), 32, 2 * off, 0, off / 32);
+      d.add_i8(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, off, DEC_CONV);
+      off += DEC_CONV;
+    }
+  }
+  if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
+  auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out) -> int {
+    out.stream = (const unsigned char *)dev_copy(sb.bytes.data(), sb.bytes.size());
+    out.chunks = (const ChunkDesc *)dev_copy(sb.chunks.data(), sb.chunks.size() * sizeof(ChunkDesc));
+    out.n_chunks = (int)sb.chunks.size();
+    return (out.stream && out.chunks) ? 0 : -1;
+  };
+  if (up_stream(e, W.enc_stream) < 0 || up_stream(d, W.dec_stream) < 0) return -1;
+  h->enc_chunks_per_step = W.enc_stream.n_chunks; h->dec_chunks_per_step = W.dec_stream.n_chunks;
   return 0;
 }
