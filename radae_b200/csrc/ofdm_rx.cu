@@ -48,7 +48,8 @@ __device__ float block_sum(float v, float *scratch) {
 // ================================================================= band-pass filter + ring append
 __global__ void __launch_bounds__(256)
 rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, float2 *__restrict__ bpf_mem,
-              const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en) {
+              const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en,
+              int *__restrict__ search_list, int *__restrict__ search_count) {
   __shared__ float2 X[RADE_BPF_MEM + RADE_NIN_MAX];
   __shared__ float h[RADE_BPF_NTAP];
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -85,6 +86,7 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
     c.ring_head = nh;                      // logical sample 0 of rx_buf now lives at ring[nh]
     c.detect_key = 0ull;
     c.candidate = 0; c.endofover = 0; c.valid_output = 0; c.uw_fail = 0; c.ran_sync = 0; c.ret = 0;
+    if (c.state != ST_SYNC) search_list[atomicAdd(&search_count[0], 1)] = s;     // work list for rx_detect_kernel
   }
 }
 
@@ -92,7 +94,7 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
 // grid (15, S): CTA = 64 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations
 constexpr int DET_TB = 64;
 struct DetectSmem {
-  float2 pw[RADE_M][RADE_NFCOARSE];
+  alignas(16) float2 pw[RADE_M][RADE_NFCOARSE];
   float2 r1[DET_TB + RADE_M];
   float2 r2[DET_TB + RADE_M];
   float part[2][4][DET_TB];
@@ -101,57 +103,70 @@ struct DetectSmem {
 
 __global__ void __launch_bounds__(256)
 rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
-                 const unsigned char *__restrict__ active) {
+                 const int *__restrict__ search_list, int *__restrict__ search_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DetectSmem &sm = *reinterpret_cast<DetectSmem *>(smem_raw);
-  const int s = blockIdx.y, tid = threadIdx.x;
-  if (active && !active[s]) return;
-  RxCtl &c = ctl[s];
-  if (c.state == ST_SYNC) return;
-  const int head = c.ring_head, t0 = blockIdx.x * DET_TB;
-  const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+  __shared__ int work;
+  const int tid = threadIdx.x;
+  const int n_items = search_count[0] * (RADE_NMF / DET_TB);
+  if (n_items == 0) return;                       // steady state: nobody is searching
   for (int i = tid; i < RADE_M * RADE_NFCOARSE; i += blockDim.x) (&sm.pw[0][0])[i] = T.p_w[i];
-  for (int i = tid; i < DET_TB + RADE_M; i += blockDim.x) {
-    sm.r1[i] = cconj(rg[ring_idx(head, t0 + i)]);
-    sm.r2[i] = cconj(rg[ring_idx(head, t0 + RADE_NMF + i)]);
-  }
-  __syncthreads();
-  const int tl = tid & (DET_TB - 1), fg = tid >> 6;
-  float2 a1[10], a2[10];
+  // persistent CTAs pull (stream, 64-offset block) items off a device-side counter
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) work = atomicAdd(&search_count[1], 1);
+    __syncthreads();
+    const int w = work;
+    if (w >= n_items) break;
+    const int s = search_list[w / (RADE_NMF / DET_TB)], t0 = (w % (RADE_NMF / DET_TB)) * DET_TB;
+    RxCtl &c = ctl[s];
+    const int head = c.ring_head;
+    const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+    for (int i = tid; i < DET_TB + RADE_M; i += blockDim.x) {
+      sm.r1[i] = cconj(rg[ring_idx(head, t0 + i)]);
+      sm.r2[i] = cconj(rg[ring_idx(head, t0 + RADE_NMF + i)]);
+    }
+    __syncthreads();
+    const int tl = tid & (DET_TB - 1), fg = tid >> 6;
+    float2 a1[10], a2[10];
 #pragma unroll
-  for (int j = 0; j < 10; j++) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
-  for (int n = 0; n < RADE_M; n++) {
-    const float2 x1 = sm.r1[tl + n], x2 = sm.r2[tl + n];
+    for (int j = 0; j < 10; j++) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
+    for (int n = 0; n < RADE_M; n++) {
+      const float2 x1 = sm.r1[tl + n], x2 = sm.r2[tl + n];
+      const float4 *wp = reinterpret_cast<const float4 *>(&sm.pw[n][fg * 10]);
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        const float4 wv = wp[j];
+        a1[2 * j].x += x1.x * wv.x - x1.y * wv.y;     a1[2 * j].y += x1.x * wv.y + x1.y * wv.x;
+        a1[2 * j + 1].x += x1.x * wv.z - x1.y * wv.w; a1[2 * j + 1].y += x1.x * wv.w + x1.y * wv.z;
+        a2[2 * j].x += x2.x * wv.x - x2.y * wv.y;     a2[2 * j].y += x2.x * wv.y + x2.y * wv.x;
+        a2[2 * j + 1].x += x2.x * wv.z - x2.y * wv.w; a2[2 * j + 1].y += x2.x * wv.w + x2.y * wv.z;
+      }
+    }
+    float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = 0;
 #pragma unroll
     for (int j = 0; j < 10; j++) {
-      const float2 w = sm.pw[n][fg * 10 + j];
-      a1[j].x += x1.x * w.x - x1.y * w.y; a1[j].y += x1.x * w.y + x1.y * w.x;
-      a2[j].x += x2.x * w.x - x2.y * w.y; a2[j].y += x2.x * w.y + x2.y * w.x;
+      const float m1 = hypotf(a1[j].x, a1[j].y), m2 = hypotf(a2[j].x, a2[j].y);
+      s1 += m1; s2 += m2;
+      const float d = m1 + m2;
+      if (d > best) { best = d; bestf = fg * 10 + j; }
     }
-  }
-  float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = 0;
+    sm.part[0][fg][tl] = s1; sm.part[1][fg][tl] = s2;
+    // arg-max with "first (t, f) wins": larger key = larger value, then smaller flat index
+    unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (0xFFFFFFFFu - (unsigned)((t0 + tl) * RADE_NFCOARSE + bestf));
 #pragma unroll
-  for (int j = 0; j < 10; j++) {
-    const float m1 = hypotf(a1[j].x, a1[j].y), m2 = hypotf(a2[j].x, a2[j].y);
-    s1 += m1; s2 += m2;
-    const float d = m1 + m2;
-    if (d > best) { best = d; bestf = fg * 10 + j; }
-  }
-  sm.part[0][fg][tl] = s1; sm.part[1][fg][tl] = s2;
-  // arg-max with "first (t, f) wins": larger key = larger value, then smaller flat index
-  unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (0xFFFFFFFFu - (unsigned)((t0 + tl) * RADE_NFCOARSE + bestf));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
-  if ((tid & 31) == 0) sm.best[tid >> 5] = key;
-  __syncthreads();
-  if (tid < 2 * DET_TB) {
-    const int half = tid >> 6, t = tid & (DET_TB - 1);
-    rowsum[((size_t)s * 2 + half) * RADE_NMF + t0 + t] = ((sm.part[half][0][t] + sm.part[half][1][t]) + sm.part[half][2][t]) + sm.part[half][3][t];
-  }
-  if (tid == 0) {
-    unsigned long long k = sm.best[0];
-    for (int i = 1; i < 8; i++) k = sm.best[i] > k ? sm.best[i] : k;
-    atomicMax(&c.detect_key, k);
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
+    if ((tid & 31) == 0) sm.best[tid >> 5] = key;
+    __syncthreads();
+    if (tid < 2 * DET_TB) {
+      const int half = tid >> 6, t = tid & (DET_TB - 1);
+      rowsum[((size_t)s * 2 + half) * RADE_NMF + t0 + t] = ((sm.part[half][0][t] + sm.part[half][1][t]) + sm.part[half][2][t]) + sm.part[half][3][t];
+    }
+    if (tid == 0) {
+      unsigned long long k = sm.best[0];
+      for (int i = 1; i < 8; i++) k = sm.best[i] > k ? sm.best[i] : k;
+      atomicMax(&c.detect_key, k);
+    }
   }
 }
 
@@ -185,13 +200,19 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
   for (int c0 = 0; c0 < nf; c0 += REF_CH) {
     const int nfc = min(REF_CH, nf - c0);
     __syncthreads();
-    for (int idx = tid; idx < nfc * RADE_M; idx += nthr) {
-      const int fi = idx / RADE_M, n = idx % RADE_M;
+    for (int idx = tid; idx < nfc * (RADE_M / 8); idx += nthr) {
+      // 8 consecutive taps of one frequency: exp(-j w n0) by sincos, then 7 rotations by exp(-j w) (|error| ~ 1e-15)
+      const int fi = idx / (RADE_M / 8), n0 = (idx % (RADE_M / 8)) * 8;
       const double f = f_start + (double)(c0 + fi) * delta;
       const double w = 2.0 * M_PI * f / RADE_FS;
-      double sn, cs; sincos(w * (double)n, &sn, &cs);
-      const float2 pn = T.p[n];
-      sm.vtab[fi][n] = dcmul(make_double2(cs, -sn), make_double2((double)pn.x, -(double)pn.y));
+      double sn, cs, s1, c1; sincos(w * (double)n0, &sn, &cs); sincos(w, &s1, &c1);
+      double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float2 pn = T.p[n0 + k];
+        sm.vtab[fi][n0 + k] = dcmul(e, make_double2((double)pn.x, -(double)pn.y));
+        e = dcmul(e, step);
+      }
     }
     __syncthreads();
     for (int item = tid; item < nfc * nt * 2; item += nthr) {
@@ -252,12 +273,12 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 // ================================================================= sync-state tracking: refine + check_pilots + slips
 constexpr int CHK_SPAN = 20 * (RADE_NUPDATE - 1) + RADE_M + 20;     // samples covered by the 48 refreshed rows of one half (1120)
 struct CheckSmem {                 // aliases RefineSmem once the refine is done
-  float2 pw[RADE_M][RADE_NFCOARSE];
+  alignas(16) float2 pw[RADE_M][RADE_NFCOARSE];
   float2 rx[2][CHK_SPAN];
 };
 struct TrackSmem {
   union { RefineSmem ref; CheckSmem chk; };
-  float part[2][RADE_NUPDATE * 2];
+  float part[4][RADE_NUPDATE * 2];
   float scratch[32];
   double spot[4];
 };
@@ -295,30 +316,35 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     sm.chk.rx[half][k] = (li < RADE_RXBUF) ? cconj(rg[ring_idx(head, li)]) : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  if (tid < RADE_NUPDATE * 2 * 2) {
-    const int rh = tid % (RADE_NUPDATE * 2), fg = tid / (RADE_NUPDATE * 2);
-    const int i = rh >> 1, half = rh & 1;
-    const float2 *x = &sm.chk.rx[half][20 * i];
-    float2 a[20];
+  if (tid < RADE_NUPDATE * 4) {
+    // thread = (row i, frequency group fg of 10): both pilot positions of row i x 10 frequencies, 40 accumulators;
+    // per tap: 2 LDS.64 (samples) + 5 LDS.128 (two frequencies each, broadcast within the warp) feed 80 FMAs
+    const int i = tid >> 2, fg = tid & 3;
+    const float2 *x0 = &sm.chk.rx[0][20 * i], *x1 = &sm.chk.rx[1][20 * i];
+    float2 a0[10], a1[10];
 #pragma unroll
-    for (int j = 0; j < 20; j++) a[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < 10; j++) { a0[j] = make_float2(0.f, 0.f); a1[j] = make_float2(0.f, 0.f); }
     for (int n = 0; n < RADE_M; n++) {
-      const float2 xv = x[n];
+      const float2 u = x0[n], v = x1[n];
+      const float4 *wp = reinterpret_cast<const float4 *>(&sm.chk.pw[n][fg * 10]);
 #pragma unroll
-      for (int j = 0; j < 20; j++) {
-        const float2 w = sm.chk.pw[n][fg * 20 + j];
-        a[j].x += xv.x * w.x - xv.y * w.y; a[j].y += xv.x * w.y + xv.y * w.x;
+      for (int j = 0; j < 5; j++) {
+        const float4 w = wp[j];
+        a0[2 * j].x += u.x * w.x - u.y * w.y;     a0[2 * j].y += u.x * w.y + u.y * w.x;
+        a0[2 * j + 1].x += u.x * w.z - u.y * w.w; a0[2 * j + 1].y += u.x * w.w + u.y * w.z;
+        a1[2 * j].x += v.x * w.x - v.y * w.y;     a1[2 * j].y += v.x * w.y + v.y * w.x;
+        a1[2 * j + 1].x += v.x * w.z - v.y * w.w; a1[2 * j + 1].y += v.x * w.w + v.y * w.z;
       }
     }
-    float sum = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 20; j++) sum += hypotf(a[j].x, a[j].y);
-    sm.part[fg][rh] = sum;
+    for (int j = 0; j < 10; j++) { s0 += hypotf(a0[j].x, a0[j].y); s1 += hypotf(a1[j].x, a1[j].y); }
+    sm.part[fg][2 * i] = s0; sm.part[fg][2 * i + 1] = s1;
   }
   __syncthreads();
   if (tid < RADE_NUPDATE * 2) {
     const int i = tid >> 1, half = tid & 1;
-    rs[half * RADE_NMF + 20 * i + rot] = sm.part[0][tid] + sm.part[1][tid];
+    rs[half * RADE_NMF + 20 * i + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
   }
   __syncthreads();
   const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);
@@ -492,10 +518,11 @@ __global__ void __launch_bounds__(256)
 rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, const float *__restrict__ rowsum,
                  int *__restrict__ uw_errors, DecStreamState *__restrict__ dec_state, int reset_dec_on_sync,
                  int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out,
-                 const unsigned char *__restrict__ active) {
+                 const unsigned char *__restrict__ active, int *__restrict__ search_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FinishSmem &sm = *reinterpret_cast<FinishSmem *>(smem_raw);
   const int s = blockIdx.x, tid = threadIdx.x;
+  if (s == 0 && tid == 0) { search_count[0] = 0; search_count[1] = 0; }      // the coarse search of this call is over
   if (active && !active[s]) { if (tid == 0) { ret_out[s] = 0; dec_active[s] = 0; nin_out[s] = ctl[s].nin; } return; }
   RxCtl &c = ctl[s];
   const int state = c.state;
@@ -587,16 +614,17 @@ int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, c
     attr_set = true;
   }
   prof->begin(K_RX_BPF);
-  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en);
+  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.search_count);
   prof->end(K_RX_BPF); prof->begin(K_RX_DETECT);
-  rx_detect_kernel<<<dim3(RADE_NMF / DET_TB, S), 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, active);
+  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > 148 * 3) det_grid = 148 * 3;
+  rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, B.search_count);
   prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
   rx_track_kernel<<<S, 256, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
   prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
   rx_finish_kernel<<<S, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
-                                                           reset_dec_on_sync, ret_out, B.dec_active, B.nin, active);
+                                                           reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_count);
   prof->end(K_RX_FINISH);
   CUDA_CHECK(cudaGetLastError());
   return 5;

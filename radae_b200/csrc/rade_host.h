@@ -45,6 +45,8 @@ struct RxBuffers {
   DecStreamState *dec_state;
   unsigned char *dec_active;  // [S] valid_output of the last call
   int *nin;                // [S]
+  int *search_list;        // [S] streams that need the coarse search this call (built by rx_bpf)
+  int *search_count;       // [2]: number of entries, work-item counter
 };
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
