@@ -172,15 +172,11 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from radae_b200 import RadeBatch, _capi, rdw
+    from radae_b200 import RadeBatch, _capi, rdw, multigpu
 
     # one NCCL broadcast of the weight blob at start-up (the only collective on this path)
     blob = open(rdw.default_weights_path(), "rb").read() if rank == 0 else None
-    if world > 1:
-        n = torch.tensor([len(blob) if rank == 0 else 0], device="cuda"); dist.broadcast(n, 0)
-        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda() if rank == 0 else torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        blob = bytes(t.cpu().numpy())
+    blob = multigpu.broadcast_weights(dist if world > 1 else None, rank, blob, device="cuda")
 
     codec_only = args.workload == "codec"
     S = args.streams or (8192 if codec_only else 1024)

@@ -27,9 +27,9 @@
 
 namespace {
 
-constexpr int SEG_LD = 97;
-constexpr int FIN_LD = 85;
-constexpr int ZIN_LD = 81;
+constexpr int SEG_LD = 100;                // float rows are 16-byte aligned (float4 reads) with strides that spread banks
+constexpr int FIN_LD = 92;
+constexpr int ZIN_LD = 84;
 constexpr int HQ_LD = 496;                 // row stride of the decoder's quantised hidden states (conflict-free A fragments)
 
 // ---------------------------------------------------------------- scalar math, bit-exact w.r.t. oracle/nnet_shim.c
@@ -119,12 +119,18 @@ __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, ui
 
 // Walk the KB k-blocks of one A operand; the weights arrive as chunks of core_kbc(NTL) k-blocks laid out [kb][nt][lane].
 // Every consumer warp calls this (acquire/release are collective); only warps with `work` issue MMAs, for their NT n-tiles.
+// A fragment of m16n8k32 (16 rows x 32 bytes) in one instruction: four 8x8 b16 matrices = rows 0-7 / 8-15 x bytes 0-15 / 16-31
+__device__ __forceinline__ void ldsm_a(uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3, const int8_t *lane_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(smem_u32(lane_ptr)));
+}
+
 template <int NT>
 __device__ __forceinline__ void gemm_stream(Cursor &cx, int (&acc)[NT][4], const int (&nt)[NT], const bool (&use)[NT], bool work,
                                             const int8_t *A, int lda, int KB, int NTL) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
-  const uint32_t *r0 = reinterpret_cast<const uint32_t *>(A + g * lda) + tig;
-  const uint32_t *r1 = reinterpret_cast<const uint32_t *>(A + (g + 8) * lda) + tig;
+  const int lane = threadIdx.x & 31;
+  // ldmatrix row address of this lane: matrix (lane>>3): rows +8 for odd matrices, bytes +16 for matrices 2,3
+  const int8_t *arow = A + ((lane & 7) + ((lane >> 3) & 1) * 8) * lda + ((lane >> 4) & 1) * 16;
   const int kbc = core_kbc(NTL);
   for (int kb0 = 0; kb0 < KB; kb0 += kbc) {
     const int nk = min(kbc, KB - kb0);
@@ -132,8 +138,8 @@ __device__ __forceinline__ void gemm_stream(Cursor &cx, int (&acc)[NT][4], const
     if (work) {
 #pragma unroll 2
       for (int kb = 0; kb < nk; kb++) {
-        const int k = (kb0 + kb) * 8;
-        const uint32_t a0 = r0[k], a1 = r1[k], a2 = r0[k + 4], a3 = r1[k + 4];
+        uint32_t a0, a1, a2, a3;
+        ldsm_a(a0, a1, a2, a3, arow + (kb0 + kb) * 32);
 #pragma unroll
         for (int i = 0; i < NT; i++)
           if (use[i]) {                        // warp-uniform
@@ -147,17 +153,28 @@ __device__ __forceinline__ void gemm_stream(Cursor &cx, int (&acc)[NT][4], const
 }
 
 // ---------------------------------------------------------------- float layers: sequential-in-j accumulation
-// thread (s = tid&15, grp = tid>>4 of NGRP) owns outputs o = grp + NGRP*i of stream s; W rows come from one staged chunk
-template <int NOUT, int NACC, int NGRP>
-__device__ __forceinline__ void dense_chunk(Cursor &cx, float (&acc)[NACC], const float *xrow, int K, int grp) {
-  const float *W = reinterpret_cast<const float *>(cx.acquire());
-#pragma unroll 4
-  for (int j = 0; j < K; j++) {
-    const float x = xrow[j];
-    const float *wj = W + j * NOUT + grp;
-#pragma unroll
-    for (int i = 0; i < NACC; i++)
-      if (grp + NGRP * i < NOUT) acc[i] = __fadd_rn(acc[i], __fmul_rn(wj[NGRP * i], x));
+// thread (s = tid&15, grp = tid>>4) owns the four outputs o = 4*grp .. 4*grp+3 of stream s; the W rows of the concat segment
+// come from one staged chunk and are read as one broadcast LDS.128 per input, the inputs as one LDS.128 per four.
+// acc[i] = ((acc[i] + W[j0][o] x[j0]) + W[j0+1][o] x[j0+1]) + ...  — separately rounded, in input order
+template <int NOUT>
+__device__ __forceinline__ void dense_chunk(Cursor &cx, float (&acc)[4], const float *xrow, int K, int grp) {
+  const float4 *W4 = reinterpret_cast<const float4 *>(cx.acquire());
+  if (grp < NOUT / 4) {
+    const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+#pragma unroll 2
+    for (int j = 0; j < K; j += 4) {
+      const float4 x = x4[j >> 2];
+      const float4 w0 = W4[(j + 0) * (NOUT / 4) + grp], w1 = W4[(j + 1) * (NOUT / 4) + grp];
+      const float4 w2 = W4[(j + 2) * (NOUT / 4) + grp], w3 = W4[(j + 3) * (NOUT / 4) + grp];
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(w0.x, x.x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w0.y, x.x));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(w0.z, x.x)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w0.w, x.x));
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(w1.x, x.y)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w1.y, x.y));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(w1.z, x.y)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w1.w, x.y));
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(w2.x, x.z)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w2.y, x.z));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(w2.z, x.z)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w2.w, x.z));
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(w3.x, x.w)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w3.y, x.w));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(w3.z, x.w)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w3.w, x.w));
+    }
   }
   cx.release();
 }
@@ -168,12 +185,14 @@ __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, cons
                                           const int8_t *Hq, int ldh, float *hs, int ldhs, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int U = UNITS / 8;
-  const int u = warp;                        // NCW == U for both codecs
+  const bool work = warp < U;                // NCW >= U; surplus warps only keep the chunk pipeline moving
+  const int u = work ? warp : 0;
   int ai[3][4] = {}, ar[3][4] = {};
   const int nt[3] = {u, U + u, 2 * U + u};
   const bool use[3] = {true, true, true};
-  gemm_stream<3>(cx, ai, nt, use, true, Xin, ldx, Li.K / 32, 3 * U);
-  gemm_stream<3>(cx, ar, nt, use, true, Hq, ldh, Lr.K / 32, 3 * U);
+  gemm_stream<3>(cx, ai, nt, use, work, Xin, ldx, Li.K / 32, 3 * U);
+  gemm_stream<3>(cx, ar, nt, use, work, Hq, ldh, Lr.K / 32, 3 * U);
+  if (!work) return;
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const int row = g + ((e & 2) ? 8 : 0);
@@ -245,7 +264,7 @@ struct EncSmem {
 __global__ void __launch_bounds__((ENC_NCW + 1) * 32, 1)
 core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
                     float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NCW = ENC_NCW, NCT = NCW * 32, NGRP = NCT / 16;
+  constexpr int NCW = ENC_NCW, NCT = NCW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -304,18 +323,20 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     // ---- dense1: tanh(W f + b), 84 -> 64
     {
       float a[4] = {0.f, 0.f, 0.f, 0.f};
-      dense_chunk<64, 4, NGRP>(cx, a, sm.fin[sl], ENC_IN, grp);
+      dense_chunk<64>(cx, a, sm.fin[sl], ENC_IN, grp);
+      if (grp < 64 / 4) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int o = grp + NGRP * i;
-        float y = tanh_r(__fadd_rn(a[i], W.enc_dense1.bias[o]));
-        sm.seg[sl][o] = y;
-        cur[sl][o] = quant8(y);
+        for (int i = 0; i < 4; i++) {
+          const int o = 4 * grp + i;
+          float y = tanh_r(__fadd_rn(a[i], W.enc_dense1.bias[o]));
+          sm.seg[sl][o] = y;
+          cur[sl][o] = quant8(y);
+        }
       }
     }
     consumer_sync<NCW>();
-    float zacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    dense_chunk<80, 5, NGRP>(cx, zacc, sm.seg[sl], 64, grp);
+    float zacc[4] = {0.f, 0.f, 0.f, 0.f};
+    dense_chunk<80>(cx, zacc, sm.seg[sl], 64, grp);
     consumer_sync<NCW>();
 
     int off = 64;
@@ -326,7 +347,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
                          &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU,
                          [&](int row, int j, float h) { sm.seg[row][j] = h; cur[row][off + j] = quant8(h); });
       consumer_sync<NCW>();
-      dense_chunk<80, 5, NGRP>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
+      dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
       consumer_sync<NCW>();
       off += ENC_GRU;
       // conv l (k = 2): tap 0 = concat prefix of step t-dilation, tap 1 = current prefix
@@ -334,17 +355,15 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
       conv_layer<ENC_CONV, NCW>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red,
                                 [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
-      dense_chunk<80, 5, NGRP>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
+      dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
       consumer_sync<NCW>();
       off += ENC_CONV;
     }
     // ---- z = zdense(cat) + b   (bottleneck 3: linear, src/rade_enc.c:107-113)
-    if (sg < S && (!active || active[sg])) {
-#pragma unroll
-      for (int i = 0; i < 5; i++) {
-        const int o = grp + NGRP * i;
-        z_out[((size_t)sg * T + t) * RADE_LATENT + o] = __fadd_rn(zacc[i], W.enc_zdense.bias[o]);
-      }
+    if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / 4) {
+      const float4 bz = reinterpret_cast<const float4 *>(W.enc_zdense.bias)[grp];
+      reinterpret_cast<float4 *>(z_out + ((size_t)sg * T + t) * RADE_LATENT)[grp] =
+          make_float4(__fadd_rn(zacc[0], bz.x), __fadd_rn(zacc[1], bz.y), __fadd_rn(zacc[2], bz.z), __fadd_rn(zacc[3], bz.w));
     }
   }
 
@@ -431,10 +450,10 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     // ---- dense1: tanh(W z + b), 80 -> 96
     {
       float a[4] = {0.f, 0.f, 0.f, 0.f};
-      dense_chunk<96, 4, NGRP>(cx, a, sm.zin[sl], DEC_IN, grp);
+      dense_chunk<96>(cx, a, sm.zin[sl], DEC_IN, grp);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int o = grp + NGRP * i;
+        const int o = 4 * grp + i;               // 24 groups x 4 = 96 outputs
         float y = tanh_r(__fadd_rn(a[i], W.dec_dense1.bias[o]));
         sm.seg[sl][o] = y;
         cur[sl][o] = quant8(y);
@@ -442,7 +461,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     }
     consumer_sync<NCW>();
     float oacc[4] = {0.f, 0.f, 0.f, 0.f};
-    dense_chunk<DEC_OUT, 4, NGRP>(cx, oacc, sm.seg[sl], 96, grp);
+    dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], 96, grp);
     consumer_sync<NCW>();
 
     int off = 96;
@@ -470,13 +489,13 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
         }
       }
       consumer_sync<NCW>();
-      dense_chunk<DEC_OUT, 4, NGRP>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
+      dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
       consumer_sync<NCW>();
       off += DEC_GRU;
       conv_layer<DEC_CONV, NCW>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,
                                 [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
-      dense_chunk<DEC_OUT, 4, NGRP>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
+      dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
       consumer_sync<NCW>();
       off += DEC_CONV;
     }
@@ -484,7 +503,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     if (sg < S && (!active || active[sg])) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int o = grp + NGRP * i;
+        const int o = 4 * grp + i;
         if (o >= DEC_OUT) continue;
         const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
         if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;

@@ -25,6 +25,11 @@ enum { ST_SEARCH = 0, ST_CANDIDATE = 1, ST_SYNC = 2 };
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ double2 dcmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// acc += a*b with four FMAs (the compiler otherwise emits FMUL+FFMA+FADD per component pair)
+__device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
 __device__ __forceinline__ int ring_idx(int head, int i) { int k = head + i; return k >= RADE_RXBUF ? k - RADE_RXBUF : k; }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -71,7 +76,7 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
 #pragma unroll 4
       for (int k = 0; k < RADE_BPF_NTAP; k++) {
         const float2 v = X[i + k + off];
-        acc.x += h[k] * v.x; acc.y += h[k] * v.y;
+        acc.x = fmaf(h[k], v.x, acc.x); acc.y = fmaf(h[k], v.y, acc.y);
       }
       rg[ring_idx(head, i)] = cmul(acc, cconj(cmul(ph, T.bpf_exp[i])));                                         // mix up
     }
@@ -137,10 +142,8 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         const float4 wv = wp[j];
-        a1[2 * j].x += x1.x * wv.x - x1.y * wv.y;     a1[2 * j].y += x1.x * wv.y + x1.y * wv.x;
-        a1[2 * j + 1].x += x1.x * wv.z - x1.y * wv.w; a1[2 * j + 1].y += x1.x * wv.w + x1.y * wv.z;
-        a2[2 * j].x += x2.x * wv.x - x2.y * wv.y;     a2[2 * j].y += x2.x * wv.y + x2.y * wv.x;
-        a2[2 * j + 1].x += x2.x * wv.z - x2.y * wv.w; a2[2 * j + 1].y += x2.x * wv.w + x2.y * wv.z;
+        cmac(a1[2 * j], x1, make_float2(wv.x, wv.y)); cmac(a1[2 * j + 1], x1, make_float2(wv.z, wv.w));
+        cmac(a2[2 * j], x2, make_float2(wv.x, wv.y)); cmac(a2[2 * j + 1], x2, make_float2(wv.z, wv.w));
       }
     }
     float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = 0;
@@ -175,8 +178,8 @@ constexpr int REF_CH = 21;        // frequencies per chunk
 constexpr int REF_NT = 16;        // max timing offsets
 struct RefineSmem {
   double2 vtab[REF_CH][RADE_M];   // conj(p[n]) * exp(-j w n)
-  float2 ra[REF_NT + RADE_M];     // rx[t_lo ...]
-  float2 rb[REF_NT + RADE_M];     // rx[t_lo + Nmf ...]
+  double2 ra[REF_NT + RADE_M];    // rx[t_lo ...] widened once (the reference up-casts csingle to complex128 in np.dot)
+  double2 rb[REF_NT + RADE_M];    // rx[t_lo + Nmf ...]
   float2 d1[REF_CH][REF_NT];
   float2 d2[REF_CH][REF_NT];
   float red_mag[8]; int red_ord[8];
@@ -194,8 +197,9 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
   const double delta = (f_start + f_step) - f_start;
   if (tid == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
   for (int i = tid; i < nt + RADE_M; i += nthr) {
-    sm.ra[i] = rg[ring_idx(head, t_lo + i)];
-    sm.rb[i] = rg[ring_idx(head, t_lo + RADE_NMF + i)];
+    const float2 a = rg[ring_idx(head, t_lo + i)], b = rg[ring_idx(head, t_lo + RADE_NMF + i)];
+    sm.ra[i] = make_double2((double)a.x, (double)a.y);
+    sm.rb[i] = make_double2((double)b.x, (double)b.y);
   }
   for (int c0 = 0; c0 < nf; c0 += REF_CH) {
     const int nfc = min(REF_CH, nf - c0);
@@ -217,12 +221,13 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
     __syncthreads();
     for (int item = tid; item < nfc * nt * 2; item += nthr) {
       const int half = item & 1, ti = (item >> 1) % nt, fi = (item >> 1) / nt;
-      const float2 *r = half ? sm.rb : sm.ra;
+      const double2 *r = half ? sm.rb : sm.ra;
       double ax = 0.0, ay = 0.0;
+#pragma unroll 4
       for (int n = 0; n < RADE_M; n++) {
-        const double2 v = sm.vtab[fi][n];
-        const double rx = (double)r[ti + n].x, ry = (double)r[ti + n].y;
-        ax += rx * v.x - ry * v.y; ay += rx * v.y + ry * v.x;
+        const double2 v = sm.vtab[fi][n], x = r[ti + n];
+        ax = fma(x.x, v.x, ax); ax = fma(-x.y, v.y, ax);
+        ay = fma(x.x, v.y, ay); ay = fma(x.y, v.x, ay);
       }
       if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
         const double f = f_start + (double)(c0 + fi) * delta;
@@ -278,7 +283,7 @@ struct CheckSmem {                 // aliases RefineSmem once the refine is done
 };
 struct TrackSmem {
   union { RefineSmem ref; CheckSmem chk; };
-  float part[4][RADE_NUPDATE * 2];
+  float part[5][RADE_NUPDATE * 2];
   float scratch[32];
   double spot[4];
 };
@@ -318,7 +323,8 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   __syncthreads();
   if (tid < RADE_NUPDATE * 4) {
     // thread = (row i, frequency group fg of 10): both pilot positions of row i x 10 frequencies, 40 accumulators;
-    // per tap: 2 LDS.64 (samples) + 5 LDS.128 (two frequencies each, broadcast within the warp) feed 80 FMAs
+    // per tap: 2 LDS.64 (samples) + 5 LDS.128 (two frequencies each; the four groups of a warp hit disjoint banks)
+    // feed 80 FMAs
     const int i = tid >> 2, fg = tid & 3;
     const float2 *x0 = &sm.chk.rx[0][20 * i], *x1 = &sm.chk.rx[1][20 * i];
     float2 a0[10], a1[10];
@@ -330,10 +336,8 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         const float4 w = wp[j];
-        a0[2 * j].x += u.x * w.x - u.y * w.y;     a0[2 * j].y += u.x * w.y + u.y * w.x;
-        a0[2 * j + 1].x += u.x * w.z - u.y * w.w; a0[2 * j + 1].y += u.x * w.w + u.y * w.z;
-        a1[2 * j].x += v.x * w.x - v.y * w.y;     a1[2 * j].y += v.x * w.y + v.y * w.x;
-        a1[2 * j + 1].x += v.x * w.z - v.y * w.w; a1[2 * j + 1].y += v.x * w.w + v.y * w.z;
+        cmac(a0[2 * j], u, make_float2(w.x, w.y)); cmac(a0[2 * j + 1], u, make_float2(w.z, w.w));
+        cmac(a1[2 * j], v, make_float2(w.x, w.y)); cmac(a1[2 * j + 1], v, make_float2(w.z, w.w));
       }
     }
     float s0 = 0.f, s1 = 0.f;
@@ -342,10 +346,8 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     sm.part[fg][2 * i] = s0; sm.part[fg][2 * i + 1] = s1;
   }
   __syncthreads();
-  if (tid < RADE_NUPDATE * 2) {
-    const int i = tid >> 1, half = tid & 1;
-    rs[half * RADE_NMF + 20 * i + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
-  }
+  if (tid < RADE_NUPDATE * 2)
+    rs[(tid & 1) * RADE_NMF + 20 * (tid >> 1) + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
   __syncthreads();
   const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);
   // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
@@ -429,12 +431,10 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   }
   if (tid < (RADE_NS + 2) * RADE_NC) {              // 180 DFT outputs, 160-point each
     const int r = tid / RADE_NC, cc = tid % RADE_NC;
-    float ax = 0.f, ay = 0.f;
-    for (int k = 0; k < RADE_M; k++) {
-      const float2 x = sm.xs[r][k], wv = T.Wfwd[k * RADE_NC + cc];
-      ax += x.x * wv.x - x.y * wv.y; ay += x.x * wv.y + x.y * wv.x;
-    }
-    sm.sym[r][cc] = make_float2(ax, ay);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < RADE_M; k++) cmac(acc, sm.xs[r][k], T.Wfwd[k * RADE_NC + cc]);
+    sm.sym[r][cc] = acc;
   }
   __syncthreads();
   if (!endofover) {

@@ -61,7 +61,7 @@ struct __align__(16) DecStreamState {
 // order the layer walk consumes them; a producer warp TMA-bulk-copies chunk after chunk into a shared-memory ring.
 #define CORE_STAGE_BYTES 32768
 #define CORE_NSTAGES 4
-#define ENC_NCW 8                             // consumer warps (encoder): 8 GRU unit tiles -> one per warp
+#define ENC_NCW 10                            // consumer warps (encoder): 20 groups of 4 zdense outputs; 8 of them own a GRU unit tile
 #define DEC_NCW 12                            // consumer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
 
 struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
