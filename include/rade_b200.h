@@ -99,6 +99,16 @@ RADE_EXPORT int rade_b200_profile_n_kernels(void);
 RADE_EXPORT const char *rade_b200_profile_kernel_name(int k);
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts);
 
+/* --- host-side sample link: per-stream FIFOs in pinned host memory in front of rade_b200_rx.
+ * push: samples [S][960] appended per stream.  rx: every stream with >= nin[s] samples queued is advanced by exactly
+ * one rade_rx call (the others are left untouched, `active` = 0); outputs as rade_b200_rx. --- */
+typedef struct rade_b200_hostlink rade_b200_hostlink;
+RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples);
+RADE_EXPORT void rade_b200_hostlink_close(rade_b200_hostlink *h);
+RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples);
+RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out, int *ret, float *eoo_out);
+RADE_EXPORT const unsigned char *rade_b200_hostlink_active(rade_b200_hostlink *h);
+
 /* --- host-buffer channel call (for end-to-end measurements through host memory): tx, rx [S][960] --- */
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx);
 

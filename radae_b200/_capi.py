@@ -56,6 +56,9 @@ SIGNATURES = {
     "rade_b200_profile_enable": (_I, [_P, _I]), "rade_b200_profile_n_kernels": (_I, []),
     "rade_b200_profile_kernel_name": (C.c_char_p, [_I]), "rade_b200_profile_read": (_I, [_P, _P, _P]),
     "rade_b200_channel": (_I, [_P, _P, _P]),
+    "rade_b200_hostlink_open": (_P, [_P, _I]), "rade_b200_hostlink_close": (None, [_P]),
+    "rade_b200_hostlink_push": (_I, [_P, _P]), "rade_b200_hostlink_rx": (_I, [_P, _P, _P, _P]),
+    "rade_b200_hostlink_active": (_P, [_P]),
     # test hook
     "rade_b200_debug_tables": (_I, [_I, _P, _I]),
 }

@@ -75,10 +75,11 @@ class RadeBatch:
         return f
 
     # ---- transmitter
-    def tx(self, features_in):
+    def tx(self, features_in, out=None):
         f, pf = _np(features_in, np.float32)
         assert f.size == self.S * NFEAT
-        out = np.empty((self.S, NMF), np.complex64)
+        if out is None:
+            out = np.empty((self.S, NMF), np.complex64)
         _check(self.lib.rade_b200_tx(self.h, out.ctypes.data, pf), "tx")
         return out
 
@@ -155,11 +156,12 @@ class RadeBatch:
     def link_pop_dev(self, d_rx_in, d_active):
         _check(self.lib.rade_b200_link_pop_dev(self.h, d_rx_in, d_active), "link_pop_dev")
 
-    def channel(self, tx):
+    def channel(self, tx, out=None):
         """host-buffer channel call: tx [S][960] complex64 -> rx [S][960]"""
         t, pt = _np(tx, np.complex64)
         assert t.shape == (self.S, NMF)
-        out = np.empty((self.S, NMF), np.complex64)
+        if out is None:
+            out = np.empty((self.S, NMF), np.complex64)
         _check(self.lib.rade_b200_channel(self.h, out.ctypes.data, pt), "channel")
         return out
 
@@ -172,3 +174,31 @@ class RadeBatch:
         ms = np.zeros(n, np.float32); cnt = np.zeros(n, np.int32)
         _check(self.lib.rade_b200_profile_read(self.h, ms.ctypes.data, cnt.ctypes.data), "profile_read")
         return {self.lib.rade_b200_profile_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n) if cnt[k]}
+
+
+class HostLink:
+    """Pinned per-stream sample FIFOs in front of the receiver (rade_b200_hostlink_*): push 960 samples per stream,
+    rx() advances every stream that has nin[s] samples queued.  Output arrays are allocated once and reused."""
+
+    def __init__(self, batch, capacity=4096):
+        self.b, self.lib = batch, batch.lib
+        self.h = self.lib.rade_b200_hostlink_open(batch.h, capacity)
+        if not self.h:
+            raise RuntimeError("rade_b200_hostlink_open failed")
+        S = batch.S
+        self.features = np.zeros((S, NFEAT), np.float32)
+        self.ret = np.zeros(S, np.int32)
+        self.eoo = np.zeros((S, NEOO_BITS), np.float32)
+
+    def push(self, samples):
+        x, px = _np(samples, np.complex64)
+        assert x.shape == (self.b.S, NMF)
+        _check(self.lib.rade_b200_hostlink_push(self.h, px), "hostlink_push")
+
+    def rx(self):
+        _check(self.lib.rade_b200_hostlink_rx(self.h, self.features.ctypes.data, self.ret.ctypes.data, self.eoo.ctypes.data), "hostlink_rx")
+        return self.features, self.ret, self.eoo
+
+    def close(self):
+        if self.h:
+            self.lib.rade_b200_hostlink_close(self.h); self.h = None

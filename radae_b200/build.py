@@ -14,7 +14,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 WEIGHTS = os.path.join(HERE, "weights", "model19_check3.rdw")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function", "-DIS_BUILDING_RADE_API=1",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function,-fopenmp", "-DIS_BUILDING_RADE_API=1",
               "-I", INCLUDE, "-I", CSRC]
 
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs +
-                   ["-Xlinker", "--no-undefined", "-lcudart"], check=True)
+                   ["-Xlinker", "--no-undefined", "-lcudart", "-lgomp"], check=True)
     return LIB
 
 

@@ -224,13 +224,13 @@ RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float
   return RADE_NMF;
 }
 RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *features_in) {
+  // copies go straight from / to the caller's buffers: truly asynchronous when they are pinned (cudaHostAlloc /
+  // cudaHostRegister), staged by the driver when they are pageable
   const size_t S = b->S;
-  memcpy(b->h_feat, features_in, S * RADE_NFEAT * sizeof(float));
-  CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, b->h_feat, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, features_in, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
   if (rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0) return -1;
-  CUDA_CHECK(cudaMemcpyAsync(b->h_cplx, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(tx_out, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
-  memcpy(tx_out, b->h_cplx, S * RADE_NMF * sizeof(float2));
   return RADE_NMF;
 }
 RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits) {
@@ -247,9 +247,8 @@ RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
   if (eoo_launch(b->tables, b->eoo_bits, b->has_eoo_bits, b->d_tx_eoo, b->S, b->stream) < 0) return -1;
   b->prof.end(K_EOO);
   b->launches += 1;
-  CUDA_CHECK(cudaMemcpyAsync(b->h_cplx, b->d_tx_eoo, S * RADE_NEOO * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(tx_eoo_out, b->d_tx_eoo, S * RADE_NEOO * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
-  memcpy(tx_eoo_out, b->h_cplx, S * RADE_NEOO * sizeof(float2));
   return RADE_NEOO;
 }
 
@@ -354,6 +353,77 @@ RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsign
   b->launches += 1;
   return 0;
 }
+
+// ---- host-side sample link (batched host I/O around the C ABI): per-stream FIFOs in pinned host memory
+// between whatever produces receive samples and rade_b200_rx, which wants nin[s] in {800, 960, 1120} fresh samples per
+// stream per call.  push appends 960 samples per stream; rx gathers nin[s] samples for every stream that has them
+// (OpenMP over streams), marks the others inactive, runs rade_b200_rx and refreshes nin[] in the same round trip.
+struct rade_b200_hostlink {
+  rade_batch *b; int cap;
+  float2 *fifo; long long *wr, *rd; int *nin;
+  float2 *rx_in; unsigned char *active;
+};
+RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples) {
+  if (capacity_samples < 2 * RADE_NIN_MAX) capacity_samples = 4096;
+  rade_b200_hostlink *h = new rade_b200_hostlink();
+  h->b = b; h->cap = capacity_samples;
+  const size_t S = b->S;
+  bool ok = cudaMallocHost((void **)&h->fifo, S * h->cap * sizeof(float2)) == cudaSuccess &&
+            cudaMallocHost((void **)&h->rx_in, S * RADE_NIN_MAX * sizeof(float2)) == cudaSuccess &&
+            cudaMallocHost((void **)&h->active, S) == cudaSuccess && cudaMallocHost((void **)&h->nin, S * sizeof(int)) == cudaSuccess;
+  if (!ok) { fprintf(stderr, "libradae_b200: cannot allocate pinned host FIFOs\n"); delete h; return nullptr; }
+  h->wr = new long long[S](); h->rd = new long long[S]();
+  memset(h->rx_in, 0, S * RADE_NIN_MAX * sizeof(float2));
+  for (size_t s = 0; s < S; s++) h->nin[s] = RADE_NMF;
+  return h;
+}
+RADE_EXPORT void rade_b200_hostlink_close(rade_b200_hostlink *h) {
+  if (!h) return;
+  cudaFreeHost(h->fifo); cudaFreeHost(h->rx_in); cudaFreeHost(h->active); cudaFreeHost(h->nin);
+  delete[] h->wr; delete[] h->rd; delete h;
+}
+RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples) {
+  const int S = h->b->S, cap = h->cap;
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < S; s++) {
+    if (h->wr[s] - h->rd[s] + RADE_NMF > cap) continue;            // full: drop (the consumer is not keeping up)
+    const float2 *src = (const float2 *)samples + (size_t)s * RADE_NMF;
+    float2 *dst = h->fifo + (size_t)s * cap;
+    const int w = (int)(h->wr[s] % cap), first = (cap - w < RADE_NMF) ? cap - w : RADE_NMF;
+    memcpy(dst + w, src, first * sizeof(float2));
+    if (first < RADE_NMF) memcpy(dst, src + first, (RADE_NMF - first) * sizeof(float2));
+    h->wr[s] += RADE_NMF;
+  }
+  return 0;
+}
+RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out, int *ret, float *eoo_out) {
+  rade_batch *b = h->b;
+  const int S = b->S, cap = h->cap;
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < S; s++) {
+    const int n = h->nin[s];
+    const bool ok = h->wr[s] - h->rd[s] >= n;
+    h->active[s] = ok ? 1 : 0;
+    if (!ok) continue;
+    const float2 *src = h->fifo + (size_t)s * cap;
+    float2 *dst = h->rx_in + (size_t)s * RADE_NIN_MAX;
+    const int r = (int)(h->rd[s] % cap), first = (cap - r < n) ? cap - r : n;
+    memcpy(dst, src + r, first * sizeof(float2));
+    if (first < n) memcpy(dst + first, src, (n - first) * sizeof(float2));
+    h->rd[s] += n;
+  }
+  const size_t Sz = S;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, h->rx_in, Sz * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(b->d_active, h->active, Sz, cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)b->d_rx_in, b->d_active) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(features_out, b->d_feat_out, Sz * RADE_NFEAT * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(ret, b->d_ret, Sz * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (eoo_out) CUDA_CHECK(cudaMemcpyAsync(eoo_out, b->rx.eoo, Sz * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->nin, b->rx.nin, Sz * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+RADE_EXPORT const unsigned char *rade_b200_hostlink_active(rade_b200_hostlink *h) { return h->active; }
 
 // ---- per-kernel timing (CUDA events on the context's stream).  enable=1 starts recording an event pair around every
 // kernel launch; rade_b200_profile_read synchronises, returns per-kernel-class total milliseconds and launch counts

@@ -120,3 +120,33 @@ def test_full_loop_tx_to_rx_on_device_roundtrip():
         best = min(np.mean((out - inp[k:k + len(out)]) ** 2) for k in range(0, 12 * 8, 12) if k + len(out) <= len(inp))
         assert best < 0.5
     b.close()
+
+
+def test_hostlink_fifo_feeds_the_same_call_sequence(golden):
+    """rade_b200_hostlink_*: samples arrive 960 at a time for every stream, the receiver takes nin[s] when it can;
+    each stream must see exactly the call sequence of the golden trace (same nin, same return codes, same features)"""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import HostLink
+    gs = [golden("rx_" + n) for n in SCENARIOS]
+    S = len(gs)
+    b = RadeBatch(S); link = HostLink(b)
+    n_push = min(len(g["rx_in"]) for g in gs) // 960
+    rets = [[] for _ in range(S)]; feats = [[] for _ in range(S)]
+    import ctypes
+    for k in range(n_push + 2):
+        if k < n_push:
+            link.push(np.stack([g["rx_in"][960 * k:960 * (k + 1)] for g in gs]))
+        f, ret, _ = link.rx()
+        act = np.ctypeslib.as_array(ctypes.cast(b.lib.rade_b200_hostlink_active(link.h), ctypes.POINTER(ctypes.c_ubyte)), shape=(S,))
+        for s in range(S):
+            if act[s]:
+                rets[s].append(int(ret[s]))
+                if ret[s] & 1: feats[s].append(f[s].copy())
+    for s, g in enumerate(gs):
+        n = len(rets[s])
+        assert n >= n_push - 2
+        assert np.array_equal(np.array(rets[s]), g["ret"][:n]), SCENARIOS[s]
+        nf = len(feats[s])
+        assert np.sqrt(np.mean((np.array(feats[s]) - g["features"][:nf]) ** 2)) < 1e-4
+    link.close(); b.close()
