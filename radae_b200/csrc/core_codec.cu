@@ -182,7 +182,7 @@ __device__ __forceinline__ void dense_chunk(Cursor &cx, float (&acc)[4], const f
 // GRU layer: warp w owns unit tile w (8 hidden units x 16 streams); gates z,r,n of a unit land in the same accumulator slot
 template <int UNITS, typename Emit>
 __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, const I8LayerDev &Lr, const int8_t *Xin, int ldx,
-                                          const int8_t *Hq, int ldh, float *hs, int ldhs, Emit emit) {
+                                          const int8_t *Hq, int ldh, float *hs, int ldhs, int ts, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int U = UNITS / 8;
   const bool work = warp < U;                // NCW >= U; surplus warps only keep the chunk pipeline moving
@@ -196,6 +196,7 @@ __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, cons
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const int row = g + ((e & 2) ? 8 : 0);
+    if (row >= ts) continue;                  // 8-stream tiles leave MMA rows 8..15 unused
     const int j = u * 8 + 2 * tig + (e & 1);
     float z = sigmoid_r(__fadd_rn(lin(ai[0][e], Li.scale[j], Li.bias[j]), lin(ar[0][e], Lr.scale[j], Lr.bias[j])));
     float r = sigmoid_r(__fadd_rn(lin(ai[1][e], Li.scale[UNITS + j], Li.bias[UNITS + j]),
@@ -213,7 +214,7 @@ __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, cons
 // K range, the exact int32 partial sums meet in shared memory `red[2][16][N]`, then all consumer threads run the epilogue
 template <int N, int NCW, typename Emit>
 __device__ __forceinline__ void conv_layer(Cursor &cx, const I8LayerDev &L, const int8_t *Aold, const int8_t *Acur, int Ktap, int lda,
-                                           int *red, Emit emit) {
+                                           int *red, int ts, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int NTL = N / 8;
   constexpr int UNITS = 2 * NTL;
@@ -244,7 +245,7 @@ __device__ __forceinline__ void conv_layer(Cursor &cx, const I8LayerDev &L, cons
       }
   }
   consumer_sync<NCW>();
-  for (int e = threadIdx.x; e < CORE_TS * N; e += NCW * 32) {
+  for (int e = threadIdx.x; e < ts * N; e += NCW * 32) {
     const int row = e / N, n = e % N;
     emit(row, n, lin(red[row * N + n] + red[(CORE_TS + row) * N + n], L.scale[n], L.bias[n]));
   }
@@ -263,16 +264,16 @@ struct EncSmem {
 
 __global__ void __launch_bounds__((ENC_NCW + 1) * 32, 1)
 core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
-                    float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
+                    float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T, int ts) {
   constexpr int NCW = ENC_NCW, NCT = NCW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
   const int tid = threadIdx.x;
-  const int s0 = blockIdx.x * CORE_TS;
+  const int s0 = blockIdx.x * ts;               // ts = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
 
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
-  if (tid < CORE_TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
+  if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
     for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -285,11 +286,11 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
   }
   // ---- consumer warps
   Cursor cx{&sm.pipe, 0, 0u};
-  const int sl = tid & 15, grp = tid >> 4;
+  const int sl = tid % ts, grp = tid / ts;
   const int sg = s0 + sl;
 
   for (int r = 0; r < CORE_TS; r++) {
-    const bool ok = s0 + r < S;
+    const bool ok = r < ts && s0 + r < S;
     const EncStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * ENC_GRU; i += NCT) sm.hs[r][i] = ok ? st->h[i] : 0.f;
     for (int i = tid; i < ENC_LDA / 4; i += NCT) {
@@ -309,7 +310,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     for (int i = tid; i < CORE_TS * ENC_IN; i += NCT) {
       const int r = i / ENC_IN, k = i % ENC_IN;
       float v = 0.f;
-      if (s0 + r < S) {
+      if (r < ts && s0 + r < S) {
         if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
         else {                                   // API layout: [S][4T][36]; 20 used features + aux = -1 (src/rade_api.c:426-432)
           const int fr = k / 21, f = k % 21;
@@ -344,7 +345,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     for (int l = 0; l < 5; l++) {
       // GRU l: input = cur[0:off), recurrent input = quantised h(t-1) = prev1[off : off+64)
       gru_layer<ENC_GRU>(cx, W.enc_gru_in[l], W.enc_gru_rec[l], &cur[0][0], ENC_LDA, &prev1[0][off], ENC_LDA,
-                         &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU,
+                         &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU, ts,
                          [&](int row, int j, float h) { sm.seg[row][j] = h; cur[row][off + j] = quant8(h); });
       consumer_sync<NCW>();
       dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
@@ -352,7 +353,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
       off += ENC_GRU;
       // conv l (k = 2): tap 0 = concat prefix of step t-dilation, tap 1 = current prefix
       const int8_t *old = (dil[l] == 1) ? &prev1[0][0] : &prev2[0][0];
-      conv_layer<ENC_CONV, NCW>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red,
+      conv_layer<ENC_CONV, NCW>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red, ts,
                                 [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
       dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
@@ -369,7 +370,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
 
   const int last = (T + 2) % 3, last2 = (T + 1) % 3;
   for (int r = 0; r < CORE_TS; r++) {
-    if (s0 + r >= S || (active && !active[s0 + r])) continue;
+    if (r >= ts || s0 + r >= S || (active && !active[s0 + r])) continue;
     EncStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * ENC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
     for (int i = tid; i < ENC_LDA / 4; i += NCT) {
@@ -396,16 +397,17 @@ struct DecSmem {
 __global__ void __launch_bounds__((DEC_NCW + 1) * 32, 1)
 core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
                     float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
-                    const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NCW = DEC_NCW, NCT = NCW * 32, NGRP = NCT / 16;
+                    const uint8_t *__restrict__ active, int S, int T, int ts) {
+  constexpr int NCW = DEC_NCW, NCT = NCW * 32;
+  const int NGRP = NCT / ts;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DecSmem &sm = *reinterpret_cast<DecSmem *>(smem_raw);
   const int tid = threadIdx.x;
-  const int s0 = blockIdx.x * CORE_TS;
+  const int s0 = blockIdx.x * ts;               // ts = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
 
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
-  if (tid < CORE_TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
+  if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
     for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -417,11 +419,11 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     return;
   }
   Cursor cx{&sm.pipe, 0, 0u};
-  const int sl = tid & 15, grp = tid >> 4;
+  const int sl = tid % ts, grp = tid / ts;
   const int sg = s0 + sl;
 
   for (int r = 0; r < CORE_TS; r++) {
-    const bool ok = s0 + r < S;
+    const bool ok = r < ts && s0 + r < S;
     const DecStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * DEC_GRU; i += NCT) {
       float h = ok ? st->h[i] : 0.f;
@@ -443,7 +445,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
 
     for (int i = tid; i < CORE_TS * DEC_IN; i += NCT) {
       const int r = i / DEC_IN, k = i % DEC_IN;
-      sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
+      sm.zin[r][k] = (r < ts && s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
     }
     consumer_sync<NCW>();
 
@@ -454,6 +456,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int o = 4 * grp + i;               // 24 groups x 4 = 96 outputs
+        if (o >= 96) continue;
         float y = tanh_r(__fadd_rn(a[i], W.dec_dense1.bias[o]));
         sm.seg[sl][o] = y;
         cur[sl][o] = quant8(y);
@@ -469,7 +472,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     for (int l = 0; l < 5; l++) {
       // GRU l on cur[0:off); its new state is kept un-gated (src/rade_dec.c:66-67)
       gru_layer<DEC_GRU>(cx, W.dec_gru_in[l], W.dec_gru_rec[l], &cur[0][0], DEC_LDA, &hq_rd[0][l * DEC_GRU], HQ_LD,
-                         &sm.hs[0][l * DEC_GRU], 5 * DEC_GRU,
+                         &sm.hs[0][l * DEC_GRU], 5 * DEC_GRU, ts,
                          [&](int row, int j, float h) { hq_wr[row][l * DEC_GRU + j] = quant8(h); });
       consumer_sync<NCW>();
       // GLU l: out = h * sigmoid(Wg h + b)  -> concat;  12 n-tiles, one per warp, a single 9 KB chunk
@@ -483,6 +486,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int row = g + ((e & 2) ? 8 : 0);
+          if (row >= ts) continue;
           const int n = warp * 8 + 2 * tig + (e & 1);
           float y = __fmul_rn(sm.hs[row][l * DEC_GRU + n], sigmoid_r(lin(acc[0][e], L.scale[n], L.bias[n])));
           sm.seg[row][n] = y; cur[row][off + n] = quant8(y);
@@ -492,7 +496,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
       dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
       consumer_sync<NCW>();
       off += DEC_GRU;
-      conv_layer<DEC_CONV, NCW>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,
+      conv_layer<DEC_CONV, NCW>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red, ts,
                                 [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
       dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
@@ -522,7 +526,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
 
   const int last = (T + 1) & 1;      // buffer that held the final step's concat
   for (int r = 0; r < CORE_TS; r++) {
-    if (s0 + r >= S || (active && !active[s0 + r])) continue;
+    if (r >= ts || s0 + r >= S || (active && !active[s0 + r])) continue;
     DecStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * DEC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
     for (int i = tid; i < DEC_LDA / 4; i += NCT)
@@ -533,6 +537,12 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
 }  // namespace
 
 // ----------------------------------------------------------------- host launchers
+// streams per CTA: a full 16-row MMA tile when that still fills the 148 SMs, otherwise 8 so twice as many SMs work
+static int core_tile_streams(int S) {
+  const char *e = getenv("RADE_B200_TILE_STREAMS");
+  if (e && (atoi(e) == 8 || atoi(e) == 16)) return atoi(e);
+  return ((S + 15) / 16 >= 148) ? 16 : 8;
+}
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                         const uint8_t *active, int S, int T, cudaStream_t stream) {
   static bool attr_set = false;
@@ -540,8 +550,9 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
     CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
     attr_set = true;
   }
-  const int grid = (S + CORE_TS - 1) / CORE_TS;
-  core_encoder_kernel<<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem), stream>>>(W, state, in, in_mode, z, active, S, T);
+  const int ts = core_tile_streams(S);
+  const int grid = (S + ts - 1) / ts;
+  core_encoder_kernel<<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem), stream>>>(W, state, in, in_mode, z, active, S, T, ts);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -553,8 +564,9 @@ int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const fl
     CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
     attr_set = true;
   }
-  const int grid = (S + CORE_TS - 1) / CORE_TS;
-  core_decoder_kernel<<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+  const int ts = core_tile_streams(S);
+  const int grid = (S + ts - 1) / ts;
+  core_decoder_kernel<<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T, ts);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -30,6 +30,38 @@ __device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
   acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
 }
+// Coarse-grid correlations for two sample windows x0, x1 (already conjugated) against the pilot p shifted to the grid
+// frequencies +-2.5k Hz, k = 6*kg .. 6*kg+5:  D(+-f_k) = A_k +- j B_k with A_k = sum_n y[n] cos(w_k n), B_k = sum_n y[n] sin(w_k n),
+// y[n] = x[n] p[n]  (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; p_w = exp(j w n) p there).
+// One (cos, sin) pair serves the +f and -f grid points: 4 FMAs per tap per pair instead of 8.
+__device__ __forceinline__ void corr6(float2 (&A0)[6], float2 (&B0)[6], float2 (&A1)[6], float2 (&B1)[6], const float2 *x0,
+                                      const float2 *x1, const float2 *ps, const float2 (*cs)[RADE_CSK], int kg) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
+#pragma unroll 2
+  for (int n = 0; n < RADE_M; n++) {
+    const float2 pn = ps[n];
+    const float2 y0 = cmul(x0[n], pn), y1 = cmul(x1[n], pn);
+    const float4 *t = reinterpret_cast<const float4 *>(&cs[n][kg * 6]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float4 q = t[j];                       // (cos_k, sin_k, cos_k+1, sin_k+1)
+      A0[2 * j].x = fmaf(y0.x, q.x, A0[2 * j].x); A0[2 * j].y = fmaf(y0.y, q.x, A0[2 * j].y);
+      B0[2 * j].x = fmaf(y0.x, q.y, B0[2 * j].x); B0[2 * j].y = fmaf(y0.y, q.y, B0[2 * j].y);
+      A0[2 * j + 1].x = fmaf(y0.x, q.z, A0[2 * j + 1].x); A0[2 * j + 1].y = fmaf(y0.y, q.z, A0[2 * j + 1].y);
+      B0[2 * j + 1].x = fmaf(y0.x, q.w, B0[2 * j + 1].x); B0[2 * j + 1].y = fmaf(y0.y, q.w, B0[2 * j + 1].y);
+      A1[2 * j].x = fmaf(y1.x, q.x, A1[2 * j].x); A1[2 * j].y = fmaf(y1.y, q.x, A1[2 * j].y);
+      B1[2 * j].x = fmaf(y1.x, q.y, B1[2 * j].x); B1[2 * j].y = fmaf(y1.y, q.y, B1[2 * j].y);
+      A1[2 * j + 1].x = fmaf(y1.x, q.z, A1[2 * j + 1].x); A1[2 * j + 1].y = fmaf(y1.y, q.z, A1[2 * j + 1].y);
+      B1[2 * j + 1].x = fmaf(y1.x, q.w, B1[2 * j + 1].x); B1[2 * j + 1].y = fmaf(y1.y, q.w, B1[2 * j + 1].y);
+    }
+  }
+}
+// |D(+f_k)|, |D(-f_k)| from A, B
+__device__ __forceinline__ void mags_pm(float2 A, float2 B, float &mp, float &mm) {
+  mp = hypotf(A.x - B.y, A.y + B.x);
+  mm = hypotf(A.x + B.y, A.y - B.x);
+}
 __device__ __forceinline__ int ring_idx(int head, int i) { int k = head + i; return k >= RADE_RXBUF ? k - RADE_RXBUF : k; }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -99,7 +131,8 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
 // grid (15, S): CTA = 64 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations
 constexpr int DET_TB = 64;
 struct DetectSmem {
-  alignas(16) float2 pw[RADE_M][RADE_NFCOARSE];
+  alignas(16) float2 cs[RADE_M][RADE_CSK];
+  float2 ps[RADE_M];
   float2 r1[DET_TB + RADE_M];
   float2 r2[DET_TB + RADE_M];
   float part[2][4][DET_TB];
@@ -115,7 +148,8 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
   const int tid = threadIdx.x;
   const int n_items = search_count[0] * (RADE_NMF / DET_TB);
   if (n_items == 0) return;                       // steady state: nobody is searching
-  for (int i = tid; i < RADE_M * RADE_NFCOARSE; i += blockDim.x) (&sm.pw[0][0])[i] = T.p_w[i];
+  for (int i = tid; i < RADE_M * RADE_CSK; i += blockDim.x) (&sm.cs[0][0])[i] = T.cs_tab[i];
+  for (int i = tid; i < RADE_M; i += blockDim.x) sm.ps[i] = T.p[i];
   // persistent CTAs pull (stream, 64-offset block) items off a device-side counter
   for (;;) {
     __syncthreads();
@@ -132,27 +166,26 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       sm.r2[i] = cconj(rg[ring_idx(head, t0 + RADE_NMF + i)]);
     }
     __syncthreads();
-    const int tl = tid & (DET_TB - 1), fg = tid >> 6;
-    float2 a1[10], a2[10];
+    const int tl = tid & (DET_TB - 1), fg = tid >> 6;      // fg = k group: k = 6 fg .. 6 fg + 5
+    float2 A0[6], B0[6], A1[6], B1[6];
+    corr6(A0, B0, A1, B1, &sm.r1[tl], &sm.r2[tl], sm.ps, sm.cs, fg);
+    float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = RADE_NFCOARSE;
 #pragma unroll
-    for (int j = 0; j < 10; j++) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
-    for (int n = 0; n < RADE_M; n++) {
-      const float2 x1 = sm.r1[tl + n], x2 = sm.r2[tl + n];
-      const float4 *wp = reinterpret_cast<const float4 *>(&sm.pw[n][fg * 10]);
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        const float4 wv = wp[j];
-        cmac(a1[2 * j], x1, make_float2(wv.x, wv.y)); cmac(a1[2 * j + 1], x1, make_float2(wv.z, wv.w));
-        cmac(a2[2 * j], x2, make_float2(wv.x, wv.y)); cmac(a2[2 * j + 1], x2, make_float2(wv.z, wv.w));
+    for (int j = 0; j < 6; j++) {
+      const int k = fg * 6 + j;
+      if (k > 20) continue;
+      float p1, m1, p2, m2;
+      mags_pm(A0[j], B0[j], p1, m1); mags_pm(A1[j], B1[j], p2, m2);
+      if (k < 20) {                                   // +2.5k Hz -> grid index 20 + k
+        s1 += p1; s2 += p2;
+        const float d = p1 + p2; const int fi = 20 + k;
+        if (d > best || (d == best && fi < bestf)) { best = d; bestf = fi; }
       }
-    }
-    float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = 0;
-#pragma unroll
-    for (int j = 0; j < 10; j++) {
-      const float m1 = hypotf(a1[j].x, a1[j].y), m2 = hypotf(a2[j].x, a2[j].y);
-      s1 += m1; s2 += m2;
-      const float d = m1 + m2;
-      if (d > best) { best = d; bestf = fg * 10 + j; }
+      if (k > 0) {                                    // -2.5k Hz -> grid index 20 - k
+        s1 += m1; s2 += m2;
+        const float d = m1 + m2; const int fi = 20 - k;
+        if (d > best || (d == best && fi < bestf)) { best = d; bestf = fi; }
+      }
     }
     sm.part[0][fg][tl] = s1; sm.part[1][fg][tl] = s2;
     // arg-max with "first (t, f) wins": larger key = larger value, then smaller flat index
@@ -278,7 +311,8 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 // ================================================================= sync-state tracking: refine + check_pilots + slips
 constexpr int CHK_SPAN = 20 * (RADE_NUPDATE - 1) + RADE_M + 20;     // samples covered by the 48 refreshed rows of one half (1120)
 struct CheckSmem {                 // aliases RefineSmem once the refine is done
-  alignas(16) float2 pw[RADE_M][RADE_NFCOARSE];
+  alignas(16) float2 cs[RADE_M][RADE_CSK];
+  float2 ps[RADE_M];
   float2 rx[2][CHK_SPAN];
 };
 struct TrackSmem {
@@ -314,7 +348,8 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   // through shared memory (p_w table + the 1120-sample span the rows cover) and register-tiled 1 x 20 per thread
   const int rot = c.n_check % 20;
   __syncthreads();                                   // everyone is done with sm.ref before it is overwritten
-  for (int i = tid; i < RADE_M * RADE_NFCOARSE; i += blockDim.x) (&sm.chk.pw[0][0])[i] = T.p_w[i];
+  for (int i = tid; i < RADE_M * RADE_CSK; i += blockDim.x) (&sm.chk.cs[0][0])[i] = T.cs_tab[i];
+  for (int i = tid; i < RADE_M; i += blockDim.x) sm.chk.ps[i] = T.p[i];
   for (int i = tid; i < 2 * CHK_SPAN; i += blockDim.x) {
     const int half = i / CHK_SPAN, k = i % CHK_SPAN;
     const int li = rot + k + half * RADE_NMF;
@@ -322,28 +357,21 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   }
   __syncthreads();
   if (tid < RADE_NUPDATE * 4) {
-    // thread = (row i, frequency group fg of 10): both pilot positions of row i x 10 frequencies, 40 accumulators;
-    // per tap: 2 LDS.64 (samples) + 5 LDS.128 (two frequencies each; the four groups of a warp hit disjoint banks)
-    // feed 80 FMAs
-    const int i = tid >> 2, fg = tid & 3;
-    const float2 *x0 = &sm.chk.rx[0][20 * i], *x1 = &sm.chk.rx[1][20 * i];
-    float2 a0[10], a1[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) { a0[j] = make_float2(0.f, 0.f); a1[j] = make_float2(0.f, 0.f); }
-    for (int n = 0; n < RADE_M; n++) {
-      const float2 u = x0[n], v = x1[n];
-      const float4 *wp = reinterpret_cast<const float4 *>(&sm.chk.pw[n][fg * 10]);
-#pragma unroll
-      for (int j = 0; j < 5; j++) {
-        const float4 w = wp[j];
-        cmac(a0[2 * j], u, make_float2(w.x, w.y)); cmac(a0[2 * j + 1], u, make_float2(w.z, w.w));
-        cmac(a1[2 * j], v, make_float2(w.x, w.y)); cmac(a1[2 * j + 1], v, make_float2(w.z, w.w));
-      }
-    }
+    // thread = (row i, k group kg): both pilot positions of row i x 6 (cos, sin) pairs = up to 12 grid frequencies each
+    const int i = tid >> 2, kg = tid & 3;
+    float2 A0[6], B0[6], A1[6], B1[6];
+    corr6(A0, B0, A1, B1, &sm.chk.rx[0][20 * i], &sm.chk.rx[1][20 * i], sm.chk.ps, sm.chk.cs, kg);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 10; j++) { s0 += hypotf(a0[j].x, a0[j].y); s1 += hypotf(a1[j].x, a1[j].y); }
-    sm.part[fg][2 * i] = s0; sm.part[fg][2 * i + 1] = s1;
+    for (int j = 0; j < 6; j++) {
+      const int k = kg * 6 + j;
+      if (k > 20) continue;
+      float p0, m0, p1, m1;
+      mags_pm(A0[j], B0[j], p0, m0); mags_pm(A1[j], B1[j], p1, m1);
+      if (k < 20) { s0 += p0; s1 += p1; }
+      if (k > 0) { s0 += m0; s1 += m1; }
+    }
+    sm.part[kg][2 * i] = s0; sm.part[kg][2 * i + 1] = s1;
   }
   __syncthreads();
   if (tid < RADE_NUPDATE * 2)

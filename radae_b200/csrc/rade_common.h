@@ -23,6 +23,7 @@
 #define RADE_NUM_USED_FEATURES 20
 #define RADE_NEOO_BITS 180
 #define RADE_NFCOARSE 40
+#define RADE_CSK 24                            // padded k per row of cs_tab
 #define RADE_NUPDATE 48
 #define RADE_NMF_UNSYNC 25
 #define RADE_SYNCED_ONE_SEC 8
@@ -91,7 +92,8 @@ struct DspTables {
   const float2 *Pend;
   const float2 *p;         // [160] time-domain pilot symbol, pend [160]
   const float2 *pend;
-  const float2 *p_w;       // [160][40] coarse-frequency-shifted pilots
+  const float2 *p_w;       // [160][40] coarse-frequency-shifted pilots (reference table; kept for the debug hook)
+  const float2 *cs_tab;    // [160][24] (cos, sin)(2*pi*2.5k*n/Fs), k = 0..20 (+3 zero pads): the coarse grid is +-2.5k Hz
   const float2 *Pmat;      // [30][2][3] LS projectors
   const float2 *eq_rot;    // [30] exp(-j w_c a)
   const float *bpf_h;      // [101]

@@ -26,7 +26,7 @@ extern "C" const unsigned char rade_b200_default_weights_end[];
 #include <complex>
 struct DspTablesHost {
   std::vector<float> w, bpf_h, fcoarse;
-  std::vector<std::complex<float>> Winv, Wfwd, P, Pend, p, pend, p_w, Pmat, eq_rot, bpf_exp, eoo_base;
+  std::vector<std::complex<float>> Winv, Wfwd, P, Pend, p, pend, p_w, cs_tab, Pmat, eq_rot, bpf_exp, eoo_base;
   double pilot_gain;
   float bpf_bw, bpf_centre, bpf_alpha;
 };

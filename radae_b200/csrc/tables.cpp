@@ -65,6 +65,13 @@ void dsp_tables_host(DspTablesHost &T) {
       T.p_w[n * RADE_NFCOARSE + i] = cf((float)v.real(), (float)v.imag());
     }
   }
+  // symmetric coarse grid: f = +-2.5k Hz, k = 0..20 -> one (cos, sin) pair serves two grid points (ofdm_rx.cu corr6)
+  T.cs_tab.assign(M * RADE_CSK, cf(0, 0));
+  for (int n = 0; n < M; n++)
+    for (int k = 0; k <= 20; k++) {
+      double a = 2 * M_PI * (2.5 * k) / RADE_FS * n;
+      T.cs_tab[n * RADE_CSK + k] = cf((float)std::cos(a), (float)std::sin(a));
+    }
   // LS projectors: Pmat[c] = inv(A^T A) A^T, A = [[1, e^{-j w_{m-1} a}], [1, e^{-j w_m a}], [1, e^{-j w_{m+1} a}]]
   const double a = 0.0025 * RADE_FS;
   T.Pmat.resize(NC * 6); T.eq_rot.resize(NC);
@@ -124,7 +131,7 @@ int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> 
   };
 #define UPC(field, vec) if (!(D->field = (const float2 *)up(vec.data(), vec.size() * sizeof(cf)))) return -1;
   UPC(Winv, T.Winv) UPC(Wfwd, T.Wfwd) UPC(P, T.P) UPC(Pend, T.Pend) UPC(p, T.p) UPC(pend, T.pend)
-  UPC(p_w, T.p_w) UPC(Pmat, T.Pmat) UPC(eq_rot, T.eq_rot) UPC(bpf_exp, T.bpf_exp) UPC(eoo_base, T.eoo_base)
+  UPC(p_w, T.p_w) UPC(cs_tab, T.cs_tab) UPC(Pmat, T.Pmat) UPC(eq_rot, T.eq_rot) UPC(bpf_exp, T.bpf_exp) UPC(eoo_base, T.eoo_base)
 #undef UPC
   if (!(D->bpf_h = (const float *)up(T.bpf_h.data(), T.bpf_h.size() * 4))) return -1;
   if (!(D->fcoarse = (const float *)up(T.fcoarse.data(), T.fcoarse.size() * 4))) return -1;

@@ -22,9 +22,12 @@ def test_golden_vectors(golden):
     b.close()
 
 
+@pytest.mark.parametrize("tile", [8, 16])
 @pytest.mark.parametrize("S,T", [(1, 5), (16, 3), (37, 7), (200, 4)])
-def test_bit_exact_vs_oracle_ragged_tiles(S, T):
+def test_bit_exact_vs_oracle_ragged_tiles(S, T, tile, monkeypatch):
+    """both CTA tile shapes (8 or 16 streams per CTA; the library picks by batch size, the env var pins it)"""
     need_gpu()
+    monkeypatch.setenv("RADE_B200_TILE_STREAMS", str(tile))
     from radae_b200 import RadeBatch
     x = pack_enc_input(synth_features(S, 4 * T, seed=7 + S))
     o = CoreOraclePort(n_streams=S)
@@ -36,8 +39,10 @@ def test_bit_exact_vs_oracle_ragged_tiles(S, T):
     b.close()
 
 
-def test_state_carries_across_calls_and_reset():
+@pytest.mark.parametrize("tile", [8, 16])
+def test_state_carries_across_calls_and_reset(tile, monkeypatch):
     need_gpu()
+    monkeypatch.setenv("RADE_B200_TILE_STREAMS", str(tile))
     from radae_b200 import RadeBatch
     S, T = 20, 9
     x = pack_enc_input(synth_features(S, 4 * T, seed=3))
@@ -118,4 +123,20 @@ def test_dnnw_blob_is_accepted_as_weights(golden):
     x = pack_enc_input(g["features36"])
     b = RadeBatch(x.shape[0], weights=bytes(blob))
     assert np.array_equal(b.core_encode(x), g["z_c_int8"])
+    b.close()
+
+
+def test_large_batch_full_tiles_vs_oracle():
+    """2400 streams -> 150 CTAs of 16 streams (the automatic choice above 2368 streams), 2 steps"""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    S, T = 2400, 2
+    x = pack_enc_input(synth_features(64, 4 * T, seed=31))
+    x = np.ascontiguousarray(np.tile(x, (S // 64 + 1, 1, 1))[:S])
+    x[:, :, :83] += (np.arange(S, dtype=np.float32)[:, None, None] * 1e-4)
+    o = CoreOraclePort(n_streams=S)
+    zo = o.encode(x, nthreads=16); fo = o.decode(zo, nthreads=16)
+    b = RadeBatch(S)
+    assert np.array_equal(b.core_encode(x), zo)
+    assert np.array_equal(b.core_decode(zo), fo)
     b.close()
