@@ -287,7 +287,8 @@ def run_gpu(args):
     # ---- end to end through the host-buffer C ABI (pinned host in, host out, every step), wall clock
     e2e = None
     if rank == 0 or world > 1:
-        e2e = run_e2e(b, S, feats_host, codec_only, max(3, K // 2), world, dist if world > 1 else None, torch)
+        e2e = run_e2e(b, S, feats_host, codec_only, max(3, K // 2), world, dist if world > 1 else None, torch,
+                      n_ctx=args.e2e_contexts, weights=blob, device=local)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -312,49 +313,77 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch):
-    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed"""
-    b.reset()
+def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weights=None, device=0):
+    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed.
+    The S streams are served by n_ctx independent contexts (rade_b200_open each), one host thread per context, so one
+    context's PCIe copies overlap the other's kernels — every call is still the synchronous reference-style call."""
+    import threading
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import HostLink
     n_feat_frames = feats_host.shape[1]
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    bounds = [(S * i) // n_ctx for i in range(n_ctx + 1)]
+    ctxs = []
+    for i in range(n_ctx):
+        lo, hi = bounds[i], bounds[i + 1]
+        n = hi - lo
+        c = {"b": RadeBatch(n, device=device, weights=weights), "n": n}
+        fh = feats_host[lo:hi]
+        if codec_only:
+            x = np.ascontiguousarray(np.concatenate([fh.reshape(n, n_feat_frames, 12, 36)[..., :20],
+                                     -np.ones((n, n_feat_frames, 12, 1), np.float32)], axis=-1).reshape(n, n_feat_frames, 3, 84))
+            c["x"] = [np.ascontiguousarray(x[:, j]) for j in range(n_feat_frames)]
+        else:
+            c["b"].channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5 + i)
+            c["link"] = HostLink(c["b"])
+            c["tx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
+            c["rx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
+            c["feats"] = []
+            for j in range(n_feat_frames):
+                a = pin((n, 432), torch.float32); a[...] = fh[:, j]; c["feats"].append(a)
+        ctxs.append(c)
+
+    def step(c, k):
+        if codec_only:
+            z = c["b"].core_encode(c["x"][k % n_feat_frames])
+            c["b"].core_decode(z)
+        else:
+            c["b"].tx(c["feats"][k % n_feat_frames], out=c["tx"])      # H2D features (pinned), D2H tx samples
+            c["b"].channel(c["tx"], out=c["rx"])                        # H2D tx, D2H rx (the channel is a simulator outside rade_api.h)
+            c["link"].push(c["rx"])                                     # pinned host FIFO, C/OpenMP
+            c["link"].rx()                                              # gather nin[s] per stream, H2D rx_in, D2H features/ret/eoo/nin
+
+    def run(c, k0, n):
+        for k in range(k0, k0 + n):
+            step(c, k)
+
+    def run_all(k0, n):
+        th = [threading.Thread(target=run, args=(c, k0, n)) for c in ctxs]
+        for t in th: t.start()
+        for t in th: t.join()
+
     if codec_only:
-        x = np.ascontiguousarray(np.concatenate([feats_host.reshape(S, n_feat_frames, 12, 36)[..., :20],
-                                 -np.ones((S, n_feat_frames, 12, 1), np.float32)], axis=-1).reshape(S, n_feat_frames, 3, 84))
-        def step(k):
-            z = b.core_encode(x[:, k % n_feat_frames])
-            b.core_decode(z)
         h2d = S * (3 * 84 * 4 + 3 * 80 * 4); d2h = S * (3 * 80 * 4 + 3 * 84 * 4)
     else:
-        b.channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5)
-        from radae_b200.batch import HostLink
-        link = HostLink(b)
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-        tx_h = pin((S, 960, 2), torch.float32).view(np.complex64).reshape(S, 960)
-        rx_h = pin((S, 960, 2), torch.float32).view(np.complex64).reshape(S, 960)
-        def step(k):
-            b.tx(feats_frames[k % n_feat_frames], out=tx_h)                     # H2D features (pinned), D2H tx samples
-            b.channel(tx_h, out=rx_h)                                           # H2D tx, D2H rx (the channel is a simulator outside rade_api.h)
-            link.push(rx_h)                                                     # host FIFO (pinned), C/OpenMP
-            link.rx()                                                           # gather nin[s] per stream, H2D rx_in, D2H features/ret/eoo/nin
-        feats_frames = []
-        for i in range(n_feat_frames):
-            a = pin((S, 432), torch.float32); a[...] = feats_host[:, i]; feats_frames.append(a)
         h2d = S * (432 * 4 + 960 * 8 + 1120 * 8 + 1); d2h = S * (960 * 8 + 960 * 8 + 432 * 4 + 4 + 180 * 4 + 4)
-    for k in range(12 if not codec_only else 2):
-        step(k)
-    b.synchronize()
+    run_all(0, 12 if not codec_only else 2)                           # warm-up incl. acquisition
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    for k in range(K):
-        step(100 + k)
-    b.synchronize()
+    run_all(100, K)
+    for c in ctxs:
+        c["b"].synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    for c in ctxs:
+        if "link" in c: c["link"].close()
+        c["b"].close()
     return {"value": S * world * F_PER_STEP * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": K, "timing": "host wall clock around K steps incl. host FIFO bookkeeping (pinned buffers), max over ranks"}
+            "steps": K, "contexts": n_ctx,
+            "timing": "host wall clock around K synchronous steps per context (pinned buffers, host FIFO in C), %d contexts on %d host threads, max over ranks" % (n_ctx, n_ctx)}
 
 
 def main():
@@ -366,6 +395,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-contexts", type=int, default=2, help="host threads / contexts serving the streams in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

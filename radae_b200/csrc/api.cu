@@ -173,6 +173,7 @@ RADE_EXPORT int rade_b200_reset(rade_batch *b) { return reset_state(b); }
 
 // ------------------------------------------------------------------ core codec
 RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float *d_features, int n_steps) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_CORE_ENC);
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features, 0, d_z, nullptr, b->S, n_steps, b->stream) < 0) return -1;
   b->prof.end(K_CORE_ENC);
@@ -180,6 +181,7 @@ RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float
   return 0;
 }
 RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, const float *d_z, int n_steps) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_CORE_DEC);
   if (core_decoder_launch(b->weights.dev, b->rx.dec_state, d_z, d_features, 0, nullptr, nullptr, b->S, n_steps, b->stream) < 0) return -1;
   b->prof.end(K_CORE_DEC);
@@ -187,6 +189,7 @@ RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, cons
   return 0;
 }
 RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *features, int n_steps) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t nin = (size_t)b->S * n_steps * ENC_IN, nout = (size_t)b->S * n_steps * RADE_LATENT;
   if (ensure_core_staging(b, nin) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, features, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
@@ -196,6 +199,7 @@ RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *feat
   return 0;
 }
 RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const float *z, int n_steps) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t nin = (size_t)b->S * n_steps * RADE_LATENT, nout = (size_t)b->S * n_steps * DEC_OUT;
   if (ensure_core_staging(b, nout) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, z, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
@@ -207,6 +211,7 @@ RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const floa
 
 // ------------------------------------------------------------------ transmitter
 RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_OFDM_MOD);
   if (ofdm_mod_launch(b->tables, d_z, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
   b->prof.end(K_OFDM_MOD);
@@ -214,6 +219,7 @@ RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const
   return 0;
 }
 RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_features_in) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   // 3 core-encoder steps on the API feature layout (src/rade_api.c:411-434) then transmitter_one (radae_txe.py:127)
   b->prof.begin(K_CORE_ENC);
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, b->stream) < 0) return -1;
@@ -224,6 +230,7 @@ RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float
   return RADE_NMF;
 }
 RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *features_in) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   // copies go straight from / to the caller's buffers: truly asynchronous when they are pinned (cudaHostAlloc /
   // cudaHostRegister), staged by the driver when they are pageable
   const size_t S = b->S;
@@ -234,6 +241,7 @@ RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *feat
   return RADE_NMF;
 }
 RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
   std::vector<int> ones(S, 1);
   CUDA_CHECK(cudaMemcpyAsync(b->eoo_bits, eoo_bits, S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyHostToDevice, b->stream));
@@ -242,6 +250,7 @@ RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits) 
   return 0;
 }
 RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
   b->prof.begin(K_EOO);
   if (eoo_launch(b->tables, b->eoo_bits, b->has_eoo_bits, b->d_tx_eoo, b->S, b->stream) < 0) return -1;
@@ -255,6 +264,7 @@ RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
 // ------------------------------------------------------------------ receiver
 RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out, const RADE_COMP *d_rx_in,
                                  const unsigned char *d_active) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
   int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, b->S, 1, reset_dec, d_ret, b->stream, &b->prof);
   if (n < 0) return -1;
@@ -271,12 +281,14 @@ RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_re
 }
 RADE_EXPORT const int *rade_b200_nin_dev(rade_batch *b) { return b->rx.nin; }
 RADE_EXPORT int rade_b200_nin(rade_batch *b, int *nin) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   CUDA_CHECK(cudaMemcpyAsync(nin, b->rx.nin, sizeof(int) * b->S, cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return 0;
 }
 RADE_EXPORT int rade_b200_rx(rade_batch *b, float *features_out, int *ret, float *eoo_out, const RADE_COMP *rx_in,
                              const unsigned char *active) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
   CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, rx_in, S * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
   if (active) CUDA_CHECK(cudaMemcpyAsync(b->d_active, active, S, cudaMemcpyHostToDevice, b->stream));
@@ -288,6 +300,7 @@ RADE_EXPORT int rade_b200_rx(rade_batch *b, float *features_out, int *ret, float
   return 0;
 }
 RADE_EXPORT int rade_b200_rx_get_status(rade_batch *b, rade_b200_rx_status *status) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   std::vector<RxCtl> ctl(b->S); std::vector<int> uw(b->S);
   CUDA_CHECK(cudaMemcpyAsync(ctl.data(), b->rx.ctl, sizeof(RxCtl) * b->S, cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaMemcpyAsync(uw.data(), b->rx.uw_errors, sizeof(int) * b->S, cudaMemcpyDeviceToHost, b->stream));
@@ -301,6 +314,7 @@ RADE_EXPORT int rade_b200_rx_get_status(rade_batch *b, rade_b200_rx_status *stat
   return 0;
 }
 RADE_EXPORT int rade_b200_rx_get_z_hat(rade_batch *b, float *z_hat) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   CUDA_CHECK(cudaMemcpyAsync(z_hat, b->rx.z_hat, (size_t)b->S * 240 * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return 0;
@@ -310,18 +324,21 @@ RADE_EXPORT int rade_b200_rx_get_z_hat(rade_batch *b, float *z_hat) {
 RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx, const RADE_COMP *d_G1,
                                             const RADE_COMP *d_G2, const RADE_COMP *d_noise, int n, int delay,
                                             float mp_gain, float freq_offset_hz, float phase0, float sigma, float gain) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   if (channel_apply_launch((float2 *)d_rx, (const float2 *)d_tx, (const float2 *)d_G1, (const float2 *)d_G2, (const float2 *)d_noise,
                            b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) return -1;
   b->launches += 1;
   return 0;
 }
 RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_cfg *cfg) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   if (cfg->delay_samples < 0 || cfg->delay_samples > 64) return -1;
   b->chan_cfg = *cfg;
   CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * b->S, b->stream));
   return 0;
 }
 RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const rade_b200_channel_cfg &c = b->chan_cfg;
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));       // radae.py:570-574, Rb = 80/0.04
   b->prof.begin(K_CHANNEL);
@@ -332,6 +349,7 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
   return 0;
 }
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
   CUDA_CHECK(cudaMemcpyAsync(b->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
   if (rade_b200_channel_dev(b, (RADE_COMP *)b->d_rx_in, (const RADE_COMP *)b->d_tx) < 0) return -1;
@@ -340,6 +358,7 @@ RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP 
   return 0;
 }
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_LINK_PUSH);
   if (link_push_launch(b->link_ring, b->link_wr, (const float2 *)d_samples, b->S, b->stream) < 0) return -1;
   b->prof.end(K_LINK_PUSH);
@@ -347,6 +366,7 @@ RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_sample
   return 0;
 }
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsigned char *d_active) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_LINK_POP);
   if (link_pop_launch(b->link_ring, b->link_wr, b->link_rd, b->rx.ctl, (float2 *)d_rx_in, d_active, b->S, b->stream) < 0) return -1;
   b->prof.end(K_LINK_POP);
@@ -364,6 +384,7 @@ struct rade_b200_hostlink {
   float2 *rx_in; unsigned char *active;
 };
 RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples) {
+  cudaSetDevice(b->device);
   if (capacity_samples < 2 * RADE_NIN_MAX) capacity_samples = 4096;
   rade_b200_hostlink *h = new rade_b200_hostlink();
   h->b = b; h->cap = capacity_samples;
@@ -398,6 +419,7 @@ RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *
 }
 RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out, int *ret, float *eoo_out) {
   rade_batch *b = h->b;
+  cudaSetDevice(b->device);
   const int S = b->S, cap = h->cap;
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < S; s++) {
@@ -437,6 +459,7 @@ RADE_EXPORT const char *rade_b200_profile_kernel_name(int k) {
   return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts) {
+  cudaSetDevice(b->device);        // the current device is per host thread
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   for (int k = 0; k < K_COUNT; k++) {
     float tot = 0.f; int n = 0;
