@@ -279,15 +279,22 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": byts, "achieved_gbs": round(byts / per_launch_ms / 1e6, 2),
                          "frac_of_hbm": round(byts / per_launch_ms / 1e6 / hbm_peak, 5)}
     dom = max(kernels, key=lambda n: kernels[n]["share"])
+    traffic = None
+    try:                                                  # DRAM bytes per launch from the committed ncu --set full capture
+        import glob
+        for fn in sorted(glob.glob(os.path.join(REPO, "profiles", "r*_traffic.json"))):
+            traffic = json.load(open(fn))["bytes_per_launch"].get(dom, traffic)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac_of_hbm"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                "frac": kernels[dom]["frac_of_hbm"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
                 "share_of_step": kernels[dom]["share"],
                 "note": "compute/latency-bound at this batch: algorithmic bytes are tiny next to the int8/fp32/fp64 math (DESIGN.md §Roofline)"}
 
     # ---- end to end through the host-buffer C ABI (pinned host in, host out, every step), wall clock
     e2e = None
     if rank == 0 or world > 1:
-        e2e = run_e2e(b, S, feats_host, codec_only, max(3, K // 2), world, dist if world > 1 else None, torch,
+        e2e = run_e2e(b, S, feats_host, codec_only, K, world, dist if world > 1 else None, torch,
                       n_ctx=args.e2e_contexts, weights=blob, device=local)
 
     cpu_base = None
@@ -357,10 +364,14 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
         for k in range(k0, k0 + n):
             step(c, k)
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=n_ctx)                      # persistent host threads, one per context
+
     def run_all(k0, n):
-        th = [threading.Thread(target=run, args=(c, k0, n)) for c in ctxs]
-        for t in th: t.start()
-        for t in th: t.join()
+        if n_ctx == 1:
+            run(ctxs[0], k0, n)
+        else:
+            list(pool.map(lambda c: run(c, k0, n), ctxs))
 
     if codec_only:
         h2d = S * (3 * 84 * 4 + 3 * 80 * 4); d2h = S * (3 * 80 * 4 + 3 * 84 * 4)
@@ -378,6 +389,7 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    pool.shutdown()
     for c in ctxs:
         if "link" in c: c["link"].close()
         c["b"].close()
@@ -395,7 +407,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-contexts", type=int, default=2, help="host threads / contexts serving the streams in the e2e leg")
+    ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

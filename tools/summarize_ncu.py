@@ -39,6 +39,7 @@ KEYS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_active.avg", "smsp__inst_executed.sum")
+traffic = {}
 for fn in sorted(os.listdir(GO)):
     if not (fn.endswith(f"_{tag}.ncu-rep") and fn.startswith("prof_")):
         continue
@@ -51,9 +52,13 @@ for fn in sorted(os.listdir(GO)):
     with open(os.path.join(OUT, f"{tag}_{kname}_ncu_full.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kname} -s 20 -c 1  python bench.py --steps 3 --warmup 3\n")
         if len(rr) > 2:
+            tb = 0.0
             for h, u, v in zip(rr[0], rr[1], rr[2]):
                 if h in KEYS or h == "Kernel Name":
                     f.write(f"{h:80s} {u:14s} {v}\n")
+                if h in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tb += float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+            traffic[kname] = tb
         if len(sr) > 2:
             hdr, data = sr[1], sr[2:]
             isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
@@ -75,4 +80,8 @@ for fn in sorted(os.listdir(GO)):
             f.write("\n# hottest SASS lines\n")
             for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:12]:
                 f.write(f"{r[isamp]:>6s} {r[iex]:>9s}  {r[isrc][:110]}\n")
+import json
+if traffic:
+    json.dump({"how": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, bench.py default workload (1024 streams)",
+               "bytes_per_launch": traffic}, open(os.path.join(OUT, f"{tag}_traffic.json"), "w"), indent=1)
 print("written:", sorted(os.listdir(OUT)))
