@@ -69,6 +69,16 @@ int reset_state(rade_batch *b) {
   return 0;
 }
 
+// Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host buffer, or nullptr for pageable memory.
+// With an alias the big sample buffers are read / written by the kernels directly over PCIe (no staging copy, the
+// transfer overlaps the compute of the other CTAs); pageable buffers take the cudaMemcpyAsync path.
+void *pinned_alias(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
+  cudaGetLastError();
+  return nullptr;
+}
+
 int ensure_core_staging(rade_batch *b, size_t floats) {
   if (floats <= b->core_cap) return 0;
   if (b->d_core_in) { cudaFree(b->d_core_in); cudaFree(b->d_core_out); }
@@ -107,6 +117,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   b->d_core_in = b->d_core_out = nullptr;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
   b->prof.stream = b->stream;
+  if (core_codec_init_device() < 0 || rx_dsp_init_device() < 0) { delete b; return nullptr; }
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   DspTablesHost th; dsp_tables_host(th);
@@ -235,8 +246,12 @@ RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *feat
   // cudaHostRegister), staged by the driver when they are pageable
   const size_t S = b->S;
   CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, features_in, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-  if (rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0) return -1;
-  CUDA_CHECK(cudaMemcpyAsync(tx_out, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  if (void *alias = pinned_alias(tx_out)) {            // modulator writes the samples straight into the caller's pinned buffer
+    if (rade_b200_tx_dev(b, (RADE_COMP *)alias, b->d_feat_in) < 0) return -1;
+  } else {
+    if (rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0) return -1;
+    CUDA_CHECK(cudaMemcpyAsync(tx_out, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  }
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return RADE_NMF;
 }
@@ -351,9 +366,10 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx) {
   cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
-  CUDA_CHECK(cudaMemcpyAsync(b->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
-  if (rade_b200_channel_dev(b, (RADE_COMP *)b->d_rx_in, (const RADE_COMP *)b->d_tx) < 0) return -1;
-  CUDA_CHECK(cudaMemcpyAsync(rx, b->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  const void *src = pinned_alias(tx); void *dst = pinned_alias(rx);
+  if (!src) { CUDA_CHECK(cudaMemcpyAsync(b->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, b->stream)); src = b->d_tx; }
+  if (rade_b200_channel_dev(b, (RADE_COMP *)(dst ? dst : (void *)b->d_rx_in), (const RADE_COMP *)src) < 0) return -1;
+  if (!dst) CUDA_CHECK(cudaMemcpyAsync(rx, b->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return 0;
 }
@@ -435,9 +451,11 @@ RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out
     h->rd[s] += n;
   }
   const size_t Sz = S;
-  CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, h->rx_in, Sz * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream));
+  // the gathered samples sit in our own pinned buffer: the band-pass kernel reads them in place over PCIe
+  const void *rx_alias = pinned_alias(h->rx_in);
+  if (!rx_alias) { CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, h->rx_in, Sz * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream)); rx_alias = b->d_rx_in; }
   CUDA_CHECK(cudaMemcpyAsync(b->d_active, h->active, Sz, cudaMemcpyHostToDevice, b->stream));
-  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)b->d_rx_in, b->d_active) < 0) return -1;
+  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)rx_alias, b->d_active) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(features_out, b->d_feat_out, Sz * RADE_NFEAT * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaMemcpyAsync(ret, b->d_ret, Sz * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   if (eoo_out) CUDA_CHECK(cudaMemcpyAsync(eoo_out, b->rx.eoo, Sz * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));

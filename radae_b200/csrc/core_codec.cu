@@ -543,13 +543,15 @@ static int core_tile_streams(int S) {
   if (e && (atoi(e) == 8 || atoi(e) == 16)) return atoi(e);
   return ((S + 15) / 16 >= 148) ? 16 : 8;
 }
+// per-device kernel attributes (opt-in to > 48 KB dynamic shared memory); called by rade_b200_open on its device
+int core_codec_init_device() {
+  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
+  return 0;
+}
+
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                         const uint8_t *active, int S, int T, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-    attr_set = true;
-  }
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   core_encoder_kernel<<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem), stream>>>(W, state, in, in_mode, z, active, S, T, ts);
@@ -559,11 +561,6 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
 
 int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
                         int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
-    attr_set = true;
-  }
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   core_decoder_kernel<<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T, ts);

@@ -74,3 +74,6 @@ struct Profiler {
   void end(int k) { if (on) rec(k); }
   void rec(int k) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); ev[k].push_back(e); }
 };
+
+int core_codec_init_device();
+int rx_dsp_init_device();
