@@ -14,7 +14,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
-    return lambda name: np.load(os.path.join(GOLDEN, name + ".npz"))
+
+    def load(name):
+        d = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+        if "rx_in_int16" in d:          # off-air recording: int16 -> (x, 0) complex, unscaled (int16tof32.py --zeropad)
+            d["rx_in"] = d["rx_in_int16"].astype(np.float32).astype(np.complex64)
+        return d
+    return load
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -9,7 +9,7 @@ import pytest
 from gpu_util import need_gpu, relrms
 
 pytestmark = pytest.mark.gpu
-SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus"]
+SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso"]
 
 
 def run_single(g):

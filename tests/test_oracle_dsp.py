@@ -5,7 +5,7 @@ import pytest
 from oracle import dsp as od
 from oracle.core import CoreOraclePort
 
-SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus"]
+SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso"]
 
 
 def relrms(a, b):

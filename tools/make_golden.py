@@ -153,13 +153,23 @@ def main():
         "slip_plus":  dict(seed=14, EbNodB=20.0, freq_offset=5.0, lead=od.NMF + 424, n_mf=36, resample=0.995),
         "slip_minus": dict(seed=15, EbNodB=20.0, freq_offset=-3.0, lead=od.NMF + 944, n_mf=36, resample=1.005),
     }
+    # a real off-air RADE V1 recording shipped with the reference (8 kHz s16); fed the way the
+    # reference's ctest does: int16 -> (x, 0) complex, unscaled (int16tof32.py --zeropad, CMakeLists.txt:400-406)
+    import wave
+    with wave.open(os.path.join(refenv.REF, "wav/long_qso.wav")) as w:
+        assert w.getframerate() == 8000 and w.getnchannels() == 1 and w.getsampwidth() == 2
+        offair = np.frombuffer(w.readframes(12 * 8000), np.int16).copy()
+    scenarios["offair_long_qso"] = dict(offair=True)
     for name, scn in scenarios.items():
-        n_mf = scn["n_mf"]
-        feats = synth_features(1, 12 * n_mf, seed=100 + scn["seed"])
-        enc = CoreOracleRef("int8", 1)
-        z_all = enc.encode(pack_enc_input(feats))[0].reshape(n_mf, 240)
-        frames = [od.transmitter_one(z_all[i]) for i in range(n_mf)]
-        rx_in = make_rx_input(scn, frames, od.eoo_frame(bits))
+        if scn.get("offair"):
+            rx_in = offair.astype(np.float32).astype(np.complex64)
+        else:
+            n_mf = scn["n_mf"]
+            feats = synth_features(1, 12 * n_mf, seed=100 + scn["seed"])
+            enc = CoreOracleRef("int8", 1)
+            z_all = enc.encode(pack_enc_input(feats))[0].reshape(n_mf, 240)
+            frames = [od.transmitter_one(z_all[i]) for i in range(n_mf)]
+            rx_in = make_rx_input(scn, frames, od.eoo_frame(bits))
         with refenv.quiet():
             rxr = radae_rxe.radae_rx(ck, bypass_dec=True, v=0)
         sched = RowSchedule()
@@ -198,7 +208,8 @@ def main():
         ber = float(np.mean(eoos[0] * bits < 0)) if eoos else -1
         print(f"{name}: calls={len(trace['ret'])} valid={n_valid} eoo={len(eoos)} eoo_ber={ber:.3f} final_state={trace['state'][-1]} "
               f"nin set={sorted(set(trace['nin']))} fmax_end={trace['fmax'][-1]:.2f}")
-        np.savez_compressed(os.path.join(GOLD, f"rx_{name}.npz"), rx_in=rx_in, eoo_bits=bits,
+        rx_store = dict(rx_in_int16=offair) if scn.get("offair") else dict(rx_in=rx_in)
+        np.savez_compressed(os.path.join(GOLD, f"rx_{name}.npz"), eoo_bits=bits, **rx_store,
                             z_hat=np.array(zs, np.float32).reshape(-1, 240), features=np.array(feats_out, np.float32).reshape(-1, 432),
                             eoo=np.array(eoos, np.float32).reshape(-1, od.N_EOO_BITS),
                             **{k: np.array(v) for k, v in trace.items()})
