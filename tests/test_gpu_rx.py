@@ -2,14 +2,39 @@
 the C ABI vs golden traces produced by the Python reference (radae_rxe.radae_rx) and vs the numpy oracle.
 
 Tolerances: nin / return code / state / tmax / uw_errors bit exact; fmax 1e-6 Hz; z_hat (PSK symbols) 1e-5 relative
-RMS; features: identical decoder arithmetic, so the same z_hat gives the same features — compared at 1e-4 RMS after
-the symbol-level differences pass through the int8 decoder (occasional quantisation flips)."""
+RMS.  Features: the decoder arithmetic is bit-identical to the reference C path (the golden z_hat pushed through the
+CUDA decoder reproduces the golden features EXACTLY — asserted below), so feature differences can only come from the
+~5e-7 relative fp32 re-association differences in z_hat flipping one floor(.5+127x) quantisation somewhere in the
+recurrent decoder.  Until the first such flip the features are identical; after it they stay within a few 1e-3 (one
+int8 step through the decoder gains) and the perturbation decays.  Asserted: exact-decoder check, most frames < 1e-6,
+every frame < 0.02 RMS, whole run < 5e-3 RMS (the reference's own C-vs-Python bar is |delta loss| < 0.01)."""
 import numpy as np
 import pytest
 from gpu_util import need_gpu, relrms
 
 pytestmark = pytest.mark.gpu
 SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso"]
+
+
+def check_features(feats, g, name=""):
+    """see module docstring"""
+    from radae_b200 import RadeBatch
+    ref = g["features"]
+    assert feats.shape == ref.shape, name
+    if len(ref) == 0:
+        return
+    per = np.sqrt(np.mean((feats - ref) ** 2, axis=1))
+    assert per.max() < 0.02, (name, per.max())
+    assert np.sqrt(np.mean(per ** 2)) < 5e-3, name
+    first_flip = int(np.argmax(per > 1e-6)) if (per > 1e-6).any() else len(per)
+    assert first_flip >= min(8, len(per)), (name, first_flip)          # identical for at least the first second
+    # decoder parity proper: golden z_hat -> CUDA decoder == golden features, bit for bit (fresh decoder state at the
+    # first valid frame, exactly like the golden run whose C decoder started from rade_init_decoder)
+    b = RadeBatch(1)
+    out = b.core_decode(g["z_hat"].reshape(1, -1, 80))[0].reshape(-1, 12, 21)
+    api = np.zeros((out.shape[0], 12, 36), np.float32); api[:, :, :20] = out[:, :, :20]
+    assert np.array_equal(api.reshape(-1, 432), ref), name
+    b.close()
 
 
 def run_single(g):
@@ -38,8 +63,7 @@ def test_rade_rx_single_stream_vs_reference_golden(golden, name):
     assert np.array_equal(np.array(tr["nin"]), g["nin"])
     assert np.array_equal(np.array(tr["ret"]), g["ret"])
     assert np.array_equal(np.array(tr["sync"]), (g["state"] == 2).astype(int))
-    assert feats.shape == g["features"].shape
-    assert np.sqrt(np.mean((feats - g["features"]) ** 2)) < 1e-4
+    check_features(feats, g, name)
     if len(eoos):
         assert np.max(np.abs(eoos - g["eoo"])) < 1e-3
 
@@ -83,7 +107,7 @@ def test_batched_rx_mixed_states_vs_golden(golden):
         assert np.max(np.abs(np.array(tr[s]["fmax"]) - g["fmax"])) < 1e-6, SCENARIOS[s]
         assert np.max(np.abs(np.array(tr[s]["snr"]) - g["snr"])) < 1e-2, SCENARIOS[s]
         assert relrms(np.array(zs[s]), g["z_hat"]) < 1e-5, SCENARIOS[s]
-        assert np.sqrt(np.mean((np.array(fs[s]) - g["features"]) ** 2)) < 1e-4, SCENARIOS[s]
+        check_features(np.array(fs[s]).reshape(-1, 432), g, SCENARIOS[s])
     b.close()
 
 
@@ -148,5 +172,6 @@ def test_hostlink_fifo_feeds_the_same_call_sequence(golden):
         assert n >= n_push - 2
         assert np.array_equal(np.array(rets[s]), g["ret"][:n]), SCENARIOS[s]
         nf = len(feats[s])
-        assert np.sqrt(np.mean((np.array(feats[s]) - g["features"][:nf]) ** 2)) < 1e-4
+        per = np.sqrt(np.mean((np.array(feats[s]).reshape(nf, 432) - g["features"][:nf]) ** 2, axis=1)) if nf else np.zeros(0)
+        assert per.size == 0 or (per.max() < 0.02 and np.sqrt(np.mean(per ** 2)) < 5e-3), SCENARIOS[s]
     link.close(); b.close()
