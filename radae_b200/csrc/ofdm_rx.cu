@@ -34,6 +34,18 @@ __device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
 // frequencies +-2.5k Hz, k = 6*kg .. 6*kg+5:  D(+-f_k) = A_k +- j B_k with A_k = sum_n y[n] cos(w_k n), B_k = sum_n y[n] sin(w_k n),
 // y[n] = x[n] p[n]  (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; p_w = exp(j w n) p there).
 // One (cos, sin) pair serves the +f and -f grid points: 4 FMAs per tap per pair instead of 8.
+// Blackwell packed fp32: one FFMA2 does two independent IEEE FMAs on a register pair (SASS FFMA2 .F32x2)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                     rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+// complex product with two packed FMAs: x*p = x.x*(p.x, p.y) + x.y*(-p.y, p.x)
+__device__ __forceinline__ float2 cmul2(float2 x, float2 p) {
+  return ffma2(splat(x.x), p, ffma2(splat(x.y), make_float2(-p.y, p.x), make_float2(0.f, 0.f)));
+}
 __device__ __forceinline__ void corr6(float2 (&A0)[6], float2 (&B0)[6], float2 (&A1)[6], float2 (&B1)[6], const float2 *x0,
                                       const float2 *x1, const float2 *ps, const float2 (*cs)[RADE_CSK], int kg) {
 #pragma unroll
@@ -41,19 +53,15 @@ __device__ __forceinline__ void corr6(float2 (&A0)[6], float2 (&B0)[6], float2 (
 #pragma unroll 2
   for (int n = 0; n < RADE_M; n++) {
     const float2 pn = ps[n];
-    const float2 y0 = cmul(x0[n], pn), y1 = cmul(x1[n], pn);
+    const float2 y0 = cmul2(x0[n], pn), y1 = cmul2(x1[n], pn);
     const float4 *t = reinterpret_cast<const float4 *>(&cs[n][kg * 6]);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const float4 q = t[j];                       // (cos_k, sin_k, cos_k+1, sin_k+1)
-      A0[2 * j].x = fmaf(y0.x, q.x, A0[2 * j].x); A0[2 * j].y = fmaf(y0.y, q.x, A0[2 * j].y);
-      B0[2 * j].x = fmaf(y0.x, q.y, B0[2 * j].x); B0[2 * j].y = fmaf(y0.y, q.y, B0[2 * j].y);
-      A0[2 * j + 1].x = fmaf(y0.x, q.z, A0[2 * j + 1].x); A0[2 * j + 1].y = fmaf(y0.y, q.z, A0[2 * j + 1].y);
-      B0[2 * j + 1].x = fmaf(y0.x, q.w, B0[2 * j + 1].x); B0[2 * j + 1].y = fmaf(y0.y, q.w, B0[2 * j + 1].y);
-      A1[2 * j].x = fmaf(y1.x, q.x, A1[2 * j].x); A1[2 * j].y = fmaf(y1.y, q.x, A1[2 * j].y);
-      B1[2 * j].x = fmaf(y1.x, q.y, B1[2 * j].x); B1[2 * j].y = fmaf(y1.y, q.y, B1[2 * j].y);
-      A1[2 * j + 1].x = fmaf(y1.x, q.z, A1[2 * j + 1].x); A1[2 * j + 1].y = fmaf(y1.y, q.z, A1[2 * j + 1].y);
-      B1[2 * j + 1].x = fmaf(y1.x, q.w, B1[2 * j + 1].x); B1[2 * j + 1].y = fmaf(y1.y, q.w, B1[2 * j + 1].y);
+      A0[2 * j] = ffma2(y0, splat(q.x), A0[2 * j]);         B0[2 * j] = ffma2(y0, splat(q.y), B0[2 * j]);
+      A0[2 * j + 1] = ffma2(y0, splat(q.z), A0[2 * j + 1]); B0[2 * j + 1] = ffma2(y0, splat(q.w), B0[2 * j + 1]);
+      A1[2 * j] = ffma2(y1, splat(q.x), A1[2 * j]);         B1[2 * j] = ffma2(y1, splat(q.y), B1[2 * j]);
+      A1[2 * j + 1] = ffma2(y1, splat(q.z), A1[2 * j + 1]); B1[2 * j + 1] = ffma2(y1, splat(q.w), B1[2 * j + 1]);
     }
   }
 }
@@ -206,8 +214,11 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
   }
 }
 
+// named barrier for a sub-group of the CTA's warps (n threads, multiple of 32)
+__device__ __forceinline__ void group_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 // ================================================================= fine timing / frequency refinement (shared by track & finish)
-constexpr int REF_CH = 21;        // frequencies per chunk
+constexpr int REF_CH = 11;        // frequencies per chunk
 constexpr int REF_NT = 16;        // max timing offsets
 struct RefineSmem {
   double2 vtab[REF_CH][RADE_M];   // conj(p[n]) * exp(-j w n)
@@ -223,9 +234,9 @@ struct RefineSmem {
 __device__ __forceinline__ int arange_len(double start, double stop, double step) { return (int)ceil((stop - start) / step); }
 
 // searches t in [t_lo, t_lo+nt) x f in arange(f_start, f_stop, f_step); result in sm.best_* (best_found == 0: nothing beat 0)
+// Executed by a group of `nthr` threads (`tid` = index within the group) that synchronise on named barrier `bar`.
 __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *rg, int head, int t_lo, int nt,
-                             double f_start, double f_stop, double f_step) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+                             double f_start, double f_stop, double f_step, int tid, int nthr, int bar) {
   const int nf = arange_len(f_start, f_stop, f_step);
   const double delta = (f_start + f_step) - f_start;
   if (tid == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
@@ -236,7 +247,7 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
   }
   for (int c0 = 0; c0 < nf; c0 += REF_CH) {
     const int nfc = min(REF_CH, nf - c0);
-    __syncthreads();
+    group_sync(bar, nthr);
     for (int idx = tid; idx < nfc * (RADE_M / 8); idx += nthr) {
       // 8 consecutive taps of one frequency: exp(-j w n0) by sincos, then 7 rotations by exp(-j w) (|error| ~ 1e-15)
       const int fi = idx / (RADE_M / 8), n0 = (idx % (RADE_M / 8)) * 8;
@@ -251,17 +262,20 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
         e = dcmul(e, step);
       }
     }
-    __syncthreads();
+    group_sync(bar, nthr);
     for (int item = tid; item < nfc * nt * 2; item += nthr) {
       const int half = item & 1, ti = (item >> 1) % nt, fi = (item >> 1) / nt;
       const double2 *r = half ? sm.rb : sm.ra;
-      double ax = 0.0, ay = 0.0;
-#pragma unroll 4
-      for (int n = 0; n < RADE_M; n++) {
-        const double2 v = sm.vtab[fi][n], x = r[ti + n];
+      double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;      // two partial sums per component: halves the FMA dependency chain
+#pragma unroll 2
+      for (int n = 0; n < RADE_M; n += 2) {
+        const double2 v = sm.vtab[fi][n], x = r[ti + n], v2 = sm.vtab[fi][n + 1], x2 = r[ti + n + 1];
         ax = fma(x.x, v.x, ax); ax = fma(-x.y, v.y, ax);
         ay = fma(x.x, v.y, ay); ay = fma(x.y, v.x, ay);
+        bx = fma(x2.x, v2.x, bx); bx = fma(-x2.y, v2.y, bx);
+        by = fma(x2.x, v2.y, by); by = fma(x2.y, v2.x, by);
       }
+      ax += bx; ay += by;
       if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
         const double f = f_start + (double)(c0 + fi) * delta;
         double sn, cs; sincos(2.0 * M_PI * f / RADE_FS * (double)RADE_NMF, &sn, &cs);
@@ -269,7 +283,7 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
         sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y);
       } else sm.d1[fi][ti] = make_float2((float)ax, (float)ay);
     }
-    __syncthreads();
+    group_sync(bar, nthr);
     float bm = -1.f; int bo = 0x7fffffff;
     for (int k = tid; k < nfc * nt; k += nthr) {
       const int fi = k / nt, ti = k % nt;
@@ -284,7 +298,7 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
       if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
     }
     if ((tid & 31) == 0) { sm.red_mag[tid >> 5] = bm; sm.red_ord[tid >> 5] = bo; }
-    __syncthreads();
+    group_sync(bar, nthr);
     if (tid == 0) {
       for (int i = 1; i < (nthr >> 5); i++)
         if (sm.red_mag[i] > bm || (sm.red_mag[i] == bm && sm.red_ord[i] < bo)) { bm = sm.red_mag[i]; bo = sm.red_ord[i]; }
@@ -295,7 +309,7 @@ __device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *r
       }
     }
   }
-  __syncthreads();
+  group_sync(bar, nthr);
 }
 
 // sigma_r = (mean|Dt1| + mean|Dt2|) / (2*sqrt(pi/2)) from the row sums, float32 like the reference's np.mean
@@ -310,19 +324,21 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 
 // ================================================================= sync-state tracking: refine + check_pilots + slips
 constexpr int CHK_SPAN = 20 * (RADE_NUPDATE - 1) + RADE_M + 20;     // samples covered by the 48 refreshed rows of one half (1120)
-struct CheckSmem {                 // aliases RefineSmem once the refine is done
+struct CheckSmem {
   alignas(16) float2 cs[RADE_M][RADE_CSK];
   float2 ps[RADE_M];
   float2 rx[2][CHK_SPAN];
 };
 struct TrackSmem {
-  union { RefineSmem ref; CheckSmem chk; };
+  RefineSmem ref;                  // warps 6-9
+  CheckSmem chk;                   // warps 0-5
   float part[5][RADE_NUPDATE * 2];
   float scratch[32];
   double spot[4];
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int TRACK_THREADS = 320;                // warps 0-5: row refresh (192 threads), warps 6-9: refine (128 threads)
+__global__ void __launch_bounds__(TRACK_THREADS)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
                 int *__restrict__ uw_errors, const unsigned char *__restrict__ active) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -335,48 +351,50 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   const float2 *rg = ring + (size_t)s * RADE_RXBUF;
   float *rs = rowsum + (size_t)s * 2 * RADE_NMF;
 
-  // ---- refine: t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, 0.1)   (radae_rxe.py:202-205)
+  // Two independent jobs run CONCURRENTLY on disjoint warp groups (they only meet at the __syncthreads below):
+  //   warps 6-9: refine — t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, 0.1), complex128   (radae_rxe.py:202-205)
+  //   warps 0-5: check_pilots' refresh of 48 rows of the |Dt| row sums (deterministic schedule, radae/dsp.py:288-295)
   const int tmax0 = c.tmax; const double fmax0 = c.fmax;
-  const int t_lo = max(0, tmax0 - 8);
-  refine_block(sm.ref, T, rg, head, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1);
+  const int rot = c.n_check % 20;
+  if (tid >= 192) {
+    const int t_lo = max(0, tmax0 - 8);
+    refine_block(sm.ref, T, rg, head, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1, tid - 192, TRACK_THREADS - 192, 1);
+  } else {
+    // rows t_i = 20 i + rot (both pilot positions): 96 (row, half) x 40 grid frequencies x 160-tap complex correlations,
+    // staged through shared memory ((cos, sin) table + the 1120-sample span the rows cover), corr6 register tiling
+    for (int i = tid; i < RADE_M * RADE_CSK; i += 192) (&sm.chk.cs[0][0])[i] = T.cs_tab[i];
+    for (int i = tid; i < RADE_M; i += 192) sm.chk.ps[i] = T.p[i];
+    for (int i = tid; i < 2 * CHK_SPAN; i += 192) {
+      const int half = i / CHK_SPAN, k = i % CHK_SPAN;
+      const int li = rot + k + half * RADE_NMF;
+      sm.chk.rx[half][k] = (li < RADE_RXBUF) ? cconj(rg[ring_idx(head, li)]) : make_float2(0.f, 0.f);
+    }
+    group_sync(2, 192);
+    {
+      // thread = (row i, k group kg): both pilot positions of row i x 6 (cos, sin) pairs = up to 12 grid frequencies each
+      const int i = tid >> 2, kg = tid & 3;
+      float2 A0[6], B0[6], A1[6], B1[6];
+      corr6(A0, B0, A1, B1, &sm.chk.rx[0][20 * i], &sm.chk.rx[1][20 * i], sm.chk.ps, sm.chk.cs, kg);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        const int k = kg * 6 + j;
+        if (k > 20) continue;
+        float p0, m0, p1, m1;
+        mags_pm(A0[j], B0[j], p0, m0); mags_pm(A1[j], B1[j], p1, m1);
+        if (k < 20) { s0 += p0; s1 += p1; }
+        if (k > 0) { s0 += m0; s1 += m1; }
+      }
+      sm.part[kg][2 * i] = s0; sm.part[kg][2 * i + 1] = s1;
+    }
+    group_sync(2, 192);
+    if (tid < RADE_NUPDATE * 2)
+      rs[(tid & 1) * RADE_NMF + 20 * (tid >> 1) + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
+  }
+  __syncthreads();
   int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
   const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
   const double fmax = 0.9 * fmax0 + 0.1 * fhat;
-
-  // ---- check_pilots: refresh 48 rows of the |Dt| row sums (deterministic schedule), thresholds, spot correlations
-  // rows t_i = 20 i + rot (both pilot positions): 96 (row, half) x 40 frequencies x 160-tap complex correlations, staged
-  // through shared memory (p_w table + the 1120-sample span the rows cover) and register-tiled 1 x 20 per thread
-  const int rot = c.n_check % 20;
-  __syncthreads();                                   // everyone is done with sm.ref before it is overwritten
-  for (int i = tid; i < RADE_M * RADE_CSK; i += blockDim.x) (&sm.chk.cs[0][0])[i] = T.cs_tab[i];
-  for (int i = tid; i < RADE_M; i += blockDim.x) sm.chk.ps[i] = T.p[i];
-  for (int i = tid; i < 2 * CHK_SPAN; i += blockDim.x) {
-    const int half = i / CHK_SPAN, k = i % CHK_SPAN;
-    const int li = rot + k + half * RADE_NMF;
-    sm.chk.rx[half][k] = (li < RADE_RXBUF) ? cconj(rg[ring_idx(head, li)]) : make_float2(0.f, 0.f);
-  }
-  __syncthreads();
-  if (tid < RADE_NUPDATE * 4) {
-    // thread = (row i, k group kg): both pilot positions of row i x 6 (cos, sin) pairs = up to 12 grid frequencies each
-    const int i = tid >> 2, kg = tid & 3;
-    float2 A0[6], B0[6], A1[6], B1[6];
-    corr6(A0, B0, A1, B1, &sm.chk.rx[0][20 * i], &sm.chk.rx[1][20 * i], sm.chk.ps, sm.chk.cs, kg);
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      const int k = kg * 6 + j;
-      if (k > 20) continue;
-      float p0, m0, p1, m1;
-      mags_pm(A0[j], B0[j], p0, m0); mags_pm(A1[j], B1[j], p1, m1);
-      if (k < 20) { s0 += p0; s1 += p1; }
-      if (k > 0) { s0 += m0; s1 += m1; }
-    }
-    sm.part[kg][2 * i] = s0; sm.part[kg][2 * i + 1] = s1;
-  }
-  __syncthreads();
-  if (tid < RADE_NUPDATE * 2)
-    rs[(tid & 1) * RADE_NMF + 20 * (tid >> 1) + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
-  __syncthreads();
   const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);
   // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
   {
@@ -595,7 +613,7 @@ rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
     // first fix after acquisition: t in [max(0,tmax-1), tmax+2), f in arange(fmax-10, fmax+10, 0.25)  (radae_rxe.py:267-273)
     const int tm = c.tmax; const double fm = c.fmax;
     const int t_lo = max(0, tm - 1);
-    refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25);
+    refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, blockDim.x, 1);
     if (tid == 0) {
       if (sm.ref.best_found) { c.tmax = sm.ref.best_t; c.fmax = sm.ref.best_f; }
       c.fmax += c.foff_err; c.foff_err = 0.0;
@@ -647,7 +665,7 @@ int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, c
   int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > 148 * 3) det_grid = 148 * 3;
   rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, B.search_count);
   prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
-  rx_track_kernel<<<S, 256, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
+  rx_track_kernel<<<S, TRACK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
   prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
