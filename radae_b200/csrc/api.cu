@@ -55,7 +55,8 @@ int reset_state(rade_batch *b) {
   CUDA_CHECK(cudaMemsetAsync(b->rx.z_hat, 0, sizeof(float) * 240 * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->rx.eoo, 0, sizeof(float) * RADE_NEOO_BITS * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->rx.dec_active, 0, S, b->stream));
-  CUDA_CHECK(cudaMemsetAsync(b->rx.search_count, 0, 2 * sizeof(int), b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->rx.counters, 0, 8 * sizeof(int), b->stream));
+  b->rx.parity = 0;
   CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->link_wr, 0, sizeof(long long) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->link_rd, 0, sizeof(long long) * S, b->stream));
@@ -136,7 +137,8 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   bad |= dalloc(b, &b->rx.dec_active, S);
   bad |= dalloc(b, &b->rx.nin, S);
   bad |= dalloc(b, &b->rx.search_list, S);
-  bad |= dalloc(b, &b->rx.search_count, 2);
+  bad |= dalloc(b, &b->rx.track_list, S);
+  bad |= dalloc(b, &b->rx.counters, 8);
   bad |= dalloc(b, &b->chan_state, S);
   bad |= dalloc(b, &b->link_ring, S * LINK_CAP);
   bad |= dalloc(b, &b->link_wr, S);

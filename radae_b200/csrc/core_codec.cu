@@ -24,6 +24,7 @@
 // Per-stream HBM state: GRU h (fp32) + int8 concat of step t-1 (and t-2 for the encoder's dilation-2 convs).
 #include "rade_common.h"
 #include "rade_host.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -51,31 +52,6 @@ __device__ __forceinline__ int8_t quant8(float x) {
 }
 __device__ __forceinline__ float lin(int acc, float scale, float bias) {
   return __fadd_rn(__fmul_rn((float)acc, scale), bias);
-}
-
-// ---------------------------------------------------------------- mbarrier / TMA bulk copy primitives
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (long long spin = 0; !done; spin++) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (spin > (1ll << 26)) { printf("libradae_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
-}
-// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` as a byte count
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 struct PipeSmem {
@@ -276,7 +252,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
   if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
     for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
   if (!sm.any_active) return;
@@ -410,7 +386,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
     for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
   if (!sm.any_active) return;

@@ -17,6 +17,7 @@
 //   rx_bpf -> rx_detect (search/candidate streams) -> rx_track (sync streams) -> rx_demod (sync streams) -> rx_finish
 #include "rade_common.h"
 #include "rade_host.h"
+#include "tma.cuh"
 
 namespace {
 
@@ -30,9 +31,9 @@ __device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
   acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
 }
-// Coarse-grid correlations for two sample windows x0, x1 (already conjugated) against the pilot p shifted to the grid
+// Coarse-grid correlations for two sample windows x0, x1 against the pilot p shifted to the grid
 // frequencies +-2.5k Hz, k = 6*kg .. 6*kg+5:  D(+-f_k) = A_k +- j B_k with A_k = sum_n y[n] cos(w_k n), B_k = sum_n y[n] sin(w_k n),
-// y[n] = x[n] p[n]  (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; p_w = exp(j w n) p there).
+// y[n] = conj(x[n]) p[n]  (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; p_w = exp(j w n) p there).
 // One (cos, sin) pair serves the +f and -f grid points: 4 FMAs per tap per pair instead of 8.
 // Blackwell packed fp32: one FFMA2 does two independent IEEE FMAs on a register pair (SASS FFMA2 .F32x2)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -42,18 +43,16 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2 *>(&rd);
 }
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
-// complex product with two packed FMAs: x*p = x.x*(p.x, p.y) + x.y*(-p.y, p.x)
-__device__ __forceinline__ float2 cmul2(float2 x, float2 p) {
-  return ffma2(splat(x.x), p, ffma2(splat(x.y), make_float2(-p.y, p.x), make_float2(0.f, 0.f)));
-}
 __device__ __forceinline__ void corr6(float2 (&A0)[6], float2 (&B0)[6], float2 (&A1)[6], float2 (&B1)[6], const float2 *x0,
-                                      const float2 *x1, const float2 *ps, const float2 (*cs)[RADE_CSK], int kg) {
+                                      const float2 *x1, const float4 *ps4, const float2 (*cs)[RADE_CSK], int kg) {
 #pragma unroll
   for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
 #pragma unroll 2
   for (int n = 0; n < RADE_M; n++) {
-    const float2 pn = ps[n];
-    const float2 y0 = cmul2(x0[n], pn), y1 = cmul2(x1[n], pn);
+    const float4 pp = ps4[n];                      // (p.x, p.y, p.y, -p.x): y = conj(x) p with two packed FMAs
+    const float2 a = x0[n], c = x1[n];
+    const float2 y0 = ffma2(splat(a.x), make_float2(pp.x, pp.y), ffma2(splat(a.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
+    const float2 y1 = ffma2(splat(c.x), make_float2(pp.x, pp.y), ffma2(splat(c.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
     const float4 *t = reinterpret_cast<const float4 *>(&cs[n][kg * 6]);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -94,7 +93,7 @@ __device__ float block_sum(float v, float *scratch) {
 __global__ void __launch_bounds__(256)
 rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, float2 *__restrict__ bpf_mem,
               const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en,
-              int *__restrict__ search_list, int *__restrict__ search_count) {
+              int *__restrict__ search_list, int *__restrict__ track_list, int *__restrict__ counters) {
   __shared__ float2 X[RADE_BPF_MEM + RADE_NIN_MAX];
   __shared__ float h[RADE_BPF_NTAP];
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -131,7 +130,8 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
     c.ring_head = nh;                      // logical sample 0 of rx_buf now lives at ring[nh]
     c.detect_key = 0ull;
     c.candidate = 0; c.endofover = 0; c.valid_output = 0; c.uw_fail = 0; c.ran_sync = 0; c.ret = 0;
-    if (c.state != ST_SYNC) search_list[atomicAdd(&search_count[0], 1)] = s;     // work list for rx_detect_kernel
+    if (c.state != ST_SYNC) search_list[atomicAdd(&counters[0], 1)] = s;         // work list of rx_detect / rx_finish
+    else track_list[atomicAdd(&counters[2], 1)] = s;                              // work list of rx_track
   }
 }
 
@@ -139,29 +139,34 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
 // grid (15, S): CTA = 64 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations
 constexpr int DET_TB = 64;
 struct DetectSmem {
-  alignas(16) float2 cs[RADE_M][RADE_CSK];
-  float2 ps[RADE_M];
+  AcqTables tab;                   // one TMA bulk copy per CTA
   float2 r1[DET_TB + RADE_M];
   float2 r2[DET_TB + RADE_M];
   float part[2][4][DET_TB];
   unsigned long long best[8];
+  uint64_t tab_bar;
 };
 
 __global__ void __launch_bounds__(256)
 rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
-                 const int *__restrict__ search_list, int *__restrict__ search_count) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                 const int *__restrict__ search_list, int *__restrict__ counters) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   DetectSmem &sm = *reinterpret_cast<DetectSmem *>(smem_raw);
   __shared__ int work;
   const int tid = threadIdx.x;
-  const int n_items = search_count[0] * (RADE_NMF / DET_TB);
-  if (n_items == 0) return;                       // steady state: nobody is searching
-  for (int i = tid; i < RADE_M * RADE_CSK; i += blockDim.x) (&sm.cs[0][0])[i] = T.cs_tab[i];
-  for (int i = tid; i < RADE_M; i += blockDim.x) sm.ps[i] = T.p[i];
+  const int n_items = counters[0] * (RADE_NMF / DET_TB);
+  if ((int)blockIdx.x >= n_items) return;         // steady state: (almost) nobody is searching
+  if (tid == 0) {
+    mbar_init(&sm.tab_bar, 1); mbar_fence_init();
+    mbar_expect_tx(&sm.tab_bar, (uint32_t)sizeof(AcqTables));
+    bulk_g2s(&sm.tab, T.acq_tab, (uint32_t)sizeof(AcqTables), &sm.tab_bar);
+  }
+  __syncthreads();
+  mbar_wait(&sm.tab_bar, 0);
   // persistent CTAs pull (stream, 64-offset block) items off a device-side counter
   for (;;) {
     __syncthreads();
-    if (tid == 0) work = atomicAdd(&search_count[1], 1);
+    if (tid == 0) work = atomicAdd(&counters[1], 1);
     __syncthreads();
     const int w = work;
     if (w >= n_items) break;
@@ -170,13 +175,13 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
     const int head = c.ring_head;
     const float2 *rg = ring + (size_t)s * RADE_RXBUF;
     for (int i = tid; i < DET_TB + RADE_M; i += blockDim.x) {
-      sm.r1[i] = cconj(rg[ring_idx(head, t0 + i)]);
-      sm.r2[i] = cconj(rg[ring_idx(head, t0 + RADE_NMF + i)]);
+      sm.r1[i] = rg[ring_idx(head, t0 + i)];
+      sm.r2[i] = rg[ring_idx(head, t0 + RADE_NMF + i)];
     }
     __syncthreads();
     const int tl = tid & (DET_TB - 1), fg = tid >> 6;      // fg = k group: k = 6 fg .. 6 fg + 5
     float2 A0[6], B0[6], A1[6], B1[6];
-    corr6(A0, B0, A1, B1, &sm.r1[tl], &sm.r2[tl], sm.ps, sm.cs, fg);
+    corr6(A0, B0, A1, B1, &sm.r1[tl], &sm.r2[tl], sm.tab.ps4, sm.tab.cs, fg);
     float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = RADE_NFCOARSE;
 #pragma unroll
     for (int j = 0; j < 6; j++) {
@@ -213,9 +218,6 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
     }
   }
 }
-
-// named barrier for a sub-group of the CTA's warps (n threads, multiple of 32)
-__device__ __forceinline__ void group_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // ================================================================= fine timing / frequency refinement (shared by track & finish)
 constexpr int REF_CH = 11;        // frequencies per chunk
@@ -323,118 +325,306 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 }
 
 // ================================================================= sync-state tracking: refine + check_pilots + slips
-constexpr int CHK_SPAN = 20 * (RADE_NUPDATE - 1) + RADE_M + 20;     // samples covered by the 48 refreshed rows of one half (1120)
-struct CheckSmem {
-  alignas(16) float2 cs[RADE_M][RADE_CSK];
-  float2 ps[RADE_M];
-  float2 rx[2][CHK_SPAN];
+// Persistent kernel: one CTA per SM walks the list of streams in sync (built by rx_bpf).  The constant tables (37 KB) are
+// bulk-copied into shared memory once per CTA; a producer warp prefetches the NEXT stream's sample ring (in logical
+// order), |Dt| row sums and control block with TMA bulk copies into the other half of a double buffer while the 15
+// consumer warps work on the current one:
+//   warps 0-11  check_pilots' refresh of 48 rows of the |Dt| row sums (fp32, packed FFMA2; even/odd tap split per lane pair)
+//   warps 12-14 refine: 16 timing x 20(21) frequency x 2 pilot positions in complex128, 8 timing offsets per thread
+//               from a sliding register window (2 shared-memory loads per 32 DFMA)
+// then sigma_r, the four complex128 spot correlations, slips and the sync-state part of the state machine.
+constexpr int TRK_REFRESH = 384, TRK_REFINE = 96, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
+constexpr int TRK_NF = 21;                        // max len(np.arange(fmax-1, fmax+1, 0.1))
+constexpr int TRK_RLEN = REF_NT + RADE_M + 8;     // widened window + sliding-window over-read
+struct TrackStage {
+  alignas(128) float2 rx[RADE_RXBUF];             // rx_buf in LOGICAL order (two bulk copies around ring_head)
+  float rs[2 * RADE_NMF];                         // row sums
+  RxCtl ctl;
 };
 struct TrackSmem {
-  RefineSmem ref;                  // warps 6-9
-  CheckSmem chk;                   // warps 0-5
-  float part[5][RADE_NUPDATE * 2];
+  AcqTables tab;
+  TrackStage st[2];
+  double2 ra[TRK_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
+  double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
+  double2 rb[TRK_RLEN];                           // rx[t_lo + Nmf ...]
+  float2 d1[TRK_NF][REF_NT];
+  float2 d2[TRK_NF][REF_NT];
+  float red_mag[4]; int red_ord[4];
+  float best_mag; int best_t; int best_found; double best_f;
   float scratch[32];
   double spot[4];
+  uint64_t full[2], empty[2], tab_bar;
 };
+static_assert(sizeof(RxCtl) % 16 == 0 && sizeof(TrackStage) % 128 == 0, "bulk-copy alignment");
 
-constexpr int TRACK_THREADS = 320;                // warps 0-5: row refresh (192 threads), warps 6-9: refine (128 threads)
-__global__ void __launch_bounds__(TRACK_THREADS)
+// block-wide sum over the consumer threads (named barrier 3; the producer warp does not take part)
+__device__ float consumer_sum(float v, float *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  group_sync(3, TRK_CONSUMERS);
+  if (lane == 0) scratch[w] = v;
+  group_sync(3, TRK_CONSUMERS);
+  float t = (threadIdx.x < TRK_CONSUMERS / 32) ? scratch[threadIdx.x] : 0.f;
+  if (w == 0) { t = warp_sum(t); if (lane == 0) scratch[0] = t; }
+  group_sync(3, TRK_CONSUMERS);
+  return scratch[0];
+}
+
+__global__ void __launch_bounds__(TRK_THREADS, 1)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
-                int *__restrict__ uw_errors, const unsigned char *__restrict__ active) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                int *__restrict__ uw_errors, const int *__restrict__ track_list, const int *__restrict__ counters,
+                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
-  const int s = blockIdx.x, tid = threadIdx.x;
-  if (active && !active[s]) return;
-  RxCtl &c = ctl[s];
-  if (c.state != ST_SYNC) return;
-  const int head = c.ring_head;
-  const float2 *rg = ring + (size_t)s * RADE_RXBUF;
-  float *rs = rowsum + (size_t)s * 2 * RADE_NMF;
-
-  // Two independent jobs run CONCURRENTLY on disjoint warp groups (they only meet at the __syncthreads below):
-  //   warps 6-9: refine — t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, 0.1), complex128   (radae_rxe.py:202-205)
-  //   warps 0-5: check_pilots' refresh of 48 rows of the |Dt| row sums (deterministic schedule, radae/dsp.py:288-295)
-  const int tmax0 = c.tmax; const double fmax0 = c.fmax;
-  const int rot = c.n_check % 20;
-  if (tid >= 192) {
-    const int t_lo = max(0, tmax0 - 8);
-    refine_block(sm.ref, T, rg, head, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1, tid - 192, TRACK_THREADS - 192, 1);
-  } else {
-    // rows t_i = 20 i + rot (both pilot positions): 96 (row, half) x 40 grid frequencies x 160-tap complex correlations,
-    // staged through shared memory ((cos, sin) table + the 1120-sample span the rows cover), corr6 register tiling
-    for (int i = tid; i < RADE_M * RADE_CSK; i += 192) (&sm.chk.cs[0][0])[i] = T.cs_tab[i];
-    for (int i = tid; i < RADE_M; i += 192) sm.chk.ps[i] = T.p[i];
-    for (int i = tid; i < 2 * CHK_SPAN; i += 192) {
-      const int half = i / CHK_SPAN, k = i % CHK_SPAN;
-      const int li = rot + k + half * RADE_NMF;
-      sm.chk.rx[half][k] = (li < RADE_RXBUF) ? cconj(rg[ring_idx(head, li)]) : make_float2(0.f, 0.f);
+  const int tid = threadIdx.x;
+  const int n_items = counters[2];
+  if ((int)blockIdx.x >= n_items) return;
+  if (tid == 0) {
+    mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1); mbar_init(&sm.empty[0], 1); mbar_init(&sm.empty[1], 1);
+    mbar_init(&sm.tab_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid >= TRK_CONSUMERS) {                     // ---- producer warp: TMA prefetch, one stream ahead
+    if (tid == TRK_CONSUMERS) {
+      mbar_expect_tx(&sm.tab_bar, (uint32_t)sizeof(AcqTables));
+      bulk_g2s(&sm.tab, T.acq_tab, (uint32_t)sizeof(AcqTables), &sm.tab_bar);
+      int k = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
+        const int b = k & 1;
+        if (k >= 2) mbar_wait(&sm.empty[b], ((k >> 1) - 1) & 1);
+        const int s = track_list[it];
+        const int head = ctl[s].ring_head;        // even by construction (nin is 800 / 960 / 1120)
+        const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+        TrackStage &st = sm.st[b];
+        mbar_expect_tx(&sm.full[b], (uint32_t)(sizeof(float2) * RADE_RXBUF + sizeof(float) * 2 * RADE_NMF + sizeof(RxCtl)));
+        bulk_g2s(st.rx, rg + head, (uint32_t)(sizeof(float2) * (RADE_RXBUF - head)), &sm.full[b]);
+        if (head) bulk_g2s(st.rx + (RADE_RXBUF - head), rg, (uint32_t)(sizeof(float2) * head), &sm.full[b]);
+        bulk_g2s(st.rs, rowsum + (size_t)s * 2 * RADE_NMF, (uint32_t)(sizeof(float) * 2 * RADE_NMF), &sm.full[b]);
+        bulk_g2s(&st.ctl, ctl + s, (uint32_t)sizeof(RxCtl), &sm.full[b]);
+      }
     }
-    group_sync(2, 192);
-    {
-      // thread = (row i, k group kg): both pilot positions of row i x 6 (cos, sin) pairs = up to 12 grid frequencies each
-      const int i = tid >> 2, kg = tid & 3;
+    return;
+  }
+  mbar_wait(&sm.tab_bar, 0);
+  int k = 0;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
+    const int b = k & 1;
+    const int s = track_list[it];
+    mbar_wait(&sm.full[b], (k >> 1) & 1);
+    TrackStage &st = sm.st[b];
+    const int tmax0 = st.ctl.tmax; const double fmax0 = st.ctl.fmax;
+    const int rot = st.ctl.n_check % 20;
+    if (tid < TRK_REFRESH) {
+      // ---- check_pilots row refresh (radae/dsp.py:288-295, deterministic schedule): rows t_i = 20 i + rot, both pilot
+      // positions, 40 grid frequencies.  lane = (row i, k group kg, tap parity ks): conflict-free shared-memory reads
+      const int ks = tid & 1, kg = (tid >> 1) & 3, i = tid >> 3;
+      const float2 *x0 = st.rx + rot + 20 * i, *x1 = x0 + RADE_NMF;
       float2 A0[6], B0[6], A1[6], B1[6];
-      corr6(A0, B0, A1, B1, &sm.chk.rx[0][20 * i], &sm.chk.rx[1][20 * i], sm.chk.ps, sm.chk.cs, kg);
+#pragma unroll
+      for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
+#pragma unroll 2
+      for (int n = ks; n < RADE_M; n += 2) {
+        const float4 pp = sm.tab.ps4[n];
+        const float2 a = x0[n], c = x1[n];
+        const float2 y0 = ffma2(splat(a.x), make_float2(pp.x, pp.y), ffma2(splat(a.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
+        const float2 y1 = ffma2(splat(c.x), make_float2(pp.x, pp.y), ffma2(splat(c.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
+        const float4 *t = reinterpret_cast<const float4 *>(&sm.tab.cs[n][kg * 6]);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float4 q = t[j];
+          A0[2 * j] = ffma2(y0, splat(q.x), A0[2 * j]);         B0[2 * j] = ffma2(y0, splat(q.y), B0[2 * j]);
+          A0[2 * j + 1] = ffma2(y0, splat(q.z), A0[2 * j + 1]); B0[2 * j + 1] = ffma2(y0, splat(q.w), B0[2 * j + 1]);
+          A1[2 * j] = ffma2(y1, splat(q.x), A1[2 * j]);         B1[2 * j] = ffma2(y1, splat(q.y), B1[2 * j]);
+          A1[2 * j + 1] = ffma2(y1, splat(q.z), A1[2 * j + 1]); B1[2 * j + 1] = ffma2(y1, splat(q.w), B1[2 * j + 1]);
+        }
+      }
+      // the even-tap lane finishes k = 6 kg + {0,1,2}, the odd-tap lane k = 6 kg + {3,4,5}: swap the other three partials
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
-        const int k = kg * 6 + j;
-        if (k > 20) continue;
-        float p0, m0, p1, m1;
-        mags_pm(A0[j], B0[j], p0, m0); mags_pm(A1[j], B1[j], p1, m1);
-        if (k < 20) { s0 += p0; s1 += p1; }
-        if (k > 0) { s0 += m0; s1 += m1; }
-      }
-      sm.part[kg][2 * i] = s0; sm.part[kg][2 * i + 1] = s1;
-    }
-    group_sync(2, 192);
-    if (tid < RADE_NUPDATE * 2)
-      rs[(tid & 1) * RADE_NMF + 20 * (tid >> 1) + rot] = ((sm.part[0][tid] + sm.part[1][tid]) + sm.part[2][tid]) + sm.part[3][tid];
-  }
-  __syncthreads();
-  int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
-  const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
-  const double fmax = 0.9 * fmax0 + 0.1 * fhat;
-  const float sigma_r = sigma_r_from_rowsums(rs, sm.scratch);
-  // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
-  {
-    const int wp = tid >> 5, lane = tid & 31;
-    if (wp < 4) {
-      const int o = tmax + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
-      const float2 *q = (wp < 2) ? T.p : T.pend;
-      const double w = 2.0 * M_PI * fmax / RADE_FS;
-      double ax = 0.0, ay = 0.0;
-      for (int n = lane; n < RADE_M; n += 32) {
-        double sn, cs; sincos(w * (double)n, &sn, &cs);
-        const float2 x = rg[ring_idx(head, o + n)];
-        const double2 v = dcmul(make_double2(cs, -sn), make_double2((double)x.x, (double)x.y));     // w_vec * rx
-        const double2 r = dcmul(make_double2(v.x, -v.y), make_double2((double)q[n].x, (double)q[n].y));
-        ax += r.x; ay += r.y;
+      for (int j = 0; j < 3; j++) {
+        float2 mine[4], send[4];
+        mine[0] = ks ? A0[j + 3] : A0[j]; send[0] = ks ? A0[j] : A0[j + 3];
+        mine[1] = ks ? B0[j + 3] : B0[j]; send[1] = ks ? B0[j] : B0[j + 3];
+        mine[2] = ks ? A1[j + 3] : A1[j]; send[2] = ks ? A1[j] : A1[j + 3];
+        mine[3] = ks ? B1[j + 3] : B1[j]; send[3] = ks ? B1[j] : B1[j + 3];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          mine[q].x += __shfl_xor_sync(0xffffffffu, send[q].x, 1);
+          mine[q].y += __shfl_xor_sync(0xffffffffu, send[q].y, 1);
+        }
+        const int kk = kg * 6 + ks * 3 + j;
+        if (kk <= 20) {
+          float p0, m0, p1, m1;
+          mags_pm(mine[0], mine[1], p0, m0); mags_pm(mine[2], mine[3], p1, m1);
+          if (kk < 20) { s0 += p0; s1 += p1; }
+          if (kk > 0) { s0 += m0; s1 += m1; }
+        }
       }
 #pragma unroll
-      for (int k = 16; k > 0; k >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, k); ay += __shfl_xor_sync(0xffffffffu, ay, k); }
-      if (lane == 0) sm.spot[wp] = hypot(ax, ay);
+      for (int o = 1; o < 8; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+      if ((tid & 7) == 0) {
+        const int r = 20 * i + rot;
+        st.rs[r] = s0; st.rs[RADE_NMF + r] = s1;
+        float *rs = rowsum + (size_t)s * 2 * RADE_NMF;
+        rs[r] = s0; rs[RADE_NMF + r] = s1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.rs is overwritten by a bulk copy two streams later
+      }
+    } else {
+      // ---- refine (radae_rxe.py:202-205, radae/dsp.py:233-270): t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, .1)
+      const int g = tid - TRK_REFRESH;
+      const int t_lo = max(0, tmax0 - 8), nt = tmax0 + 8 - t_lo;
+      const double f_start = fmax0 - 1, f_stop = fmax0 + 1, f_step = 0.1;
+      const int nf = min(arange_len(f_start, f_stop, f_step), TRK_NF);
+      const double delta = (f_start + f_step) - f_start;
+      if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
+      for (int i2 = g; i2 < TRK_RLEN; i2 += TRK_REFINE) {
+        const bool in = i2 < nt + RADE_M;
+        const float2 a = in ? st.rx[t_lo + i2] : make_float2(0.f, 0.f), c = in ? st.rx[t_lo + RADE_NMF + i2] : make_float2(0.f, 0.f);
+        sm.ra[i2] = make_double2((double)a.x, (double)a.y);
+        sm.rb[i2] = make_double2((double)c.x, (double)c.y);
+      }
+      group_sync(1, TRK_REFINE);
+      for (int task = g; task < nf * 4; task += TRK_REFINE) {
+        // task = (frequency fi, pilot position half, timing group tg): 8 timing offsets from a sliding register window;
+        // the steering vector conj(p[n]) exp(-j w n) is generated on the fly by one complex rotation per tap
+        // (|error| ~ 2e-14 after 160 taps, far below the csingle rounding the reference applies to the result)
+        const int fi = task >> 2, half = (task >> 1) & 1, tg = task & 1;
+        const double2 *r = (half ? sm.rb : sm.ra) + tg * 8;
+        const double f = f_start + (double)fi * delta;
+        const double w = 2.0 * M_PI * f / RADE_FS;
+        double s1, c1; sincos(w, &s1, &c1);
+        const double2 step = make_double2(c1, -s1);
+        double2 e = make_double2(1.0, 0.0);
+        double2 acc[8], x[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 7; q++) x[q] = r[q];
+#pragma unroll 1
+        for (int n = 0; n < RADE_M; n += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            x[(u + 7) & 7] = r[n + u + 7];
+            const double2 v = dcmul(e, sm.tab.pcd[n + u]);
+            e = dcmul(e, step);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const double2 xx = x[(u + q) & 7];
+              acc[q].x = fma(xx.x, v.x, acc[q].x); acc[q].x = fma(-xx.y, v.y, acc[q].x);
+              acc[q].y = fma(xx.x, v.y, acc[q].y); acc[q].y = fma(xx.y, v.x, acc[q].y);
+            }
+          }
+        }
+        double2 ramp = make_double2(1.0, 0.0);
+        if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
+          double sn, cs; sincos(2.0 * M_PI * f / RADE_FS * (double)RADE_NMF, &sn, &cs);
+          ramp = make_double2(cs, -sn);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int ti = tg * 8 + q;
+          if (ti < nt) {
+            if (half) { const double2 e = dcmul(acc[q], ramp); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
+            else sm.d1[fi][ti] = make_float2((float)acc[q].x, (float)acc[q].y);
+          }
+        }
+      }
+      group_sync(1, TRK_REFINE);
+      float bm = -1.f; int bo = 0x7fffffff;
+      for (int q = g; q < nf * nt; q += TRK_REFINE) {
+        const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
+        const float2 a = sm.d1[fi][ti], c = sm.d2[fi][ti];
+        const float m = hypotf(a.x + c.x, a.y + c.y);
+        if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
+        if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
+      }
+      if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
+      group_sync(1, TRK_REFINE);
+      if (g == 0) {
+        for (int q = 1; q < TRK_REFINE / 32; q++)
+          if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
+        if (bm > 0.f) {             // strict > against the initial Dtmax = 0 (radae/dsp.py:262)
+          sm.best_mag = bm; sm.best_found = 1;
+          sm.best_t = t_lo + bo % nt;
+          sm.best_f = f_start + (double)(bo / nt) * delta;
+        }
+      }
     }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-4 / 5.0));
-    const double Dthresh_eoo = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
-    const double D = sm.spot[0] + sm.spot[1], De = sm.spot[2] + sm.spot[3];
-    const int valid = D > Dthresh, endofover = De > Dthresh_eoo;
-    c.Dthresh = (float)Dthresh; c.Dtmax12 = (float)D; c.Dtmax12_eoo = (float)De;
-    // timing slips (radae_rxe.py:208-218): the adjusted tmax is used for this call's extraction too
-    int nin = RADE_NMF;
-    if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
-    if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
-    c.nin = nin; c.tmax = tmax; c.fmax = fmax; c.n_check += 1;
-    c.synced_count += 1;
-    int uw_fail = 0;
-    if (c.synced_count % RADE_SYNCED_ONE_SEC == 0) {
-      if (uw_errors[s] > RADE_UW_THRESH) uw_fail = 1;
-      uw_errors[s] = 0;
+    group_sync(3, TRK_CONSUMERS);
+    int tmax = sm.best_found ? sm.best_t : tmax0;
+    const double fhat = sm.best_found ? sm.best_f : fmax0;
+    const double fmax = 0.9 * fmax0 + 0.1 * fhat;
+    // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (radae/dsp.py:297-300)
+    float sigma_r;
+    {
+      float a = 0.f, c = 0.f;
+      for (int q = tid; q < RADE_NMF; q += TRK_CONSUMERS) { a += st.rs[q]; c += st.rs[RADE_NMF + q]; }
+      const float sa = consumer_sum(a, sm.scratch), sb = consumer_sum(c, sm.scratch);
+      const float kf = 1.2533141373155001f;
+      sigma_r = ((sa / (float)(RADE_NMF * RADE_NFCOARSE)) / kf + (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / kf) / 2.0f;
     }
-    c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = !endofover; c.ran_sync = 1;
+    // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
+    {
+      const int wp = tid >> 5, lane = tid & 31;
+      if (wp < 4) {
+        const int o = tmax + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
+        const double w = 2.0 * M_PI * fmax / RADE_FS;
+        double sn, cs, s32, c32; sincos(w * (double)lane, &sn, &cs); sincos(w * 32.0, &s32, &c32);
+        double2 e = make_double2(cs, -sn); const double2 step = make_double2(c32, -s32);
+        double ax = 0.0, ay = 0.0;
+#pragma unroll
+        for (int n = lane; n < RADE_M; n += 32) {
+          const float2 xv = st.rx[o + n];
+          const float2 qf = (wp < 2) ? make_float2(sm.tab.ps4[n].x, sm.tab.ps4[n].y) : sm.tab.pend[n];
+          const double2 v = dcmul(e, make_double2((double)xv.x, (double)xv.y));                       // w_vec * rx
+          const double2 r2 = dcmul(make_double2(v.x, -v.y), make_double2((double)qf.x, (double)qf.y));
+          ax += r2.x; ay += r2.y;
+          e = dcmul(e, step);
+        }
+#pragma unroll
+        for (int q = 16; q > 0; q >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, q); ay += __shfl_xor_sync(0xffffffffu, ay, q); }
+        if (lane == 0) sm.spot[wp] = hypot(ax, ay);
+      }
+    }
+    group_sync(3, TRK_CONSUMERS);
+    if (tid == 0) {
+      RxCtl &c = ctl[s];
+      const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-4 / 5.0));
+      const double Dthresh_eoo = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
+      const double D = sm.spot[0] + sm.spot[1], De = sm.spot[2] + sm.spot[3];
+      const int valid = D > Dthresh, endofover = De > Dthresh_eoo;
+      c.Dthresh = (float)Dthresh; c.Dtmax12 = (float)D; c.Dtmax12_eoo = (float)De;
+      // timing slips (radae_rxe.py:208-218): the adjusted tmax is used for this call's extraction too
+      int nin = RADE_NMF;
+      if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
+      if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
+      c.tmax = tmax; c.fmax = fmax; c.n_check = st.ctl.n_check + 1;
+      const int synced_count = st.ctl.synced_count + 1;
+      c.synced_count = synced_count;
+      int uw_fail = 0;
+      if (synced_count % RADE_SYNCED_ONE_SEC == 0) {
+        if (uw_errors[s] > RADE_UW_THRESH) uw_fail = 1;
+        uw_errors[s] = 0;
+      }
+      const int valid_output = !endofover;
+      c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = valid_output; c.ran_sync = 1;
+      // sync-state branch of the state machine (radae_rxe.py:276-296); search / candidate streams: rx_finish_kernel
+      int next = ST_SYNC, vc = st.ctl.valid_count;
+      if (valid) vc = RADE_NMF_UNSYNC;
+      else { vc -= 1; if (vc == 0) next = ST_SEARCH; }
+      if (endofover || uw_fail) next = ST_SEARCH;
+      if (next == ST_SEARCH) nin = RADE_NMF;
+      c.valid_count = vc; c.state = next; c.nin = nin;
+      const int ret = valid_output | (endofover << 1);
+      c.ret = ret; ret_out[s] = ret; dec_active[s] = (unsigned char)valid_output; nin_out[s] = nin;
+    }
+    group_sync(3, TRK_CONSUMERS);
+    if (tid == 0) mbar_arrive(&sm.empty[b]);
   }
 }
 
@@ -554,80 +744,84 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
 }
 
 // ================================================================= coarse-search post-processing + state machine
+// Streams that entered this call in search / candidate state (the sync-state branch lives at the end of rx_track_kernel).
+// CTAs stride over the search list; inactive streams only get their outputs filled in.
 struct FinishSmem {
   RefineSmem ref;
   float scratch[32];
-  int do_refine, to_sync;
+  int do_refine;
 };
 
 __global__ void __launch_bounds__(256)
 rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, const float *__restrict__ rowsum,
                  int *__restrict__ uw_errors, DecStreamState *__restrict__ dec_state, int reset_dec_on_sync,
                  int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out,
-                 const unsigned char *__restrict__ active, int *__restrict__ search_count) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                 const unsigned char *__restrict__ active, const int *__restrict__ search_list,
+                 const int *__restrict__ counters, int *__restrict__ counters_next, int S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   FinishSmem &sm = *reinterpret_cast<FinishSmem *>(smem_raw);
-  const int s = blockIdx.x, tid = threadIdx.x;
-  if (s == 0 && tid == 0) { search_count[0] = 0; search_count[1] = 0; }      // the coarse search of this call is over
-  if (active && !active[s]) { if (tid == 0) { ret_out[s] = 0; dec_active[s] = 0; nin_out[s] = ctl[s].nin; } return; }
-  RxCtl &c = ctl[s];
-  const int state = c.state;
-  if (state != ST_SYNC) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid < 4) counters_next[tid] = 0;       // the set the NEXT call's kernels will count into
+  if (active)
+    for (int s = blockIdx.x * blockDim.x + tid; s < S; s += gridDim.x * blockDim.x)
+      if (!active[s]) { ret_out[s] = 0; dec_active[s] = 0; nin_out[s] = ctl[s].nin; }
+  const int n_items = counters[0];
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const int s = search_list[w];
+    RxCtl &c = ctl[s];
+    const int state = c.state;
     // detect_pilots epilogue (radae/dsp.py:217-231)
     const float sigma_r = sigma_r_from_rowsums(rowsum + (size_t)s * 2 * RADE_NMF, sm.scratch);
     if (tid == 0) {
       const unsigned long long key = c.detect_key;
       const float val = __uint_as_float((unsigned)(key >> 32));
       const unsigned idx = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-      if (val > 0.f) { c.tmax = (int)(idx / RADE_NFCOARSE); c.fmax = (double)T.fcoarse[idx % RADE_NFCOARSE]; }
-      else { c.tmax = 0; c.fmax = 0.0; }
+      int tmax = 0; double fmax = 0.0;
+      if (val > 0.f) { tmax = (int)(idx / RADE_NFCOARSE); fmax = (double)T.fcoarse[idx % RADE_NFCOARSE]; }
+      c.tmax = tmax; c.fmax = fmax;
       const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
       c.Dthresh = (float)Dthresh; c.Dtmax12 = val;
-      c.candidate = ((double)val > Dthresh) ? 1 : 0;
+      const int candidate = ((double)val > Dthresh) ? 1 : 0;
+      c.candidate = candidate;
+      // state machine on the state held at entry (radae_rxe.py:248-275)
+      int next = state, do_refine = 0;
+      if (state == ST_SEARCH) {
+        if (candidate) { next = ST_CANDIDATE; c.tmax_candidate = tmax; c.valid_count = 1; }
+      } else {
+        if (candidate && abs(tmax - c.tmax_candidate) < RADE_NCP) {
+          const int vc = c.valid_count + 1;
+          c.valid_count = vc;
+          if (vc > 3) {
+            next = ST_SYNC; do_refine = 1;
+            c.synced_count = 0; c.uw_fail = 0; uw_errors[s] = 0; c.valid_count = RADE_NMF_UNSYNC;
+          }
+        } else next = ST_SEARCH;
+      }
+      c.state = next;
+      sm.do_refine = do_refine;
     }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    // state machine on the state held at entry (radae_rxe.py:248-293)
-    int next = state, do_refine = 0;
-    if (state == ST_SEARCH) {
-      if (c.candidate) { next = ST_CANDIDATE; c.tmax_candidate = c.tmax; c.valid_count = 1; }
-    } else if (state == ST_CANDIDATE) {
-      if (c.candidate && abs(c.tmax - c.tmax_candidate) < RADE_NCP) {
-        c.valid_count += 1;
-        if (c.valid_count > 3) {
-          next = ST_SYNC; do_refine = 1;
-          c.synced_count = 0; c.uw_fail = 0; uw_errors[s] = 0; c.valid_count = RADE_NMF_UNSYNC;
-        }
-      } else next = ST_SEARCH;
-    } else {
-      if (c.candidate) c.valid_count = RADE_NMF_UNSYNC;
-      else { c.valid_count -= 1; if (c.valid_count == 0) next = ST_SEARCH; }
-      if (c.endofover || c.uw_fail) next = ST_SEARCH;
+    __syncthreads();
+    if (sm.do_refine) {
+      // first fix after acquisition: t in [max(0,tmax-1), tmax+2), f in arange(fmax-10, fmax+10, 0.25)  (radae_rxe.py:267-273)
+      const int tm = c.tmax; const double fm = c.fmax;
+      const int t_lo = max(0, tm - 1);
+      refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, blockDim.x, 1);
+      if (tid == 0) {
+        if (sm.ref.best_found) { c.tmax = sm.ref.best_t; c.fmax = sm.ref.best_f; }
+        c.fmax += c.foff_err; c.foff_err = 0.0;
+      }
+      if (reset_dec_on_sync) {        // model.core_decoder_statefull.module.reset() (radae_rxe.py:263)
+        uint32_t *d = reinterpret_cast<uint32_t *>(dec_state + s);
+        for (int i = tid; i < (int)(sizeof(DecStreamState) / 4); i += blockDim.x) d[i] = 0u;
+      }
     }
-    c.state = next;
-    sm.do_refine = do_refine; sm.to_sync = do_refine;
-  }
-  __syncthreads();
-  if (sm.do_refine) {
-    // first fix after acquisition: t in [max(0,tmax-1), tmax+2), f in arange(fmax-10, fmax+10, 0.25)  (radae_rxe.py:267-273)
-    const int tm = c.tmax; const double fm = c.fmax;
-    const int t_lo = max(0, tm - 1);
-    refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, blockDim.x, 1);
+    __syncthreads();
     if (tid == 0) {
-      if (sm.ref.best_found) { c.tmax = sm.ref.best_t; c.fmax = sm.ref.best_f; }
-      c.fmax += c.foff_err; c.foff_err = 0.0;
+      if (c.state == ST_SEARCH) c.nin = RADE_NMF;      // radae_rxe.py:294-296
+      c.ret = c.valid_output | (c.endofover << 1);
+      ret_out[s] = c.ret; dec_active[s] = (unsigned char)c.valid_output; nin_out[s] = c.nin;
     }
-    if (reset_dec_on_sync) {        // model.core_decoder_statefull.module.reset() (radae_rxe.py:263)
-      uint32_t *d = reinterpret_cast<uint32_t *>(dec_state + s);
-      for (int i = tid; i < (int)(sizeof(DecStreamState) / 4); i += blockDim.x) d[i] = 0u;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (c.state == ST_SEARCH) c.nin = RADE_NMF;      // radae_rxe.py:294-296
-    c.ret = c.valid_output | (c.endofover << 1);
-    ret_out[s] = c.ret; dec_active[s] = (unsigned char)c.valid_output; nin_out[s] = c.nin;
+    __syncthreads();
   }
 }
 
@@ -657,20 +851,25 @@ int rx_dsp_init_device() {
   return 0;
 }
 
-int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof) {
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  int *cnt = B.counters + 4 * B.parity, *cnt_next = B.counters + 4 * (B.parity ^ 1);
+  B.parity ^= 1;
   prof->begin(K_RX_BPF);
-  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.search_count);
+  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt);
   prof->end(K_RX_BPF); prof->begin(K_RX_DETECT);
-  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > 148 * 3) det_grid = 148 * 3;
-  rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, B.search_count);
+  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 3) det_grid = n_sm * 3;
+  rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
   prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
-  rx_track_kernel<<<S, TRACK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, active);
+  rx_track_kernel<<<S < n_sm ? S : n_sm, TRK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.track_list,
+                                                                               cnt, ret_out, B.dec_active, B.nin);
   prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
-  rx_finish_kernel<<<S, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
-                                                           reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_count);
+  rx_finish_kernel<<<S < 2 * n_sm ? S : 2 * n_sm, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
+      reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_list, cnt, cnt_next, S);
   prof->end(K_RX_FINISH);
   CUDA_CHECK(cudaGetLastError());
   return 5;

@@ -94,6 +94,7 @@ struct DspTables {
   const float2 *pend;
   const float2 *p_w;       // [160][40] coarse-frequency-shifted pilots (reference table; kept for the debug hook)
   const float2 *cs_tab;    // [160][24] (cos, sin)(2*pi*2.5k*n/Fs), k = 0..20 (+3 zero pads): the coarse grid is +-2.5k Hz
+  const unsigned char *acq_tab;  // AcqTables (below): cs_tab + pilot tables packed for ONE TMA bulk copy into shared memory
   const float2 *Pmat;      // [30][2][3] LS projectors
   const float2 *eq_rot;    // [30] exp(-j w_c a)
   const float *bpf_h;      // [101]
@@ -102,6 +103,14 @@ struct DspTables {
   const float *fcoarse;    // [40]
   float pilot_gain;
   float p0_abs;            // |P[0]|
+};
+
+// constant block the acquisition kernels keep resident in shared memory (rx_detect / rx_track), filled by one bulk copy
+struct __align__(128) AcqTables {
+  float2 cs[RADE_M][RADE_CSK];   // (cos, sin) of the symmetric coarse grid
+  float4 ps4[RADE_M];            // (p.x, p.y, p.y, -p.x): conj(x)*p = x.x*(.x,.y) + x.y*(.z,.w) with two packed FMAs
+  double2 pcd[RADE_M];           // conj(p) widened to complex128 (refine steering vectors)
+  float2 pend[RADE_M];           // end-of-over pilot symbol
 };
 
 // per-stream receiver control block (everything radae_rx keeps between calls, radae_rxe.py:128-142)

@@ -46,7 +46,10 @@ struct RxBuffers {
   unsigned char *dec_active;  // [S] valid_output of the last call
   int *nin;                // [S]
   int *search_list;        // [S] streams that need the coarse search this call (built by rx_bpf)
-  int *search_count;       // [2]: number of entries, work-item counter
+  int *track_list;         // [S] streams in sync this call (built by rx_bpf) -> persistent rx_track CTAs
+  int *counters;           // [2][4] ping-pong by call parity: {search entries, search work-item counter, track entries, -};
+                           //        rx_finish of call k zeroes the set call k+1 will use
+  int parity;              // host-side: which counter set the next call uses
 };
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
@@ -60,7 +63,7 @@ int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, cons
                     unsigned char *active, int S, cudaStream_t stream);
 int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream);
 struct Profiler;
-int rx_dsp_launch(const DspTables &T, const RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof);
 
 // ---- optional per-kernel timing with CUDA events on the context's stream (rade_b200_profile_*)

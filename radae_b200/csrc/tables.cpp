@@ -135,6 +135,18 @@ int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> 
 #undef UPC
   if (!(D->bpf_h = (const float *)up(T.bpf_h.data(), T.bpf_h.size() * 4))) return -1;
   if (!(D->fcoarse = (const float *)up(T.fcoarse.data(), T.fcoarse.size() * 4))) return -1;
+  {
+    std::vector<unsigned char> blob(sizeof(AcqTables), 0);
+    AcqTables *A = reinterpret_cast<AcqTables *>(blob.data());
+    for (int n = 0; n < RADE_M; n++) {
+      for (int k = 0; k < RADE_CSK; k++) A->cs[n][k] = f2(T.cs_tab[n * RADE_CSK + k]);
+      const float px = T.p[n].real(), py = T.p[n].imag();
+      A->ps4[n] = make_float4(px, py, py, -px);
+      A->pcd[n] = make_double2((double)px, -(double)py);
+      A->pend[n] = f2(T.pend[n]);
+    }
+    if (!(D->acq_tab = (const unsigned char *)up(blob.data(), blob.size()))) return -1;
+  }
   D->pilot_gain = (float)T.pilot_gain;
   D->p0_abs = std::abs(T.P[0]);
   return 0;
