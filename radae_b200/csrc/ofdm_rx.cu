@@ -327,14 +327,16 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 // ================================================================= sync-state tracking: refine + check_pilots + slips
 // Persistent kernel: one CTA per SM walks the list of streams in sync (built by rx_bpf).  The constant tables (37 KB) are
 // bulk-copied into shared memory once per CTA; a producer warp prefetches the NEXT stream's sample ring (in logical
-// order), |Dt| row sums and control block with TMA bulk copies into the other half of a double buffer while the 15
+// order), |Dt| row sums and control block with TMA bulk copies into the other half of a double buffer while the 16
 // consumer warps work on the current one:
 //   warps 0-11  check_pilots' refresh of 48 rows of the |Dt| row sums (fp32, packed FFMA2; even/odd tap split per lane pair)
-//   warps 12-14 refine: 16 timing x 20(21) frequency x 2 pilot positions in complex128, 8 timing offsets per thread
-//               from a sliding register window (2 shared-memory loads per 32 DFMA)
+//   warps 12-15 refine: 16 timing x 20(21) frequency x 2 pilot positions in complex128 as a real GEMM on the FP64
+//               tensor cores (DMMA m8n8k4: 256 FMA per instruction instead of 32)
 // then sigma_r, the four complex128 spot correlations, slips and the sync-state part of the state machine.
-constexpr int TRK_REFRESH = 384, TRK_REFINE = 96, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
+constexpr int TRK_REFRESH = 384, TRK_REFINE = 128, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
 constexpr int TRK_NF = 21;                        // max len(np.arange(fmax-1, fmax+1, 0.1))
+constexpr int TRK_NFP = 24;                       // padded to 6 DMMA n-tiles of 4 complex columns
+constexpr int TRK_VLD = 165;                      // vtab row: tap n lives at n + (n >> 5); 165 = 5 mod 8 spreads f over the banks
 constexpr int TRK_RLEN = REF_NT + RADE_M + 8;     // widened window + sliding-window over-read
 struct TrackStage {
   alignas(128) float2 rx[RADE_RXBUF];             // rx_buf in LOGICAL order (two bulk copies around ring_head)
@@ -344,11 +346,13 @@ struct TrackStage {
 struct TrackSmem {
   AcqTables tab;
   TrackStage st[2];
+  double2 vtab[TRK_NFP][TRK_VLD];                 // conj(p[n]) exp(-j w_f n)
+  double2 ramp[TRK_NFP];                          // exp(-j w_f Nmf)
   double2 ra[TRK_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
   double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
   double2 rb[TRK_RLEN];                           // rx[t_lo + Nmf ...]
-  float2 d1[TRK_NF][REF_NT];
-  float2 d2[TRK_NF][REF_NT];
+  float2 d1[TRK_NFP][REF_NT];
+  float2 d2[TRK_NFP][REF_NT];
   float red_mag[4]; int red_ord[4];
   float best_mag; int best_t; int best_found; double best_f;
   float scratch[32];
@@ -484,49 +488,62 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
         sm.ra[i2] = make_double2((double)a.x, (double)a.y);
         sm.rb[i2] = make_double2((double)c.x, (double)c.y);
       }
+      // steering vectors conj(p[n]) exp(-j w_f n) for all f: thread = (f, 32-tap segment), one sincos pair + 31 rotations
+      for (int task = g; task < TRK_NFP * 5; task += TRK_REFINE) {
+        const int fi = task / 5, seg = task % 5;
+        double2 *row = sm.vtab[fi] + 33 * seg;
+        if (fi < nf) {
+          const double f = f_start + (double)fi * delta;
+          const double w = 2.0 * M_PI * f / RADE_FS;
+          double sn, cs, s1, c1; sincos(w * (double)(32 * seg), &sn, &cs); sincos(w, &s1, &c1);
+          double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
+#pragma unroll 4
+          for (int q = 0; q < 32; q++) { row[q] = dcmul(e, sm.tab.pcd[32 * seg + q]); e = dcmul(e, step); }
+          if (seg == 0) {           // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
+            sincos(w * (double)RADE_NMF, &sn, &cs);
+            sm.ramp[fi] = make_double2(cs, -sn);
+          }
+        } else {
+          for (int q = 0; q < 32; q++) row[q] = make_double2(0.0, 0.0);
+        }
+      }
       group_sync(1, TRK_REFINE);
-      for (int task = g; task < nf * 4; task += TRK_REFINE) {
-        // task = (frequency fi, pilot position half, timing group tg): 8 timing offsets from a sliding register window;
-        // the steering vector conj(p[n]) exp(-j w n) is generated on the fly by one complex rotation per tap
-        // (|error| ~ 2e-14 after 160 taps, far below the csingle rounding the reference applies to the result)
-        const int fi = task >> 2, half = (task >> 1) & 1, tg = task & 1;
-        const double2 *r = (half ? sm.rb : sm.ra) + tg * 8;
-        const double f = f_start + (double)fi * delta;
-        const double w = 2.0 * M_PI * f / RADE_FS;
-        double s1, c1; sincos(w, &s1, &c1);
-        const double2 step = make_double2(c1, -s1);
-        double2 e = make_double2(1.0, 0.0);
-        double2 acc[8], x[8];
+      {
+        // D[t][f] = sum_n rx[t+n] v_f[n] as a real GEMM on the FP64 tensor cores (DMMA m8n8k4): A = Toeplitz view of the
+        // widened samples [8 t][(n, re/im)], B = [(n, re/im)][(f, re/im)] built on the fly from vtab.  Warp = (pilot
+        // position, 8-row t tile); 6 n-tiles = 24 frequencies; K = 320 in 80 steps of two taps.
+        const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
+        const int half = wr >> 1, mt = wr & 1;
+        const double *ap = reinterpret_cast<const double *>((half ? sm.rb : sm.ra) + mt * 8 + gq + (c >> 1)) + (c & 1);
+        const int reim = gq & 1, comp = c & 1;
+        const unsigned flip = (reim == 0 && comp == 1) ? 0x80000000u : 0u;      // B = [vr; -vi] for Re columns, [vi; vr] for Im
+        const double *bp[6];
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = make_double2(0.0, 0.0);
+        for (int q = 0; q < 6; q++) bp[q] = reinterpret_cast<const double *>(sm.vtab[q * 4 + (gq >> 1)] + (c >> 1)) + (comp ^ reim);
+        double acc[6][2];
 #pragma unroll
-        for (int q = 0; q < 7; q++) x[q] = r[q];
+        for (int q = 0; q < 6; q++) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll 1
-        for (int n = 0; n < RADE_M; n += 8) {
+        for (int blk = 0; blk < 5; blk++) {
+#pragma unroll 4
+          for (int kk = 0; kk < 16; kk++) {
+            const double av = ap[4 * (16 * blk + kk)];
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            x[(u + 7) & 7] = r[n + u + 7];
-            const double2 v = dcmul(e, sm.tab.pcd[n + u]);
-            e = dcmul(e, step);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              const double2 xx = x[(u + q) & 7];
-              acc[q].x = fma(xx.x, v.x, acc[q].x); acc[q].x = fma(-xx.y, v.y, acc[q].x);
-              acc[q].y = fma(xx.x, v.y, acc[q].y); acc[q].y = fma(xx.y, v.x, acc[q].y);
+            for (int q = 0; q < 6; q++) {
+              double bv = bp[q][2 * (33 * blk + 2 * kk)];
+              bv = __hiloint2double(__double2hiint(bv) ^ flip, __double2loint(bv));
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(acc[q][0]), "+d"(acc[q][1]) : "d"(av), "d"(bv));
             }
           }
         }
-        double2 ramp = make_double2(1.0, 0.0);
-        if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
-          double sn, cs; sincos(2.0 * M_PI * f / RADE_FS * (double)RADE_NMF, &sn, &cs);
-          ramp = make_double2(cs, -sn);
-        }
+        const int ti = mt * 8 + gq;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          const int ti = tg * 8 + q;
-          if (ti < nt) {
-            if (half) { const double2 e = dcmul(acc[q], ramp); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
-            else sm.d1[fi][ti] = make_float2((float)acc[q].x, (float)acc[q].y);
+        for (int q = 0; q < 6; q++) {
+          const int fi = q * 4 + c;
+          if (fi < nf && ti < nt) {
+            if (half) { const double2 e = dcmul(make_double2(acc[q][0], acc[q][1]), sm.ramp[fi]); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
+            else sm.d1[fi][ti] = make_float2((float)acc[q][0], (float)acc[q][1]);
           }
         }
       }
