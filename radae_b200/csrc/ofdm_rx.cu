@@ -377,7 +377,7 @@ __device__ float consumer_sum(float v, float *scratch) {
 __global__ void __launch_bounds__(TRK_THREADS, 1)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
                 int *__restrict__ uw_errors, const int *__restrict__ track_list, const int *__restrict__ counters,
-                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
+                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out, int dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -420,6 +420,7 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     const int tmax0 = st.ctl.tmax; const double fmax0 = st.ctl.fmax;
     const int rot = st.ctl.n_check % 20;
     if (tid < TRK_REFRESH) {
+      if (!(dbg & 1)) {
       // ---- check_pilots row refresh (radae/dsp.py:288-295, deterministic schedule): rows t_i = 20 i + rot, both pilot
       // positions, 40 grid frequencies.  lane = (row i, k group kg, tap parity ks): conflict-free shared-memory reads
       const int ks = tid & 1, kg = (tid >> 1) & 3, i = tid >> 3;
@@ -474,6 +475,7 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
         rs[r] = s0; rs[RADE_NMF + r] = s1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.rs is overwritten by a bulk copy two streams later
       }
+      }
     } else {
       // ---- refine (radae_rxe.py:202-205, radae/dsp.py:233-270): t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, .1)
       const int g = tid - TRK_REFRESH;
@@ -489,7 +491,7 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
         sm.rb[i2] = make_double2((double)c.x, (double)c.y);
       }
       // steering vectors conj(p[n]) exp(-j w_f n) for all f: thread = (f, 32-tap segment), one sincos pair + 31 rotations
-      for (int task = g; task < TRK_NFP * 5; task += TRK_REFINE) {
+      for (int task = g; task < ((dbg & 2) ? 0 : TRK_NFP * 5); task += TRK_REFINE) {
         const int fi = task / 5, seg = task % 5;
         double2 *row = sm.vtab[fi] + 33 * seg;
         if (fi < nf) {
@@ -524,7 +526,7 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
 #pragma unroll
         for (int q = 0; q < 6; q++) acc[q][0] = acc[q][1] = 0.0;
 #pragma unroll 1
-        for (int blk = 0; blk < 5; blk++) {
+        for (int blk = 0; blk < ((dbg & 2) ? 0 : 5); blk++) {
 #pragma unroll 4
           for (int kk = 0; kk < 16; kk++) {
             const double av = ap[4 * (16 * blk + kk)];
@@ -872,6 +874,7 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof) {
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  static const int dbg = getenv("RADE_B200_TRACK_DEBUG") ? atoi(getenv("RADE_B200_TRACK_DEBUG")) : 0;   // timing experiments only
   int *cnt = B.counters + 4 * B.parity, *cnt_next = B.counters + 4 * (B.parity ^ 1);
   B.parity ^= 1;
   prof->begin(K_RX_BPF);
@@ -881,7 +884,7 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
   prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
   rx_track_kernel<<<S < n_sm ? S : n_sm, TRK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.track_list,
-                                                                               cnt, ret_out, B.dec_active, B.nin);
+                                                                               cnt, ret_out, B.dec_active, B.nin, dbg);
   prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
