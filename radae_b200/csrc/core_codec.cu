@@ -54,27 +54,28 @@ __device__ __forceinline__ float lin(int acc, float scale, float bias) {
   return __fadd_rn(__fmul_rn((float)acc, scale), bias);
 }
 
-struct PipeSmem {
-  alignas(128) unsigned char ring[CORE_NSTAGES][CORE_STAGE_BYTES];
-  alignas(8) uint64_t full[CORE_NSTAGES];
-  alignas(8) uint64_t empty[CORE_NSTAGES];
+template <int NST> struct PipeSmem {
+  alignas(128) unsigned char ring[NST][CORE_STAGE_BYTES];
+  alignas(8) uint64_t full[NST];
+  alignas(8) uint64_t empty[NST];
+  alignas(8) uint64_t state_bar;           // per-stream state rows, bulk-copied once at kernel start
 };
 
 // consumer-side cursor over the chunk stream; every consumer thread carries an identical copy
-struct Cursor {
-  PipeSmem *p; int stage; uint32_t phase;
+template <int NST> struct Cursor {
+  PipeSmem<NST> *p; int stage; uint32_t phase;
   __device__ __forceinline__ const unsigned char *acquire() { mbar_wait(&p->full[stage], phase); return p->ring[stage]; }
   __device__ __forceinline__ void release() {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&p->empty[stage]);
-    if (++stage == CORE_NSTAGES) { stage = 0; phase ^= 1; }
+    if (++stage == NST) { stage = 0; phase ^= 1; }
   }
 };
 
 template <int NCW> __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
 
 // producer: lane 0 of the last warp streams every chunk of every step
-__device__ void producer_loop(PipeSmem *p, const CodecStreamDev &ws, int T) {
+template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int T) {
   int stage = 0; uint32_t phase = 0;
   for (int t = 0; t < T; t++)
     for (int c = 0; c < ws.n_chunks; c++) {
@@ -82,7 +83,7 @@ __device__ void producer_loop(PipeSmem *p, const CodecStreamDev &ws, int T) {
       mbar_wait(&p->empty[stage], phase ^ 1);
       mbar_expect_tx(&p->full[stage], d.bytes);
       bulk_g2s(p->ring[stage], ws.stream + d.offset, d.bytes, &p->full[stage]);
-      if (++stage == CORE_NSTAGES) { stage = 0; phase ^= 1; }
+      if (++stage == NST) { stage = 0; phase ^= 1; }
     }
 }
 
@@ -101,8 +102,8 @@ __device__ __forceinline__ void ldsm_a(uint32_t &a0, uint32_t &a1, uint32_t &a2,
                : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(smem_u32(lane_ptr)));
 }
 
-template <int NT>
-__device__ __forceinline__ void gemm_stream(Cursor &cx, int (&acc)[NT][4], const int (&nt)[NT], const bool (&use)[NT], bool work,
+template <int NT, typename CX>
+__device__ __forceinline__ void gemm_stream(CX &cx, int (&acc)[NT][4], const int (&nt)[NT], const bool (&use)[NT], bool work,
                                             const int8_t *A, int lda, int KB, int NTL) {
   const int lane = threadIdx.x & 31;
   // ldmatrix row address of this lane: matrix (lane>>3): rows +8 for odd matrices, bytes +16 for matrices 2,3
@@ -129,40 +130,54 @@ __device__ __forceinline__ void gemm_stream(Cursor &cx, int (&acc)[NT][4], const
 }
 
 // ---------------------------------------------------------------- float layers: sequential-in-j accumulation
-// thread (s = tid&15, grp = tid>>4) owns the four outputs o = 4*grp .. 4*grp+3 of stream s; the W rows of the concat segment
-// come from one staged chunk and are read as one broadcast LDS.128 per input, the inputs as one LDS.128 per four.
+// thread (s = tid % TS, grp = tid / TS) owns the OPT outputs o = OPT*grp .. OPT*grp+OPT-1 of stream s (OPT = 4 for 16-stream
+// tiles, 2 for 8-stream tiles, so every consumer warp takes part either way); the W rows of the concat segment come from one
+// staged chunk and are read as one broadcast vector load per input, the inputs as one LDS.128 per four.
 // acc[i] = ((acc[i] + W[j0][o] x[j0]) + W[j0+1][o] x[j0+1]) + ...  — separately rounded, in input order
-template <int NOUT>
-__device__ __forceinline__ void dense_chunk(Cursor &cx, float (&acc)[4], const float *xrow, int K, int grp) {
-  const float4 *W4 = reinterpret_cast<const float4 *>(cx.acquire());
-  if (grp < NOUT / 4) {
+template <int OPT> struct VecOf;
+template <> struct VecOf<4> { typedef float4 type; };
+template <> struct VecOf<2> { typedef float2 type; };
+template <int OPT> __device__ __forceinline__ void mac_seq(float (&acc)[OPT], const typename VecOf<OPT>::type w, float x);
+template <> __device__ __forceinline__ void mac_seq<4>(float (&acc)[4], const float4 w, float x) {
+  acc[0] = __fadd_rn(acc[0], __fmul_rn(w.x, x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w.y, x));
+  acc[2] = __fadd_rn(acc[2], __fmul_rn(w.z, x)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w.w, x));
+}
+template <> __device__ __forceinline__ void mac_seq<2>(float (&acc)[2], const float2 w, float x) {
+  acc[0] = __fadd_rn(acc[0], __fmul_rn(w.x, x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w.y, x));
+}
+template <int NOUT, int OPT, typename CX>
+__device__ __forceinline__ void dense_chunk(CX &cx, float (&acc)[OPT], const float *xrow, int K, int grp) {
+  typedef typename VecOf<OPT>::type V;
+  const V *Wv = reinterpret_cast<const V *>(cx.acquire());
+  if (grp < NOUT / OPT) {
     const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
 #pragma unroll 2
     for (int j = 0; j < K; j += 4) {
       const float4 x = x4[j >> 2];
-      const float4 w0 = W4[(j + 0) * (NOUT / 4) + grp], w1 = W4[(j + 1) * (NOUT / 4) + grp];
-      const float4 w2 = W4[(j + 2) * (NOUT / 4) + grp], w3 = W4[(j + 3) * (NOUT / 4) + grp];
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(w0.x, x.x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w0.y, x.x));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(w0.z, x.x)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w0.w, x.x));
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(w1.x, x.y)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w1.y, x.y));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(w1.z, x.y)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w1.w, x.y));
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(w2.x, x.z)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w2.y, x.z));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(w2.z, x.z)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w2.w, x.z));
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(w3.x, x.w)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w3.y, x.w));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(w3.z, x.w)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w3.w, x.w));
+      const V w0 = Wv[(j + 0) * (NOUT / OPT) + grp], w1 = Wv[(j + 1) * (NOUT / OPT) + grp];
+      const V w2 = Wv[(j + 2) * (NOUT / OPT) + grp], w3 = Wv[(j + 3) * (NOUT / OPT) + grp];
+      mac_seq<OPT>(acc, w0, x.x); mac_seq<OPT>(acc, w1, x.y); mac_seq<OPT>(acc, w2, x.z); mac_seq<OPT>(acc, w3, x.w);
     }
   }
   cx.release();
 }
 
-// GRU layer: warp w owns unit tile w (8 hidden units x 16 streams); gates z,r,n of a unit land in the same accumulator slot
-template <int UNITS, typename Emit>
-__device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, const I8LayerDev &Lr, const int8_t *Xin, int ldx,
-                                          const int8_t *Hq, int ldh, float *hs, int ldhs, int ts, Emit emit) {
+// GRU layer: warp w owns unit tile w (8 hidden units x 16 streams); gates z,r,n of a unit land in the same accumulator slot.
+// The per-output scale / bias values are fetched BEFORE the GEMM so their L2 latency hides behind it.
+template <int UNITS, int TS, typename CX, typename Emit>
+__device__ __forceinline__ void gru_layer(CX &cx, const I8LayerDev &Li, const I8LayerDev &Lr, const int8_t *Xin, int ldx,
+                                          const int8_t *Hq, int ldh, float *hs, int ldhs, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int U = UNITS / 8;
   const bool work = warp < U;                // NCW >= U; surplus warps only keep the chunk pipeline moving
   const int u = work ? warp : 0;
+  const int j0 = u * 8 + 2 * tig;
+  float2 si[3], bi[3], sr[3], br[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    si[q] = *reinterpret_cast<const float2 *>(Li.scale + q * UNITS + j0); bi[q] = *reinterpret_cast<const float2 *>(Li.bias + q * UNITS + j0);
+    sr[q] = *reinterpret_cast<const float2 *>(Lr.scale + q * UNITS + j0); br[q] = *reinterpret_cast<const float2 *>(Lr.bias + q * UNITS + j0);
+  }
   int ai[3][4] = {}, ar[3][4] = {};
   const int nt[3] = {u, U + u, 2 * U + u};
   const bool use[3] = {true, true, true};
@@ -172,13 +187,13 @@ __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, cons
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const int row = g + ((e & 2) ? 8 : 0);
-    if (row >= ts) continue;                  // 8-stream tiles leave MMA rows 8..15 unused
-    const int j = u * 8 + 2 * tig + (e & 1);
-    float z = sigmoid_r(__fadd_rn(lin(ai[0][e], Li.scale[j], Li.bias[j]), lin(ar[0][e], Lr.scale[j], Lr.bias[j])));
-    float r = sigmoid_r(__fadd_rn(lin(ai[1][e], Li.scale[UNITS + j], Li.bias[UNITS + j]),
-                                  lin(ar[1][e], Lr.scale[UNITS + j], Lr.bias[UNITS + j])));
-    float n = tanh_r(__fadd_rn(lin(ai[2][e], Li.scale[2 * UNITS + j], Li.bias[2 * UNITS + j]),
-                               __fmul_rn(lin(ar[2][e], Lr.scale[2 * UNITS + j], Lr.bias[2 * UNITS + j]), r)));
+    if (row >= TS) continue;                  // 8-stream tiles leave MMA rows 8..15 unused
+    const int j = j0 + (e & 1);
+#define PICK(v) ((e & 1) ? (v).y : (v).x)
+    float z = sigmoid_r(__fadd_rn(lin(ai[0][e], PICK(si[0]), PICK(bi[0])), lin(ar[0][e], PICK(sr[0]), PICK(br[0]))));
+    float r = sigmoid_r(__fadd_rn(lin(ai[1][e], PICK(si[1]), PICK(bi[1])), lin(ar[1][e], PICK(sr[1]), PICK(br[1]))));
+    float n = tanh_r(__fadd_rn(lin(ai[2][e], PICK(si[2]), PICK(bi[2])), __fmul_rn(lin(ar[2][e], PICK(sr[2]), PICK(br[2])), r)));
+#undef PICK
     float hold = hs[row * ldhs + j];
     float h = __fadd_rn(__fmul_rn(z, hold), __fmul_rn(__fsub_rn(1.f, z), n));
     hs[row * ldhs + j] = h;
@@ -187,14 +202,21 @@ __device__ __forceinline__ void gru_layer(Cursor &cx, const I8LayerDev &Li, cons
 }
 
 // conv1d (k=2): work unit = (n-tile, tap); units are dealt round-robin to the consumer warps, each accumulates its tap's
-// K range, the exact int32 partial sums meet in shared memory `red[2][16][N]`, then all consumer threads run the epilogue
-template <int N, int NCW, typename Emit>
-__device__ __forceinline__ void conv_layer(Cursor &cx, const I8LayerDev &L, const int8_t *Aold, const int8_t *Acur, int Ktap, int lda,
-                                           int *red, int ts, Emit emit) {
+// K range, the exact int32 partial sums meet in shared memory `red[2][TS][N]`, then all consumer threads run the epilogue
+template <int N, int NCW, int TS, typename CX, typename Emit>
+__device__ __forceinline__ void conv_layer(CX &cx, const I8LayerDev &L, const int8_t *Aold, const int8_t *Acur, int Ktap, int lda,
+                                           int *red, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int NTL = N / 8;
   constexpr int UNITS = 2 * NTL;
   constexpr int PER = (UNITS + NCW - 1) / NCW;
+  constexpr int NEP = (TS * N + NCW * 32 - 1) / (NCW * 32);      // epilogue elements per thread
+  float es[NEP], eb[NEP];
+#pragma unroll
+  for (int q = 0; q < NEP; q++) {
+    const int e = threadIdx.x + q * NCW * 32;
+    es[q] = (e < TS * N) ? L.scale[e % N] : 0.f; eb[q] = (e < TS * N) ? L.bias[e % N] : 0.f;
+  }
 #pragma unroll
   for (int tap = 0; tap < 2; tap++) {
     int acc[PER][4] = {};
@@ -216,65 +238,82 @@ __device__ __forceinline__ void conv_layer(Cursor &cx, const I8LayerDev &L, cons
         for (int e = 0; e < 4; e++) {
           const int row = g + ((e & 2) ? 8 : 0);
           const int n = nt[i] * 8 + 2 * tig + (e & 1);
-          red[(tap * CORE_TS + row) * N + n] = acc[i][e];
+          if (row < TS) red[(tap * TS + row) * N + n] = acc[i][e];
         }
       }
   }
   consumer_sync<NCW>();
-  for (int e = threadIdx.x; e < ts * N; e += NCW * 32) {
-    const int row = e / N, n = e % N;
-    emit(row, n, lin(red[row * N + n] + red[(CORE_TS + row) * N + n], L.scale[n], L.bias[n]));
+#pragma unroll
+  for (int q = 0; q < NEP; q++) {
+    const int e = threadIdx.x + q * NCW * 32;
+    if (e < TS * N) {
+      const int row = e / N, n = e % N;
+      emit(row, n, lin(red[row * N + n] + red[(TS + row) * N + n], es[q], eb[q]));
+    }
   }
 }
 
 // ================================================================= encoder
-struct EncSmem {
-  PipeSmem pipe;
-  int8_t cb[3][CORE_TS][ENC_LDA];
-  float hs[CORE_TS][5 * ENC_GRU];
-  float seg[CORE_TS][SEG_LD];
-  float fin[CORE_TS][FIN_LD];
-  int red[2 * CORE_TS * ENC_CONV];
+template <int TS, int NST> struct EncSmem {
+  PipeSmem<NST> pipe;
+  alignas(16) int8_t cb[3][TS][ENC_LDA];
+  alignas(16) float hs[TS][5 * ENC_GRU];
+  alignas(16) float seg[TS][SEG_LD];
+  alignas(16) float fin[TS][FIN_LD];
+  int red[2 * TS * ENC_CONV];
   int any_active;
 };
 
+template <int TS, int NST>
 __global__ void __launch_bounds__((ENC_NCW + 1) * 32, 1)
 core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
-                    float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T, int ts) {
-  constexpr int NCW = ENC_NCW, NCT = NCW * 32;
+                    float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
+  constexpr int NCW = ENC_NCW, NCT = NCW * 32, OPT = TS / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  EncSmem &sm = *reinterpret_cast<EncSmem *>(smem_raw);
+  typedef EncSmem<TS, NST> Smem;
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  const int s0 = blockIdx.x * ts;               // ts = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
+  const int s0 = blockIdx.x * TS;               // TS = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
 
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
-  if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
+  if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (!sm.any_active) return;
   if (tid >= NCT) {                               // ---- producer warp
-    if (tid == NCT) producer_loop(&sm.pipe, W.enc_stream, T);
+    if (tid == NCT) {
+      // per-stream state rows first (one bulk copy per array, all in flight at once), then the weight stream
+      const int rows = min(TS, S - s0);
+      mbar_expect_tx(&sm.pipe.state_bar, (uint32_t)(rows * (sizeof(float) * 5 * ENC_GRU + 2 * ENC_LDA)));
+      for (int r = 0; r < rows; r++) {
+        const EncStreamState *st = state + (s0 + r);
+        bulk_g2s(sm.hs[r], st->h, sizeof(float) * 5 * ENC_GRU, &sm.pipe.state_bar);
+        bulk_g2s(sm.cb[2][r], st->cat1, ENC_LDA, &sm.pipe.state_bar);
+        bulk_g2s(sm.cb[1][r], st->cat2, ENC_LDA, &sm.pipe.state_bar);
+      }
+      producer_loop<NST>(&sm.pipe, W.enc_stream, T);
+    }
     return;
   }
   // ---- consumer warps
-  Cursor cx{&sm.pipe, 0, 0u};
-  const int sl = tid % ts, grp = tid / ts;
+  Cursor<NST> cx{&sm.pipe, 0, 0u};
+  const int sl = tid % TS, grp = tid / TS;
   const int sg = s0 + sl;
 
-  for (int r = 0; r < CORE_TS; r++) {
-    const bool ok = r < ts && s0 + r < S;
-    const EncStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * ENC_GRU; i += NCT) sm.hs[r][i] = ok ? st->h[i] : 0.f;
+  for (int r = 0; r < TS; r++) {
+    const bool ok = s0 + r < S;
     for (int i = tid; i < ENC_LDA / 4; i += NCT) {
-      reinterpret_cast<uint32_t *>(sm.cb[2][r])[i] = ok ? reinterpret_cast<const uint32_t *>(st->cat1)[i] : 0u;
-      reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = ok ? reinterpret_cast<const uint32_t *>(st->cat2)[i] : 0u;
       reinterpret_cast<uint32_t *>(sm.cb[0][r])[i] = 0u;
+      if (!ok) { reinterpret_cast<uint32_t *>(sm.cb[2][r])[i] = 0u; reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = 0u; }
     }
+    if (!ok) for (int i = tid; i < 5 * ENC_GRU; i += NCT) sm.hs[r][i] = 0.f;
   }
+  mbar_wait(&sm.pipe.state_bar, 0);
   consumer_sync<NCW>();
 
   constexpr int dil[5] = {1, 2, 2, 2, 2};
@@ -283,10 +322,10 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     int8_t(*prev1)[ENC_LDA] = sm.cb[(t + 2) % 3];
     int8_t(*prev2)[ENC_LDA] = sm.cb[(t + 1) % 3];
 
-    for (int i = tid; i < CORE_TS * ENC_IN; i += NCT) {
+    for (int i = tid; i < TS * ENC_IN; i += NCT) {
       const int r = i / ENC_IN, k = i % ENC_IN;
       float v = 0.f;
-      if (r < ts && s0 + r < S) {
+      if (s0 + r < S) {
         if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
         else {                                   // API layout: [S][4T][36]; 20 used features + aux = -1 (src/rade_api.c:426-432)
           const int fr = k / 21, f = k % 21;
@@ -299,54 +338,58 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
 
     // ---- dense1: tanh(W f + b), 84 -> 64
     {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      dense_chunk<64>(cx, a, sm.fin[sl], ENC_IN, grp);
-      if (grp < 64 / 4) {
+      float a[OPT], bd[OPT];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int o = 4 * grp + i;
-          float y = tanh_r(__fadd_rn(a[i], W.enc_dense1.bias[o]));
+      for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 64 / OPT) ? W.enc_dense1.bias[OPT * grp + i] : 0.f; }
+      dense_chunk<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
+      if (grp < 64 / OPT) {
+#pragma unroll
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          float y = tanh_r(__fadd_rn(a[i], bd[i]));
           sm.seg[sl][o] = y;
           cur[sl][o] = quant8(y);
         }
       }
     }
     consumer_sync<NCW>();
-    float zacc[4] = {0.f, 0.f, 0.f, 0.f};
-    dense_chunk<80>(cx, zacc, sm.seg[sl], 64, grp);
+    float zacc[OPT];
+#pragma unroll
+    for (int i = 0; i < OPT; i++) zacc[i] = 0.f;
+    dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], 64, grp);
     consumer_sync<NCW>();
 
     int off = 64;
 #pragma unroll 1
     for (int l = 0; l < 5; l++) {
       // GRU l: input = cur[0:off), recurrent input = quantised h(t-1) = prev1[off : off+64)
-      gru_layer<ENC_GRU>(cx, W.enc_gru_in[l], W.enc_gru_rec[l], &cur[0][0], ENC_LDA, &prev1[0][off], ENC_LDA,
-                         &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU, ts,
-                         [&](int row, int j, float h) { sm.seg[row][j] = h; cur[row][off + j] = quant8(h); });
+      gru_layer<ENC_GRU, TS>(cx, W.enc_gru_in[l], W.enc_gru_rec[l], &cur[0][0], ENC_LDA, &prev1[0][off], ENC_LDA,
+                             &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU,
+                             [&](int row, int j, float h) { sm.seg[row][j] = h; cur[row][off + j] = quant8(h); });
       consumer_sync<NCW>();
-      dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
+      dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
       consumer_sync<NCW>();
       off += ENC_GRU;
       // conv l (k = 2): tap 0 = concat prefix of step t-dilation, tap 1 = current prefix
       const int8_t *old = (dil[l] == 1) ? &prev1[0][0] : &prev2[0][0];
-      conv_layer<ENC_CONV, NCW>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red, ts,
-                                [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
+      conv_layer<ENC_CONV, NCW, TS>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red,
+                                    [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
-      dense_chunk<80>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
+      dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
       consumer_sync<NCW>();
       off += ENC_CONV;
     }
     // ---- z = zdense(cat) + b   (bottleneck 3: linear, src/rade_enc.c:107-113)
-    if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / 4) {
-      const float4 bz = reinterpret_cast<const float4 *>(W.enc_zdense.bias)[grp];
-      reinterpret_cast<float4 *>(z_out + ((size_t)sg * T + t) * RADE_LATENT)[grp] =
-          make_float4(__fadd_rn(zacc[0], bz.x), __fadd_rn(zacc[1], bz.y), __fadd_rn(zacc[2], bz.z), __fadd_rn(zacc[3], bz.w));
+    if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / OPT) {
+#pragma unroll
+      for (int i = 0; i < OPT; i++)
+        z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
     }
   }
 
   const int last = (T + 2) % 3, last2 = (T + 1) % 3;
-  for (int r = 0; r < CORE_TS; r++) {
-    if (r >= ts || s0 + r >= S || (active && !active[s0 + r])) continue;
+  for (int r = 0; r < TS; r++) {
+    if (s0 + r >= S || (active && !active[s0 + r])) continue;
     EncStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * ENC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
     for (int i = tid; i < ENC_LDA / 4; i += NCT) {
@@ -357,59 +400,72 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
 }
 
 // ================================================================= decoder
-struct DecSmem {
-  PipeSmem pipe;
-  int8_t cb[2][CORE_TS][DEC_LDA];
-  int8_t hq[2][CORE_TS][HQ_LD];
-  float hs[CORE_TS][5 * DEC_GRU];
-  float seg[CORE_TS][SEG_LD];
-  float zin[CORE_TS][ZIN_LD];
-  int red[2 * CORE_TS * DEC_CONV];
+template <int TS, int NST> struct DecSmem {
+  PipeSmem<NST> pipe;
+  alignas(16) int8_t cb[2][TS][DEC_LDA];
+  alignas(16) int8_t hq[2][TS][HQ_LD];
+  alignas(16) float hs[TS][5 * DEC_GRU];
+  alignas(16) float seg[TS][SEG_LD];
+  alignas(16) float zin[TS][ZIN_LD];
+  int red[2 * TS * DEC_CONV];
   int any_active;
 };
 
 // out_mode 0: features [S][T][84];  out_mode 1: API layout [S][4T][36] (20 used, rest zero, src/rade_api.c:488-500)
 // uw_count (optional): += number of steps whose first aux symbol (feature 20) is > 0 (src/rade_api.c:502-505)
+template <int TS, int NST>
 __global__ void __launch_bounds__((DEC_NCW + 1) * 32, 1)
 core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
                     float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
-                    const uint8_t *__restrict__ active, int S, int T, int ts) {
-  constexpr int NCW = DEC_NCW, NCT = NCW * 32;
-  const int NGRP = NCT / ts;
+                    const uint8_t *__restrict__ active, int S, int T) {
+  constexpr int NCW = DEC_NCW, NCT = NCW * 32, OPT = TS / 4;
+  constexpr int NGRP = NCT / TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  DecSmem &sm = *reinterpret_cast<DecSmem *>(smem_raw);
+  typedef DecSmem<TS, NST> Smem;
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
-  const int s0 = blockIdx.x * ts;               // ts = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
+  const int s0 = blockIdx.x * TS;               // TS = 16 (full MMA tile) or 8 (more CTAs when the batch is small)
 
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
-  if (tid < ts && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
+  if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < CORE_NSTAGES; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (!sm.any_active) return;
   if (tid >= NCT) {
-    if (tid == NCT) producer_loop(&sm.pipe, W.dec_stream, T);
+    if (tid == NCT) {
+      const int rows = min(TS, S - s0);
+      mbar_expect_tx(&sm.pipe.state_bar, (uint32_t)(rows * (sizeof(float) * 5 * DEC_GRU + DEC_LDA)));
+      for (int r = 0; r < rows; r++) {
+        const DecStreamState *st = state + (s0 + r);
+        bulk_g2s(sm.hs[r], st->h, sizeof(float) * 5 * DEC_GRU, &sm.pipe.state_bar);
+        bulk_g2s(sm.cb[1][r], st->cat1, DEC_LDA, &sm.pipe.state_bar);
+      }
+      producer_loop<NST>(&sm.pipe, W.dec_stream, T);
+    }
     return;
   }
-  Cursor cx{&sm.pipe, 0, 0u};
-  const int sl = tid % ts, grp = tid / ts;
+  Cursor<NST> cx{&sm.pipe, 0, 0u};
+  const int sl = tid % TS, grp = tid / TS;
   const int sg = s0 + sl;
 
-  for (int r = 0; r < CORE_TS; r++) {
-    const bool ok = r < ts && s0 + r < S;
-    const DecStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * DEC_GRU; i += NCT) {
-      float h = ok ? st->h[i] : 0.f;
-      sm.hs[r][i] = h;
-      sm.hq[0][r][i] = quant8(h);
-    }
+  for (int r = 0; r < TS; r++) {
+    const bool ok = s0 + r < S;
     for (int i = tid; i < DEC_LDA / 4; i += NCT) {
-      reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = ok ? reinterpret_cast<const uint32_t *>(st->cat1)[i] : 0u;
       reinterpret_cast<uint32_t *>(sm.cb[0][r])[i] = 0u;
+      if (!ok) reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = 0u;
     }
+    if (!ok) for (int i = tid; i < 5 * DEC_GRU; i += NCT) sm.hs[r][i] = 0.f;
+  }
+  mbar_wait(&sm.pipe.state_bar, 0);
+  consumer_sync<NCW>();
+  for (int i = tid; i < TS * 5 * DEC_GRU; i += NCT) {
+    const int r = i / (5 * DEC_GRU), k = i % (5 * DEC_GRU);
+    sm.hq[0][r][k] = quant8(sm.hs[r][k]);
   }
   consumer_sync<NCW>();
 
@@ -419,79 +475,87 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     int8_t(*hq_rd)[HQ_LD] = sm.hq[t & 1];
     int8_t(*hq_wr)[HQ_LD] = sm.hq[(t + 1) & 1];
 
-    for (int i = tid; i < CORE_TS * DEC_IN; i += NCT) {
+    for (int i = tid; i < TS * DEC_IN; i += NCT) {
       const int r = i / DEC_IN, k = i % DEC_IN;
-      sm.zin[r][k] = (r < ts && s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
+      sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
     }
     consumer_sync<NCW>();
 
     // ---- dense1: tanh(W z + b), 80 -> 96
     {
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      dense_chunk<96>(cx, a, sm.zin[sl], DEC_IN, grp);
+      float a[OPT], bd[OPT];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int o = 4 * grp + i;               // 24 groups x 4 = 96 outputs
-        if (o >= 96) continue;
-        float y = tanh_r(__fadd_rn(a[i], W.dec_dense1.bias[o]));
-        sm.seg[sl][o] = y;
-        cur[sl][o] = quant8(y);
+      for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 96 / OPT) ? W.dec_dense1.bias[OPT * grp + i] : 0.f; }
+      dense_chunk<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
+      if (grp < 96 / OPT) {
+#pragma unroll
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          float y = tanh_r(__fadd_rn(a[i], bd[i]));
+          sm.seg[sl][o] = y;
+          cur[sl][o] = quant8(y);
+        }
       }
     }
     consumer_sync<NCW>();
-    float oacc[4] = {0.f, 0.f, 0.f, 0.f};
-    dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], 96, grp);
+    float oacc[OPT];
+#pragma unroll
+    for (int i = 0; i < OPT; i++) oacc[i] = 0.f;
+    dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], 96, grp);
     consumer_sync<NCW>();
 
     int off = 96;
 #pragma unroll 1
     for (int l = 0; l < 5; l++) {
       // GRU l on cur[0:off); its new state is kept un-gated (src/rade_dec.c:66-67)
-      gru_layer<DEC_GRU>(cx, W.dec_gru_in[l], W.dec_gru_rec[l], &cur[0][0], DEC_LDA, &hq_rd[0][l * DEC_GRU], HQ_LD,
-                         &sm.hs[0][l * DEC_GRU], 5 * DEC_GRU, ts,
-                         [&](int row, int j, float h) { hq_wr[row][l * DEC_GRU + j] = quant8(h); });
+      gru_layer<DEC_GRU, TS>(cx, W.dec_gru_in[l], W.dec_gru_rec[l], &cur[0][0], DEC_LDA, &hq_rd[0][l * DEC_GRU], HQ_LD,
+                             &sm.hs[0][l * DEC_GRU], 5 * DEC_GRU,
+                             [&](int row, int j, float h) { hq_wr[row][l * DEC_GRU + j] = quant8(h); });
       consumer_sync<NCW>();
       // GLU l: out = h * sigmoid(Wg h + b)  -> concat;  12 n-tiles, one per warp, a single 9 KB chunk
       {
         const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+        const I8LayerDev &L = W.dec_glu[l];
+        const float2 gs = *reinterpret_cast<const float2 *>(L.scale + warp * 8 + 2 * tig);
+        const float2 gb = *reinterpret_cast<const float2 *>(L.bias + warp * 8 + 2 * tig);
         int acc[1][4] = {};
         const int nt[1] = {warp};
         const bool use[1] = {true};
         gemm_stream<1>(cx, acc, nt, use, true, &hq_wr[0][l * DEC_GRU], HQ_LD, DEC_GRU / 32, DEC_GRU / 8);
-        const I8LayerDev &L = W.dec_glu[l];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int row = g + ((e & 2) ? 8 : 0);
-          if (row >= ts) continue;
+          if (row >= TS) continue;
           const int n = warp * 8 + 2 * tig + (e & 1);
-          float y = __fmul_rn(sm.hs[row][l * DEC_GRU + n], sigmoid_r(lin(acc[0][e], L.scale[n], L.bias[n])));
+          float y = __fmul_rn(sm.hs[row][l * DEC_GRU + n], sigmoid_r(lin(acc[0][e], (e & 1) ? gs.y : gs.x, (e & 1) ? gb.y : gb.x)));
           sm.seg[row][n] = y; cur[row][off + n] = quant8(y);
         }
       }
       consumer_sync<NCW>();
-      dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
+      dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
       consumer_sync<NCW>();
       off += DEC_GRU;
-      conv_layer<DEC_CONV, NCW>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red, ts,
-                                [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
+      conv_layer<DEC_CONV, NCW, TS>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,
+                                    [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
       consumer_sync<NCW>();
-      dense_chunk<DEC_OUT>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
+      dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
       consumer_sync<NCW>();
       off += DEC_CONV;
     }
 
     if (sg < S && (!active || active[sg])) {
+      if (grp < DEC_OUT / OPT) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int o = 4 * grp + i;
-        if (o >= DEC_OUT) continue;
-        const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
-        if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;
-        else {
-          const int fr = o / 21, f = o % 21;
-          if (f < 20) out[((size_t)sg * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f] = v;
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
+          if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;
+          else {
+            const int fr = o / 21, f = o % 21;
+            if (f < 20) out[((size_t)sg * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f] = v;
+          }
+          if (o == 20 && uw_count && v > 0.f) atomicAdd(&uw_count[sg], 1);
         }
-        if (o == 20 && uw_count && v > 0.f) atomicAdd(&uw_count[sg], 1);
       }
       if (out_mode == 1) {            // zero the 16 unused slots of each 36-wide vector
         for (int k = grp; k < 4 * 16; k += NGRP)
@@ -501,8 +565,8 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   }
 
   const int last = (T + 1) & 1;      // buffer that held the final step's concat
-  for (int r = 0; r < CORE_TS; r++) {
-    if (r >= ts || s0 + r >= S || (active && !active[s0 + r])) continue;
+  for (int r = 0; r < TS; r++) {
+    if (s0 + r >= S || (active && !active[s0 + r])) continue;
     DecStreamState *st = state + (s0 + r);
     for (int i = tid; i < 5 * DEC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
     for (int i = tid; i < DEC_LDA / 4; i += NCT)
@@ -519,10 +583,14 @@ static int core_tile_streams(int S) {
   if (e && (atoi(e) == 8 || atoi(e) == 16)) return atoi(e);
   return ((S + 15) / 16 >= 148) ? 16 : 8;
 }
+// weight-ring depth: 8-stream tiles have the shared memory for a deeper ring
+constexpr int NST16 = 4, NST8 = 5;
 // per-device kernel attributes (opt-in to > 48 KB dynamic shared memory); called by rade_b200_open on its device
 int core_codec_init_device() {
-  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem)));
-  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel<16, NST16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem<16, NST16>)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel<8, NST8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem<8, NST8>)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel<16, NST16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem<16, NST16>)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel<8, NST8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem<8, NST8>)));
   return 0;
 }
 
@@ -530,7 +598,10 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
                         const uint8_t *active, int S, int T, cudaStream_t stream) {
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
-  core_encoder_kernel<<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem), stream>>>(W, state, in, in_mode, z, active, S, T, ts);
+  if (ts == 16)
+    core_encoder_kernel<16, NST16><<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem<16, NST16>), stream>>>(W, state, in, in_mode, z, active, S, T);
+  else
+    core_encoder_kernel<8, NST8><<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem<8, NST8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -539,7 +610,10 @@ int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const fl
                         int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
-  core_decoder_kernel<<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T, ts);
+  if (ts == 16)
+    core_decoder_kernel<16, NST16><<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem<16, NST16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+  else
+    core_decoder_kernel<8, NST8><<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem<8, NST8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
