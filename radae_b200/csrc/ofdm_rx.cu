@@ -90,12 +90,15 @@ __device__ float block_sum(float v, float *scratch) {
 }
 
 // ================================================================= band-pass filter + ring append
-__global__ void __launch_bounds__(256)
+// 101-tap real FIR on complex samples.  Each thread produces four consecutive outputs from a sliding register window
+// (one LDS.128 = two new samples per two taps) with the taps as constant-bank operands of the FMAs.
+__constant__ float c_bpf_h[RADE_BPF_NTAP + 3];
+constexpr int BPF_THREADS = 288;                  // 4 outputs per thread, nin <= 1120
+__global__ void __launch_bounds__(BPF_THREADS)
 rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, float2 *__restrict__ bpf_mem,
               const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en,
               int *__restrict__ search_list, int *__restrict__ track_list, int *__restrict__ counters) {
-  __shared__ float2 X[RADE_BPF_MEM + RADE_NIN_MAX];
-  __shared__ float h[RADE_BPF_NTAP];
+  __shared__ __align__(16) float2 X[RADE_BPF_MEM + RADE_NIN_MAX + 42];
   const int s = blockIdx.x, tid = threadIdx.x;
   if (active && !active[s]) return;
   RxCtl &c = ctl[s];
@@ -106,24 +109,41 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
     const float2 ph = c.bpf_phase;
     const int off = c.bpf_first ? 2 : 0;
     float2 *mem = bpf_mem + (size_t)s * RADE_BPF_MEM;
-    if (tid < RADE_BPF_NTAP) h[tid] = T.bpf_h[tid];
-    for (int i = tid; i < RADE_BPF_MEM; i += blockDim.x) X[i] = mem[i];
-    for (int i = tid; i < nin; i += blockDim.x) X[RADE_BPF_MEM + i] = cmul(xin[i], cmul(ph, T.bpf_exp[i]));   // mix down
+    for (int i = tid; i < RADE_BPF_MEM; i += BPF_THREADS) X[i] = mem[i];
+    for (int i = tid; i < nin; i += BPF_THREADS) X[RADE_BPF_MEM + i] = cmul(xin[i], cmul(ph, T.bpf_exp[i]));   // mix down
+    for (int i = RADE_BPF_MEM + nin + tid; i < RADE_BPF_MEM + RADE_NIN_MAX + 42; i += BPF_THREADS) X[i] = make_float2(0.f, 0.f);
     __syncthreads();
-    for (int i = tid; i < nin; i += blockDim.x) {
-      float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 4
-      for (int k = 0; k < RADE_BPF_NTAP; k++) {
-        const float2 v = X[i + k + off];
-        acc.x = fmaf(h[k], v.x, acc.x); acc.y = fmaf(h[k], v.y, acc.y);
+    const int i0 = 4 * tid;
+    if (i0 < nin) {
+      // out[i0 + q] = sum_k h[k] X[i0 + q + k + off], k ascending (same summation order as a plain tap loop)
+      const float4 *Xv = reinterpret_cast<const float4 *>(X + i0 + off);
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float4 w0 = Xv[0], w1 = Xv[1];              // samples k..k+1, k+2..k+3
+#pragma unroll
+      for (int k = 0; k < RADE_BPF_NTAP + 1; k += 2) {
+        const float4 w2 = Xv[k / 2 + 2];          // samples k+4, k+5
+        const float h0 = c_bpf_h[k], h1 = c_bpf_h[k + 1];        // h[101] = 0 pads the odd tap count
+        acc[0].x = fmaf(h0, w0.x, acc[0].x); acc[0].y = fmaf(h0, w0.y, acc[0].y);
+        acc[1].x = fmaf(h0, w0.z, acc[1].x); acc[1].y = fmaf(h0, w0.w, acc[1].y);
+        acc[2].x = fmaf(h0, w1.x, acc[2].x); acc[2].y = fmaf(h0, w1.y, acc[2].y);
+        acc[3].x = fmaf(h0, w1.z, acc[3].x); acc[3].y = fmaf(h0, w1.w, acc[3].y);
+        if (k + 1 < RADE_BPF_NTAP) {
+          acc[0].x = fmaf(h1, w0.z, acc[0].x); acc[0].y = fmaf(h1, w0.w, acc[0].y);
+          acc[1].x = fmaf(h1, w1.x, acc[1].x); acc[1].y = fmaf(h1, w1.y, acc[1].y);
+          acc[2].x = fmaf(h1, w1.z, acc[2].x); acc[2].y = fmaf(h1, w1.w, acc[2].y);
+          acc[3].x = fmaf(h1, w2.x, acc[3].x); acc[3].y = fmaf(h1, w2.y, acc[3].y);
+        }
+        w0 = w1; w1 = w2;
       }
-      rg[ring_idx(head, i)] = cmul(acc, cconj(cmul(ph, T.bpf_exp[i])));                                         // mix up
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (i0 + q < nin) rg[ring_idx(head, i0 + q)] = cmul(acc[q], cconj(cmul(ph, T.bpf_exp[i0 + q])));      // mix up
     }
     __syncthreads();
-    for (int i = tid; i < RADE_BPF_MEM; i += blockDim.x) mem[i] = X[nin + i];
+    for (int i = tid; i < RADE_BPF_MEM; i += BPF_THREADS) mem[i] = X[nin + i];
     if (tid == 0) { c.bpf_phase = cmul(ph, T.bpf_exp[nin - 1]); c.bpf_first = 0; }
   } else {
-    for (int i = tid; i < nin; i += blockDim.x) rg[ring_idx(head, i)] = xin[i];
+    for (int i = tid; i < nin; i += BPF_THREADS) rg[ring_idx(head, i)] = xin[i];
   }
   if (tid == 0) {
     int nh = head + nin; if (nh >= RADE_RXBUF) nh -= RADE_RXBUF;
@@ -220,98 +240,133 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
 }
 
 // ================================================================= fine timing / frequency refinement (shared by track & finish)
-constexpr int REF_CH = 11;        // frequencies per chunk
-constexpr int REF_NT = 16;        // max timing offsets
+// acquisition.refine (radae/dsp.py:233-270): argmax over (f outer, t inner) of |Dt1 + Dt2|, strict >, with
+//   Dt1[t,f] = sum_n rx[t+n] conj(p[n]) exp(-j w_f n),  Dt2 = same at t + Nmf times exp(-j w_f Nmf),
+// computed in complex128 and rounded to csingle like the reference.  Here: a real GEMM on the FP64 tensor cores
+// (DMMA m8n8k4, 256 FMA per instruction): A = Toeplitz view of the widened samples [8 t][(n, re/im)], B = [(n, re/im)]
+// [(f, re/im)] formed on the fly from the steering table vtab; 24 frequencies (6 n-tiles) per pass.
+constexpr int REF_NT = 16;                        // max timing offsets
+constexpr int REF_NFP = 24;                       // frequencies per pass = 6 DMMA n-tiles of 4 complex columns
+constexpr int REF_VLD = 165;                      // vtab row: tap n lives at n + (n >> 5); 165 = 5 mod 8 spreads f over the banks
+constexpr int REF_RLEN = REF_NT + RADE_M + 8;     // widened window (+ over-read of the last k-step)
+constexpr int REF_THREADS = 128;                  // four warps
 struct RefineSmem {
-  double2 vtab[REF_CH][RADE_M];   // conj(p[n]) * exp(-j w n)
-  double2 ra[REF_NT + RADE_M];    // rx[t_lo ...] widened once (the reference up-casts csingle to complex128 in np.dot)
-  double2 rb[REF_NT + RADE_M];    // rx[t_lo + Nmf ...]
-  float2 d1[REF_CH][REF_NT];
-  float2 d2[REF_CH][REF_NT];
-  float red_mag[8]; int red_ord[8];
+  double2 vtab[REF_NFP][REF_VLD];                 // conj(p[n]) exp(-j w_f n)
+  double2 ramp[REF_NFP];                          // exp(-j w_f Nmf)
+  double2 ra[REF_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
+  double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
+  double2 rb[REF_RLEN];                           // rx[t_lo + Nmf ...]
+  float2 d1[REF_NFP][REF_NT];
+  float2 d2[REF_NFP][REF_NT];
+  float red_mag[4]; int red_ord[4];
   float best_mag; int best_t; int best_found; double best_f;
 };
 
 // values of np.arange(start, stop, step) for float64: v[i] = start + i*((start+step)-start), len = ceil((stop-start)/step)
 __device__ __forceinline__ int arange_len(double start, double stop, double step) { return (int)ceil((stop - start) / step); }
 
-// searches t in [t_lo, t_lo+nt) x f in arange(f_start, f_stop, f_step); result in sm.best_* (best_found == 0: nothing beat 0)
-// Executed by a group of `nthr` threads (`tid` = index within the group) that synchronise on named barrier `bar`.
-__device__ void refine_block(RefineSmem &sm, const DspTables &T, const float2 *rg, int head, int t_lo, int nt,
-                             double f_start, double f_stop, double f_step, int tid, int nthr, int bar) {
-  const int nf = arange_len(f_start, f_stop, f_step);
+// Searches t in [t_lo, t_lo+nt) x f in arange(f_start, f_stop, f_step); result in sm.best_* (best_found == 0: nothing beat 0).
+// Executed by REF_THREADS threads (g = index within the group) that synchronise on named barrier `bar`.
+// load(i) returns rx_buf[i] (logical index).  WIDE_T: nt > 8 -> warp = (pilot position, 8-row t tile) x 6 n-tiles;
+// otherwise warp = (pilot position, half of the n-tiles) with a single t tile.
+template <bool WIDE_T, typename Load>
+__device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Load load, int t_lo, int nt,
+                            double f_start, double f_stop, double f_step, int g, int bar) {
+  constexpr int NQ = WIDE_T ? 6 : 3;              // n-tiles per warp
+  const int nf_all = arange_len(f_start, f_stop, f_step);
   const double delta = (f_start + f_step) - f_start;
-  if (tid == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
-  for (int i = tid; i < nt + RADE_M; i += nthr) {
-    const float2 a = rg[ring_idx(head, t_lo + i)], b = rg[ring_idx(head, t_lo + RADE_NMF + i)];
-    sm.ra[i] = make_double2((double)a.x, (double)a.y);
-    sm.rb[i] = make_double2((double)b.x, (double)b.y);
+  if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
+  for (int i2 = g; i2 < REF_RLEN; i2 += REF_THREADS) {
+    const bool in = i2 < nt + RADE_M;
+    const float2 a = in ? load(t_lo + i2) : make_float2(0.f, 0.f), c = in ? load(t_lo + RADE_NMF + i2) : make_float2(0.f, 0.f);
+    sm.ra[i2] = make_double2((double)a.x, (double)a.y);
+    sm.rb[i2] = make_double2((double)c.x, (double)c.y);
   }
-  for (int c0 = 0; c0 < nf; c0 += REF_CH) {
-    const int nfc = min(REF_CH, nf - c0);
-    group_sync(bar, nthr);
-    for (int idx = tid; idx < nfc * (RADE_M / 8); idx += nthr) {
-      // 8 consecutive taps of one frequency: exp(-j w n0) by sincos, then 7 rotations by exp(-j w) (|error| ~ 1e-15)
-      const int fi = idx / (RADE_M / 8), n0 = (idx % (RADE_M / 8)) * 8;
-      const double f = f_start + (double)(c0 + fi) * delta;
-      const double w = 2.0 * M_PI * f / RADE_FS;
-      double sn, cs, s1, c1; sincos(w * (double)n0, &sn, &cs); sincos(w, &s1, &c1);
-      double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float2 pn = T.p[n0 + k];
-        sm.vtab[fi][n0 + k] = dcmul(e, make_double2((double)pn.x, -(double)pn.y));
-        e = dcmul(e, step);
-      }
-    }
-    group_sync(bar, nthr);
-    for (int item = tid; item < nfc * nt * 2; item += nthr) {
-      const int half = item & 1, ti = (item >> 1) % nt, fi = (item >> 1) / nt;
-      const double2 *r = half ? sm.rb : sm.ra;
-      double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;      // two partial sums per component: halves the FMA dependency chain
-#pragma unroll 2
-      for (int n = 0; n < RADE_M; n += 2) {
-        const double2 v = sm.vtab[fi][n], x = r[ti + n], v2 = sm.vtab[fi][n + 1], x2 = r[ti + n + 1];
-        ax = fma(x.x, v.x, ax); ax = fma(-x.y, v.y, ax);
-        ay = fma(x.x, v.y, ay); ay = fma(x.y, v.x, ay);
-        bx = fma(x2.x, v2.x, bx); bx = fma(-x2.y, v2.y, bx);
-        by = fma(x2.x, v2.y, by); by = fma(x2.y, v2.x, by);
-      }
-      ax += bx; ay += by;
-      if (half) {                 // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
+  for (int c0 = 0; c0 < nf_all; c0 += REF_NFP) {
+    const int nf = min(REF_NFP, nf_all - c0);
+    group_sync(bar, REF_THREADS);                 // previous pass done with vtab / d1 / d2
+    // steering vectors for this pass: thread = (f, 32-tap segment), one sincos pair + 31 rotations (|error| ~ 1e-15)
+    for (int task = g; task < REF_NFP * 5; task += REF_THREADS) {
+      const int fi = task / 5, seg = task % 5;
+      double2 *row = sm.vtab[fi] + 33 * seg;
+      if (fi < nf) {
         const double f = f_start + (double)(c0 + fi) * delta;
-        double sn, cs; sincos(2.0 * M_PI * f / RADE_FS * (double)RADE_NMF, &sn, &cs);
-        const double2 e = dcmul(make_double2(ax, ay), make_double2(cs, -sn));
-        sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y);
-      } else sm.d1[fi][ti] = make_float2((float)ax, (float)ay);
+        const double w = 2.0 * M_PI * f / RADE_FS;
+        double sn, cs, s1, c1; sincos(w * (double)(32 * seg), &sn, &cs); sincos(w, &s1, &c1);
+        double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
+#pragma unroll 4
+        for (int q = 0; q < 32; q++) { row[q] = dcmul(e, pcd[32 * seg + q]); e = dcmul(e, step); }
+        if (seg == 0) {             // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
+          sincos(w * (double)RADE_NMF, &sn, &cs);
+          sm.ramp[fi] = make_double2(cs, -sn);
+        }
+      } else {
+        for (int q = 0; q < 32; q++) row[q] = make_double2(0.0, 0.0);
+      }
     }
-    group_sync(bar, nthr);
+    group_sync(bar, REF_THREADS);
+    {
+      const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
+      const int half = wr >> 1, mt = WIDE_T ? (wr & 1) : 0, q0 = WIDE_T ? 0 : 3 * (wr & 1);
+      const double *ap = reinterpret_cast<const double *>((half ? sm.rb : sm.ra) + mt * 8 + gq + (c >> 1)) + (c & 1);
+      const int reim = gq & 1, comp = c & 1;
+      const unsigned flip = (reim == 0 && comp == 1) ? 0x80000000u : 0u;      // B = [vr; -vi] for Re columns, [vi; vr] for Im
+      const double *bp[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) bp[q] = reinterpret_cast<const double *>(sm.vtab[(q0 + q) * 4 + (gq >> 1)] + (c >> 1)) + (comp ^ reim);
+      double acc[NQ][2];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll 1
+      for (int blk = 0; blk < 5; blk++) {
+#pragma unroll 4
+        for (int kk = 0; kk < 16; kk++) {
+          const double av = ap[4 * (16 * blk + kk)];
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            double bv = bp[q][2 * (33 * blk + 2 * kk)];
+            bv = __hiloint2double(__double2hiint(bv) ^ flip, __double2loint(bv));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(acc[q][0]), "+d"(acc[q][1]) : "d"(av), "d"(bv));
+          }
+        }
+      }
+      const int ti = mt * 8 + gq;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int fi = (q0 + q) * 4 + c;
+        if (fi < nf && ti < nt) {
+          if (half) { const double2 e = dcmul(make_double2(acc[q][0], acc[q][1]), sm.ramp[fi]); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
+          else sm.d1[fi][ti] = make_float2((float)acc[q][0], (float)acc[q][1]);
+        }
+      }
+    }
+    group_sync(bar, REF_THREADS);
     float bm = -1.f; int bo = 0x7fffffff;
-    for (int k = tid; k < nfc * nt; k += nthr) {
-      const int fi = k / nt, ti = k % nt;
-      const float2 a = sm.d1[fi][ti], b = sm.d2[fi][ti];
-      const float m = hypotf(a.x + b.x, a.y + b.y);
-      const int ord = (c0 + fi) * nt + ti;          // f outer loop, t inner loop
-      if (m > bm || (m == bm && ord < bo)) { bm = m; bo = ord; }
+    for (int q = g; q < nf * nt; q += REF_THREADS) {
+      const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
+      const float2 a = sm.d1[fi][ti], c = sm.d2[fi][ti];
+      const float m = hypotf(a.x + c.x, a.y + c.y);
+      if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
       if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
     }
-    if ((tid & 31) == 0) { sm.red_mag[tid >> 5] = bm; sm.red_ord[tid >> 5] = bo; }
-    group_sync(bar, nthr);
-    if (tid == 0) {
-      for (int i = 1; i < (nthr >> 5); i++)
-        if (sm.red_mag[i] > bm || (sm.red_mag[i] == bm && sm.red_ord[i] < bo)) { bm = sm.red_mag[i]; bo = sm.red_ord[i]; }
-      if (bm > sm.best_mag) {     // strict >, chunks are visited in increasing f
+    if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
+    group_sync(bar, REF_THREADS);
+    if (g == 0) {
+      for (int q = 1; q < REF_THREADS / 32; q++)
+        if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
+      if (bm > sm.best_mag) {       // strict >: passes are visited in increasing f, the initial Dtmax is 0 (radae/dsp.py:262)
         sm.best_mag = bm; sm.best_found = 1;
         sm.best_t = t_lo + bo % nt;
-        sm.best_f = f_start + (double)(bo / nt) * delta;
+        sm.best_f = f_start + (double)(c0 + bo / nt) * delta;
       }
     }
   }
-  group_sync(bar, nthr);
+  group_sync(bar, REF_THREADS);
 }
 
 // sigma_r = (mean|Dt1| + mean|Dt2|) / (2*sqrt(pi/2)) from the row sums, float32 like the reference's np.mean
@@ -333,11 +388,7 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
 //   warps 12-15 refine: 16 timing x 20(21) frequency x 2 pilot positions in complex128 as a real GEMM on the FP64
 //               tensor cores (DMMA m8n8k4: 256 FMA per instruction instead of 32)
 // then sigma_r, the four complex128 spot correlations, slips and the sync-state part of the state machine.
-constexpr int TRK_REFRESH = 384, TRK_REFINE = 128, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
-constexpr int TRK_NF = 21;                        // max len(np.arange(fmax-1, fmax+1, 0.1))
-constexpr int TRK_NFP = 24;                       // padded to 6 DMMA n-tiles of 4 complex columns
-constexpr int TRK_VLD = 165;                      // vtab row: tap n lives at n + (n >> 5); 165 = 5 mod 8 spreads f over the banks
-constexpr int TRK_RLEN = REF_NT + RADE_M + 8;     // widened window + sliding-window over-read
+constexpr int TRK_REFRESH = 384, TRK_REFINE = REF_THREADS, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
 struct TrackStage {
   alignas(128) float2 rx[RADE_RXBUF];             // rx_buf in LOGICAL order (two bulk copies around ring_head)
   float rs[2 * RADE_NMF];                         // row sums
@@ -346,15 +397,7 @@ struct TrackStage {
 struct TrackSmem {
   AcqTables tab;
   TrackStage st[2];
-  double2 vtab[TRK_NFP][TRK_VLD];                 // conj(p[n]) exp(-j w_f n)
-  double2 ramp[TRK_NFP];                          // exp(-j w_f Nmf)
-  double2 ra[TRK_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
-  double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
-  double2 rb[TRK_RLEN];                           // rx[t_lo + Nmf ...]
-  float2 d1[TRK_NFP][REF_NT];
-  float2 d2[TRK_NFP][REF_NT];
-  float red_mag[4]; int red_ord[4];
-  float best_mag; int best_t; int best_found; double best_f;
+  RefineSmem ref;
   float scratch[32];
   double spot[4];
   uint64_t full[2], empty[2], tab_bar;
@@ -377,7 +420,7 @@ __device__ float consumer_sum(float v, float *scratch) {
 __global__ void __launch_bounds__(TRK_THREADS, 1)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
                 int *__restrict__ uw_errors, const int *__restrict__ track_list, const int *__restrict__ counters,
-                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out, int dbg) {
+                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -420,7 +463,6 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     const int tmax0 = st.ctl.tmax; const double fmax0 = st.ctl.fmax;
     const int rot = st.ctl.n_check % 20;
     if (tid < TRK_REFRESH) {
-      if (!(dbg & 1)) {
       // ---- check_pilots row refresh (radae/dsp.py:288-295, deterministic schedule): rows t_i = 20 i + rot, both pilot
       // positions, 40 grid frequencies.  lane = (row i, k group kg, tap parity ks): conflict-free shared-memory reads
       const int ks = tid & 1, kg = (tid >> 1) & 3, i = tid >> 3;
@@ -475,108 +517,16 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
         rs[r] = s0; rs[RADE_NMF + r] = s1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.rs is overwritten by a bulk copy two streams later
       }
-      }
     } else {
       // ---- refine (radae_rxe.py:202-205, radae/dsp.py:233-270): t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, .1)
-      const int g = tid - TRK_REFRESH;
-      const int t_lo = max(0, tmax0 - 8), nt = tmax0 + 8 - t_lo;
-      const double f_start = fmax0 - 1, f_stop = fmax0 + 1, f_step = 0.1;
-      const int nf = min(arange_len(f_start, f_stop, f_step), TRK_NF);
-      const double delta = (f_start + f_step) - f_start;
-      if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
-      for (int i2 = g; i2 < TRK_RLEN; i2 += TRK_REFINE) {
-        const bool in = i2 < nt + RADE_M;
-        const float2 a = in ? st.rx[t_lo + i2] : make_float2(0.f, 0.f), c = in ? st.rx[t_lo + RADE_NMF + i2] : make_float2(0.f, 0.f);
-        sm.ra[i2] = make_double2((double)a.x, (double)a.y);
-        sm.rb[i2] = make_double2((double)c.x, (double)c.y);
-      }
-      // steering vectors conj(p[n]) exp(-j w_f n) for all f: thread = (f, 32-tap segment), one sincos pair + 31 rotations
-      for (int task = g; task < ((dbg & 2) ? 0 : TRK_NFP * 5); task += TRK_REFINE) {
-        const int fi = task / 5, seg = task % 5;
-        double2 *row = sm.vtab[fi] + 33 * seg;
-        if (fi < nf) {
-          const double f = f_start + (double)fi * delta;
-          const double w = 2.0 * M_PI * f / RADE_FS;
-          double sn, cs, s1, c1; sincos(w * (double)(32 * seg), &sn, &cs); sincos(w, &s1, &c1);
-          double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
-#pragma unroll 4
-          for (int q = 0; q < 32; q++) { row[q] = dcmul(e, sm.tab.pcd[32 * seg + q]); e = dcmul(e, step); }
-          if (seg == 0) {           // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
-            sincos(w * (double)RADE_NMF, &sn, &cs);
-            sm.ramp[fi] = make_double2(cs, -sn);
-          }
-        } else {
-          for (int q = 0; q < 32; q++) row[q] = make_double2(0.0, 0.0);
-        }
-      }
-      group_sync(1, TRK_REFINE);
-      {
-        // D[t][f] = sum_n rx[t+n] v_f[n] as a real GEMM on the FP64 tensor cores (DMMA m8n8k4): A = Toeplitz view of the
-        // widened samples [8 t][(n, re/im)], B = [(n, re/im)][(f, re/im)] built on the fly from vtab.  Warp = (pilot
-        // position, 8-row t tile); 6 n-tiles = 24 frequencies; K = 320 in 80 steps of two taps.
-        const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
-        const int half = wr >> 1, mt = wr & 1;
-        const double *ap = reinterpret_cast<const double *>((half ? sm.rb : sm.ra) + mt * 8 + gq + (c >> 1)) + (c & 1);
-        const int reim = gq & 1, comp = c & 1;
-        const unsigned flip = (reim == 0 && comp == 1) ? 0x80000000u : 0u;      // B = [vr; -vi] for Re columns, [vi; vr] for Im
-        const double *bp[6];
-#pragma unroll
-        for (int q = 0; q < 6; q++) bp[q] = reinterpret_cast<const double *>(sm.vtab[q * 4 + (gq >> 1)] + (c >> 1)) + (comp ^ reim);
-        double acc[6][2];
-#pragma unroll
-        for (int q = 0; q < 6; q++) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll 1
-        for (int blk = 0; blk < ((dbg & 2) ? 0 : 5); blk++) {
-#pragma unroll 4
-          for (int kk = 0; kk < 16; kk++) {
-            const double av = ap[4 * (16 * blk + kk)];
-#pragma unroll
-            for (int q = 0; q < 6; q++) {
-              double bv = bp[q][2 * (33 * blk + 2 * kk)];
-              bv = __hiloint2double(__double2hiint(bv) ^ flip, __double2loint(bv));
-              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                           : "+d"(acc[q][0]), "+d"(acc[q][1]) : "d"(av), "d"(bv));
-            }
-          }
-        }
-        const int ti = mt * 8 + gq;
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-          const int fi = q * 4 + c;
-          if (fi < nf && ti < nt) {
-            if (half) { const double2 e = dcmul(make_double2(acc[q][0], acc[q][1]), sm.ramp[fi]); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
-            else sm.d1[fi][ti] = make_float2((float)acc[q][0], (float)acc[q][1]);
-          }
-        }
-      }
-      group_sync(1, TRK_REFINE);
-      float bm = -1.f; int bo = 0x7fffffff;
-      for (int q = g; q < nf * nt; q += TRK_REFINE) {
-        const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
-        const float2 a = sm.d1[fi][ti], c = sm.d2[fi][ti];
-        const float m = hypotf(a.x + c.x, a.y + c.y);
-        if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
-        if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
-      }
-      if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
-      group_sync(1, TRK_REFINE);
-      if (g == 0) {
-        for (int q = 1; q < TRK_REFINE / 32; q++)
-          if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
-        if (bm > 0.f) {             // strict > against the initial Dtmax = 0 (radae/dsp.py:262)
-          sm.best_mag = bm; sm.best_found = 1;
-          sm.best_t = t_lo + bo % nt;
-          sm.best_f = f_start + (double)(bo / nt) * delta;
-        }
-      }
+      const int t_lo = max(0, tmax0 - 8);
+      const float2 *rxl = st.rx;
+      refine_dmma<true>(sm.ref, sm.tab.pcd, [rxl](int i) { return rxl[i]; }, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1,
+                        tid - TRK_REFRESH, 1);
     }
     group_sync(3, TRK_CONSUMERS);
-    int tmax = sm.best_found ? sm.best_t : tmax0;
-    const double fhat = sm.best_found ? sm.best_f : fmax0;
+    int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
+    const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
     const double fmax = 0.9 * fmax0 + 0.1 * fhat;
     // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (radae/dsp.py:297-300)
     float sigma_r;
@@ -824,7 +774,12 @@ rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       // first fix after acquisition: t in [max(0,tmax-1), tmax+2), f in arange(fmax-10, fmax+10, 0.25)  (radae_rxe.py:267-273)
       const int tm = c.tmax; const double fm = c.fmax;
       const int t_lo = max(0, tm - 1);
-      refine_block(sm.ref, T, ring + (size_t)s * RADE_RXBUF, c.ring_head, t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, blockDim.x, 1);
+      if (tid < REF_THREADS) {
+        const float2 *rg = ring + (size_t)s * RADE_RXBUF; const int head = c.ring_head;
+        refine_dmma<false>(sm.ref, reinterpret_cast<const AcqTables *>(T.acq_tab)->pcd, [rg, head](int i) { return rg[ring_idx(head, i)]; },
+                           t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, 1);
+      }
+      __syncthreads();
       if (tid == 0) {
         if (sm.ref.best_found) { c.tmax = sm.ref.best_t; c.fmax = sm.ref.best_f; }
         c.fmax += c.foff_err; c.foff_err = 0.0;
@@ -864,6 +819,12 @@ int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStrea
 }
 
 int rx_dsp_init_device() {
+  {
+    DspTablesHost th; dsp_tables_host(th);
+    float h[RADE_BPF_NTAP + 3] = {0.f};
+    for (int i = 0; i < RADE_BPF_NTAP; i++) h[i] = th.bpf_h[i];
+    CUDA_CHECK(cudaMemcpyToSymbol(c_bpf_h, h, sizeof(h)));
+  }
   CUDA_CHECK(cudaFuncSetAttribute(rx_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetectSmem)));
   CUDA_CHECK(cudaFuncSetAttribute(rx_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
   CUDA_CHECK(cudaFuncSetAttribute(rx_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinishSmem)));
@@ -874,17 +835,16 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof) {
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-  static const int dbg = getenv("RADE_B200_TRACK_DEBUG") ? atoi(getenv("RADE_B200_TRACK_DEBUG")) : 0;   // timing experiments only
   int *cnt = B.counters + 4 * B.parity, *cnt_next = B.counters + 4 * (B.parity ^ 1);
   B.parity ^= 1;
   prof->begin(K_RX_BPF);
-  rx_bpf_kernel<<<S, 256, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt);
+  rx_bpf_kernel<<<S, BPF_THREADS, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt);
   prof->end(K_RX_BPF); prof->begin(K_RX_DETECT);
   int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 3) det_grid = n_sm * 3;
   rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
   prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
   rx_track_kernel<<<S < n_sm ? S : n_sm, TRK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.track_list,
-                                                                               cnt, ret_out, B.dec_active, B.nin, dbg);
+                                                                               cnt, ret_out, B.dec_active, B.nin);
   prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
