@@ -56,21 +56,17 @@ __global__ void channel_apply_kernel(float2 *__restrict__ rx, const float2 *__re
 
 constexpr int NSIN = 16;
 
-// path gain at absolute time t (samples): (1/sqrt(2*NSIN)) * sum_i exp(j(2*pi*f_i*t/Fs + phi_i)), f_i ~ N(0, (spread/2)^2)
-__device__ float2 path_gain(unsigned long long seed, uint32_t stream, uint32_t path, double t, float spread) {
-  float re = 0.f, im = 0.f;
-  for (int i = 0; i < NSIN; i++) {
-    uint32_t c[4] = {(uint32_t)i, path, stream, 0x5EEDu};
-    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const float rr = sqrtf(-2.f * logf(u01(c[0])));
-    float s1, c1; sincospif(2.f * u01(c[1]), &s1, &c1);
-    const double f = 0.5 * (double)spread * (double)(rr * c1);           // Gaussian Doppler: sigma_f = spread/2
-    double sn, cs;
-    sincos(2.0 * M_PI * (f * t / RADE_FS + (double)u01(c[2])), &sn, &cs);
-    re += (float)cs; im += (float)sn;
-  }
-  const float a = rsqrtf(2.f * NSIN);
-  return make_float2(a * re, a * im);
+// one sinusoid of a path gain at absolute time t (samples): exp(j(2*pi*f_i*t/Fs + phi_i)), f_i ~ N(0, (spread/2)^2);
+// the gain is (1/sqrt(2*NSIN)) * the sum over i = 0..NSIN-1
+__device__ float2 path_gain_term(unsigned long long seed, uint32_t stream, uint32_t path, int i, double t, float spread) {
+  uint32_t c[4] = {(uint32_t)i, path, stream, 0x5EEDu};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float rr = sqrtf(-2.f * logf(u01(c[0])));
+  float s1, c1; sincospif(2.f * u01(c[1]), &s1, &c1);
+  const double f = 0.5 * (double)spread * (double)(rr * c1);           // Gaussian Doppler: sigma_f = spread/2
+  double sn, cs;
+  sincos(2.0 * M_PI * (f * t / RADE_FS + (double)u01(c[2])), &sn, &cs);
+  return make_float2((float)cs, (float)sn);
 }
 
 // streaming generator form: one CTA per stream, one modem frame (960 samples) per call
@@ -86,15 +82,26 @@ channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, Ch
   const float2 *txs = tx + (size_t)s * RADE_NMF;
   for (int i = tid; i < 64; i += blockDim.x) stx[i] = cs_.delay[i];
   for (int i = tid; i < RADE_NMF; i += blockDim.x) stx[64 + i] = txs[i];
-  if (tid < 4) {
-    if (doppler > 0.f) g[tid] = path_gain(seed, s, tid >> 1, (double)(t0 + (tid & 1) * RADE_NMF), doppler);
-    else g[tid] = (tid < 2) ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f);
+  if (tid < 4 * NSIN) {                         // 4 gains x 16 sinusoids, one per thread, summed with shuffles
+    const int gi = tid / NSIN, i = tid % NSIN;
+    float2 v = make_float2(0.f, 0.f);
+    if (doppler > 0.f) v = path_gain_term(seed, s, gi >> 1, i, (double)(t0 + (gi & 1) * RADE_NMF), doppler);
+#pragma unroll
+    for (int o = NSIN / 2; o > 0; o >>= 1) { v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o); }
+    if (i == 0) {
+      const float a = rsqrtf(2.f * NSIN);
+      g[gi] = (doppler > 0.f) ? make_float2(a * v.x, a * v.y) : ((gi < 2) ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f));
+    }
   }
   // per-stream frequency offset: freq0 + U(-1,1)*freq_spread, fixed for the life of the stream
   uint32_t c[4] = {0u, 0u, (uint32_t)s, 0xF0FFu};
   philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const double f = (double)freq0 + (double)freq_spread * (2.0 * (double)u01(c[0]) - 1.0);
   const double dphi = 2.0 * M_PI * f / RADE_FS;
+  // carrier exp(j(ph0 + dphi (i+1))): one complex128 sincos per thread, then rotations by exp(j dphi 256)
+  double sn, cs, sb, cb;
+  sincos(ph0 + dphi * (double)(tid + 1), &sn, &cs);
+  sincos(dphi * 256.0, &sb, &cb);
   __syncthreads();
   float2 *out = rx + (size_t)s * RADE_NMF;
   for (int i = tid; i < RADE_NMF; i += blockDim.x) {
@@ -104,11 +111,11 @@ channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, Ch
     float2 mp = cmul(stx[64 + i], g1);
     const float2 e = cmul(stx[64 + i - d], g2);   // g2 of the current instant: gains vary by <1e-3 over the 2 ms delay
     mp.x += e.x; mp.y += e.y;
-    double sn, cs;
-    sincos(ph0 + dphi * (double)(i + 1), &sn, &cs);
     const float2 v = cmul(mp, make_float2((float)cs, (float)sn));
     const float2 nz = cnormal(seed, s, (unsigned long long)(t0 + i), 0xA11CEu);
     out[i] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
+    const double c2 = cs * cb - sn * sb, s2 = sn * cb + cs * sb;
+    cs = c2; sn = s2;
   }
   __syncthreads();
   for (int i = tid; i < 64; i += blockDim.x) cs_.delay[i] = stx[RADE_NMF + i];

@@ -620,13 +620,17 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   const double w = 2.0 * M_PI * c.fmax / RADE_FS;
   const double2 P0 = make_double2(c.rx_phase_re, c.rx_phase_im);
   // rx_phase_vec[n] = rx_phase * exp(-j w (n+1)) (closed form of the recursion radae_rxe.py:227-231), stored csingle;
-  // keep only the M samples of each symbol after Ncp + time_offset = 16
-  for (int idx = tid; idx < (RADE_NS + 2) * RADE_M; idx += blockDim.x) {
-    const int r = idx / RADE_M, k = idx % RADE_M;
-    const int n = r * RADE_SYM + RADE_NCP + RADE_TIME_OFFSET + k;
-    double sn, cs; sincos(w * (double)(n + 1), &sn, &cs);
-    const double2 v = dcmul(P0, make_double2(cs, -sn));
-    sm.xs[r][k] = cmul(rg[ring_idx(head, tmax - RADE_NCP + n)], make_float2((float)v.x, (float)v.y));
+  // keep only the M samples of each symbol after Ncp + time_offset = 16.  Thread t owns sample k = t of every symbol
+  // (t < 160): one complex128 sincos, then one rotation by exp(-j w 192) per symbol.
+  if (tid < RADE_M) {
+    const int n0 = RADE_NCP + RADE_TIME_OFFSET + tid;
+    double sn, cs, ss, cc; sincos(w * (double)(n0 + 1), &sn, &cs); sincos(w * (double)RADE_SYM, &ss, &cc);
+    double2 v = dcmul(P0, make_double2(cs, -sn)); const double2 step = make_double2(cc, -ss);
+#pragma unroll
+    for (int r = 0; r < RADE_NS + 2; r++) {
+      sm.xs[r][tid] = cmul(rg[ring_idx(head, tmax - RADE_NCP + n0 + r * RADE_SYM)], make_float2((float)v.x, (float)v.y));
+      v = dcmul(v, step);
+    }
   }
   __syncthreads();
   if (tid == 0) {
