@@ -72,7 +72,12 @@ template <int NST> struct Cursor {
   }
 };
 
-template <int NCW> __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory"); }
+// named barriers: the consumer warps are split into I-warps (int8 layers) and F-warps (float layers)
+enum { BAR_I = 1, BAR_F = 2, BAR_SEG_FULL = 3 /* +buf */, BAR_SEG_EMPTY = 5 /* +buf */, BAR_D1 = 7, BAR_ALL = 8 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+template <int NI> __device__ __forceinline__ void i_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NI * 32) : "memory"); }
+__device__ __forceinline__ void f_sync() { asm volatile("bar.sync 2, %0;" ::"n"(CORE_NF * 32) : "memory"); }
 
 // producer: lane 0 of the last warp streams every chunk of every step
 template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int T) {
@@ -129,47 +134,55 @@ __device__ __forceinline__ void gemm_stream(CX &cx, int (&acc)[NT][4], const int
   }
 }
 
+// chunks a warp group does not need are acquired and released untouched (keeps the ring's arrival counts uniform)
+template <typename CX> __device__ __forceinline__ void skip_chunks(CX &cx, int n) {
+  for (int i = 0; i < n; i++) { cx.acquire(); cx.release(); }
+}
+__device__ __forceinline__ int i8_chunks(int K, int N) { const int kbc = core_kbc(N / 8); return (K / 32 + kbc - 1) / kbc; }
+__device__ __forceinline__ int f32_chunks(int K, int NOUTP) { const int rpc = core_f32_rpc(NOUTP); return (K + rpc - 1) / rpc; }
+
 // ---------------------------------------------------------------- float layers: sequential-in-j accumulation
-// thread (s = tid % TS, grp = tid / TS) owns the OPT outputs o = OPT*grp .. OPT*grp+OPT-1 of stream s (OPT = 4 for 16-stream
-// tiles, 2 for 8-stream tiles, so every consumer warp takes part either way); the W rows of the concat segment come from one
-// staged chunk and are read as one broadcast vector load per input, the inputs as one LDS.128 per four.
+// Run by the F-warps concurrently with the int8 layers.  F-thread (s = ft % TS, grp = ft / TS) owns the OPT = TS outputs
+// o = OPT*grp .. OPT*grp+OPT-1 of stream s; the W rows of the concat segment (zero-padded to NOUTP floats) come from the
+// staged chunk(s) as broadcast LDS.128, the inputs as one LDS.128 per four.
 // acc[i] = ((acc[i] + W[j0][o] x[j0]) + W[j0+1][o] x[j0+1]) + ...  — separately rounded, in input order
-template <int OPT> struct VecOf;
-template <> struct VecOf<4> { typedef float4 type; };
-template <> struct VecOf<2> { typedef float2 type; };
-template <int OPT> __device__ __forceinline__ void mac_seq(float (&acc)[OPT], const typename VecOf<OPT>::type w, float x);
-template <> __device__ __forceinline__ void mac_seq<4>(float (&acc)[4], const float4 w, float x) {
-  acc[0] = __fadd_rn(acc[0], __fmul_rn(w.x, x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w.y, x));
-  acc[2] = __fadd_rn(acc[2], __fmul_rn(w.z, x)); acc[3] = __fadd_rn(acc[3], __fmul_rn(w.w, x));
-}
-template <> __device__ __forceinline__ void mac_seq<2>(float (&acc)[2], const float2 w, float x) {
-  acc[0] = __fadd_rn(acc[0], __fmul_rn(w.x, x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(w.y, x));
-}
-template <int NOUT, int OPT, typename CX>
-__device__ __forceinline__ void dense_chunk(CX &cx, float (&acc)[OPT], const float *xrow, int K, int grp) {
-  typedef typename VecOf<OPT>::type V;
-  const V *Wv = reinterpret_cast<const V *>(cx.acquire());
-  if (grp < NOUT / OPT) {
-    const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-#pragma unroll 2
-    for (int j = 0; j < K; j += 4) {
-      const float4 x = x4[j >> 2];
-      const V w0 = Wv[(j + 0) * (NOUT / OPT) + grp], w1 = Wv[(j + 1) * (NOUT / OPT) + grp];
-      const V w2 = Wv[(j + 2) * (NOUT / OPT) + grp], w3 = Wv[(j + 3) * (NOUT / OPT) + grp];
-      mac_seq<OPT>(acc, w0, x.x); mac_seq<OPT>(acc, w1, x.y); mac_seq<OPT>(acc, w2, x.z); mac_seq<OPT>(acc, w3, x.w);
-    }
+template <int OPT>
+__device__ __forceinline__ void mac_row(float (&acc)[OPT], const float4 *wrow, float x) {
+#pragma unroll
+  for (int v = 0; v < OPT / 4; v++) {
+    const float4 w = wrow[v];
+    acc[4 * v + 0] = __fadd_rn(acc[4 * v + 0], __fmul_rn(w.x, x)); acc[4 * v + 1] = __fadd_rn(acc[4 * v + 1], __fmul_rn(w.y, x));
+    acc[4 * v + 2] = __fadd_rn(acc[4 * v + 2], __fmul_rn(w.z, x)); acc[4 * v + 3] = __fadd_rn(acc[4 * v + 3], __fmul_rn(w.w, x));
   }
-  cx.release();
+}
+template <int NOUTP, int OPT, typename CX>
+__device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[OPT], const float *xrow, int K, int grp) {
+  constexpr int RPC = core_f32_rpc(NOUTP);
+  const bool act = grp < NOUTP / OPT;
+  for (int r0 = 0; r0 < K; r0 += RPC) {
+    const int n = min(RPC, K - r0);
+    const float4 *W4 = reinterpret_cast<const float4 *>(cx.acquire()) + grp * (OPT / 4);
+    if (act) {
+      const float4 *x4 = reinterpret_cast<const float4 *>(xrow + r0);
+#pragma unroll 2
+      for (int j = 0; j < n; j += 4) {
+        const float4 x = x4[j >> 2];
+        mac_row<OPT>(acc, W4 + (j + 0) * (NOUTP / 4), x.x); mac_row<OPT>(acc, W4 + (j + 1) * (NOUTP / 4), x.y);
+        mac_row<OPT>(acc, W4 + (j + 2) * (NOUTP / 4), x.z); mac_row<OPT>(acc, W4 + (j + 3) * (NOUTP / 4), x.w);
+      }
+    }
+    cx.release();
+  }
 }
 
-// GRU layer: warp w owns unit tile w (8 hidden units x 16 streams); gates z,r,n of a unit land in the same accumulator slot.
+// GRU layer (I-warps): warp w owns unit tile w (8 hidden units x 16 streams); gates z,r,n of a unit land in the same accumulator slot.
 // The per-output scale / bias values are fetched BEFORE the GEMM so their L2 latency hides behind it.
 template <int UNITS, int TS, typename CX, typename Emit>
 __device__ __forceinline__ void gru_layer(CX &cx, const I8LayerDev &Li, const I8LayerDev &Lr, const int8_t *Xin, int ldx,
                                           const int8_t *Hq, int ldh, float *hs, int ldhs, Emit emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
   constexpr int U = UNITS / 8;
-  const bool work = warp < U;                // NCW >= U; surplus warps only keep the chunk pipeline moving
+  const bool work = warp < U;                // one unit tile per I-warp
   const int u = work ? warp : 0;
   const int j0 = u * 8 + 2 * tig;
   float2 si[3], bi[3], sr[3], br[3];
@@ -242,7 +255,7 @@ __device__ __forceinline__ void conv_layer(CX &cx, const I8LayerDev &L, const in
         }
       }
   }
-  consumer_sync<NCW>();
+  i_sync<NCW>();
 #pragma unroll
   for (int q = 0; q < NEP; q++) {
     const int e = threadIdx.x + q * NCW * 32;
@@ -258,17 +271,17 @@ template <int TS, int NST> struct EncSmem {
   PipeSmem<NST> pipe;
   alignas(16) int8_t cb[3][TS][ENC_LDA];
   alignas(16) float hs[TS][5 * ENC_GRU];
-  alignas(16) float seg[TS][SEG_LD];
+  alignas(16) float seg[3][TS][SEG_LD];       // [0], [1]: segments handed from the I-warps to the F-warps; [2]: dense1 output
   alignas(16) float fin[TS][FIN_LD];
   int red[2 * TS * ENC_CONV];
   int any_active;
 };
 
 template <int TS, int NST>
-__global__ void __launch_bounds__((ENC_NCW + 1) * 32, 1)
+__global__ void __launch_bounds__((ENC_NI + CORE_NF + 1) * 32, 1)
 core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
                     float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NCW = ENC_NCW, NCT = NCW * 32, OPT = TS / 4;
+  constexpr int NI = ENC_NI, NIT = NI * 32, NCT = (NI + CORE_NF) * 32, OPT = TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef EncSmem<TS, NST> Smem;
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -279,7 +292,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
   __syncthreads();
   if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + CORE_NF); }
     mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
@@ -300,90 +313,115 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     }
     return;
   }
-  // ---- consumer warps
   Cursor<NST> cx{&sm.pipe, 0, 0u};
-  const int sl = tid % TS, grp = tid / TS;
-  const int sg = s0 + sl;
 
+  if (tid >= NIT) {
+    // =========================== F-warps: input staging, dense1, incremental zdense, z output
+    const int ft = tid - NIT, sl = ft % TS, grp = ft / TS;
+    const int sg = s0 + sl;
+    bar_arrive(BAR_SEG_EMPTY + 0, NCT); bar_arrive(BAR_SEG_EMPTY + 1, NCT);       // both hand-over buffers start free
+    bar_sync(BAR_ALL, NCT);                                                       // concat buffers initialised by the I-warps
+    for (int t = 0; t < T; t++) {
+      int8_t(*cur)[ENC_LDA] = sm.cb[t % 3];
+      for (int i = ft; i < TS * ENC_IN; i += CORE_NF * 32) {
+        const int r = i / ENC_IN, k = i % ENC_IN;
+        float v = 0.f;
+        if (s0 + r < S) {
+          if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
+          else {                                 // API layout: [S][4T][36]; 20 used features + aux = -1 (src/rade_api.c:426-432)
+            const int fr = k / 21, f = k % 21;
+            v = (f == 20) ? -1.f : in[((size_t)(s0 + r) * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f];
+          }
+        }
+        sm.fin[r][k] = v;
+      }
+      f_sync();
+      // ---- dense1: tanh(W f + b), 84 -> 64
+      {
+        float a[OPT], bd[OPT];
+#pragma unroll
+        for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 64 / OPT) ? W.enc_dense1.bias[OPT * grp + i] : 0.f; }
+        dense_seg<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
+        if (grp < 64 / OPT) {
+#pragma unroll
+          for (int i = 0; i < OPT; i++) {
+            const int o = OPT * grp + i;
+            float y = tanh_r(__fadd_rn(a[i], bd[i]));
+            sm.seg[2][sl][o] = y;
+            cur[sl][o] = quant8(y);
+          }
+        }
+      }
+      f_sync();
+      bar_arrive(BAR_D1, NCT);                   // the I-warps may start GRU 1
+      float zacc[OPT];
+#pragma unroll
+      for (int i = 0; i < OPT; i++) zacc[i] = 0.f;
+      dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[2][sl], 64, grp);
+      int off = 64;
+#pragma unroll 1
+      for (int l = 0; l < 5; l++) {
+        skip_chunks(cx, i8_chunks(off, 3 * ENC_GRU) + i8_chunks(ENC_GRU, 3 * ENC_GRU));
+        bar_sync(BAR_SEG_FULL + 1, NCT);
+        dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[1][sl], ENC_GRU, grp);
+        bar_arrive(BAR_SEG_EMPTY + 1, NCT);
+        off += ENC_GRU;
+        skip_chunks(cx, 2 * i8_chunks(off, ENC_CONV));
+        bar_sync(BAR_SEG_FULL + 0, NCT);
+        dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[0][sl], ENC_CONV, grp);
+        bar_arrive(BAR_SEG_EMPTY + 0, NCT);
+        off += ENC_CONV;
+      }
+      // ---- z = zdense(cat) + b   (bottleneck 3: linear, src/rade_enc.c:107-113)
+      if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / OPT) {
+#pragma unroll
+        for (int i = 0; i < OPT; i++)
+          z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
+      }
+    }
+    return;
+  }
+
+  // =========================== I-warps: GRU / conv layers on the tensor cores + their epilogues
   for (int r = 0; r < TS; r++) {
     const bool ok = s0 + r < S;
-    for (int i = tid; i < ENC_LDA / 4; i += NCT) {
+    for (int i = tid; i < ENC_LDA / 4; i += NIT) {
       reinterpret_cast<uint32_t *>(sm.cb[0][r])[i] = 0u;
       if (!ok) { reinterpret_cast<uint32_t *>(sm.cb[2][r])[i] = 0u; reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = 0u; }
     }
-    if (!ok) for (int i = tid; i < 5 * ENC_GRU; i += NCT) sm.hs[r][i] = 0.f;
+    if (!ok) for (int i = tid; i < 5 * ENC_GRU; i += NIT) sm.hs[r][i] = 0.f;
   }
   mbar_wait(&sm.pipe.state_bar, 0);
-  consumer_sync<NCW>();
+  bar_sync(BAR_ALL, NCT);
 
   constexpr int dil[5] = {1, 2, 2, 2, 2};
   for (int t = 0; t < T; t++) {
     int8_t(*cur)[ENC_LDA] = sm.cb[t % 3];
     int8_t(*prev1)[ENC_LDA] = sm.cb[(t + 2) % 3];
     int8_t(*prev2)[ENC_LDA] = sm.cb[(t + 1) % 3];
-
-    for (int i = tid; i < TS * ENC_IN; i += NCT) {
-      const int r = i / ENC_IN, k = i % ENC_IN;
-      float v = 0.f;
-      if (s0 + r < S) {
-        if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
-        else {                                   // API layout: [S][4T][36]; 20 used features + aux = -1 (src/rade_api.c:426-432)
-          const int fr = k / 21, f = k % 21;
-          v = (f == 20) ? -1.f : in[((size_t)(s0 + r) * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f];
-        }
-      }
-      sm.fin[r][k] = v;
-    }
-    consumer_sync<NCW>();
-
-    // ---- dense1: tanh(W f + b), 84 -> 64
-    {
-      float a[OPT], bd[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 64 / OPT) ? W.enc_dense1.bias[OPT * grp + i] : 0.f; }
-      dense_chunk<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
-      if (grp < 64 / OPT) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          float y = tanh_r(__fadd_rn(a[i], bd[i]));
-          sm.seg[sl][o] = y;
-          cur[sl][o] = quant8(y);
-        }
-      }
-    }
-    consumer_sync<NCW>();
-    float zacc[OPT];
-#pragma unroll
-    for (int i = 0; i < OPT; i++) zacc[i] = 0.f;
-    dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], 64, grp);
-    consumer_sync<NCW>();
-
+    skip_chunks(cx, f32_chunks(ENC_IN, 64) + f32_chunks(64, RADE_LATENT));
+    bar_sync(BAR_D1, NCT);                       // dense1 output (int8) is in cur[:, 0:64)
     int off = 64;
 #pragma unroll 1
     for (int l = 0; l < 5; l++) {
       // GRU l: input = cur[0:off), recurrent input = quantised h(t-1) = prev1[off : off+64)
+      bar_sync(BAR_SEG_EMPTY + 1, NCT);
       gru_layer<ENC_GRU, TS>(cx, W.enc_gru_in[l], W.enc_gru_rec[l], &cur[0][0], ENC_LDA, &prev1[0][off], ENC_LDA,
                              &sm.hs[0][l * ENC_GRU], 5 * ENC_GRU,
-                             [&](int row, int j, float h) { sm.seg[row][j] = h; cur[row][off + j] = quant8(h); });
-      consumer_sync<NCW>();
-      dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], ENC_GRU, grp);
-      consumer_sync<NCW>();
+                             [&](int row, int j, float h) { sm.seg[1][row][j] = h; cur[row][off + j] = quant8(h); });
+      bar_arrive(BAR_SEG_FULL + 1, NCT);
+      i_sync<NI>();
+      skip_chunks(cx, f32_chunks(ENC_GRU, RADE_LATENT));
       off += ENC_GRU;
       // conv l (k = 2): tap 0 = concat prefix of step t-dilation, tap 1 = current prefix
       const int8_t *old = (dil[l] == 1) ? &prev1[0][0] : &prev2[0][0];
-      conv_layer<ENC_CONV, NCW, TS>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red,
-                                    [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
-      consumer_sync<NCW>();
-      dense_chunk<80, OPT>(cx, zacc, sm.seg[sl], ENC_CONV, grp);
-      consumer_sync<NCW>();
+      bar_sync(BAR_SEG_EMPTY + 0, NCT);
+      conv_layer<ENC_CONV, NI, TS>(cx, W.enc_conv[l], old, &cur[0][0], off, ENC_LDA, sm.red,
+                                   [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[0][row][n] = y; cur[row][off + n] = quant8(y); });
+      bar_arrive(BAR_SEG_FULL + 0, NCT);
+      i_sync<NI>();
+      skip_chunks(cx, f32_chunks(ENC_CONV, RADE_LATENT));
       off += ENC_CONV;
-    }
-    // ---- z = zdense(cat) + b   (bottleneck 3: linear, src/rade_enc.c:107-113)
-    if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / OPT) {
-#pragma unroll
-      for (int i = 0; i < OPT; i++)
-        z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
     }
   }
 
@@ -391,8 +429,8 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
   for (int r = 0; r < TS; r++) {
     if (s0 + r >= S || (active && !active[s0 + r])) continue;
     EncStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * ENC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
-    for (int i = tid; i < ENC_LDA / 4; i += NCT) {
+    for (int i = tid; i < 5 * ENC_GRU; i += NIT) st->h[i] = sm.hs[r][i];
+    for (int i = tid; i < ENC_LDA / 4; i += NIT) {
       reinterpret_cast<uint32_t *>(st->cat1)[i] = reinterpret_cast<const uint32_t *>(sm.cb[last][r])[i];
       reinterpret_cast<uint32_t *>(st->cat2)[i] = reinterpret_cast<const uint32_t *>(sm.cb[last2][r])[i];
     }
@@ -405,7 +443,7 @@ template <int TS, int NST> struct DecSmem {
   alignas(16) int8_t cb[2][TS][DEC_LDA];
   alignas(16) int8_t hq[2][TS][HQ_LD];
   alignas(16) float hs[TS][5 * DEC_GRU];
-  alignas(16) float seg[TS][SEG_LD];
+  alignas(16) float seg[3][TS][SEG_LD];
   alignas(16) float zin[TS][ZIN_LD];
   int red[2 * TS * DEC_CONV];
   int any_active;
@@ -414,12 +452,12 @@ template <int TS, int NST> struct DecSmem {
 // out_mode 0: features [S][T][84];  out_mode 1: API layout [S][4T][36] (20 used, rest zero, src/rade_api.c:488-500)
 // uw_count (optional): += number of steps whose first aux symbol (feature 20) is > 0 (src/rade_api.c:502-505)
 template <int TS, int NST>
-__global__ void __launch_bounds__((DEC_NCW + 1) * 32, 1)
+__global__ void __launch_bounds__((DEC_NI + CORE_NF + 1) * 32, 1)
 core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
                     float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
                     const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NCW = DEC_NCW, NCT = NCW * 32, OPT = TS / 4;
-  constexpr int NGRP = NCT / TS;
+  constexpr int NI = DEC_NI, NIT = NI * 32, NCT = (NI + CORE_NF) * 32, OPT = TS;
+  constexpr int NGRP = CORE_NF * 32 / TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef DecSmem<TS, NST> Smem;
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -430,7 +468,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   __syncthreads();
   if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NCW); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + CORE_NF); }
     mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
@@ -450,60 +488,100 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     return;
   }
   Cursor<NST> cx{&sm.pipe, 0, 0u};
-  const int sl = tid % TS, grp = tid / TS;
-  const int sg = s0 + sl;
 
+  if (tid >= NIT) {
+    // =========================== F-warps: z staging, dense1, incremental output layer, feature output
+    const int ft = tid - NIT, sl = ft % TS, grp = ft / TS;
+    const int sg = s0 + sl;
+    bar_arrive(BAR_SEG_EMPTY + 0, NCT); bar_arrive(BAR_SEG_EMPTY + 1, NCT);
+    bar_sync(BAR_ALL, NCT);
+    for (int t = 0; t < T; t++) {
+      int8_t(*cur)[DEC_LDA] = sm.cb[t & 1];
+      for (int i = ft; i < TS * DEC_IN; i += CORE_NF * 32) {
+        const int r = i / DEC_IN, k = i % DEC_IN;
+        sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
+      }
+      f_sync();
+      // ---- dense1: tanh(W z + b), 80 -> 96
+      {
+        float a[OPT], bd[OPT];
+#pragma unroll
+        for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = W.dec_dense1.bias[OPT * grp + i]; }
+        dense_seg<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
+#pragma unroll
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          float y = tanh_r(__fadd_rn(a[i], bd[i]));
+          sm.seg[2][sl][o] = y;
+          cur[sl][o] = quant8(y);
+        }
+      }
+      f_sync();
+      bar_arrive(BAR_D1, NCT);
+      float oacc[OPT];
+#pragma unroll
+      for (int i = 0; i < OPT; i++) oacc[i] = 0.f;
+      dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[2][sl], 96, grp);
+      int off = 96;
+#pragma unroll 1
+      for (int l = 0; l < 5; l++) {
+        skip_chunks(cx, i8_chunks(off, 3 * DEC_GRU) + i8_chunks(DEC_GRU, 3 * DEC_GRU) + i8_chunks(DEC_GRU, DEC_GRU));
+        bar_sync(BAR_SEG_FULL + 1, NCT);
+        dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[1][sl], DEC_GRU, grp);
+        bar_arrive(BAR_SEG_EMPTY + 1, NCT);
+        off += DEC_GRU;
+        skip_chunks(cx, 2 * i8_chunks(off, DEC_CONV));
+        bar_sync(BAR_SEG_FULL + 0, NCT);
+        dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[0][sl], DEC_CONV, grp);
+        bar_arrive(BAR_SEG_EMPTY + 0, NCT);
+        off += DEC_CONV;
+      }
+      if (sg < S && (!active || active[sg])) {
+#pragma unroll
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          if (o >= DEC_OUT) continue;
+          const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
+          if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;
+          else {
+            const int fr = o / 21, f = o % 21;
+            if (f < 20) out[((size_t)sg * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f] = v;
+          }
+          if (o == 20 && uw_count && v > 0.f) atomicAdd(&uw_count[sg], 1);
+        }
+        if (out_mode == 1) {            // zero the 16 unused slots of each 36-wide vector
+          for (int k = grp; k < 4 * 16; k += NGRP)
+            out[((size_t)sg * 4 * T + 4 * t + k / 16) * RADE_NB_TOTAL_FEATURES + 20 + (k % 16)] = 0.f;
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== I-warps
   for (int r = 0; r < TS; r++) {
     const bool ok = s0 + r < S;
-    for (int i = tid; i < DEC_LDA / 4; i += NCT) {
+    for (int i = tid; i < DEC_LDA / 4; i += NIT) {
       reinterpret_cast<uint32_t *>(sm.cb[0][r])[i] = 0u;
       if (!ok) reinterpret_cast<uint32_t *>(sm.cb[1][r])[i] = 0u;
     }
-    if (!ok) for (int i = tid; i < 5 * DEC_GRU; i += NCT) sm.hs[r][i] = 0.f;
+    if (!ok) for (int i = tid; i < 5 * DEC_GRU; i += NIT) sm.hs[r][i] = 0.f;
   }
   mbar_wait(&sm.pipe.state_bar, 0);
-  consumer_sync<NCW>();
-  for (int i = tid; i < TS * 5 * DEC_GRU; i += NCT) {
+  i_sync<NI>();
+  for (int i = tid; i < TS * 5 * DEC_GRU; i += NIT) {
     const int r = i / (5 * DEC_GRU), k = i % (5 * DEC_GRU);
     sm.hq[0][r][k] = quant8(sm.hs[r][k]);
   }
-  consumer_sync<NCW>();
+  bar_sync(BAR_ALL, NCT);
 
   for (int t = 0; t < T; t++) {
     int8_t(*cur)[DEC_LDA] = sm.cb[t & 1];
     int8_t(*prev1)[DEC_LDA] = sm.cb[(t + 1) & 1];
     int8_t(*hq_rd)[HQ_LD] = sm.hq[t & 1];
     int8_t(*hq_wr)[HQ_LD] = sm.hq[(t + 1) & 1];
-
-    for (int i = tid; i < TS * DEC_IN; i += NCT) {
-      const int r = i / DEC_IN, k = i % DEC_IN;
-      sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
-    }
-    consumer_sync<NCW>();
-
-    // ---- dense1: tanh(W z + b), 80 -> 96
-    {
-      float a[OPT], bd[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 96 / OPT) ? W.dec_dense1.bias[OPT * grp + i] : 0.f; }
-      dense_chunk<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
-      if (grp < 96 / OPT) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          float y = tanh_r(__fadd_rn(a[i], bd[i]));
-          sm.seg[sl][o] = y;
-          cur[sl][o] = quant8(y);
-        }
-      }
-    }
-    consumer_sync<NCW>();
-    float oacc[OPT];
-#pragma unroll
-    for (int i = 0; i < OPT; i++) oacc[i] = 0.f;
-    dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], 96, grp);
-    consumer_sync<NCW>();
-
+    skip_chunks(cx, f32_chunks(DEC_IN, 96) + f32_chunks(96, DEC_OUTP));
+    bar_sync(BAR_D1, NCT);
     int off = 96;
 #pragma unroll 1
     for (int l = 0; l < 5; l++) {
@@ -511,8 +589,9 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
       gru_layer<DEC_GRU, TS>(cx, W.dec_gru_in[l], W.dec_gru_rec[l], &cur[0][0], DEC_LDA, &hq_rd[0][l * DEC_GRU], HQ_LD,
                              &sm.hs[0][l * DEC_GRU], 5 * DEC_GRU,
                              [&](int row, int j, float h) { hq_wr[row][l * DEC_GRU + j] = quant8(h); });
-      consumer_sync<NCW>();
+      i_sync<NI>();
       // GLU l: out = h * sigmoid(Wg h + b)  -> concat;  12 n-tiles, one per warp, a single 9 KB chunk
+      bar_sync(BAR_SEG_EMPTY + 1, NCT);
       {
         const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
         const I8LayerDev &L = W.dec_glu[l];
@@ -528,39 +607,20 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
           if (row >= TS) continue;
           const int n = warp * 8 + 2 * tig + (e & 1);
           float y = __fmul_rn(sm.hs[row][l * DEC_GRU + n], sigmoid_r(lin(acc[0][e], (e & 1) ? gs.y : gs.x, (e & 1) ? gb.y : gb.x)));
-          sm.seg[row][n] = y; cur[row][off + n] = quant8(y);
+          sm.seg[1][row][n] = y; cur[row][off + n] = quant8(y);
         }
       }
-      consumer_sync<NCW>();
-      dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], DEC_GRU, grp);
-      consumer_sync<NCW>();
+      bar_arrive(BAR_SEG_FULL + 1, NCT);
+      i_sync<NI>();
+      skip_chunks(cx, f32_chunks(DEC_GRU, DEC_OUTP));
       off += DEC_GRU;
-      conv_layer<DEC_CONV, NCW, TS>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,
-                                    [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[row][n] = y; cur[row][off + n] = quant8(y); });
-      consumer_sync<NCW>();
-      dense_chunk<DEC_OUT, OPT>(cx, oacc, sm.seg[sl], DEC_CONV, grp);
-      consumer_sync<NCW>();
+      bar_sync(BAR_SEG_EMPTY + 0, NCT);
+      conv_layer<DEC_CONV, NI, TS>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,
+                                   [&](int row, int n, float v) { float y = tanh_r(v); sm.seg[0][row][n] = y; cur[row][off + n] = quant8(y); });
+      bar_arrive(BAR_SEG_FULL + 0, NCT);
+      i_sync<NI>();
+      skip_chunks(cx, f32_chunks(DEC_CONV, DEC_OUTP));
       off += DEC_CONV;
-    }
-
-    if (sg < S && (!active || active[sg])) {
-      if (grp < DEC_OUT / OPT) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
-          if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;
-          else {
-            const int fr = o / 21, f = o % 21;
-            if (f < 20) out[((size_t)sg * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f] = v;
-          }
-          if (o == 20 && uw_count && v > 0.f) atomicAdd(&uw_count[sg], 1);
-        }
-      }
-      if (out_mode == 1) {            // zero the 16 unused slots of each 36-wide vector
-        for (int k = grp; k < 4 * 16; k += NGRP)
-          out[((size_t)sg * 4 * T + 4 * t + k / 16) * RADE_NB_TOTAL_FEATURES + 20 + (k % 16)] = 0.f;
-      }
     }
   }
 
@@ -568,8 +628,8 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   for (int r = 0; r < TS; r++) {
     if (s0 + r >= S || (active && !active[s0 + r])) continue;
     DecStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * DEC_GRU; i += NCT) st->h[i] = sm.hs[r][i];
-    for (int i = tid; i < DEC_LDA / 4; i += NCT)
+    for (int i = tid; i < 5 * DEC_GRU; i += NIT) st->h[i] = sm.hs[r][i];
+    for (int i = tid; i < DEC_LDA / 4; i += NIT)
       reinterpret_cast<uint32_t *>(st->cat1)[i] = reinterpret_cast<const uint32_t *>(sm.cb[last][r])[i];
   }
 }
@@ -599,9 +659,9 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)
-    core_encoder_kernel<16, NST16><<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem<16, NST16>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_kernel<16, NST16><<<grid, (ENC_NI + CORE_NF + 1) * 32, sizeof(EncSmem<16, NST16>), stream>>>(W, state, in, in_mode, z, active, S, T);
   else
-    core_encoder_kernel<8, NST8><<<grid, (ENC_NCW + 1) * 32, sizeof(EncSmem<8, NST8>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_kernel<8, NST8><<<grid, (ENC_NI + CORE_NF + 1) * 32, sizeof(EncSmem<8, NST8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -611,9 +671,9 @@ int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const fl
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)
-    core_decoder_kernel<16, NST16><<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem<16, NST16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_kernel<16, NST16><<<grid, (DEC_NI + CORE_NF + 1) * 32, sizeof(DecSmem<16, NST16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   else
-    core_decoder_kernel<8, NST8><<<grid, (DEC_NCW + 1) * 32, sizeof(DecSmem<8, NST8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_kernel<8, NST8><<<grid, (DEC_NI + CORE_NF + 1) * 32, sizeof(DecSmem<8, NST8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

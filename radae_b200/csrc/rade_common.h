@@ -62,8 +62,10 @@ struct __align__(16) DecStreamState {
 // order the layer walk consumes them; a producer warp TMA-bulk-copies chunk after chunk into a shared-memory ring.
 #define CORE_STAGE_BYTES 32768
 #define CORE_NSTAGES 4
-#define ENC_NCW 10                            // consumer warps (encoder): 20 groups of 4 zdense outputs; 8 of them own a GRU unit tile
-#define DEC_NCW 12                            // consumer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
+#define ENC_NI 8                              // int8-layer warps (encoder): one GRU unit tile each, three conv (n-tile, tap) units each
+#define DEC_NI 12                             // int8-layer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
+#define CORE_NF 3                             // float-layer warps (dense1 + the incremental zdense / output accumulation)
+#define DEC_OUTP 96                           // dec_output rows are padded from 84 to 96 floats in the weight stream
 
 struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
 struct F32LayerDev { const float *bias; int K; int N; };

@@ -12,6 +12,8 @@ struct CoreWeightsHolder {
 };
 // k-blocks (32 inputs each) of an int8 layer with NTL n-tiles (8 outputs each) that fit one pipeline stage
 static inline __host__ __device__ int core_kbc(int NTL) { int k = CORE_STAGE_BYTES / (NTL * 256); return k < 1 ? 1 : k; }
+// rows of a float layer (padded width noutp) per pipeline stage, multiple of 4
+static inline __host__ __device__ constexpr int core_f32_rpc(int noutp) { return (CORE_STAGE_BYTES / (noutp * 4)) & ~3; }
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h);
 void core_weights_free(CoreWeightsHolder *h);
 

@@ -152,7 +152,16 @@ struct StreamBuilder {
       add(t.data(), t.size() * 4);
     }
   }
-  void add_f32_rows(const float *Wf, int NOUT, int j0, int nrows) { add(Wf + (size_t)j0 * NOUT, (size_t)nrows * NOUT * 4); }
+  // rows [j0, j0+nrows) of a float [K][NOUT] matrix, each row zero-padded to NOUTP floats, core_f32_rpc(NOUTP) rows per chunk
+  void add_f32_rows(const float *Wf, int NOUT, int NOUTP, int j0, int nrows) {
+    const int rpc = core_f32_rpc(NOUTP);
+    for (int r0 = 0; r0 < nrows; r0 += rpc) {
+      const int n = std::min(rpc, nrows - r0);
+      std::vector<float> t((size_t)n * NOUTP, 0.f);
+      for (int r = 0; r < n; r++) memcpy(&t[(size_t)r * NOUTP], Wf + (size_t)(j0 + r0 + r) * NOUT, NOUT * sizeof(float));
+      add(t.data(), t.size() * 4);
+    }
+  }
 };
 
 }  // namespace
@@ -215,35 +224,35 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   auto F = [&](const std::string &n) { return (const float *)wf[n]->data.data(); };
   StreamBuilder e, d;
   {
-    e.add_f32_rows(F("enc_dense1"), 64, 0, ENC_IN);
-    e.add_f32_rows(F("enc_zdense"), RADE_LATENT, 0, 64);
+    e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);
+    e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, 0, 64);
     int off = 64;
     for (int l = 0; l < 5; l++) {
       std::string n = std::to_string(l + 1);
       e.add_i8(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32);
       e.add_i8(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2);
-      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, off, ENC_GRU);
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
       off += ENC_GRU;
       e.add_i8(I8("enc_conv" + n), 96, 2 * off, 0, off / 32);                    // tap 0 (oldest frame)
       e.add_i8(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32);         // tap 1 (current frame)
-      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, off, ENC_CONV);
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
       off += ENC_CONV;
     }
   }
   {
-    d.add_f32_rows(F("dec_dense1"), 96, 0, DEC_IN);
-    d.add_f32_rows(F("dec_output"), DEC_OUT, 0, 96);
+    d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);
+    d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, 0, 96);
     int off = 96;
     for (int l = 0; l < 5; l++) {
       std::string n = std::to_string(l + 1);
       d.add_i8(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32);
       d.add_i8(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3);
       d.add_i8(I8("dec_glu" + n), 96, 96, 0, 3);
-      d.add_f32_rows(F("dec_output"), DEC_OUT, off, DEC_GRU);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
       off += DEC_GRU;
       d.add_i8(I8("dec_conv" + n), 32, 2 * off, 0, off / 32);
       d.add_i8(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32);
-      d.add_f32_rows(F("dec_output"), DEC_OUT, off, DEC_CONV);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
       off += DEC_CONV;
     }
   }
