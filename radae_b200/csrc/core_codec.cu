@@ -77,7 +77,7 @@ enum { BAR_I = 1, BAR_F = 2, BAR_SEG_FULL = 3 /* +buf */, BAR_SEG_EMPTY = 5 /* +
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 template <int NI> __device__ __forceinline__ void i_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NI * 32) : "memory"); }
-__device__ __forceinline__ void f_sync() { asm volatile("bar.sync 2, %0;" ::"n"(CORE_NF * 32) : "memory"); }
+template <int NF> __device__ __forceinline__ void f_sync() { asm volatile("bar.sync 2, %0;" ::"n"(NF * 32) : "memory"); }
 
 // producer: lane 0 of the last warp streams every chunk of every step
 template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int T) {
@@ -146,13 +146,22 @@ __device__ __forceinline__ int f32_chunks(int K, int NOUTP) { const int rpc = co
 // o = OPT*grp .. OPT*grp+OPT-1 of stream s; the W rows of the concat segment (zero-padded to NOUTP floats) come from the
 // staged chunk(s) as broadcast LDS.128, the inputs as one LDS.128 per four.
 // acc[i] = ((acc[i] + W[j0][o] x[j0]) + W[j0+1][o] x[j0+1]) + ...  — separately rounded, in input order
+// (round(w.x * x), round(w.y * x)) with one packed multiply (SASS FMUL2); the accumulation stays scalar so that ptxas cannot
+// contract product and sum into an FFMA2 (it does that to mul.rn.f32x2 + add.rn.f32x2, which would round once instead of twice)
+__device__ __forceinline__ float2 prod2_rn(float wx, float wy, float x) {
+  float2 w = make_float2(wx, wy), xx = make_float2(x, x);
+  unsigned long long ra = *reinterpret_cast<unsigned long long *>(&w), rb = *reinterpret_cast<unsigned long long *>(&xx), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2 *>(&rd);
+}
 template <int OPT>
 __device__ __forceinline__ void mac_row(float (&acc)[OPT], const float4 *wrow, float x) {
 #pragma unroll
   for (int v = 0; v < OPT / 4; v++) {
     const float4 w = wrow[v];
-    acc[4 * v + 0] = __fadd_rn(acc[4 * v + 0], __fmul_rn(w.x, x)); acc[4 * v + 1] = __fadd_rn(acc[4 * v + 1], __fmul_rn(w.y, x));
-    acc[4 * v + 2] = __fadd_rn(acc[4 * v + 2], __fmul_rn(w.z, x)); acc[4 * v + 3] = __fadd_rn(acc[4 * v + 3], __fmul_rn(w.w, x));
+    const float2 p0 = prod2_rn(w.x, w.y, x), p1 = prod2_rn(w.z, w.w, x);
+    acc[4 * v + 0] = __fadd_rn(acc[4 * v + 0], p0.x); acc[4 * v + 1] = __fadd_rn(acc[4 * v + 1], p0.y);
+    acc[4 * v + 2] = __fadd_rn(acc[4 * v + 2], p1.x); acc[4 * v + 3] = __fadd_rn(acc[4 * v + 3], p1.y);
   }
 }
 template <int NOUTP, int OPT, typename CX>
@@ -278,10 +287,10 @@ template <int TS, int NST> struct EncSmem {
 };
 
 template <int TS, int NST>
-__global__ void __launch_bounds__((ENC_NI + CORE_NF + 1) * 32, 1)
+__global__ void __launch_bounds__((ENC_NI + ENC_NF + 1) * 32, 1)
 core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
                     float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NI = ENC_NI, NIT = NI * 32, NCT = (NI + CORE_NF) * 32, OPT = TS;
+  constexpr int NI = ENC_NI, NF = ENC_NF, NIT = NI * 32, NCT = (NI + NF) * 32, OPT = TS / 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef EncSmem<TS, NST> Smem;
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -292,7 +301,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
   __syncthreads();
   if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + CORE_NF); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + NF); }
     mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
@@ -323,7 +332,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     bar_sync(BAR_ALL, NCT);                                                       // concat buffers initialised by the I-warps
     for (int t = 0; t < T; t++) {
       int8_t(*cur)[ENC_LDA] = sm.cb[t % 3];
-      for (int i = ft; i < TS * ENC_IN; i += CORE_NF * 32) {
+      for (int i = ft; i < TS * ENC_IN; i += NF * 32) {
         const int r = i / ENC_IN, k = i % ENC_IN;
         float v = 0.f;
         if (s0 + r < S) {
@@ -335,7 +344,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
         }
         sm.fin[r][k] = v;
       }
-      f_sync();
+      f_sync<NF>();
       // ---- dense1: tanh(W f + b), 84 -> 64
       {
         float a[OPT], bd[OPT];
@@ -352,7 +361,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
           }
         }
       }
-      f_sync();
+      f_sync<NF>();
       bar_arrive(BAR_D1, NCT);                   // the I-warps may start GRU 1
       float zacc[OPT];
 #pragma unroll
@@ -452,12 +461,12 @@ template <int TS, int NST> struct DecSmem {
 // out_mode 0: features [S][T][84];  out_mode 1: API layout [S][4T][36] (20 used, rest zero, src/rade_api.c:488-500)
 // uw_count (optional): += number of steps whose first aux symbol (feature 20) is > 0 (src/rade_api.c:502-505)
 template <int TS, int NST>
-__global__ void __launch_bounds__((DEC_NI + CORE_NF + 1) * 32, 1)
+__global__ void __launch_bounds__((DEC_NI + DEC_NF + 1) * 32, 1)
 core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
                     float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
                     const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int NI = DEC_NI, NIT = NI * 32, NCT = (NI + CORE_NF) * 32, OPT = TS;
-  constexpr int NGRP = CORE_NF * 32 / TS;
+  constexpr int NI = DEC_NI, NF = DEC_NF, NIT = NI * 32, NCT = (NI + NF) * 32, OPT = TS;
+  constexpr int NGRP = NF * 32 / TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   typedef DecSmem<TS, NST> Smem;
   Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -468,7 +477,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   __syncthreads();
   if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
   if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + CORE_NF); }
+    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NI + NF); }
     mbar_init(&sm.pipe.state_bar, 1);
     mbar_fence_init();
   }
@@ -497,11 +506,11 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     bar_sync(BAR_ALL, NCT);
     for (int t = 0; t < T; t++) {
       int8_t(*cur)[DEC_LDA] = sm.cb[t & 1];
-      for (int i = ft; i < TS * DEC_IN; i += CORE_NF * 32) {
+      for (int i = ft; i < TS * DEC_IN; i += NF * 32) {
         const int r = i / DEC_IN, k = i % DEC_IN;
         sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
       }
-      f_sync();
+      f_sync<NF>();
       // ---- dense1: tanh(W z + b), 80 -> 96
       {
         float a[OPT], bd[OPT];
@@ -516,7 +525,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
           cur[sl][o] = quant8(y);
         }
       }
-      f_sync();
+      f_sync<NF>();
       bar_arrive(BAR_D1, NCT);
       float oacc[OPT];
 #pragma unroll
@@ -659,9 +668,9 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)
-    core_encoder_kernel<16, NST16><<<grid, (ENC_NI + CORE_NF + 1) * 32, sizeof(EncSmem<16, NST16>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_kernel<16, NST16><<<grid, (ENC_NI + ENC_NF + 1) * 32, sizeof(EncSmem<16, NST16>), stream>>>(W, state, in, in_mode, z, active, S, T);
   else
-    core_encoder_kernel<8, NST8><<<grid, (ENC_NI + CORE_NF + 1) * 32, sizeof(EncSmem<8, NST8>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_kernel<8, NST8><<<grid, (ENC_NI + ENC_NF + 1) * 32, sizeof(EncSmem<8, NST8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -671,9 +680,9 @@ int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const fl
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)
-    core_decoder_kernel<16, NST16><<<grid, (DEC_NI + CORE_NF + 1) * 32, sizeof(DecSmem<16, NST16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_kernel<16, NST16><<<grid, (DEC_NI + DEC_NF + 1) * 32, sizeof(DecSmem<16, NST16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   else
-    core_decoder_kernel<8, NST8><<<grid, (DEC_NI + CORE_NF + 1) * 32, sizeof(DecSmem<8, NST8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_kernel<8, NST8><<<grid, (DEC_NI + DEC_NF + 1) * 32, sizeof(DecSmem<8, NST8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

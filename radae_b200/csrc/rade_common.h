@@ -64,7 +64,8 @@ struct __align__(16) DecStreamState {
 #define CORE_NSTAGES 4
 #define ENC_NI 8                              // int8-layer warps (encoder): one GRU unit tile each, three conv (n-tile, tap) units each
 #define DEC_NI 12                             // int8-layer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
-#define CORE_NF 3                             // float-layer warps (dense1 + the incremental zdense / output accumulation)
+#define ENC_NF 5                              // float-layer warps (dense1 + the incremental zdense / output accumulation)
+#define DEC_NF 3
 #define DEC_OUTP 96                           // dec_output rows are padded from 84 to 96 floats in the weight stream
 
 struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
