@@ -129,8 +129,21 @@ def cpu_pipeline_rate(n_frames, warm=2, streams_per_proc=1, procs=None):
     import multiprocessing as mp
     procs = procs or os.cpu_count()
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, n_frames, warm) for i in range(procs)])
+    # one single-threaded process per core: the thread-pool sizes of numpy's BLAS / OpenMP are fixed when the child imports
+    # numpy, so the limits must be in the environment the children inherit (setting them inside the worker is too late and
+    # lets every process start one thread per core)
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, n_frames, warm) for i in range(procs)])
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     slowest = max(r[0] for r in res)
     total_F = procs * streams_per_proc * n_frames * F_PER_STEP
     return total_F / slowest, procs, res[0][1], f"{procs} procs x {streams_per_proc} stream x {n_frames} modem frames (after {warm} warm-up frames, i.e. receiver in sync), MPP-like 2-path, Eb/No 3 dB, -11 Hz"
@@ -142,7 +155,7 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     per_step = []
-    frames_per_sample = 12
+    frames_per_sample = 200
     for i in range(args.warmup + args.steps):
         rate, procs, kind, sample = cpu_pipeline_rate(frames_per_sample, warm=8)
         if i >= args.warmup:
@@ -171,6 +184,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from radae_b200 import RadeBatch, _capi, rdw, multigpu
 
@@ -299,7 +314,7 @@ def run_gpu(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, procs, kind, sample = cpu_pipeline_rate(12, warm=8)
+        rate, procs, kind, sample = cpu_pipeline_rate(200, warm=8)
         cpu_base = {"value": rate, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
                     "note": "numpy DSP restatement + " + ("reference rade_enc.c/rade_dec.c on the nnet shim" if kind == "reference" else "C core port")}
 
