@@ -470,21 +470,27 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
       float2 A0[6], B0[6], A1[6], B1[6];
 #pragma unroll
       for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
+      // software pipeline: the six shared-memory loads of tap n+2 are issued before the 28 packed FMAs of tap n
+      const float4 *csr = reinterpret_cast<const float4 *>(&sm.tab.cs[0][kg * 6]);       // row stride RADE_CSK/2 float4
+      float4 pp = sm.tab.ps4[ks], q0 = csr[ks * (RADE_CSK / 2)], q1 = csr[ks * (RADE_CSK / 2) + 1], q2 = csr[ks * (RADE_CSK / 2) + 2];
+      float2 a = x0[ks], c = x1[ks];
 #pragma unroll 2
       for (int n = ks; n < RADE_M; n += 2) {
-        const float4 pp = sm.tab.ps4[n];
-        const float2 a = x0[n], c = x1[n];
+        const int nn = (n + 2 < RADE_M) ? n + 2 : n;
+        const float4 ppn = sm.tab.ps4[nn], q0n = csr[nn * (RADE_CSK / 2)], q1n = csr[nn * (RADE_CSK / 2) + 1], q2n = csr[nn * (RADE_CSK / 2) + 2];
+        const float2 an = x0[nn], cn = x1[nn];
         const float2 y0 = ffma2(splat(a.x), make_float2(pp.x, pp.y), ffma2(splat(a.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
         const float2 y1 = ffma2(splat(c.x), make_float2(pp.x, pp.y), ffma2(splat(c.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
-        const float4 *t = reinterpret_cast<const float4 *>(&sm.tab.cs[n][kg * 6]);
+        const float4 qq[3] = {q0, q1, q2};
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          const float4 q = t[j];
+          const float4 q = qq[j];
           A0[2 * j] = ffma2(y0, splat(q.x), A0[2 * j]);         B0[2 * j] = ffma2(y0, splat(q.y), B0[2 * j]);
           A0[2 * j + 1] = ffma2(y0, splat(q.z), A0[2 * j + 1]); B0[2 * j + 1] = ffma2(y0, splat(q.w), B0[2 * j + 1]);
           A1[2 * j] = ffma2(y1, splat(q.x), A1[2 * j]);         B1[2 * j] = ffma2(y1, splat(q.y), B1[2 * j]);
           A1[2 * j + 1] = ffma2(y1, splat(q.z), A1[2 * j + 1]); B1[2 * j + 1] = ffma2(y1, splat(q.w), B1[2 * j + 1]);
         }
+        pp = ppn; q0 = q0n; q1 = q1n; q2 = q2n; a = an; c = cn;
       }
       // the even-tap lane finishes k = 6 kg + {0,1,2}, the odd-tap lane k = 6 kg + {3,4,5}: swap the other three partials
       float s0 = 0.f, s1 = 0.f;
