@@ -119,6 +119,9 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
   b->prof.stream = b->stream;
   if (core_codec_init_device() < 0 || rx_dsp_init_device() < 0) { delete b; return nullptr; }
+  if (cudaStreamCreateWithFlags(&b->rx.side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->rx.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->rx.ev_join, cudaEventDisableTiming) != cudaSuccess) { delete b; return nullptr; }
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   DspTablesHost th; dsp_tables_host(th);
@@ -168,6 +171,7 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
   cudaStreamSynchronize(b->stream);
+  if (b->rx.side_stream) cudaStreamSynchronize(b->rx.side_stream);
   for (void *p : b->allocs) cudaFree(p);
   core_weights_free(&b->weights);
   if (b->d_core_in) { cudaFree(b->d_core_in); cudaFree(b->d_core_out); }
@@ -175,6 +179,7 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   if (b->h_cplx) cudaFreeHost(b->h_cplx);
   if (b->h_int) cudaFreeHost(b->h_int);
   cudaStreamDestroy(b->stream);
+  if (b->rx.side_stream) { cudaStreamDestroy(b->rx.side_stream); cudaEventDestroy(b->rx.ev_fork); cudaEventDestroy(b->rx.ev_join); }
   delete b;
 }
 

@@ -156,18 +156,19 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
 }
 
 // ================================================================= coarse pilot search (search / candidate streams)
-// grid (15, S): CTA = 64 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations
-constexpr int DET_TB = 64;
+// work item = 32 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations; 128-thread CTAs
+// (80 registers) fit next to a resident rx_track CTA, so the search branch runs concurrently with the tracking branch
+constexpr int DET_TB = 32, DET_THREADS = 4 * DET_TB;
 struct DetectSmem {
   AcqTables tab;                   // one TMA bulk copy per CTA
   float2 r1[DET_TB + RADE_M];
   float2 r2[DET_TB + RADE_M];
   float part[2][4][DET_TB];
-  unsigned long long best[8];
+  unsigned long long best[DET_THREADS / 32];
   uint64_t tab_bar;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DET_THREADS)
 rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
                  const int *__restrict__ search_list, int *__restrict__ counters) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -199,7 +200,7 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       sm.r2[i] = rg[ring_idx(head, t0 + RADE_NMF + i)];
     }
     __syncthreads();
-    const int tl = tid & (DET_TB - 1), fg = tid >> 6;      // fg = k group: k = 6 fg .. 6 fg + 5
+    const int tl = tid & (DET_TB - 1), fg = tid / DET_TB;  // fg = k group: k = 6 fg .. 6 fg + 5
     float2 A0[6], B0[6], A1[6], B1[6];
     corr6(A0, B0, A1, B1, &sm.r1[tl], &sm.r2[tl], sm.tab.ps4, sm.tab.cs, fg);
     float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = RADE_NFCOARSE;
@@ -228,12 +229,12 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
     if ((tid & 31) == 0) sm.best[tid >> 5] = key;
     __syncthreads();
     if (tid < 2 * DET_TB) {
-      const int half = tid >> 6, t = tid & (DET_TB - 1);
+      const int half = tid / DET_TB, t = tid & (DET_TB - 1);
       rowsum[((size_t)s * 2 + half) * RADE_NMF + t0 + t] = ((sm.part[half][0][t] + sm.part[half][1][t]) + sm.part[half][2][t]) + sm.part[half][3][t];
     }
     if (tid == 0) {
       unsigned long long k = sm.best[0];
-      for (int i = 1; i < 8; i++) k = sm.best[i] > k ? sm.best[i] : k;
+      for (int i = 1; i < DET_THREADS / 32; i++) k = sm.best[i] > k ? sm.best[i] : k;
       atomicMax(&c.detect_key, k);
     }
   }
@@ -847,20 +848,28 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
   int *cnt = B.counters + 4 * B.parity, *cnt_next = B.counters + 4 * (B.parity ^ 1);
   B.parity ^= 1;
+  // Two independent branches follow the band-pass kernel: streams in sync (rx_track -> rx_demod) and streams searching
+  // (rx_detect -> rx_finish).  They touch disjoint streams, so the search branch runs on a side stream, concurrently
+  // (fork / join with events); with the per-kernel profiler on everything is serialised on the main stream instead.
+  const bool fork = !prof->on && B.side_stream;
+  cudaStream_t ss = fork ? B.side_stream : stream;
   prof->begin(K_RX_BPF);
   rx_bpf_kernel<<<S, BPF_THREADS, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt);
-  prof->end(K_RX_BPF); prof->begin(K_RX_DETECT);
-  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 3) det_grid = n_sm * 3;
-  rx_detect_kernel<<<det_grid, 256, sizeof(DetectSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
-  prof->end(K_RX_DETECT); prof->begin(K_RX_TRACK);
+  prof->end(K_RX_BPF);
+  if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_fork, stream)); CUDA_CHECK(cudaStreamWaitEvent(ss, B.ev_fork, 0)); }
+  prof->begin(K_RX_TRACK);
   rx_track_kernel<<<S < n_sm ? S : n_sm, TRK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.track_list,
                                                                                cnt, ret_out, B.dec_active, B.nin);
-  prof->end(K_RX_TRACK); prof->begin(K_RX_DEMOD);
+  prof->end(K_RX_TRACK); prof->begin(K_RX_DETECT);
+  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 4) det_grid = n_sm * 4;
+  rx_detect_kernel<<<det_grid, DET_THREADS, sizeof(DetectSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
+  prof->end(K_RX_DETECT); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
-  rx_finish_kernel<<<S < 2 * n_sm ? S : 2 * n_sm, 256, sizeof(FinishSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
+  rx_finish_kernel<<<S < 2 * n_sm ? S : 2 * n_sm, 256, sizeof(FinishSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
       reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_list, cnt, cnt_next, S);
   prof->end(K_RX_FINISH);
+  if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_join, ss)); CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join, 0)); }
   CUDA_CHECK(cudaGetLastError());
   return 5;
 }

@@ -52,6 +52,8 @@ struct RxBuffers {
   int *counters;           // [2][4] ping-pong by call parity: {search entries, search work-item counter, track entries, -};
                            //        rx_finish of call k zeroes the set call k+1 will use
   int parity;              // host-side: which counter set the next call uses
+  cudaStream_t side_stream;   // the search branch (rx_detect -> rx_finish) runs here, concurrently with rx_track -> rx_demod
+  cudaEvent_t ev_fork, ev_join;
 };
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
