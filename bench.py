@@ -226,11 +226,9 @@ def run_gpu(args):
         d_eoo = torch.zeros((S, 180), device="cuda")
 
         def step(k):
-            b.tx_dev(d_tx.data_ptr(), d_feats[k % n_feat_frames].data_ptr())
-            b.channel_dev(d_ch.data_ptr(), d_tx.data_ptr())
-            b.link_push_dev(d_ch.data_ptr())
-            b.link_pop_dev(d_rxin.data_ptr(), d_act.data_ptr())
-            b.rx_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr(), d_rxin.data_ptr(), d_act.data_ptr())
+            b.tx_dev(d_tx.data_ptr(), d_feats[k % n_feat_frames].data_ptr())        # core encoder, OFDM modulator
+            b.channel_link_dev(d_tx.data_ptr())                                     # HF channel -> per-stream sample FIFO
+            b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())      # pop nin[s], receiver DSP, core decoder
     torch.cuda.synchronize()
 
     def barrier():

@@ -91,6 +91,10 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
 /* --- loop-back link between channel output and receiver input (per-stream sample FIFO on the device): the
  * receiver consumes nin[s] in {800, 960, 1120} samples per call while the transmitter produces 960 --- */
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples /* [S][960] */);
+/* the same loop-back without the two copy kernels: channel output goes straight into the link FIFOs, the receiver pops
+   nin[s] samples per stream from them (a stream without nin[s] queued samples sits the call out: ret = 0) */
+RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx /* [S][960] */);
+RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out);
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
 
 /* --- per-kernel device timing (CUDA events on the context's stream; used by bench.py for the roofline line) --- */

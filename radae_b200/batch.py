@@ -150,6 +150,12 @@ class RadeBatch:
         _check(self.lib.rade_b200_channel_apply_dev(self.h, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq,
                                                     phase0, sigma, gain), "channel_apply_dev")
 
+    def channel_link_dev(self, d_tx):
+        _check(self.lib.rade_b200_channel_link_dev(self.h, d_tx), "channel_link_dev")
+
+    def rx_link_dev(self, d_features_out, d_ret, d_eoo_out):
+        _check(self.lib.rade_b200_rx_link_dev(self.h, d_features_out, d_ret, d_eoo_out), "rx_link_dev")
+
     def link_push_dev(self, d_samples):
         _check(self.lib.rade_b200_link_push_dev(self.h, d_samples), "link_push_dev")
 

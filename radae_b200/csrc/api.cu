@@ -288,7 +288,7 @@ RADE_EXPORT int rade_b200_rx_dev(rade_batch *b, float *d_features_out, int *d_re
                                  const unsigned char *d_active) {
   cudaSetDevice(b->device);        // the current device is per host thread
   const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
-  int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, b->S, 1, reset_dec, d_ret, b->stream, &b->prof);
+  int n = rx_dsp_launch(b->tables, b->rx, (const float2 *)d_rx_in, d_active, nullptr, b->S, 1, reset_dec, d_ret, b->stream, &b->prof);
   if (n < 0) return -1;
   b->prof.begin(K_CORE_DEC);
   // decoder last, only for streams with valid output; counts aux-symbol errors (src/rade_api.c:494-513)
@@ -365,7 +365,7 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));       // radae.py:570-574, Rb = 80/0.04
   b->prof.begin(K_CHANNEL);
   if (channel_stream_launch((float2 *)d_rx, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz,
-                            c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->stream) < 0) return -1;
+                            c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, nullptr, nullptr, b->stream) < 0) return -1;
   b->prof.end(K_CHANNEL);
   b->launches += 1;
   return 0;
@@ -378,6 +378,35 @@ RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP 
   if (rade_b200_channel_dev(b, (RADE_COMP *)(dst ? dst : (void *)b->d_rx_in), (const RADE_COMP *)src) < 0) return -1;
   if (!dst) CUDA_CHECK(cudaMemcpyAsync(rx, b->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+// loop-back runs without the two copy kernels: the channel writes straight into the per-stream link FIFOs, and the
+// receiver's band-pass kernel pops nin[s] samples per stream from them (streams without enough samples sit the call out)
+RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx) {
+  cudaSetDevice(b->device);
+  const rade_b200_channel_cfg &c = b->chan_cfg;
+  const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
+  b->prof.begin(K_CHANNEL);
+  if (channel_stream_launch(nullptr, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
+                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, b->stream) < 0) return -1;
+  b->prof.end(K_CHANNEL);
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out) {
+  cudaSetDevice(b->device);
+  const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
+  LinkSrc ls = {b->link_ring, b->link_wr, b->link_rd, b->d_active};
+  int n = rx_dsp_launch(b->tables, b->rx, nullptr, nullptr, &ls, b->S, 1, reset_dec, d_ret, b->stream, &b->prof);
+  if (n < 0) return -1;
+  b->prof.begin(K_CORE_DEC);
+  if (core_decoder_launch(b->weights.dev, b->rx.dec_state, b->rx.z_hat, d_features_out, 1, b->rx.uw_errors, b->rx.dec_active,
+                          b->S, RADE_NZMF, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_DEC);
+  b->launches += n + 1;
+  if (d_eoo_out && d_eoo_out != b->rx.eoo) {
+    CUDA_CHECK(cudaMemcpyAsync(d_eoo_out, b->rx.eoo, (size_t)b->S * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
+  }
   return 0;
 }
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {

@@ -55,6 +55,7 @@ __global__ void channel_apply_kernel(float2 *__restrict__ rx, const float2 *__re
 }
 
 constexpr int NSIN = 16;
+constexpr int LINK_CAP = 4096;
 
 // one sinusoid of a path gain at absolute time t (samples): exp(j(2*pi*f_i*t/Fs + phi_i)), f_i ~ N(0, (spread/2)^2);
 // the gain is (1/sqrt(2*NSIN)) * the sum over i = 0..NSIN-1
@@ -72,7 +73,8 @@ __device__ float2 path_gain_term(unsigned long long seed, uint32_t stream, uint3
 // streaming generator form: one CTA per stream, one modem frame (960 samples) per call
 __global__ void __launch_bounds__(256)
 channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, ChanState *__restrict__ st, int S,
-                      float sigma, float freq0, float freq_spread, float doppler, int d, float gain, unsigned long long seed) {
+                      float sigma, float freq0, float freq_spread, float doppler, int d, float gain, unsigned long long seed,
+                      float2 *__restrict__ link_ring, long long *__restrict__ link_wr) {
   __shared__ float2 stx[64 + RADE_NMF];
   __shared__ float2 g[4];                       // G1(t0), G1(t0+960), G2(t0), G2(t0+960)
   const int s = blockIdx.x, tid = threadIdx.x;
@@ -103,7 +105,10 @@ channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, Ch
   sincos(ph0 + dphi * (double)(tid + 1), &sn, &cs);
   sincos(dphi * 256.0, &sb, &cb);
   __syncthreads();
-  float2 *out = rx + (size_t)s * RADE_NMF;
+  // output: the caller's [S][960] array, or (loop-back runs) straight into the stream's link FIFO
+  float2 *out = link_ring ? link_ring + (size_t)s * LINK_CAP : rx + (size_t)s * RADE_NMF;
+  const long long lw = link_ring ? link_wr[s] : 0;
+  const int omask = link_ring ? LINK_CAP - 1 : 0x7fffffff;
   for (int i = tid; i < RADE_NMF; i += blockDim.x) {
     const float a = (float)i * (1.f / RADE_NMF);
     const float2 g1 = make_float2(g[0].x + a * (g[1].x - g[0].x), g[0].y + a * (g[1].y - g[0].y));
@@ -113,17 +118,16 @@ channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, Ch
     mp.x += e.x; mp.y += e.y;
     const float2 v = cmul(mp, make_float2((float)cs, (float)sn));
     const float2 nz = cnormal(seed, s, (unsigned long long)(t0 + i), 0xA11CEu);
-    out[i] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
+    out[(int)((lw + i) & omask)] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
     const double c2 = cs * cb - sn * sb, s2 = sn * cb + cs * sb;
     cs = c2; sn = s2;
   }
   __syncthreads();
   for (int i = tid; i < 64; i += blockDim.x) cs_.delay[i] = stx[RADE_NMF + i];
-  if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); }
+  if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); if (link_ring) link_wr[s] = lw + RADE_NMF; }
 }
 
 // ---------------------------------------------------------------- loop-back link (per-stream FIFO)
-constexpr int LINK_CAP = 4096;
 
 __global__ void link_push_kernel(float2 *__restrict__ ring, long long *__restrict__ wr, const float2 *__restrict__ in, int S) {
   const int s = blockIdx.x;
@@ -158,9 +162,10 @@ int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const f
 }
 
 int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
-                          float doppler, int d, float gain, unsigned long long seed, cudaStream_t stream) {
+                          float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
+                          cudaStream_t stream) {
   if (d < 0 || d > 64) return -1;
-  channel_stream_kernel<<<S, 256, 0, stream>>>(rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed);
+  channel_stream_kernel<<<S, 256, 0, stream>>>(rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed, link_ring, link_wr);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

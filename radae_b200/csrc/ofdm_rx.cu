@@ -97,20 +97,30 @@ constexpr int BPF_THREADS = 288;                  // 4 outputs per thread, nin <
 __global__ void __launch_bounds__(BPF_THREADS)
 rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, float2 *__restrict__ bpf_mem,
               const float2 *__restrict__ rx_in, const unsigned char *__restrict__ active, int bpf_en,
-              int *__restrict__ search_list, int *__restrict__ track_list, int *__restrict__ counters) {
+              int *__restrict__ search_list, int *__restrict__ track_list, int *__restrict__ counters, LinkSrc link) {
   __shared__ __align__(16) float2 X[RADE_BPF_MEM + RADE_NIN_MAX + 42];
+  constexpr int LINK_CAP = 4096;
   const int s = blockIdx.x, tid = threadIdx.x;
-  if (active && !active[s]) return;
   RxCtl &c = ctl[s];
   const int nin = c.nin, head = c.ring_head;
+  // input: row s of the caller's [S][1120] array, or nin samples popped from the stream's link FIFO
   const float2 *xin = rx_in + (size_t)s * RADE_NIN_MAX;
+  int xoff = 0, xmask = 0x7fffffff;
+  if (link.ring) {
+    const long long r = link.rd[s];
+    const bool ok = link.wr[s] - r >= nin;
+    __syncthreads();                                    // everybody has read rd before it moves
+    if (tid == 0) { link.active_out[s] = ok ? 1 : 0; if (ok) link.rd[s] = r + nin; }
+    if (!ok) return;
+    xin = link.ring + (size_t)s * LINK_CAP; xoff = (int)(r & (LINK_CAP - 1)); xmask = LINK_CAP - 1;
+  } else if (active && !active[s]) return;
   float2 *rg = ring + (size_t)s * RADE_RXBUF;
   if (bpf_en) {
     const float2 ph = c.bpf_phase;
     const int off = c.bpf_first ? 2 : 0;
     float2 *mem = bpf_mem + (size_t)s * RADE_BPF_MEM;
     for (int i = tid; i < RADE_BPF_MEM; i += BPF_THREADS) X[i] = mem[i];
-    for (int i = tid; i < nin; i += BPF_THREADS) X[RADE_BPF_MEM + i] = cmul(xin[i], cmul(ph, T.bpf_exp[i]));   // mix down
+    for (int i = tid; i < nin; i += BPF_THREADS) X[RADE_BPF_MEM + i] = cmul(xin[(xoff + i) & xmask], cmul(ph, T.bpf_exp[i]));   // mix down
     for (int i = RADE_BPF_MEM + nin + tid; i < RADE_BPF_MEM + RADE_NIN_MAX + 42; i += BPF_THREADS) X[i] = make_float2(0.f, 0.f);
     __syncthreads();
     const int i0 = 4 * tid;
@@ -143,7 +153,7 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
     for (int i = tid; i < RADE_BPF_MEM; i += BPF_THREADS) mem[i] = X[nin + i];
     if (tid == 0) { c.bpf_phase = cmul(ph, T.bpf_exp[nin - 1]); c.bpf_first = 0; }
   } else {
-    for (int i = tid; i < nin; i += BPF_THREADS) rg[ring_idx(head, i)] = xin[i];
+    for (int i = tid; i < nin; i += BPF_THREADS) rg[ring_idx(head, i)] = xin[(xoff + i) & xmask];
   }
   if (tid == 0) {
     int nh = head + nin; if (nh >= RADE_RXBUF) nh -= RADE_RXBUF;
@@ -842,7 +852,7 @@ int rx_dsp_init_device() {
   return 0;
 }
 
-int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, const LinkSrc *link, int S,
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof) {
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
@@ -854,7 +864,9 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   const bool fork = !prof->on && B.side_stream;
   cudaStream_t ss = fork ? B.side_stream : stream;
   prof->begin(K_RX_BPF);
-  rx_bpf_kernel<<<S, BPF_THREADS, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt);
+  LinkSrc ls = {nullptr, nullptr, nullptr, nullptr};
+  if (link) { ls = *link; active = link->active_out; }      // downstream kernels read the flags the band-pass kernel writes
+  rx_bpf_kernel<<<S, BPF_THREADS, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt, ls);
   prof->end(K_RX_BPF);
   if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_fork, stream)); CUDA_CHECK(cudaStreamWaitEvent(ss, B.ev_fork, 0)); }
   prof->begin(K_RX_TRACK);

@@ -61,13 +61,17 @@ int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float
 int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
                          int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
 int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
-                          float doppler, int d, float gain, unsigned long long seed, cudaStream_t stream);
+                          float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
+                          cudaStream_t stream);
 int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream);
 int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, const RxCtl *ctl, float2 *out,
                     unsigned char *active, int S, cudaStream_t stream);
 int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream);
 struct Profiler;
-int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, int S,
+// link source (loop-back runs): when link_ring is non-null the band-pass kernel takes nin[s] samples from the stream's link FIFO
+// (if it holds that many; otherwise the stream sits this call out) and writes the active flags itself into `active_out`
+struct LinkSrc { const float2 *ring; const long long *wr; long long *rd; unsigned char *active_out; };
+int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const unsigned char *active, const LinkSrc *link, int S,
                   int bpf_en, int reset_dec_on_sync, int *ret_out, cudaStream_t stream, Profiler *prof);
 
 // ---- optional per-kernel timing with CUDA events on the context's stream (rade_b200_profile_*)

@@ -175,3 +175,42 @@ def test_hostlink_fifo_feeds_the_same_call_sequence(golden):
         per = np.sqrt(np.mean((np.array(feats[s]).reshape(nf, 432) - g["features"][:nf]) ** 2, axis=1)) if nf else np.zeros(0)
         assert per.size == 0 or (per.max() < 0.02 and np.sqrt(np.mean(per ** 2)) < 5e-3), SCENARIOS[s]
     link.close(); b.close()
+
+
+def test_fused_loopback_equals_copy_kernels():
+    """rade_b200_channel_link_dev + rade_b200_rx_link_dev (channel writes into the link FIFOs, the band-pass kernel pops
+    from them) must give exactly what channel_dev -> link_push_dev -> link_pop_dev -> rx_dev gives"""
+    torch = need_gpu()
+    from radae_b200 import RadeBatch
+    from oracle.core import synth_features
+    S, F = 40, 14
+    feats = synth_features(S, 12 * F, seed=3).reshape(S, F, 432)
+    outs = []
+    for fused in (False, True):
+        b = RadeBatch(S)
+        b.channel_config(EbNodB=6.0, freq_offset_hz=7.0, freq_offset_spread_hz=20.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=11)
+        d_tx = torch.empty((S, 960, 2), device="cuda"); d_ch = torch.empty((S, 960, 2), device="cuda")
+        d_rxin = torch.zeros((S, 1120, 2), device="cuda"); d_act = torch.zeros(S, dtype=torch.uint8, device="cuda")
+        d_fo = torch.zeros((S, 432), device="cuda"); d_ret = torch.zeros(S, dtype=torch.int32, device="cuda")
+        d_eoo = torch.zeros((S, 180), device="cuda")
+        torch.cuda.synchronize()
+        rec = []
+        for f in range(F):
+            d_f = torch.tensor(feats[:, f]).cuda(); torch.cuda.synchronize()
+            b.tx_dev(d_tx.data_ptr(), d_f.data_ptr())
+            if fused:
+                b.channel_link_dev(d_tx.data_ptr())
+                b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
+            else:
+                b.channel_dev(d_ch.data_ptr(), d_tx.data_ptr())
+                b.link_push_dev(d_ch.data_ptr())
+                b.link_pop_dev(d_rxin.data_ptr(), d_act.data_ptr())
+                b.rx_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr(), d_rxin.data_ptr(), d_act.data_ptr())
+            b.synchronize()
+            ret = d_ret.cpu().numpy().copy()
+            rec.append((ret, d_fo.cpu().numpy()[ret & 1 == 1].copy(), np.array([x.tmax for x in b.rx_status()])))
+        outs.append(rec)
+        b.close()
+    assert sum(int((r[0] & 1).sum()) for r in outs[0]) > S * (F - 8)
+    for (r0, f0, t0), (r1, f1, t1) in zip(*outs):
+        assert np.array_equal(r0, r1) and np.array_equal(t0, t1) and np.array_equal(f0, f1)
