@@ -74,6 +74,10 @@ RADE_EXPORT int rade_b200_rx_get_z_hat(rade_batch *b, float *z_hat);
 RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx, const RADE_COMP *d_G1,
                                             const RADE_COMP *d_G2, const RADE_COMP *d_noise, int n, int delay,
                                             float mp_gain, float freq_offset_hz, float phase0, float sigma, float gain);
+/* the same with host arrays [S][n] (e.g. G1, G2 read from one of the reference's rate-Fs fading files, g_mpp.f32 ...) */
+RADE_EXPORT int rade_b200_channel_apply(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
+                                        const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float phase0,
+                                        float sigma, float gain);
 typedef struct {
   float EbNodB;               /* sigma = sqrt(Fs/(EbNo*Rb)), Rb = 2000 (radae.py:570-574) */
   float freq_offset_hz;       /* per stream: freq_offset_hz + U(-1,1)*freq_offset_spread_hz */

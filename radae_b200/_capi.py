@@ -51,6 +51,7 @@ SIGNATURES = {
     "rade_b200_rx_dev": (_I, [_P, _P, _P, _P, _P, _P]), "rade_b200_nin_dev": (_P, [_P]),
     "rade_b200_rx_get_status": (_I, [_P, _P]), "rade_b200_rx_get_z_hat": (_I, [_P, _P]),
     "rade_b200_channel_apply_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F]),
+    "rade_b200_channel_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F]),
     "rade_b200_channel_config": (_I, [_P, C.POINTER(ChannelCfg)]), "rade_b200_channel_dev": (_I, [_P, _P, _P]),
     "rade_b200_link_push_dev": (_I, [_P, _P]), "rade_b200_channel_link_dev": (_I, [_P, _P]),
     "rade_b200_rx_link_dev": (_I, [_P, _P, _P, _P]), "rade_b200_link_pop_dev": (_I, [_P, _P, _P]),

@@ -156,6 +156,17 @@ class RadeBatch:
     def rx_link_dev(self, d_features_out, d_ret, d_eoo_out):
         _check(self.lib.rade_b200_rx_link_dev(self.h, d_features_out, d_ret, d_eoo_out), "rx_link_dev")
 
+    def channel_apply(self, tx, G1, G2, noise, delay=16, mp_gain=1.0, freq_offset_hz=0.0, phase0=0.0, sigma=0.0, gain=1.0):
+        """explicit channel on host arrays [S][n] complex64 (RADAE.forward rate-Fs branch, radae/radae.py:529-599):
+        G1, G2 e.g. from a fading file (radae_b200.gfile.read_g), noise unit-variance complex normal"""
+        arrs = [np.ascontiguousarray(a, np.complex64) for a in (tx, G1, G2, noise)]
+        S, n = arrs[0].shape
+        assert S == self.S and all(a.shape == (S, n) for a in arrs)
+        out = np.empty((S, n), np.complex64)
+        _check(self.lib.rade_b200_channel_apply(self.h, out.ctypes.data, *[a.ctypes.data for a in arrs], n, delay, mp_gain,
+                                                freq_offset_hz, phase0, sigma, gain), "channel_apply")
+        return out
+
     def link_push_dev(self, d_samples):
         _check(self.lib.rade_b200_link_push_dev(self.h, d_samples), "link_push_dev")
 

@@ -74,6 +74,8 @@ int reset_state(rade_batch *b) {
 // With an alias the big sample buffers are read / written by the kernels directly over PCIe (no staging copy, the
 // transfer overlaps the compute of the other CTAs); pageable buffers take the cudaMemcpyAsync path.
 void *pinned_alias(const void *p) {
+  static const bool enabled = !(getenv("RADE_B200_ZERO_COPY") && atoi(getenv("RADE_B200_ZERO_COPY")) == 0);
+  if (!enabled) return nullptr;                 // RADE_B200_ZERO_COPY=0: always stage through cudaMemcpyAsync (DMA engines)
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
   cudaGetLastError();
@@ -351,6 +353,25 @@ RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, cons
                            b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) return -1;
   b->launches += 1;
   return 0;
+}
+// host-pointer form of the explicit channel: tx, G1, G2, noise are [S][n] complex64 host arrays (G from a fading file,
+// radae_b200/gfile.py), rx [S][n] comes back
+RADE_EXPORT int rade_b200_channel_apply(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
+                                        const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float phase0,
+                                        float sigma, float gain) {
+  cudaSetDevice(b->device);
+  const size_t bytes = (size_t)b->S * n * sizeof(float2);
+  float2 *d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void *src[4] = {tx, G1, G2, noise};
+  int rc = 0;
+  for (int i = 0; i < 5 && rc == 0; i++) if (cudaMalloc((void **)&d[i], bytes) != cudaSuccess) rc = -1;
+  for (int i = 0; i < 4 && rc == 0; i++) if (cudaMemcpyAsync(d[i], src[i], bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
+  if (rc == 0 && channel_apply_launch(d[4], d[0], d[1], d[2], d[3], b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) rc = -1;
+  if (rc == 0 && cudaMemcpyAsync(rx, d[4], bytes, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
+  for (int i = 0; i < 5; i++) if (d[i]) cudaFree(d[i]);
+  if (rc == 0) b->launches += 1;
+  return rc;
 }
 RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_cfg *cfg) {
   cudaSetDevice(b->device);        // the current device is per host thread

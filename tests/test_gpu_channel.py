@@ -58,3 +58,24 @@ def test_channel_generator_statistics():
     res = y - ph[None, :]
     assert abs(np.mean(np.abs(res) ** 2) / od.ebno_sigma(10.0) ** 2 - 1) < 0.05
     b.close()
+
+
+def test_channel_apply_host_with_fading_file(tmp_path):
+    """the reference's g-file workflow (inference.py --g_file): write / read a fading file, run the explicit channel on host
+    arrays, compare with the oracle"""
+    need_gpu()
+    from radae_b200 import RadeBatch, gfile
+    S, n = 3, 2400
+    rng = np.random.default_rng(5)
+    G1, G2, hf_gain, d = gfile.multipath_samples("mpp", nseconds=1, seed=2)
+    p = str(tmp_path / "g_mpp.f32"); gfile.write_g(p, G1, G2, hf_gain)
+    mp_gain, G = gfile.read_g(p, n_samples=n)
+    c = lambda: ((rng.standard_normal((S, n)) + 1j * rng.standard_normal((S, n))) / np.sqrt(2)).astype(np.complex64)
+    tx, nz = c(), c()
+    g1 = np.tile(G[:, 0], (S, 1)); g2 = np.tile(G[:, 1], (S, 1))
+    b = RadeBatch(S)
+    sigma = od.ebno_sigma(3.0)
+    got = b.channel_apply(tx, g1, g2, nz, delay=d, mp_gain=1.0, freq_offset_hz=-11.0, sigma=sigma)
+    ref = np.array([od.channel(tx[s], g1[s], g2[s], d, 1.0, -11.0, 0.0, sigma, nz[s]) for s in range(S)])
+    assert relrms(got, ref) < 1e-5
+    b.close()

@@ -1,8 +1,7 @@
 #!/bin/bash
-# e2e throughput vs number of host contexts/threads serving the 1024 streams
-for c in 1 2 4 8; do
-  timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-contexts $c 2>/tmp/b.err > /tmp/b.json || tail -3 /tmp/b.err
+# e2e throughput vs number of host contexts/threads serving the 1024 streams, zero-copy sample buffers on / off
+for z in 1 0; do for c in 1 2 4; do
+  RADE_B200_ZERO_COPY=$z timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-contexts $c 2>/tmp/b.err > /tmp/b.json || tail -3 /tmp/b.err
   python -c "
-import json; d=json.load(open('/tmp/b.json')); print('contexts', $c, 'e2e', round(d['e2e']['value']), 'value', round(d['value']))"
-done
-nproc; lscpu | grep -E "Model name|^CPU\(s\)"
+import json; d=json.load(open('/tmp/b.json')); print('zero_copy', $z, 'contexts', $c, 'e2e', round(d['e2e']['value']), 'value', round(d['value']))"
+done; done
