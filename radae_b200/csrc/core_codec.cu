@@ -107,12 +107,13 @@ __device__ __forceinline__ void ldsm_a(uint32_t &a0, uint32_t &a1, uint32_t &a2,
                : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(smem_u32(lane_ptr)));
 }
 
-template <int NT, typename CX>
+template <int NT, int TS, typename CX>
 __device__ __forceinline__ void gemm_stream(CX &cx, int (&acc)[NT][4], const int (&nt)[NT], const bool (&use)[NT], bool work,
                                             const int8_t *A, int lda, int KB, int NTL) {
   const int lane = threadIdx.x & 31;
-  // ldmatrix row address of this lane: matrix (lane>>3): rows +8 for odd matrices, bytes +16 for matrices 2,3
-  const int8_t *arow = A + ((lane & 7) + ((lane >> 3) & 1) * 8) * lda + ((lane >> 4) & 1) * 16;
+  // ldmatrix row address of this lane: matrix (lane>>3): rows +8 for odd matrices, bytes +16 for matrices 2,3.  8-stream tiles
+  // have no rows 8..15: those lanes re-read rows 0..7 (the MMA rows they feed are never used) instead of whatever lies behind
+  const int8_t *arow = A + ((lane & 7) + (TS == 16 ? ((lane >> 3) & 1) * 8 : 0)) * lda + ((lane >> 4) & 1) * 16;
   const int kbc = core_kbc(NTL);
   for (int kb0 = 0; kb0 < KB; kb0 += kbc) {
     const int nk = min(kbc, KB - kb0);
@@ -203,8 +204,8 @@ __device__ __forceinline__ void gru_layer(CX &cx, const I8LayerDev &Li, const I8
   int ai[3][4] = {}, ar[3][4] = {};
   const int nt[3] = {u, U + u, 2 * U + u};
   const bool use[3] = {true, true, true};
-  gemm_stream<3>(cx, ai, nt, use, work, Xin, ldx, Li.K / 32, 3 * U);
-  gemm_stream<3>(cx, ar, nt, use, work, Hq, ldh, Lr.K / 32, 3 * U);
+  gemm_stream<3, TS>(cx, ai, nt, use, work, Xin, ldx, Li.K / 32, 3 * U);
+  gemm_stream<3, TS>(cx, ar, nt, use, work, Hq, ldh, Lr.K / 32, 3 * U);
   if (!work) return;
 #pragma unroll
   for (int e = 0; e < 4; e++) {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void conv_layer(CX &cx, const I8LayerDev &L, const in
       use[i] = mine;
       any |= mine;
     }
-    gemm_stream<PER>(cx, acc, ntc, use, any, tap ? Acur : Aold, lda, Ktap / 32, NTL);
+    gemm_stream<PER, TS>(cx, acc, ntc, use, any, tap ? Acur : Aold, lda, Ktap / 32, NTL);
 #pragma unroll
     for (int i = 0; i < PER; i++)
       if (nt[i] >= 0) {
@@ -609,7 +610,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
         int acc[1][4] = {};
         const int nt[1] = {warp};
         const bool use[1] = {true};
-        gemm_stream<1>(cx, acc, nt, use, true, &hq_wr[0][l * DEC_GRU], HQ_LD, DEC_GRU / 32, DEC_GRU / 8);
+        gemm_stream<1, TS>(cx, acc, nt, use, true, &hq_wr[0][l * DEC_GRU], HQ_LD, DEC_GRU / 32, DEC_GRU / 8);
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int row = g + ((e & 2) ? 8 : 0);
