@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-contexts", type=int, default=4, help="host threads / contexts serving the streams in the e2e leg")
+    ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

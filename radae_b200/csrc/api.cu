@@ -73,9 +73,15 @@ int reset_state(rade_batch *b) {
 // Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host buffer, or nullptr for pageable memory.
 // With an alias the big sample buffers are read / written by the kernels directly over PCIe (no staging copy, the
 // transfer overlaps the compute of the other CTAs); pageable buffers take the cudaMemcpyAsync path.
-void *pinned_alias(const void *p) {
-  static const bool enabled = !(getenv("RADE_B200_ZERO_COPY") && atoi(getenv("RADE_B200_ZERO_COPY")) == 0);
-  if (!enabled) return nullptr;                 // RADE_B200_ZERO_COPY=0: always stage through cudaMemcpyAsync (DMA engines)
+// RADE_B200_ZERO_COPY: 1 (default) kernels read and write pinned buffers in place; 2 writes in place, reads staged through
+// the H2D copy engine; 0 everything staged through cudaMemcpyAsync
+int zero_copy_mode() {
+  static const int mode = getenv("RADE_B200_ZERO_COPY") ? atoi(getenv("RADE_B200_ZERO_COPY")) : 1;
+  return mode;
+}
+void *pinned_alias(const void *p, bool for_read = false) {
+  const int mode = zero_copy_mode();
+  if (mode == 0 || (mode == 2 && for_read)) return nullptr;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
   cudaGetLastError();
@@ -394,7 +400,7 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx) {
   cudaSetDevice(b->device);        // the current device is per host thread
   const size_t S = b->S;
-  const void *src = pinned_alias(tx); void *dst = pinned_alias(rx);
+  const void *src = pinned_alias(tx, true); void *dst = pinned_alias(rx);
   if (!src) { CUDA_CHECK(cudaMemcpyAsync(b->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, b->stream)); src = b->d_tx; }
   if (rade_b200_channel_dev(b, (RADE_COMP *)(dst ? dst : (void *)b->d_rx_in), (const RADE_COMP *)src) < 0) return -1;
   if (!dst) CUDA_CHECK(cudaMemcpyAsync(rx, b->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
@@ -509,7 +515,7 @@ RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out
   }
   const size_t Sz = S;
   // the gathered samples sit in our own pinned buffer: the band-pass kernel reads them in place over PCIe
-  const void *rx_alias = pinned_alias(h->rx_in);
+  const void *rx_alias = pinned_alias(h->rx_in, true);
   if (!rx_alias) { CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, h->rx_in, Sz * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream)); rx_alias = b->d_rx_in; }
   CUDA_CHECK(cudaMemcpyAsync(b->d_active, h->active, Sz, cudaMemcpyHostToDevice, b->stream));
   if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)rx_alias, b->d_active) < 0) return -1;

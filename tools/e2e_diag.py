@@ -17,6 +17,13 @@ for k in range(40):
     t0=time.perf_counter(); b.tx(feats[k%8],out=tx); t1=time.perf_counter(); b.channel(tx,out=rx); t2=time.perf_counter(); link.push(rx); t3=time.perf_counter(); link.rx(); t4=time.perf_counter()
     if k>=20: T+=np.array([t1-t0,t2-t1,t3-t2,t4-t3])
 print('ms per step: tx %.3f channel %.3f push %.3f rx %.3f total %.3f'%tuple(list(T/20*1e3)+[T.sum()/20*1e3]))
+b.profile_enable(True)
+for k in range(20):
+    b.tx(feats[k%8],out=tx); b.channel(tx,out=rx); link.push(rx); link.rx()
+pr=b.profile_read(); b.profile_enable(False)
+print('device ms per launch in e2e mode (kernels read/write pinned host buffers in place):')
+for k,(ms,c) in pr.items(): print('  %-24s %.4f'%(k, ms/c))
+print('  sum %.4f'%sum(ms/c for ms,c in pr.values()))
 # raw copy speed
 import ctypes
 x=torch.empty(S*960*2,dtype=torch.float32).pin_memory(); d=torch.empty_like(x,device='cuda')
