@@ -83,7 +83,7 @@ template <int NF> __device__ __forceinline__ void f_sync() { asm volatile("bar.s
 template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int T) {
   int stage = 0; uint32_t phase = 0;
   for (int t = 0; t < T; t++)
-    for (int c = 0; c < ws.n_chunks; c++) {
+    for (int c = (t == 0 ? 0 : ws.n_prologue); c < ws.n_chunks; c++) {
       const ChunkDesc d = ws.chunks[c];
       mbar_wait(&p->empty[stage], phase ^ 1);
       mbar_expect_tx(&p->full[stage], d.bytes);
@@ -283,6 +283,7 @@ template <int TS, int NST> struct EncSmem {
   alignas(16) float hs[TS][5 * ENC_GRU];
   alignas(16) float seg[3][TS][SEG_LD];       // [0], [1]: segments handed from the I-warps to the F-warps; [2]: dense1 output
   alignas(16) float fin[TS][FIN_LD];
+  alignas(16) int8_t d1q[TS][64];             // dense1 output of the next step, parked until its concat buffer is free
   int red[2 * TS * ENC_CONV];
   int any_active;
 };
@@ -331,43 +332,55 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     const int sg = s0 + sl;
     bar_arrive(BAR_SEG_EMPTY + 0, NCT); bar_arrive(BAR_SEG_EMPTY + 1, NCT);       // both hand-over buffers start free
     bar_sync(BAR_ALL, NCT);                                                       // concat buffers initialised by the I-warps
-    for (int t = 0; t < T; t++) {
-      int8_t(*cur)[ENC_LDA] = sm.cb[t % 3];
+    // input of step t -> fin (API layout: [S][4T][36]; 20 used features + aux = -1, src/rade_api.c:426-432)
+    auto stage_input = [&](int t) {
       for (int i = ft; i < TS * ENC_IN; i += NF * 32) {
         const int r = i / ENC_IN, k = i % ENC_IN;
         float v = 0.f;
         if (s0 + r < S) {
           if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
-          else {                                 // API layout: [S][4T][36]; 20 used features + aux = -1 (src/rade_api.c:426-432)
+          else {
             const int fr = k / 21, f = k % 21;
             v = (f == 20) ? -1.f : in[((size_t)(s0 + r) * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f];
           }
         }
         sm.fin[r][k] = v;
       }
-      f_sync<NF>();
-      // ---- dense1: tanh(W f + b), 84 -> 64
-      {
-        float a[OPT], bd[OPT];
+    };
+    // dense1: tanh(W f + b), 84 -> 64, from fin into seg[2] (float, for zdense) and d1q (int8, copied into the concat buffer
+    // of its step once the I-warps are done with the previous step)
+    auto dense1 = [&]() {
+      float a[OPT];
 #pragma unroll
-        for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = (grp < 64 / OPT) ? W.enc_dense1.bias[OPT * grp + i] : 0.f; }
-        dense_seg<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
-        if (grp < 64 / OPT) {
+      for (int i = 0; i < OPT; i++) a[i] = 0.f;
+      dense_seg<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
+      if (grp < 64 / OPT) {
 #pragma unroll
-          for (int i = 0; i < OPT; i++) {
-            const int o = OPT * grp + i;
-            float y = tanh_r(__fadd_rn(a[i], bd[i]));
-            sm.seg[2][sl][o] = y;
-            cur[sl][o] = quant8(y);
-          }
+        for (int i = 0; i < OPT; i++) {
+          const int o = OPT * grp + i;
+          float y = tanh_r(__fadd_rn(a[i], W.enc_dense1.bias[o]));
+          sm.seg[2][sl][o] = y;
+          sm.d1q[sl][o] = quant8(y);
         }
       }
+    };
+    auto publish_d1 = [&](int t) {               // d1q -> cur(t)[:, 0:64), then the I-warps may start GRU 1 of step t
+      for (int i = ft; i < TS * 16; i += NF * 32)
+        reinterpret_cast<uint32_t *>(sm.cb[t % 3][i / 16])[i % 16] = reinterpret_cast<const uint32_t *>(sm.d1q[i / 16])[i % 16];
       f_sync<NF>();
-      bar_arrive(BAR_D1, NCT);                   // the I-warps may start GRU 1
+      bar_arrive(BAR_D1, NCT);
+    };
+    stage_input(0);
+    f_sync<NF>();
+    dense1();                                    // prologue chunk
+    f_sync<NF>();
+    publish_d1(0);
+    for (int t = 0; t < T; t++) {
       float zacc[OPT];
 #pragma unroll
       for (int i = 0; i < OPT; i++) zacc[i] = 0.f;
       dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[2][sl], 64, grp);
+      if (t + 1 < T) stage_input(t + 1);         // long before it is needed: the global-load latency is off the critical path
       int off = 64;
 #pragma unroll 1
       for (int l = 0; l < 5; l++) {
@@ -376,8 +389,14 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
         dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[1][sl], ENC_GRU, grp);
         bar_arrive(BAR_SEG_EMPTY + 1, NCT);
         off += ENC_GRU;
+        if (l == 4) {                            // dense1 of the NEXT step while the I-warps run the last conv layer
+          f_sync<NF>();
+          if (t + 1 < T) dense1(); else skip_chunks(cx, f32_chunks(ENC_IN, 64));
+          f_sync<NF>();
+        }
         skip_chunks(cx, 2 * i8_chunks(off, ENC_CONV));
-        bar_sync(BAR_SEG_FULL + 0, NCT);
+        bar_sync(BAR_SEG_FULL + 0, NCT);         // l == 4: the I-warps have finished this step
+        if (l == 4 && t + 1 < T) publish_d1(t + 1);
         dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[0][sl], ENC_CONV, grp);
         bar_arrive(BAR_SEG_EMPTY + 0, NCT);
         off += ENC_CONV;
@@ -409,7 +428,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
     int8_t(*cur)[ENC_LDA] = sm.cb[t % 3];
     int8_t(*prev1)[ENC_LDA] = sm.cb[(t + 2) % 3];
     int8_t(*prev2)[ENC_LDA] = sm.cb[(t + 1) % 3];
-    skip_chunks(cx, f32_chunks(ENC_IN, 64) + f32_chunks(64, RADE_LATENT));
+    skip_chunks(cx, (t == 0 ? f32_chunks(ENC_IN, 64) : 0) + f32_chunks(64, RADE_LATENT));
     bar_sync(BAR_D1, NCT);                       // dense1 output (int8) is in cur[:, 0:64)
     int off = 64;
 #pragma unroll 1
@@ -421,7 +440,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
                              [&](int row, int j, float h) { sm.seg[1][row][j] = h; cur[row][off + j] = quant8(h); });
       bar_arrive(BAR_SEG_FULL + 1, NCT);
       i_sync<NI>();
-      skip_chunks(cx, f32_chunks(ENC_GRU, RADE_LATENT));
+      skip_chunks(cx, f32_chunks(ENC_GRU, RADE_LATENT) + (l == 4 ? f32_chunks(ENC_IN, 64) : 0));
       off += ENC_GRU;
       // conv l (k = 2): tap 0 = concat prefix of step t-dilation, tap 1 = current prefix
       const int8_t *old = (dil[l] == 1) ? &prev1[0][0] : &prev2[0][0];
@@ -455,6 +474,7 @@ template <int TS, int NST> struct DecSmem {
   alignas(16) float hs[TS][5 * DEC_GRU];
   alignas(16) float seg[3][TS][SEG_LD];
   alignas(16) float zin[TS][ZIN_LD];
+  alignas(16) int8_t d1q[TS][96];
   int red[2 * TS * DEC_CONV];
   int any_active;
 };
@@ -505,33 +525,44 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     const int sg = s0 + sl;
     bar_arrive(BAR_SEG_EMPTY + 0, NCT); bar_arrive(BAR_SEG_EMPTY + 1, NCT);
     bar_sync(BAR_ALL, NCT);
-    for (int t = 0; t < T; t++) {
-      int8_t(*cur)[DEC_LDA] = sm.cb[t & 1];
+    auto stage_input = [&](int t) {
       for (int i = ft; i < TS * DEC_IN; i += NF * 32) {
         const int r = i / DEC_IN, k = i % DEC_IN;
         sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
       }
-      f_sync<NF>();
-      // ---- dense1: tanh(W z + b), 80 -> 96
-      {
-        float a[OPT], bd[OPT];
+    };
+    // dense1: tanh(W z + b), 80 -> 96, into seg[2] (float, for the output layer) and d1q (int8, published to the concat
+    // buffer of its step once the I-warps are done with the previous step)
+    auto dense1 = [&]() {
+      float a[OPT];
 #pragma unroll
-        for (int i = 0; i < OPT; i++) { a[i] = 0.f; bd[i] = W.dec_dense1.bias[OPT * grp + i]; }
-        dense_seg<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
+      for (int i = 0; i < OPT; i++) a[i] = 0.f;
+      dense_seg<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
 #pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          float y = tanh_r(__fadd_rn(a[i], bd[i]));
-          sm.seg[2][sl][o] = y;
-          cur[sl][o] = quant8(y);
-        }
+      for (int i = 0; i < OPT; i++) {
+        const int o = OPT * grp + i;
+        float y = tanh_r(__fadd_rn(a[i], W.dec_dense1.bias[o]));
+        sm.seg[2][sl][o] = y;
+        sm.d1q[sl][o] = quant8(y);
       }
+    };
+    auto publish_d1 = [&](int t) {
+      for (int i = ft; i < TS * 24; i += NF * 32)
+        reinterpret_cast<uint32_t *>(sm.cb[t & 1][i / 24])[i % 24] = reinterpret_cast<const uint32_t *>(sm.d1q[i / 24])[i % 24];
       f_sync<NF>();
       bar_arrive(BAR_D1, NCT);
+    };
+    stage_input(0);
+    f_sync<NF>();
+    dense1();                                    // prologue chunk
+    f_sync<NF>();
+    publish_d1(0);
+    for (int t = 0; t < T; t++) {
       float oacc[OPT];
 #pragma unroll
       for (int i = 0; i < OPT; i++) oacc[i] = 0.f;
       dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[2][sl], 96, grp);
+      if (t + 1 < T) stage_input(t + 1);
       int off = 96;
 #pragma unroll 1
       for (int l = 0; l < 5; l++) {
@@ -540,8 +571,14 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
         dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[1][sl], DEC_GRU, grp);
         bar_arrive(BAR_SEG_EMPTY + 1, NCT);
         off += DEC_GRU;
+        if (l == 4) {                            // dense1 of the NEXT step while the I-warps run the last conv layer
+          f_sync<NF>();
+          if (t + 1 < T) dense1(); else skip_chunks(cx, f32_chunks(DEC_IN, 96));
+          f_sync<NF>();
+        }
         skip_chunks(cx, 2 * i8_chunks(off, DEC_CONV));
         bar_sync(BAR_SEG_FULL + 0, NCT);
+        if (l == 4 && t + 1 < T) publish_d1(t + 1);
         dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[0][sl], DEC_CONV, grp);
         bar_arrive(BAR_SEG_EMPTY + 0, NCT);
         off += DEC_CONV;
@@ -590,7 +627,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
     int8_t(*prev1)[DEC_LDA] = sm.cb[(t + 1) & 1];
     int8_t(*hq_rd)[HQ_LD] = sm.hq[t & 1];
     int8_t(*hq_wr)[HQ_LD] = sm.hq[(t + 1) & 1];
-    skip_chunks(cx, f32_chunks(DEC_IN, 96) + f32_chunks(96, DEC_OUTP));
+    skip_chunks(cx, (t == 0 ? f32_chunks(DEC_IN, 96) : 0) + f32_chunks(96, DEC_OUTP));
     bar_sync(BAR_D1, NCT);
     int off = 96;
 #pragma unroll 1
@@ -622,7 +659,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
       }
       bar_arrive(BAR_SEG_FULL + 1, NCT);
       i_sync<NI>();
-      skip_chunks(cx, f32_chunks(DEC_GRU, DEC_OUTP));
+      skip_chunks(cx, f32_chunks(DEC_GRU, DEC_OUTP) + (l == 4 ? f32_chunks(DEC_IN, 96) : 0));
       off += DEC_GRU;
       bar_sync(BAR_SEG_EMPTY + 0, NCT);
       conv_layer<DEC_CONV, NI, TS>(cx, W.dec_conv[l], &prev1[0][0], &cur[0][0], off, DEC_LDA, sm.red,

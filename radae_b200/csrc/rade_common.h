@@ -71,7 +71,8 @@ struct __align__(16) DecStreamState {
 struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
 struct F32LayerDev { const float *bias; int K; int N; };
 struct ChunkDesc { unsigned int offset; unsigned int bytes; };
-struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; int n_chunks; };
+// chunks[0 .. n_prologue) are streamed once per launch (dense1 of the first step), chunks[n_prologue .. n_chunks) once per step
+struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; int n_chunks; int n_prologue; };
 struct CoreWeightsDev {
   F32LayerDev enc_dense1, enc_zdense, dec_dense1, dec_output;
   I8LayerDev enc_gru_in[5], enc_gru_rec[5], enc_conv[5];

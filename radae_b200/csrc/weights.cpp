@@ -222,9 +222,13 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   // ---- per-step weight streams, in the kernels' consumption order (keep in lock-step with core_codec.cu)
   auto I8 = [&](const std::string &n) { return (const int8_t *)w8[n]->data.data(); };
   auto F = [&](const std::string &n) { return (const float *)wf[n]->data.data(); };
+  // Order = the kernels' consumption order.  dense1 is needed once up front (prologue) and then, for the NEXT step, just before
+  // the last conv layer, so that the F-warps can have the next step's first activation ready when the I-warps finish this one.
   StreamBuilder e, d;
+  int e_pro = 0, d_pro = 0;
   {
     e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);
+    e_pro = (int)e.chunks.size();
     e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, 0, 64);
     int off = 64;
     for (int l = 0; l < 5; l++) {
@@ -233,6 +237,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
       e.add_i8(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2);
       e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
       off += ENC_GRU;
+      if (l == 4) e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);             // for the next step
       e.add_i8(I8("enc_conv" + n), 96, 2 * off, 0, off / 32);                    // tap 0 (oldest frame)
       e.add_i8(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32);         // tap 1 (current frame)
       e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
@@ -241,6 +246,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   }
   {
     d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);
+    d_pro = (int)d.chunks.size();
     d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, 0, 96);
     int off = 96;
     for (int l = 0; l < 5; l++) {
@@ -250,6 +256,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
       d.add_i8(I8("dec_glu" + n), 96, 96, 0, 3);
       d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
       off += DEC_GRU;
+      if (l == 4) d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);             // for the next step
       d.add_i8(I8("dec_conv" + n), 32, 2 * off, 0, off / 32);
       d.add_i8(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32);
       d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
@@ -257,13 +264,14 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     }
   }
   if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
-  auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out) -> int {
+  auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out, int n_pro) -> int {
+    out.n_prologue = n_pro;
     out.stream = (const unsigned char *)dev_copy(sb.bytes.data(), sb.bytes.size());
     out.chunks = (const ChunkDesc *)dev_copy(sb.chunks.data(), sb.chunks.size() * sizeof(ChunkDesc));
     out.n_chunks = (int)sb.chunks.size();
     return (out.stream && out.chunks) ? 0 : -1;
   };
-  if (up_stream(e, W.enc_stream) < 0 || up_stream(d, W.dec_stream) < 0) return -1;
+  if (up_stream(e, W.enc_stream, e_pro) < 0 || up_stream(d, W.dec_stream, d_pro) < 0) return -1;
   h->enc_chunks_per_step = W.enc_stream.n_chunks; h->dec_chunks_per_step = W.dec_stream.n_chunks;
   return 0;
 }
