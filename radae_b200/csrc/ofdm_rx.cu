@@ -415,19 +415,6 @@ struct TrackSmem {
 };
 static_assert(sizeof(RxCtl) % 16 == 0 && sizeof(TrackStage) % 128 == 0, "bulk-copy alignment");
 
-// block-wide sum over the consumer threads (named barrier 3; the producer warp does not take part)
-__device__ float consumer_sum(float v, float *scratch) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  v = warp_sum(v);
-  group_sync(3, TRK_CONSUMERS);
-  if (lane == 0) scratch[w] = v;
-  group_sync(3, TRK_CONSUMERS);
-  float t = (threadIdx.x < TRK_CONSUMERS / 32) ? scratch[threadIdx.x] : 0.f;
-  if (w == 0) { t = warp_sum(t); if (lane == 0) scratch[0] = t; }
-  group_sync(3, TRK_CONSUMERS);
-  return scratch[0];
-}
-
 __global__ void __launch_bounds__(TRK_THREADS, 1)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
                 int *__restrict__ uw_errors, const int *__restrict__ track_list, const int *__restrict__ counters,
@@ -541,44 +528,48 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
       refine_dmma<true>(sm.ref, sm.tab.pcd, [rxl](int i) { return rxl[i]; }, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1,
                         tid - TRK_REFRESH, 1);
     }
+    if (tid >= TRK_REFRESH) {
+      // spot correlations in complex128 (radae/dsp.py:305-314) by the refine warps, which finish before the row refresh does:
+      // refine warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]| at the refined timing / smoothed frequency
+      const int wp = (tid - TRK_REFRESH) >> 5, lane = tid & 31;
+      const int tm = sm.ref.best_found ? sm.ref.best_t : tmax0;
+      const double fm = 0.9 * fmax0 + 0.1 * (sm.ref.best_found ? sm.ref.best_f : fmax0);
+      const int o = tm + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
+      const double w = 2.0 * M_PI * fm / RADE_FS;
+      double sn, cs, s32, c32; sincos(w * (double)lane, &sn, &cs); sincos(w * 32.0, &s32, &c32);
+      double2 e = make_double2(cs, -sn); const double2 step = make_double2(c32, -s32);
+      double ax = 0.0, ay = 0.0;
+#pragma unroll
+      for (int n = lane; n < RADE_M; n += 32) {
+        const float2 xv = st.rx[o + n];
+        const float2 qf = (wp < 2) ? make_float2(sm.tab.ps4[n].x, sm.tab.ps4[n].y) : sm.tab.pend[n];
+        const double2 v = dcmul(e, make_double2((double)xv.x, (double)xv.y));                       // w_vec * rx
+        const double2 r2 = dcmul(make_double2(v.x, -v.y), make_double2((double)qf.x, (double)qf.y));
+        ax += r2.x; ay += r2.y;
+        e = dcmul(e, step);
+      }
+#pragma unroll
+      for (int q = 16; q > 0; q >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, q); ay += __shfl_xor_sync(0xffffffffu, ay, q); }
+      if (lane == 0) sm.spot[wp] = hypot(ax, ay);
+    }
     group_sync(3, TRK_CONSUMERS);
     int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
     const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
     const double fmax = 0.9 * fmax0 + 0.1 * fhat;
-    // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (radae/dsp.py:297-300)
-    float sigma_r;
+    // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (radae/dsp.py:297-300): per-warp partial
+    // sums now, thread 0 adds the 16 + 16 partials
     {
       float a = 0.f, c = 0.f;
       for (int q = tid; q < RADE_NMF; q += TRK_CONSUMERS) { a += st.rs[q]; c += st.rs[RADE_NMF + q]; }
-      const float sa = consumer_sum(a, sm.scratch), sb = consumer_sum(c, sm.scratch);
-      const float kf = 1.2533141373155001f;
-      sigma_r = ((sa / (float)(RADE_NMF * RADE_NFCOARSE)) / kf + (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / kf) / 2.0f;
-    }
-    // spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]|
-    {
-      const int wp = tid >> 5, lane = tid & 31;
-      if (wp < 4) {
-        const int o = tmax + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
-        const double w = 2.0 * M_PI * fmax / RADE_FS;
-        double sn, cs, s32, c32; sincos(w * (double)lane, &sn, &cs); sincos(w * 32.0, &s32, &c32);
-        double2 e = make_double2(cs, -sn); const double2 step = make_double2(c32, -s32);
-        double ax = 0.0, ay = 0.0;
-#pragma unroll
-        for (int n = lane; n < RADE_M; n += 32) {
-          const float2 xv = st.rx[o + n];
-          const float2 qf = (wp < 2) ? make_float2(sm.tab.ps4[n].x, sm.tab.ps4[n].y) : sm.tab.pend[n];
-          const double2 v = dcmul(e, make_double2((double)xv.x, (double)xv.y));                       // w_vec * rx
-          const double2 r2 = dcmul(make_double2(v.x, -v.y), make_double2((double)qf.x, (double)qf.y));
-          ax += r2.x; ay += r2.y;
-          e = dcmul(e, step);
-        }
-#pragma unroll
-        for (int q = 16; q > 0; q >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, q); ay += __shfl_xor_sync(0xffffffffu, ay, q); }
-        if (lane == 0) sm.spot[wp] = hypot(ax, ay);
-      }
+      a = warp_sum(a); c = warp_sum(c);
+      if ((tid & 31) == 0) { sm.scratch[tid >> 5] = a; sm.scratch[16 + (tid >> 5)] = c; }
     }
     group_sync(3, TRK_CONSUMERS);
     if (tid == 0) {
+      float sa = 0.f, sb = 0.f;
+      for (int q = 0; q < TRK_CONSUMERS / 32; q++) { sa += sm.scratch[q]; sb += sm.scratch[16 + q]; }
+      const float kf = 1.2533141373155001f;
+      const float sigma_r = ((sa / (float)(RADE_NMF * RADE_NFCOARSE)) / kf + (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / kf) / 2.0f;
       RxCtl &c = ctl[s];
       const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-4 / 5.0));
       const double Dthresh_eoo = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
