@@ -23,7 +23,7 @@ def test_golden_vectors(golden):
 
 
 @pytest.mark.parametrize("tile", [8, 16])
-@pytest.mark.parametrize("S,T", [(1, 5), (16, 3), (37, 7), (200, 4)])
+@pytest.mark.parametrize("S,T", [(1, 5), (16, 3), (37, 7), (200, 4), (5, 1), (300, 2)])
 def test_bit_exact_vs_oracle_ragged_tiles(S, T, tile, monkeypatch):
     """both CTA tile shapes (8 or 16 streams per CTA; the library picks by batch size, the env var pins it)"""
     need_gpu()
