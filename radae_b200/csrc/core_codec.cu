@@ -79,12 +79,16 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 template <int NI> __device__ __forceinline__ void i_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NI * 32) : "memory"); }
 template <int NF> __device__ __forceinline__ void f_sync() { asm volatile("bar.sync 2, %0;" ::"n"(NF * 32) : "memory"); }
 
+// chunk descriptors of both weight streams in constant memory: the producer must not pay a global-memory round trip per chunk
+// (the layout depends only on the layer dimensions, so one table per device serves every context)
+__constant__ ChunkDesc c_chunks[2][CORE_MAX_CHUNKS];
+
 // producer: lane 0 of the last warp streams every chunk of every step
-template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int T) {
+template <int NST> __device__ void producer_loop(PipeSmem<NST> *p, const CodecStreamDev &ws, int which, int T) {
   int stage = 0; uint32_t phase = 0;
   for (int t = 0; t < T; t++)
     for (int c = (t == 0 ? 0 : ws.n_prologue); c < ws.n_chunks; c++) {
-      const ChunkDesc d = ws.chunks[c];
+      const ChunkDesc d = c_chunks[which][c];
       mbar_wait(&p->empty[stage], phase ^ 1);
       mbar_expect_tx(&p->full[stage], d.bytes);
       bulk_g2s(p->ring[stage], ws.stream + d.offset, d.bytes, &p->full[stage]);
@@ -320,7 +324,7 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
         bulk_g2s(sm.cb[2][r], st->cat1, ENC_LDA, &sm.pipe.state_bar);
         bulk_g2s(sm.cb[1][r], st->cat2, ENC_LDA, &sm.pipe.state_bar);
       }
-      producer_loop<NST>(&sm.pipe, W.enc_stream, T);
+      producer_loop<NST>(&sm.pipe, W.enc_stream, 0, T);
     }
     return;
   }
@@ -513,7 +517,7 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
         bulk_g2s(sm.hs[r], st->h, sizeof(float) * 5 * DEC_GRU, &sm.pipe.state_bar);
         bulk_g2s(sm.cb[1][r], st->cat1, DEC_LDA, &sm.pipe.state_bar);
       }
-      producer_loop<NST>(&sm.pipe, W.dec_stream, T);
+      producer_loop<NST>(&sm.pipe, W.dec_stream, 1, T);
     }
     return;
   }
@@ -692,6 +696,11 @@ static int core_tile_streams(int S) {
 }
 // weight-ring depth: 8-stream tiles have the shared memory for a deeper ring
 constexpr int NST16 = 4, NST8 = 5;
+int core_codec_set_chunk_table(int which, const ChunkDesc *d, int n) {
+  if (n > CORE_MAX_CHUNKS) { fprintf(stderr, "libradae_b200: weight stream has %d chunks (max %d)\n", n, CORE_MAX_CHUNKS); return -1; }
+  CUDA_CHECK(cudaMemcpyToSymbol(c_chunks, d, sizeof(ChunkDesc) * n, sizeof(ChunkDesc) * CORE_MAX_CHUNKS * which));
+  return 0;
+}
 // per-device kernel attributes (opt-in to > 48 KB dynamic shared memory); called by rade_b200_open on its device
 int core_codec_init_device() {
   CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel<16, NST16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem<16, NST16>)));

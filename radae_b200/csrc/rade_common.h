@@ -71,6 +71,7 @@ struct __align__(16) DecStreamState {
 struct I8LayerDev { const float *scale; const float *bias; int K; int N; };
 struct F32LayerDev { const float *bias; int K; int N; };
 struct ChunkDesc { unsigned int offset; unsigned int bytes; };
+#define CORE_MAX_CHUNKS 96
 // chunks[0 .. n_prologue) are streamed once per launch (dense1 of the first step), chunks[n_prologue .. n_chunks) once per step
 struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; int n_chunks; int n_prologue; };
 struct CoreWeightsDev {

@@ -87,4 +87,5 @@ struct Profiler {
 };
 
 int core_codec_init_device();
+int core_codec_set_chunk_table(int which, const ChunkDesc *d, int n);
 int rx_dsp_init_device();

@@ -272,6 +272,8 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     return (out.stream && out.chunks) ? 0 : -1;
   };
   if (up_stream(e, W.enc_stream, e_pro) < 0 || up_stream(d, W.dec_stream, d_pro) < 0) return -1;
+  if (core_codec_set_chunk_table(0, e.chunks.data(), (int)e.chunks.size()) < 0 ||
+      core_codec_set_chunk_table(1, d.chunks.data(), (int)d.chunks.size()) < 0) return -1;
   h->enc_chunks_per_step = W.enc_stream.n_chunks; h->dec_chunks_per_step = W.dec_stream.n_chunks;
   return 0;
 }
