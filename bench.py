@@ -225,10 +225,20 @@ def run_gpu(args):
         d_fo = torch.zeros((S, 432), device="cuda"); d_ret = torch.zeros(S, dtype=torch.int32, device="cuda")
         d_eoo = torch.zeros((S, 180), device="cuda")
 
+        # Software pipeline over frames: the transmitter side of frame k+1 (core encoder, modulator, channel -> link FIFO) runs on
+        # a second CUDA stream concurrently with the receiver side of frame k (pop nin[s], DSP, core decoder); fork / join are
+        # INSIDE every timed step, so a step still contains one full TX and one full RX pass for every stream.
+        pipelined = not args.no_pipeline
+        b.pipeline_enable(pipelined)
+
         def step(k):
-            b.tx_dev(d_tx.data_ptr(), d_feats[k % n_feat_frames].data_ptr())        # core encoder, OFDM modulator
+            b.pipeline_fork()
+            b.tx_dev(d_tx.data_ptr(), d_feats[(k + 1) % n_feat_frames].data_ptr())  # core encoder, OFDM modulator
             b.channel_link_dev(d_tx.data_ptr())                                     # HF channel -> per-stream sample FIFO
             b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())      # pop nin[s], receiver DSP, core decoder
+            b.pipeline_join()
+        # prime the FIFO with frame 0 so that the receiver always has the frame the transmitter produced one step earlier
+        b.tx_dev(d_tx.data_ptr(), d_feats[0].data_ptr()); b.channel_link_dev(d_tx.data_ptr()); b.pipeline_join()
     torch.cuda.synchronize()
 
     def barrier():
@@ -271,6 +281,19 @@ def run_gpu(args):
     value = total_F / (dev_ms_max / 1000.0)
     sync_frac = None if codec_only else float(np.mean([s.state == 2 for s in b.rx_status()]))
 
+    # ---- the same K steps without the frame pipeline (everything on one stream), for reference
+    serial_ms = None
+    if not codec_only and not args.no_pipeline:
+        b.synchronize(); b.pipeline_enable(False)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            with torch.cuda.stream(ext):
+                l2_flush.zero_(); ev2[k][0].record(ext)
+            step(pre + W + K + k)
+            with torch.cuda.stream(ext):
+                ev2[k][1].record(ext)
+        barrier()
+        serial_ms = sum(a.elapsed_time(c) for a, c in ev2) / K
     # ---- per-kernel pass (CUDA events around every launch, inside the library, same steps; after the timed region)
     b.profile_enable(True)
     for k in range(K):
@@ -324,7 +347,10 @@ def run_gpu(args):
                            ("full TX+OFDM+MPP+demod+RX pipeline, %d concurrent streams per GPU (BASELINE configs[2]); MPP 1 Hz/2 ms, Eb/No 3 dB, -11 Hz" % S),
                            "streams_per_gpu": S, "frames_per_step_per_stream": F_PER_STEP, "l2": "flushed (256 MB memset) before every timed step",
                            "timing": "CUDA events on the library's stream around each step, summed; max over ranks",
-                           "sync_fraction": sync_frac, "acquisition_steps_before_timing": pre},
+                           "sync_fraction": sync_frac, "acquisition_steps_before_timing": pre,
+                           "pipeline": None if codec_only else ("off (one stream)" if args.no_pipeline else
+                                       "TX side of frame k+1 on a second CUDA stream, concurrent with the RX side of frame k; fork/join inside every timed step"),
+                           "ms_per_step_unpipelined": serial_ms},
                 "gpu_launches": int(launches), "wall_s": t_wall, "clocks": clocks, "roofline": roofline, "kernels": kernels,
                 "e2e": e2e, "cpu_baseline": cpu_base}
         print(json.dumps(line))
@@ -420,6 +446,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="run TX and RX of a frame back to back on one stream")
     ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
     args = ap.parse_args()
     if args.warmup < 3:

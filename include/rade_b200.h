@@ -98,6 +98,12 @@ RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_sample
 /* the same loop-back without the two copy kernels: channel output goes straight into the link FIFOs, the receiver pops
    nin[s] samples per stream from them (a stream without nin[s] queued samples sits the call out: ret = 0) */
 RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx /* [S][960] */);
+/* software pipeline over frames for device-pointer callers: with it enabled, rade_b200_tx_dev and rade_b200_channel_link_dev
+   enqueue on a second stream, so frame k+1's transmitter runs concurrently with frame k's receiver.  A step is
+   fork; tx_dev(k+1); channel_link_dev; rx_link_dev(k); join.  fork: the TX stream waits for the main stream; join: the reverse. */
+RADE_EXPORT int rade_b200_pipeline_enable(rade_batch *b, int enable);
+RADE_EXPORT int rade_b200_pipeline_fork(rade_batch *b);
+RADE_EXPORT int rade_b200_pipeline_join(rade_batch *b);
 RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out);
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
 

@@ -150,6 +150,15 @@ class RadeBatch:
         _check(self.lib.rade_b200_channel_apply_dev(self.h, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq,
                                                     phase0, sigma, gain), "channel_apply_dev")
 
+    def pipeline_enable(self, on=True):
+        _check(self.lib.rade_b200_pipeline_enable(self.h, int(on)), "pipeline_enable")
+
+    def pipeline_fork(self):
+        _check(self.lib.rade_b200_pipeline_fork(self.h), "pipeline_fork")
+
+    def pipeline_join(self):
+        _check(self.lib.rade_b200_pipeline_join(self.h), "pipeline_join")
+
     def channel_link_dev(self, d_tx):
         _check(self.lib.rade_b200_channel_link_dev(self.h, d_tx), "channel_link_dev")
 

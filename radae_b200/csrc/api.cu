@@ -12,6 +12,9 @@
 struct rade_batch {
   int S, device, flags;
   cudaStream_t stream;
+  // optional software pipeline: TX-side device calls (tx_dev, channel_link_dev) go to their own stream so that frame k+1's
+  // transmitter runs concurrently with frame k's receiver; fork / join are explicit (rade_b200_pipeline_*)
+  cudaStream_t tx_stream; cudaEvent_t ev_txfork, ev_txjoin; int pipelined;
   long long launches;
   Profiler prof;
   CoreWeightsHolder weights;
@@ -123,6 +126,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   }
   rade_batch *b = new rade_batch();
   b->S = n_streams; b->device = device; b->flags = flags; b->launches = 0; b->core_cap = 0;
+  b->tx_stream = nullptr; b->pipelined = 0;
   b->d_core_in = b->d_core_out = nullptr;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
   b->prof.stream = b->stream;
@@ -187,13 +191,46 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   if (b->h_cplx) cudaFreeHost(b->h_cplx);
   if (b->h_int) cudaFreeHost(b->h_int);
   cudaStreamDestroy(b->stream);
+  if (b->tx_stream) { cudaStreamDestroy(b->tx_stream); cudaEventDestroy(b->ev_txfork); cudaEventDestroy(b->ev_txjoin); }
   if (b->rx.side_stream) { cudaStreamDestroy(b->rx.side_stream); cudaEventDestroy(b->rx.ev_fork); cudaEventDestroy(b->rx.ev_join); }
   delete b;
 }
 
 RADE_EXPORT int rade_b200_n_streams(rade_batch *b) { return b->S; }
 RADE_EXPORT void *rade_b200_cuda_stream(rade_batch *b) { return (void *)b->stream; }
-RADE_EXPORT int rade_b200_synchronize(rade_batch *b) { CUDA_CHECK(cudaStreamSynchronize(b->stream)); return 0; }
+RADE_EXPORT int rade_b200_synchronize(rade_batch *b) {
+  if (b->tx_stream) CUDA_CHECK(cudaStreamSynchronize(b->tx_stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+// ---- software pipeline over frames for device-pointer callers: after pipeline_enable(1), rade_b200_tx_dev and
+// rade_b200_channel_link_dev enqueue on a second stream.  pipeline_fork makes that stream wait for everything enqueued so far
+// on the main stream, pipeline_join makes the main stream wait for it.  Typical step: fork; tx_dev(frame k+1);
+// channel_link_dev; rx_link_dev(frame k, main stream); join.
+RADE_EXPORT int rade_b200_pipeline_enable(rade_batch *b, int enable) {
+  cudaSetDevice(b->device);
+  if (enable && !b->tx_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&b->tx_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_txfork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_txjoin, cudaEventDisableTiming));
+  }
+  if (rade_b200_synchronize(b) < 0) return -1;
+  b->pipelined = enable ? 1 : 0;
+  return 0;
+}
+RADE_EXPORT int rade_b200_pipeline_fork(rade_batch *b) {
+  if (!b->pipelined) return 0;
+  CUDA_CHECK(cudaEventRecord(b->ev_txfork, b->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(b->tx_stream, b->ev_txfork, 0));
+  return 0;
+}
+RADE_EXPORT int rade_b200_pipeline_join(rade_batch *b) {
+  if (!b->pipelined) return 0;
+  CUDA_CHECK(cudaEventRecord(b->ev_txjoin, b->tx_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->ev_txjoin, 0));
+  return 0;
+}
+static cudaStream_t tx_side(rade_batch *b) { return (b->pipelined && !b->prof.on) ? b->tx_stream : b->stream; }
 RADE_EXPORT long long rade_b200_launch_count(rade_batch *b) { return b->launches; }
 RADE_EXPORT int rade_b200_reset(rade_batch *b) { return reset_state(b); }
 
@@ -248,9 +285,9 @@ RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float
   cudaSetDevice(b->device);        // the current device is per host thread
   // 3 core-encoder steps on the API feature layout (src/rade_api.c:411-434) then transmitter_one (radae_txe.py:127)
   b->prof.begin(K_CORE_ENC);
-  if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, b->stream) < 0) return -1;
+  if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, tx_side(b)) < 0) return -1;
   b->prof.end(K_CORE_ENC); b->prof.begin(K_OFDM_MOD);
-  if (ofdm_mod_launch(b->tables, b->z_tx, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  if (ofdm_mod_launch(b->tables, b->z_tx, (float2 *)d_tx_out, b->S, tx_side(b)) < 0) return -1;
   b->prof.end(K_OFDM_MOD);
   b->launches += 2;
   return RADE_NMF;
@@ -262,9 +299,9 @@ RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *feat
   const size_t S = b->S;
   CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, features_in, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
   if (void *alias = pinned_alias(tx_out)) {            // modulator writes the samples straight into the caller's pinned buffer
-    if (rade_b200_tx_dev(b, (RADE_COMP *)alias, b->d_feat_in) < 0) return -1;
+    if (rade_b200_pipeline_fork(b) < 0 || rade_b200_tx_dev(b, (RADE_COMP *)alias, b->d_feat_in) < 0 || rade_b200_pipeline_join(b) < 0) return -1;
   } else {
-    if (rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0) return -1;
+    if (rade_b200_pipeline_fork(b) < 0 || rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0 || rade_b200_pipeline_join(b) < 0) return -1;
     CUDA_CHECK(cudaMemcpyAsync(tx_out, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   }
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -415,7 +452,7 @@ RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx)
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
   b->prof.begin(K_CHANNEL);
   if (channel_stream_launch(nullptr, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
-                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, b->stream) < 0) return -1;
+                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, tx_side(b)) < 0) return -1;
   b->prof.end(K_CHANNEL);
   b->launches += 1;
   return 0;

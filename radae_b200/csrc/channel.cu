@@ -124,6 +124,8 @@ channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, Ch
   }
   __syncthreads();
   for (int i = tid; i < 64; i += blockDim.x) cs_.delay[i] = stx[RADE_NMF + i];
+  if (link_ring) __threadfence();               // samples before the write pointer: the receiver may be running concurrently
+  __syncthreads();
   if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); if (link_ring) link_wr[s] = lw + RADE_NMF; }
 }
 

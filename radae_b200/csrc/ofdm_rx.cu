@@ -108,7 +108,8 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
   int xoff = 0, xmask = 0x7fffffff;
   if (link.ring) {
     const long long r = link.rd[s];
-    const bool ok = link.wr[s] - r >= nin;
+    const bool ok = *reinterpret_cast<const volatile long long *>(&link.wr[s]) - r >= nin;
+    __threadfence();                                    // write pointer before samples (the channel may be running concurrently)
     __syncthreads();                                    // everybody has read rd before it moves
     if (tid == 0) { link.active_out[s] = ok ? 1 : 0; if (ok) link.rd[s] = r + nin; }
     if (!ok) return;

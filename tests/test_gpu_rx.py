@@ -214,3 +214,43 @@ def test_fused_loopback_equals_copy_kernels():
     assert sum(int((r[0] & 1).sum()) for r in outs[0]) > S * (F - 8)
     for (r0, f0, t0), (r1, f1, t1) in zip(*outs):
         assert np.array_equal(r0, r1) and np.array_equal(t0, t1) and np.array_equal(f0, f1)
+
+
+def test_frame_pipeline_gives_the_same_per_stream_sequences():
+    """rade_b200_pipeline_*: TX of frame k+1 concurrent with RX of frame k.  Every stream must see the same sample sequence,
+    hence produce the same sequence of receiver calls (return codes, features) as the one-stream schedule — a call may
+    only land in a different step (the FIFO can already hold part of the next frame)."""
+    torch = need_gpu()
+    from radae_b200 import RadeBatch
+    from oracle.core import synth_features
+    S, F = 64, 16
+    feats = synth_features(S, 12 * (F + 1), seed=8).reshape(S, F + 1, 432)
+    seqs = []
+    for pipelined in (False, True):
+        b = RadeBatch(S)
+        b.channel_config(EbNodB=8.0, freq_offset_hz=-5.0, freq_offset_spread_hz=15.0, doppler_spread_hz=0.5, delay_samples=16, gain=1.0, seed=21)
+        b.pipeline_enable(pipelined)
+        d_tx = torch.empty((S, 960, 2), device="cuda")
+        d_fo = torch.zeros((S, 432), device="cuda"); d_ret = torch.zeros(S, dtype=torch.int32, device="cuda")
+        d_eoo = torch.zeros((S, 180), device="cuda")
+        d_f = [torch.tensor(feats[:, f]).cuda() for f in range(F + 1)]
+        torch.cuda.synchronize()
+        b.tx_dev(d_tx.data_ptr(), d_f[0].data_ptr()); b.channel_link_dev(d_tx.data_ptr()); b.pipeline_join(); b.synchronize()
+        seq = [[] for _ in range(S)]
+        for k in range(F):
+            b.pipeline_fork()
+            b.tx_dev(d_tx.data_ptr(), d_f[k + 1].data_ptr()); b.channel_link_dev(d_tx.data_ptr())
+            b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
+            b.pipeline_join(); b.synchronize()
+            ret = d_ret.cpu().numpy(); fo = d_fo.cpu().numpy()
+            for s in np.nonzero(ret & 1)[0]:
+                seq[s].append(fo[s].copy())
+        seqs.append(seq)
+        b.close()
+    total = 0
+    for s in range(S):
+        n = min(len(seqs[0][s]), len(seqs[1][s]))
+        assert abs(len(seqs[0][s]) - len(seqs[1][s])) <= 1, (s, len(seqs[0][s]), len(seqs[1][s]))
+        assert np.array_equal(np.array(seqs[0][s][:n]), np.array(seqs[1][s][:n])), s
+        total += n
+    assert total > S * (F - 9)
