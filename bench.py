@@ -232,11 +232,9 @@ def run_gpu(args):
         b.pipeline_enable(pipelined)
 
         def step(k):
-            b.pipeline_fork()
-            b.tx_dev(d_tx.data_ptr(), d_feats[(k + 1) % n_feat_frames].data_ptr())  # core encoder, OFDM modulator
-            b.channel_link_dev(d_tx.data_ptr())                                     # HF channel -> per-stream sample FIFO
-            b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())      # pop nin[s], receiver DSP, core decoder
-            b.pipeline_join()
+            # = fork; tx_dev (core encoder, modulator); channel_link_dev (HF channel -> per-stream FIFO); rx_link_dev (pop nin[s],
+            # receiver DSP, core decoder); join — replayed by the library as ONE CUDA graph launch per step
+            b.loopback_step_dev(d_feats[(k + 1) % n_feat_frames].data_ptr(), d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
         # prime the FIFO with frame 0 so that the receiver always has the frame the transmitter produced one step earlier
         b.tx_dev(d_tx.data_ptr(), d_feats[0].data_ptr()); b.channel_link_dev(d_tx.data_ptr()); b.pipeline_join()
     torch.cuda.synchronize()
@@ -366,6 +364,8 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
     import threading
     from radae_b200 import RadeBatch
     from radae_b200.batch import HostLink
+    # host threads of the C-side sample FIFOs: this rank's share of the cores (torchrun exports OMP_NUM_THREADS=1)
+    os.environ.setdefault("RADE_B200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, world) // max(1, n_ctx)))))
     n_feat_frames = feats_host.shape[1]
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
     bounds = [(S * i) // n_ctx for i in range(n_ctx + 1)]

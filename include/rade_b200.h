@@ -104,6 +104,10 @@ RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx 
 RADE_EXPORT int rade_b200_pipeline_enable(rade_batch *b, int enable);
 RADE_EXPORT int rade_b200_pipeline_fork(rade_batch *b);
 RADE_EXPORT int rade_b200_pipeline_join(rade_batch *b);
+/* the whole loop-back step in one call: tx_dev(d_features_next) -> channel_link_dev -> rx_link_dev (+ fork / join when the frame
+   pipeline is enabled); with RADE_B200_GRAPH=1 in the environment it is replayed as a single CUDA graph launch per step */
+RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_features_next /* [S][432] */, float *d_features_out,
+                                            int *d_ret, float *d_eoo_out);
 RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out);
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
 

@@ -150,6 +150,9 @@ class RadeBatch:
         _check(self.lib.rade_b200_channel_apply_dev(self.h, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq,
                                                     phase0, sigma, gain), "channel_apply_dev")
 
+    def loopback_step_dev(self, d_features_next, d_features_out, d_ret, d_eoo_out):
+        _check(self.lib.rade_b200_loopback_step_dev(self.h, d_features_next, d_features_out, d_ret, d_eoo_out), "loopback_step_dev")
+
     def pipeline_enable(self, on=True):
         _check(self.lib.rade_b200_pipeline_enable(self.h, int(on)), "pipeline_enable")
 

@@ -225,8 +225,10 @@ def test_frame_pipeline_gives_the_same_per_stream_sequences():
     from oracle.core import synth_features
     S, F = 64, 16
     feats = synth_features(S, 12 * (F + 1), seed=8).reshape(S, F + 1, 432)
+    import os
+    os.environ["RADE_B200_GRAPH"] = "1"          # read once per process by the library: the one-call variant replays a graph
     seqs = []
-    for pipelined in (False, True):
+    for pipelined, one_call in ((False, False), (True, False), (True, True)):
         b = RadeBatch(S)
         b.channel_config(EbNodB=8.0, freq_offset_hz=-5.0, freq_offset_spread_hz=15.0, doppler_spread_hz=0.5, delay_samples=16, gain=1.0, seed=21)
         b.pipeline_enable(pipelined)
@@ -238,10 +240,14 @@ def test_frame_pipeline_gives_the_same_per_stream_sequences():
         b.tx_dev(d_tx.data_ptr(), d_f[0].data_ptr()); b.channel_link_dev(d_tx.data_ptr()); b.pipeline_join(); b.synchronize()
         seq = [[] for _ in range(S)]
         for k in range(F):
-            b.pipeline_fork()
-            b.tx_dev(d_tx.data_ptr(), d_f[k + 1].data_ptr()); b.channel_link_dev(d_tx.data_ptr())
-            b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
-            b.pipeline_join(); b.synchronize()
+            if one_call:                 # rade_b200_loopback_step_dev: the same step replayed as one CUDA graph launch
+                b.loopback_step_dev(d_f[k + 1].data_ptr(), d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
+            else:
+                b.pipeline_fork()
+                b.tx_dev(d_tx.data_ptr(), d_f[k + 1].data_ptr()); b.channel_link_dev(d_tx.data_ptr())
+                b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
+                b.pipeline_join()
+            b.synchronize()
             ret = d_ret.cpu().numpy(); fo = d_fo.cpu().numpy()
             for s in np.nonzero(ret & 1)[0]:
                 seq[s].append(fo[s].copy())
@@ -249,8 +255,9 @@ def test_frame_pipeline_gives_the_same_per_stream_sequences():
         b.close()
     total = 0
     for s in range(S):
-        n = min(len(seqs[0][s]), len(seqs[1][s]))
-        assert abs(len(seqs[0][s]) - len(seqs[1][s])) <= 1, (s, len(seqs[0][s]), len(seqs[1][s]))
-        assert np.array_equal(np.array(seqs[0][s][:n]), np.array(seqs[1][s][:n])), s
+        for other in (1, 2):
+            n = min(len(seqs[0][s]), len(seqs[other][s]))
+            assert abs(len(seqs[0][s]) - len(seqs[other][s])) <= 1, (s, other, len(seqs[0][s]), len(seqs[other][s]))
+            assert np.array_equal(np.array(seqs[0][s][:n]), np.array(seqs[other][s][:n])), (s, other)
         total += n
     assert total > S * (F - 9)
