@@ -182,16 +182,22 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout; stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from radae_b200 import RadeBatch, _capi, rdw, multigpu
-
-    # one NCCL broadcast of the weight blob at start-up (the only collective on this path)
-    blob = open(rdw.default_weights_path(), "rb").read() if rank == 0 else None
-    blob = multigpu.broadcast_weights(dist if world > 1 else None, rank, blob, device="cuda")
+    # NCCL prints its version banner on stdout when the first communicator is created; stdout carries ONE JSON line, so
+    # file descriptor 1 points at stderr while the process group comes up and the weights are broadcast
+    sys.stdout.flush()
+    saved_fd = os.dup(1); os.dup2(2, 1)
+    try:
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # one NCCL broadcast of the weight blob at start-up (the only collective on this path)
+        blob = open(rdw.default_weights_path(), "rb").read() if rank == 0 else None
+        blob = multigpu.broadcast_weights(dist if world > 1 else None, rank, blob, device="cuda")
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
 
     codec_only = args.workload == "codec"
     S = args.streams or (8192 if codec_only else 1024)
