@@ -5,22 +5,27 @@
 //   rade_core_decoder  /root/reference/src/rade_dec.c:50-102   (PyTorch twin radae/radae_base.py:400-416)
 // and the opus DNN primitives they call (compute_generic_dense/gru/conv1d[_dilation], compute_glu).
 //
-// Design.  One CTA owns a tile of CORE_TS = 16 independent streams and walks the whole layer
-// stack for n_steps consecutive steps with every activation on chip:
-//   * warp specialisation: one PRODUCER warp issues `cp.async.bulk` (TMA 1-D bulk copies, mbarrier complete_tx) that
-//     stream the step's weights — pre-arranged on the host as one contiguous sequence of <= 32 KB chunks in consumption
-//     order — from L2 into a 4-stage shared-memory ring; NCW CONSUMER warps wait on the stage's "full" mbarrier, use
-//     the chunk and arrive on its "empty" mbarrier.  No consumer ever waits on a global/L2 load for a weight.
+// Design.  One CTA owns a tile of TS = 8 or 16 independent streams (template parameter) and walks
+// the whole layer stack for n_steps consecutive steps with every activation on chip:
+//   * a PRODUCER warp issues `cp.async.bulk` (TMA 1-D bulk copies, mbarrier complete_tx) that stream the step's weights —
+//     pre-arranged on the host as one contiguous sequence of <= 32 KB chunks in consumption order, descriptors in constant
+//     memory — from L2 into a 4/5-stage shared-memory ring; the consumer warps wait on the stage's "full" mbarrier, use the
+//     chunk and arrive on its "empty" mbarrier.  No consumer ever waits on a global/L2 load for a weight.  The per-stream state
+//     rows arrive the same way (three bulk copies per stream, once per launch).
+//   * the consumers are split into I-WARPS (int8 GRU / conv / GLU layers on the tensor cores + their epilogues) and F-WARPS
+//     (the float layers: dense1, and the wide zdense / output layer accumulated incrementally as each DenseNet segment is
+//     produced).  The float layers never feed the int8 chain within a step, so they run concurrently with it; segments are
+//     handed over through two shared-memory buffers guarded by named barriers (bar.arrive / bar.sync).  dense1 of step t+1 is
+//     computed one step ahead and published when the I-warps finish step t.
 //   * the DenseNet concat buffer lives in shared memory as int8 (exactly the quantised values floor(.5+127x) the
 //     reference feeds its int8 GEMVs) — a ring of the current and the previous one/two steps, which is also the conv1d
 //     tap memory and the GRU recurrent input, so conv "state" costs no extra storage;
-//   * int8 layers: s8 x s8 -> s32 tensor-core MMA (m16n8k32: 16 streams x 8 outputs x 32 inputs per instruction), B
-//     fragments read from the staged chunk with one conflict-free LDS.64 per lane;
+//   * int8 layers: s8 x s8 -> s32 tensor-core MMA (m16n8k32: 16 streams x 8 outputs x 32 inputs per instruction), A fragments
+//     by ldmatrix, B fragments read from the staged chunk with one conflict-free LDS.64 per lane;
 //   * epilogues (scale, bias, rational tanh/sigmoid, GRU gating, GLU) straight from the accumulator registers, each
 //     float operation separately rounded in the reference's order => bit-identical to the C oracle; conv layers split
 //     their two taps over different warps and reduce the exact int32 partial sums through shared memory;
-//   * the four float layers accumulate sequentially over inputs (the generic sgemv order), the two wide ones
-//     (enc_zdense 864->80, dec_output 736->84) incrementally as each concat segment is produced.
+//   * the float layers accumulate sequentially over inputs (the generic sgemv order): packed FMUL2 products, scalar FADDs.
 // Per-stream HBM state: GRU h (fp32) + int8 concat of step t-1 (and t-2 for the encoder's dilation-2 convs).
 #include "rade_common.h"
 #include "rade_host.h"

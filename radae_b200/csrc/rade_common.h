@@ -43,7 +43,6 @@
 #define DEC_CONV 32
 #define DEC_OUT 84
 
-#define CORE_TS 16                            // streams per CTA tile (one m16 MMA tile)
 #define ENC_LDA 880                           // smem/global row stride of the int8 concat buffer (bank-conflict-free A fragments)
 #define DEC_LDA 752
 
@@ -61,7 +60,6 @@ struct __align__(16) DecStreamState {
 // ---- weight streaming (core_codec.cu): all weights of one 40 ms step, laid out as a sequence of chunks in the exact
 // order the layer walk consumes them; a producer warp TMA-bulk-copies chunk after chunk into a shared-memory ring.
 #define CORE_STAGE_BYTES 32768
-#define CORE_NSTAGES 4
 #define ENC_NI 8                              // int8-layer warps (encoder): one GRU unit tile each, three conv (n-tile, tap) units each
 #define DEC_NI 12                             // int8-layer warps (decoder): 12 GRU unit tiles / 12 GLU n-tiles -> one per warp
 #define ENC_NF 5                              // float-layer warps (dense1 + the incremental zdense / output accumulation)
