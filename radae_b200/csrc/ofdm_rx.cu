@@ -13,8 +13,11 @@
 // Data layout per stream in HBM: rx_buf as a 2112-sample RING (no 17 KB shift per call, only the nin new samples
 // are written), 102-sample BPF history, two 960-entry row-sum vectors sum_f|Dt1|, sum_f|Dt2| (all the reference
 // ever reads back from its two 960x40 complex grids = 614 KB/stream), a 128-byte control block.
-// Kernels (one launch each per rade_rx call, every stream handled by its own CTA(s), branching on its state):
-//   rx_bpf -> rx_detect (search/candidate streams) -> rx_track (sync streams) -> rx_demod (sync streams) -> rx_finish
+// Kernels (one launch each per rade_rx call; every stream branches on its own state):
+//   rx_bpf (all streams; builds the search list and the track list)
+//     -> rx_track (persistent, streams in sync: refine on the FP64 tensor cores + row refresh + sync-state machine) -> rx_demod
+//     -> rx_detect (persistent over the search list: coarse grid search) -> rx_finish (search / candidate state machine)
+//   the second branch runs on a side stream concurrently with the first; both join before the core decoder.
 #include "rade_common.h"
 #include "rade_host.h"
 #include "tma.cuh"
