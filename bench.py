@@ -238,8 +238,8 @@ def run_gpu(args):
         b.pipeline_enable(pipelined)
 
         def step(k):
-            # = fork; tx_dev (core encoder, modulator); channel_link_dev (HF channel -> per-stream FIFO); rx_link_dev (pop nin[s],
-            # receiver DSP, core decoder); join — replayed by the library as ONE CUDA graph launch per step
+            # = fork; tx_channel_link_dev (core encoder; OFDM modulator + HF channel -> per-stream FIFO in one kernel);
+            # rx_link_dev (pop nin[s], receiver DSP, core decoder); join — 8 kernel launches
             b.loopback_step_dev(d_feats[(k + 1) % n_feat_frames].data_ptr(), d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
         # prime the FIFO with frame 0 so that the receiver always has the frame the transmitter produced one step earlier
         b.tx_dev(d_tx.data_ptr(), d_feats[0].data_ptr()); b.channel_link_dev(d_tx.data_ptr()); b.pipeline_join()

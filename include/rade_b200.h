@@ -108,6 +108,8 @@ RADE_EXPORT int rade_b200_pipeline_join(rade_batch *b);
    pipeline is enabled); with RADE_B200_GRAPH=1 in the environment it is replayed as a single CUDA graph launch per step */
 RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_features_next /* [S][432] */, float *d_features_out,
                                             int *d_ret, float *d_eoo_out);
+/* core encoder, then one kernel that modulates the frame and sends it through the channel into the link FIFOs */
+RADE_EXPORT int rade_b200_tx_channel_link_dev(rade_batch *b, const float *d_features_in /* [S][432] */);
 RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out);
 RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in /* [S][1120] */, unsigned char *d_active /* [S] */);
 

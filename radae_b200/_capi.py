@@ -54,7 +54,7 @@ SIGNATURES = {
     "rade_b200_channel_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F]),
     "rade_b200_channel_config": (_I, [_P, C.POINTER(ChannelCfg)]), "rade_b200_channel_dev": (_I, [_P, _P, _P]),
     "rade_b200_link_push_dev": (_I, [_P, _P]), "rade_b200_channel_link_dev": (_I, [_P, _P]),
-    "rade_b200_rx_link_dev": (_I, [_P, _P, _P, _P]),
+    "rade_b200_rx_link_dev": (_I, [_P, _P, _P, _P]), "rade_b200_tx_channel_link_dev": (_I, [_P, _P]),
     "rade_b200_loopback_step_dev": (_I, [_P, _P, _P, _P, _P]),
     "rade_b200_pipeline_enable": (_I, [_P, _I]), "rade_b200_pipeline_fork": (_I, [_P]), "rade_b200_pipeline_join": (_I, [_P]), "rade_b200_link_pop_dev": (_I, [_P, _P, _P]),
     "rade_b200_profile_enable": (_I, [_P, _I]), "rade_b200_profile_n_kernels": (_I, []),

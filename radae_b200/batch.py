@@ -165,6 +165,9 @@ class RadeBatch:
     def channel_link_dev(self, d_tx):
         _check(self.lib.rade_b200_channel_link_dev(self.h, d_tx), "channel_link_dev")
 
+    def tx_channel_link_dev(self, d_features_in):
+        _check(self.lib.rade_b200_tx_channel_link_dev(self.h, d_features_in), "tx_channel_link_dev")
+
     def rx_link_dev(self, d_features_out, d_ret, d_eoo_out):
         _check(self.lib.rade_b200_rx_link_dev(self.h, d_features_out, d_ret, d_eoo_out), "rx_link_dev")
 

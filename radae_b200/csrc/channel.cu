@@ -11,6 +11,7 @@
 // (seed, stream), counter = absolute sample index, Box-Muller.
 #include "rade_common.h"
 #include "rade_host.h"
+#include "ofdm_mod.cuh"
 
 namespace {
 
@@ -70,20 +71,24 @@ __device__ float2 path_gain_term(unsigned long long seed, uint32_t stream, uint3
   return make_float2((float)cs, (float)sn);
 }
 
-// streaming generator form: one CTA per stream, one modem frame (960 samples) per call
+// streaming generator form: one CTA per stream, one modem frame (960 samples) per call.  With z_mod non-null the modem frame is
+// modulated right here from the stream's 240 latents (fused OFDM modulator: the tx samples never go through HBM).
 __global__ void __launch_bounds__(256)
-channel_stream_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, ChanState *__restrict__ st, int S,
+channel_stream_kernel(DspTables T, const float *__restrict__ z_mod, float2 *__restrict__ rx, const float2 *__restrict__ tx,
+                      ChanState *__restrict__ st, int S,
                       float sigma, float freq0, float freq_spread, float doppler, int d, float gain, unsigned long long seed,
                       float2 *__restrict__ link_ring, long long *__restrict__ link_wr) {
   __shared__ float2 stx[64 + RADE_NMF];
   __shared__ float2 g[4];                       // G1(t0), G1(t0+960), G2(t0), G2(t0+960)
+  __shared__ float2 sym[RADE_NS + 1][RADE_NC];
   const int s = blockIdx.x, tid = threadIdx.x;
   ChanState &cs_ = st[s];
   const long long t0 = cs_.t;
   const double ph0 = cs_.phase;
   const float2 *txs = tx + (size_t)s * RADE_NMF;
   for (int i = tid; i < 64; i += blockDim.x) stx[i] = cs_.delay[i];
-  for (int i = tid; i < RADE_NMF; i += blockDim.x) stx[64 + i] = txs[i];
+  if (z_mod) ofdm_mod_frame(T, z_mod + (size_t)s * RADE_NZMF * RADE_LATENT, stx + 64, sym, tid);
+  else for (int i = tid; i < RADE_NMF; i += blockDim.x) stx[64 + i] = txs[i];
   if (tid < 4 * NSIN) {                         // 4 gains x 16 sinusoids, one per thread, summed with shuffles
     const int gi = tid / NSIN, i = tid % NSIN;
     float2 v = make_float2(0.f, 0.f);
@@ -163,11 +168,11 @@ int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const f
   return 0;
 }
 
-int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
+int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
                           float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
                           cudaStream_t stream) {
   if (d < 0 || d > 64) return -1;
-  channel_stream_kernel<<<S, 256, 0, stream>>>(rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed, link_ring, link_wr);
+  channel_stream_kernel<<<S, 256, 0, stream>>>(T, z_mod, rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed, link_ring, link_wr);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

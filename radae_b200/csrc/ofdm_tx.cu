@@ -9,47 +9,17 @@
 // IDFT against the reference's own Winv table (L1/L2 resident, read coalesced), cyclic prefix = tail copy,
 // PA model tanh(|x|)*x/|x|.  HBM traffic: 960 B in, 7680 B out per stream-frame, nothing else.
 #include "rade_common.h"
+#include "ofdm_mod.cuh"
 
 namespace {
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// tanh(|x|) * exp(j angle(x)) == x * tanh(|x|)/|x|
-__device__ __forceinline__ float2 pa_limit(float2 x) {
-  float mag = hypotf(x.x, x.y);
-  if (mag == 0.f) return make_float2(0.f, 0.f);
-  float s = tanhf(mag) / mag;
-  return make_float2(x.x * s, x.y * s);
-}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return mod_cmul(a, b); }
 
 __global__ void __launch_bounds__(RADE_M)
 ofdm_mod_kernel(DspTables T, const float *__restrict__ z, float2 *__restrict__ tx, int S) {
   __shared__ float2 sym[RADE_NS + 1][RADE_NC];
-  const int s = blockIdx.x, n = threadIdx.x;
-  if (n < RADE_NC) sym[0][n] = make_float2(T.pilot_gain * T.P[n].x, T.pilot_gain * T.P[n].y);
-  if (n < RADE_NS * RADE_NC) {
-    const float *zs = z + (size_t)s * RADE_NZMF * RADE_LATENT;
-    sym[1 + n / RADE_NC][n % RADE_NC] = make_float2(zs[2 * n], zs[2 * n + 1]);
-  }
-  __syncthreads();
-  float2 acc[RADE_NS + 1];
-#pragma unroll
-  for (int r = 0; r <= RADE_NS; r++) acc[r] = make_float2(0.f, 0.f);
-  for (int c = 0; c < RADE_NC; c++) {
-    const float2 w = T.Winv[c * RADE_M + n];
-#pragma unroll
-    for (int r = 0; r <= RADE_NS; r++) {
-      float2 v = cmul(sym[r][c], w);
-      acc[r].x += v.x; acc[r].y += v.y;
-    }
-  }
-  float2 *out = tx + (size_t)s * RADE_NMF;
-#pragma unroll
-  for (int r = 0; r <= RADE_NS; r++) {
-    float2 y = pa_limit(acc[r]);
-    out[r * RADE_SYM + RADE_NCP + n] = y;
-    if (n >= RADE_M - RADE_NCP) out[r * RADE_SYM + n - (RADE_M - RADE_NCP)] = y;
-  }
+  const int s = blockIdx.x;
+  ofdm_mod_frame(T, z + (size_t)s * RADE_NZMF * RADE_LATENT, tx + (size_t)s * RADE_NMF, sym, threadIdx.x);
 }
 
 // EOO frame: skeleton (P E . . . E) + optionally 3 data symbols from 180 +-1 bits

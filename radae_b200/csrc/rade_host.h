@@ -60,7 +60,7 @@ int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaS
 int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float2 *tx, int S, cudaStream_t stream);
 int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
                          int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
-int channel_stream_launch(float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
+int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
                           float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
                           cudaStream_t stream);
 int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream);

@@ -186,7 +186,7 @@ def test_fused_loopback_equals_copy_kernels():
     S, F = 40, 14
     feats = synth_features(S, 12 * F, seed=3).reshape(S, F, 432)
     outs = []
-    for fused in (False, True):
+    for fused in (0, 1, 2):              # 2: modulator fused into the channel kernel as well (rade_b200_tx_channel_link_dev)
         b = RadeBatch(S)
         b.channel_config(EbNodB=6.0, freq_offset_hz=7.0, freq_offset_spread_hz=20.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=11)
         d_tx = torch.empty((S, 960, 2), device="cuda"); d_ch = torch.empty((S, 960, 2), device="cuda")
@@ -197,11 +197,15 @@ def test_fused_loopback_equals_copy_kernels():
         rec = []
         for f in range(F):
             d_f = torch.tensor(feats[:, f]).cuda(); torch.cuda.synchronize()
-            b.tx_dev(d_tx.data_ptr(), d_f.data_ptr())
-            if fused:
+            if fused == 2:
+                b.tx_channel_link_dev(d_f.data_ptr())
+                b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
+            elif fused == 1:
+                b.tx_dev(d_tx.data_ptr(), d_f.data_ptr())
                 b.channel_link_dev(d_tx.data_ptr())
                 b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
             else:
+                b.tx_dev(d_tx.data_ptr(), d_f.data_ptr())
                 b.channel_dev(d_ch.data_ptr(), d_tx.data_ptr())
                 b.link_push_dev(d_ch.data_ptr())
                 b.link_pop_dev(d_rxin.data_ptr(), d_act.data_ptr())
@@ -212,8 +216,9 @@ def test_fused_loopback_equals_copy_kernels():
         outs.append(rec)
         b.close()
     assert sum(int((r[0] & 1).sum()) for r in outs[0]) > S * (F - 8)
-    for (r0, f0, t0), (r1, f1, t1) in zip(*outs):
-        assert np.array_equal(r0, r1) and np.array_equal(t0, t1) and np.array_equal(f0, f1)
+    for other in (1, 2):
+        for (r0, f0, t0), (r1, f1, t1) in zip(outs[0], outs[other]):
+            assert np.array_equal(r0, r1) and np.array_equal(t0, t1) and np.array_equal(f0, f1), other
 
 
 def test_frame_pipeline_gives_the_same_per_stream_sequences():
