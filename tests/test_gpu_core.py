@@ -140,3 +140,25 @@ def test_large_batch_full_tiles_vs_oracle():
     assert np.array_equal(b.core_encode(x), zo)
     assert np.array_equal(b.core_decode(zo), fo)
     b.close()
+
+
+def test_config2_full_size_8192_streams_96_steps():
+    """BASELINE configs[1] at full size: 8192 streams x 96 steps (32 modem frames of 3 steps, state carried across the 32
+    calls).  Size-independent properties: (i) the result of a stream does not depend on where it sits in the batch — 128
+    replicas of 64 distinct streams must be bit-identical to each other; (ii) the 64 distinct streams are bit-identical to
+    the oracle run over the same 96 steps."""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    S, R, T, C = 8192, 64, 96, 3
+    x64 = pack_enc_input(synth_features(R, 4 * T, seed=2025))                    # [64][96][84]
+    o = CoreOraclePort(n_streams=R)
+    z64 = o.encode(x64, nthreads=16); f64 = o.decode(z64, nthreads=16)
+    b = RadeBatch(S)
+    rep = np.arange(S) % R
+    zs, fs = [], []
+    for c0 in range(0, T, C):
+        z = b.core_encode(np.ascontiguousarray(x64[rep, c0:c0 + C]))
+        f = b.core_decode(z)
+        assert np.array_equal(z[:R], z64[:, c0:c0 + C]) and np.array_equal(f[:R], f64[:, c0:c0 + C]), c0
+        assert np.array_equal(z, z[:R][rep]) and np.array_equal(f, f[:R][rep]), c0
+    b.close()
