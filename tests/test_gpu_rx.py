@@ -266,3 +266,30 @@ def test_frame_pipeline_gives_the_same_per_stream_sequences():
             assert np.array_equal(np.array(seqs[0][s][:n]), np.array(seqs[other][s][:n])), (s, other)
         total += n
     assert total > S * (F - 9)
+
+
+def test_offair_recording_replicated_over_streams(golden):
+    """BASELINE configs[4] shape (RX side): the off-air recording replicated over N streams — every replica must reproduce
+    the single-stream golden trace (nin / return codes / sync) and give bit-identical features, wherever it sits in the batch"""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    g = golden("rx_offair_long_qso")
+    S = 96
+    b = RadeBatch(S)
+    x_all = g["rx_in"]
+    pos = 0; k = 0; feats = []
+    while k < len(g["nin"]) and pos + int(g["nin"][k]) <= len(x_all):
+        nin = b.nin()
+        assert (nin == g["nin"][k]).all(), k
+        x = np.zeros((S, 1120), np.complex64); x[:, :nin[0]] = x_all[pos:pos + nin[0]][None, :]; pos += int(nin[0])
+        f, ret, _ = b.rx(x)
+        assert (ret == g["ret"][k]).all(), k
+        if ret[0] & 1:
+            assert (f == f[0:1]).all(), k
+            feats.append(f[0].copy())
+        st = b.rx_status()
+        assert all((x_.state == 2) == (g["state"][k] == 2) for x_ in st), k
+        k += 1
+    assert k == len(g["nin"])
+    check_features(np.array(feats).reshape(-1, 432), g, "offair x96")
+    b.close()
