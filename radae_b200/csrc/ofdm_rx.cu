@@ -416,12 +416,13 @@ struct TrackSmem {
   float scratch[32];
   double spot[4];
   uint64_t full[2], empty[2], tab_bar;
+  int item[2];                     // stream handled from stage b (-1: no more work)
 };
 static_assert(sizeof(RxCtl) % 16 == 0 && sizeof(TrackStage) % 128 == 0, "bulk-copy alignment");
 
 __global__ void __launch_bounds__(TRK_THREADS, 1)
 rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
-                int *__restrict__ uw_errors, const int *__restrict__ track_list, const int *__restrict__ counters,
+                int *__restrict__ uw_errors, const int *__restrict__ track_list, int *__restrict__ counters,
                 int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
@@ -438,11 +439,15 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     if (tid == TRK_CONSUMERS) {
       mbar_expect_tx(&sm.tab_bar, (uint32_t)sizeof(AcqTables));
       bulk_g2s(&sm.tab, T.acq_tab, (uint32_t)sizeof(AcqTables), &sm.tab_bar);
-      int k = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
+      // streams are handed out dynamically (atomic counter): a CTA that starts late — its SM was still busy with another
+      // kernel of the frame pipeline — simply takes fewer of them
+      for (int k = 0;; k++) {
         const int b = k & 1;
         if (k >= 2) mbar_wait(&sm.empty[b], ((k >> 1) - 1) & 1);
+        const int it = atomicAdd(&counters[3], 1);
+        if (it >= n_items) { sm.item[b] = -1; mbar_arrive(&sm.full[b]); break; }
         const int s = track_list[it];
+        sm.item[b] = s;
         const int head = ctl[s].ring_head;        // even by construction (nin is 800 / 960 / 1120)
         const float2 *rg = ring + (size_t)s * RADE_RXBUF;
         TrackStage &st = sm.st[b];
@@ -456,11 +461,11 @@ rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     return;
   }
   mbar_wait(&sm.tab_bar, 0);
-  int k = 0;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x, k++) {
+  for (int k = 0;; k++) {
     const int b = k & 1;
-    const int s = track_list[it];
     mbar_wait(&sm.full[b], (k >> 1) & 1);
+    const int s = sm.item[b];
+    if (s < 0) break;
     TrackStage &st = sm.st[b];
     const int tmax0 = st.ctl.tmax; const double fmax0 = st.ctl.fmax;
     const int rot = st.ctl.n_check % 20;
