@@ -335,7 +335,7 @@ def run_gpu(args):
     e2e = None
     if rank == 0 or world > 1:
         e2e = run_e2e(b, S, feats_host, codec_only, K, world, dist if world > 1 else None, torch,
-                      n_ctx=args.e2e_contexts, weights=blob, device=local)
+                      n_ctx=args.e2e_contexts, weights=blob, device=local, serial=args.e2e_serial)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -363,15 +363,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weights=None, device=0):
-    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed.
-    The S streams are served by n_ctx independent contexts (rade_b200_open each), one host thread per context, so one
-    context's PCIe copies overlap the other's kernels — every call is still the synchronous reference-style call."""
+def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weights=None, device=0, serial=False):
+    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed; every call
+    is the synchronous reference-style call.  Full pipeline: like the reference's `radae_tx | ch | radae_rx` (two programs
+    joined by a pipe) the transmitter side (rade_b200_tx, rade_b200_channel, FIFO push) and the receiver side (FIFO gather +
+    rade_b200_rx) run on two host threads with a context each, joined by the pinned host sample FIFO; `--e2e-serial` runs
+    the four calls back to back on one thread instead.  n_ctx > 1 splits the streams over several such pairs."""
     import threading
     from radae_b200 import RadeBatch
     from radae_b200.batch import HostLink
     # host threads of the C-side sample FIFOs: this rank's share of the cores (torchrun exports OMP_NUM_THREADS=1)
-    os.environ.setdefault("RADE_B200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, world) // max(1, n_ctx)))))
+    duplex = not codec_only and not serial
+    os.environ.setdefault("RADE_B200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, world) // max(1, n_ctx) // (2 if duplex else 1)))))
     n_feat_frames = feats_host.shape[1]
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
     bounds = [(S * i) // n_ctx for i in range(n_ctx + 1)]
@@ -386,7 +389,8 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
                                      -np.ones((n, n_feat_frames, 12, 1), np.float32)], axis=-1).reshape(n, n_feat_frames, 3, 84))
             c["x"] = [np.ascontiguousarray(x[:, j]) for j in range(n_feat_frames)]
         else:
-            c["b"].channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5 + i)
+            c["btx"] = RadeBatch(n, device=device, weights=weights) if duplex else c["b"]     # transmitter-side context
+            c["btx"].channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5 + i)
             c["link"] = HostLink(c["b"])
             c["tx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
             c["rx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
@@ -400,14 +404,29 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
             z = c["b"].core_encode(c["x"][k % n_feat_frames])
             c["b"].core_decode(z)
         else:
-            c["b"].tx(c["feats"][k % n_feat_frames], out=c["tx"])      # H2D features (pinned), D2H tx samples
-            c["b"].channel(c["tx"], out=c["rx"])                        # H2D tx, D2H rx (the channel is a simulator outside rade_api.h)
-            c["link"].push(c["rx"])                                     # pinned host FIFO, C/OpenMP
+            tx_side(c, k)
             c["link"].rx()                                              # gather nin[s] per stream, H2D rx_in, D2H features/ret/eoo/nin
 
+    def tx_side(c, k):
+        c["btx"].tx(c["feats"][k % n_feat_frames], out=c["tx"])        # H2D features (pinned), D2H tx samples
+        c["btx"].channel(c["tx"], out=c["rx"])                          # H2D tx, D2H rx (the channel is a simulator outside rade_api.h)
+        c["link"].push(c["rx"])                                         # pinned host FIFO, C/OpenMP
+
     def run(c, k0, n):
+        if not duplex:
+            for k in range(k0, k0 + n):
+                step(c, k)
+            return
+        # two host threads joined by the sample FIFO; the transmitter may run at most two frames ahead of the receiver
+        filled, space = threading.Semaphore(0), threading.Semaphore(2)
+
+        def producer():
+            for k in range(k0, k0 + n):
+                space.acquire(); tx_side(c, k); filled.release()
+        th = threading.Thread(target=producer); th.start()
         for k in range(k0, k0 + n):
-            step(c, k)
+            filled.acquire(); c["link"].rx(); space.release()
+        th.join()
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=n_ctx)                      # persistent host threads, one per context
@@ -429,6 +448,7 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
     run_all(100, K)
     for c in ctxs:
         c["b"].synchronize()
+        if "btx" in c: c["btx"].synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device="cuda")
     if dist:
@@ -437,10 +457,14 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weight
     pool.shutdown()
     for c in ctxs:
         if "link" in c: c["link"].close()
+        if c.get("btx") is not None and c["btx"] is not c["b"]: c["btx"].close()
         c["b"].close()
     return {"value": S * world * F_PER_STEP * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": K, "contexts": n_ctx,
-            "timing": "host wall clock around K synchronous steps per context (pinned buffers, host FIFO in C), %d contexts on %d host threads, max over ranks" % (n_ctx, n_ctx)}
+            "steps": K, "contexts": n_ctx, "host_threads": n_ctx * (2 if duplex else 1),
+            "timing": ("host wall clock around K modem frames per stream; transmitter side (rade_b200_tx, rade_b200_channel, FIFO push) and "
+                       "receiver side (FIFO gather, rade_b200_rx) on two host threads joined by the pinned host FIFO, like radae_tx | ch | radae_rx; "
+                       "every call synchronous; max over ranks") if duplex else
+                      "host wall clock around K synchronous steps (tx, channel, push, rx back to back on one host thread), pinned buffers, host FIFO in C; max over ranks"}
 
 
 def main():
@@ -452,6 +476,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: tx, channel, push, rx back to back on ONE host thread")
     ap.add_argument("--no-pipeline", action="store_true", help="run TX and RX of a frame back to back on one stream")
     ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
     args = ap.parse_args()

@@ -557,7 +557,8 @@ RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsign
 // (OpenMP over streams), marks the others inactive, runs rade_b200_rx and refreshes nin[] in the same round trip.
 struct rade_b200_hostlink {
   rade_batch *b; int cap; int nthreads;
-  float2 *fifo; long long *wr, *rd; int *nin;
+  float2 *fifo; volatile long long *wr, *rd; int *nin;      // single producer (push) / single consumer (rx) per stream: the two
+                                                            // may run on different host threads
   float2 *rx_in; unsigned char *active;
 };
 RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples) {
@@ -582,7 +583,7 @@ RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capac
 RADE_EXPORT void rade_b200_hostlink_close(rade_b200_hostlink *h) {
   if (!h) return;
   cudaFreeHost(h->fifo); cudaFreeHost(h->rx_in); cudaFreeHost(h->active); cudaFreeHost(h->nin);
-  delete[] h->wr; delete[] h->rd; delete h;
+  delete[] const_cast<long long *>(h->wr); delete[] const_cast<long long *>(h->rd); delete h;
 }
 RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples) {
   const int S = h->b->S, cap = h->cap;
@@ -594,7 +595,7 @@ RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *
     const int w = (int)(h->wr[s] % cap), first = (cap - w < RADE_NMF) ? cap - w : RADE_NMF;
     memcpy(dst + w, src, first * sizeof(float2));
     if (first < RADE_NMF) memcpy(dst, src + first, (RADE_NMF - first) * sizeof(float2));
-    h->wr[s] += RADE_NMF;
+    h->wr[s] = h->wr[s] + RADE_NMF;
   }
   return 0;
 }
@@ -613,7 +614,7 @@ RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out
     const int r = (int)(h->rd[s] % cap), first = (cap - r < n) ? cap - r : n;
     memcpy(dst, src + r, first * sizeof(float2));
     if (first < n) memcpy(dst + first, src, (n - first) * sizeof(float2));
-    h->rd[s] += n;
+    h->rd[s] = h->rd[s] + n;
   }
   const size_t Sz = S;
   // the gathered samples sit in our own pinned buffer: the band-pass kernel reads them in place over PCIe
