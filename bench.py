@@ -155,7 +155,7 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     per_step = []
-    frames_per_sample = 200
+    frames_per_sample = args.ref_frames
     for i in range(args.warmup + args.steps):
         rate, procs, kind, sample = cpu_pipeline_rate(frames_per_sample, warm=8)
         if i >= args.warmup:
@@ -476,6 +476,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-frames", type=int, default=200, help="--impl reference: modem frames per process and step (bounded sample)")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: tx, channel, push, rx back to back on ONE host thread")
     ap.add_argument("--no-pipeline", action="store_true", help="run TX and RX of a frame back to back on one stream")
     ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
