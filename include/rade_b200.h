@@ -44,6 +44,16 @@ RADE_EXPORT int rade_b200_tx_set_eoo_bits(rade_batch *b, const float *eoo_bits);
 RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out);
 /* OFDM modulator alone (transmitter_one, radae/dsp.py:340-378): z [S][3][80] -> tx [S][960] */
 RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z);
+/* radae_tx(bypass_enc=True).do_radae_tx (radae_txe.py:122-132; what src/rade_api.c:411-436 calls after its own C encoder):
+ * z [S][3][80] from the caller's core encoder -> modulator (+ the TX filter below when enabled) -> tx [S][960] */
+RADE_EXPORT int rade_b200_tx_z_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z);
+RADE_EXPORT int rade_b200_tx_z(rade_batch *b, RADE_COMP *tx_out, const float *z);
+/* radae_tx(txbpf_en=True) (radae_txe.py:74-81, :130-132, :141-143): 101-tap complex band-pass filter (the receive
+ * filter's band, state carried from call to call) + clip to unit magnitude on every frame rade_b200_tx[_dev],
+ * rade_b200_tx_z[_dev] and rade_b200_tx_eoo produce.  Off by default (src/rade_api.c never sets it); enabling or
+ * disabling restarts the filter.  The fused loop-back calls (tx_channel_link_dev, loopback_step_dev) refuse to run
+ * while it is enabled. */
+RADE_EXPORT int rade_b200_tx_bpf_enable(rade_batch *b, int enable);
 
 /* --- receiver: rade_nin / rade_rx / rade_sync / rade_snrdB_3k_est per stream ---
  * rx_in [S][1120]: row s holds nin[s] fresh samples (800 | 960 | 1120);  features_out [S][432];

@@ -358,21 +358,36 @@ class RadaeTx:
     """One stream. `core` = a CoreOraclePort/CoreOracleRef with n_streams == 1 (the C encoder path,
     src/rade_api.c:411-434)."""
 
-    def __init__(self, core):
+    def __init__(self, core, txbpf_en=False):
         self.core = core
         self.eoo_bits = None
+        self.txbpf = ComplexBPF() if txbpf_en else None      # same band as the receive filter (radae_txe.py:74-81)
+
+    def _bpf_clip(self, tx):
+        """optional TX filter + unit-magnitude clip (radae_txe.py:130-132, :141-143), all in float32 / complex64"""
+        if self.txbpf is None:
+            return tx
+        y = self.txbpf.bpf(tx)
+        mag = np.abs(y).astype(np.float32)
+        ang = np.angle(y).astype(np.float32)
+        rot = (np.cos(ang).astype(np.float32) + 1j * np.sin(ang).astype(np.float32)).astype(np.complex64)
+        return (np.clip(mag, 0, 1).astype(np.float32) * rot).astype(np.complex64)
 
     def do_radae_tx(self, features432):
         f = np.asarray(features432, np.float32).reshape(1, 12, NB_TOTAL_FEATURES)
         x = np.concatenate([f[:, :, :NUM_USED_FEATURES], -np.ones((1, 12, 1), np.float32)], axis=2).reshape(1, 3, 84)
         z = self.core.encode(x)[0]
-        return transmitter_one(z), z
+        return self._bpf_clip(transmitter_one(z)), z
+
+    def do_radae_tx_from_z(self, z240):
+        """bypass_enc=True: the caller ran the core encoder (src/rade_api.c:411-434 -> radae_txe.py:122-124)"""
+        return self._bpf_clip(transmitter_one(np.asarray(z240, np.float32).reshape(NZMF, LATENT)))
 
     def set_eoo_bits(self, bits):
         self.eoo_bits = np.asarray(bits, np.float32).copy()
 
     def do_eoo(self):
-        return eoo_frame(self.eoo_bits)
+        return self._bpf_clip(eoo_frame(self.eoo_bits))
 
 
 SEARCH, CANDIDATE, SYNC = 0, 1, 2

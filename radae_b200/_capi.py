@@ -47,6 +47,7 @@ SIGNATURES = {
     "rade_b200_tx_dev": (_I, [_P, _P, _P]), "rade_b200_tx": (_I, [_P, _P, _P]),
     "rade_b200_tx_set_eoo_bits": (_I, [_P, _P]), "rade_b200_tx_eoo": (_I, [_P, _P]),
     "rade_b200_ofdm_mod_dev": (_I, [_P, _P, _P]),
+    "rade_b200_tx_z_dev": (_I, [_P, _P, _P]), "rade_b200_tx_z": (_I, [_P, _P, _P]), "rade_b200_tx_bpf_enable": (_I, [_P, _I]),
     "rade_b200_nin": (_I, [_P, _P]), "rade_b200_rx": (_I, [_P, _P, _P, _P, _P, _P]),
     "rade_b200_rx_dev": (_I, [_P, _P, _P, _P, _P, _P]), "rade_b200_nin_dev": (_P, [_P]),
     "rade_b200_rx_get_status": (_I, [_P, _P]), "rade_b200_rx_get_z_hat": (_I, [_P, _P]),

@@ -83,6 +83,18 @@ class RadeBatch:
         _check(self.lib.rade_b200_tx(self.h, out.ctypes.data, pf), "tx")
         return out
 
+    def tx_z(self, z):
+        """bypass_enc transmitter: z [S][3][80] from the caller's core encoder -> tx [S][960]"""
+        zz, pz = _np(z, np.float32)
+        assert zz.size == self.S * 240
+        out = np.empty((self.S, NMF), np.complex64)
+        _check(self.lib.rade_b200_tx_z(self.h, out.ctypes.data, pz), "tx_z")
+        return out
+
+    def tx_bpf_enable(self, on=True):
+        """radae_tx(txbpf_en=True): band-pass filter + clip on every transmitted frame (restarts the filter)"""
+        _check(self.lib.rade_b200_tx_bpf_enable(self.h, int(on)), "tx_bpf_enable")
+
     def tx_set_eoo_bits(self, bits):
         b, pb = _np(bits, np.float32)
         assert b.size == self.S * NEOO_BITS
@@ -131,6 +143,9 @@ class RadeBatch:
 
     def tx_dev(self, d_tx_out, d_features_in):
         _check(self.lib.rade_b200_tx_dev(self.h, d_tx_out, d_features_in), "tx_dev")
+
+    def tx_z_dev(self, d_tx_out, d_z):
+        _check(self.lib.rade_b200_tx_z_dev(self.h, d_tx_out, d_z), "tx_z_dev")
 
     def ofdm_mod_dev(self, d_tx_out, d_z):
         _check(self.lib.rade_b200_ofdm_mod_dev(self.h, d_tx_out, d_z), "ofdm_mod_dev")

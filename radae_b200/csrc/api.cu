@@ -34,6 +34,7 @@ struct rade_batch {
   // transmitter
   float *z_tx;                // [S][240]
   float *eoo_bits; int *has_eoo_bits;
+  TxBpfState *tx_bpf; int tx_bpf_en;      // optional TX band-pass filter + clip (radae_tx(txbpf_en=True)), allocated on first enable
   // device staging for the host-pointer API
   float *d_feat_in, *d_feat_out, *d_z, *d_core_in, *d_core_out; size_t core_cap;
   float2 *d_tx, *d_tx_eoo, *d_rx_in;
@@ -69,6 +70,7 @@ int reset_state(rade_batch *b) {
   CUDA_CHECK(cudaMemsetAsync(b->link_wr, 0, sizeof(long long) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->link_rd, 0, sizeof(long long) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->has_eoo_bits, 0, sizeof(int) * S, b->stream));
+  if (b->tx_bpf) CUDA_CHECK(cudaMemsetAsync(b->tx_bpf, 0, sizeof(TxBpfState) * S, b->stream));
   const double foff_err = (b->flags & RADE_FOFF_TEST) ? 10.0 : 0.0;     // src/rade_api.c:263-264
   if (rx_init_launch(b->rx.ctl, b->rx.uw_errors, S, foff_err, b->stream) < 0) return -1;
   std::vector<int> nin(S, RADE_NMF);
@@ -287,6 +289,26 @@ RADE_EXPORT int rade_b200_ofdm_mod_dev(rade_batch *b, RADE_COMP *d_tx_out, const
   b->launches += 1;
   return 0;
 }
+// optional TX band-pass filter + clip on the frame the modulator has just written (radae_txe.py:130-132, :141-143)
+static int tx_bpf_stage(rade_batch *b, float2 *d_frames, int n, cudaStream_t stream) {
+  if (!b->tx_bpf_en) return 0;
+  b->prof.begin(K_TX_BPF);
+  if (tx_bpf_clip_launch(b->tables, d_frames, (size_t)n, n, b->tx_bpf, b->S, stream) < 0) return -1;
+  b->prof.end(K_TX_BPF);
+  b->launches += 1;
+  return 0;
+}
+RADE_EXPORT int rade_b200_tx_bpf_enable(rade_batch *b, int enable) {
+  cudaSetDevice(b->device);        // the current device is per host thread
+  if (enable && !b->tx_bpf && dalloc(b, &b->tx_bpf, (size_t)b->S) < 0) return -1;
+  if (b->tx_bpf) {                 // switching the filter on or off starts from a new filter object
+    if (rade_b200_synchronize(b) < 0) return -1;
+    CUDA_CHECK(cudaMemsetAsync(b->tx_bpf, 0, sizeof(TxBpfState) * b->S, b->stream));
+    CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  }
+  b->tx_bpf_en = enable != 0;
+  return 0;
+}
 RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_features_in) {
   cudaSetDevice(b->device);        // the current device is per host thread
   // 3 core-encoder steps on the API feature layout (src/rade_api.c:411-434) then transmitter_one (radae_txe.py:127)
@@ -296,6 +318,27 @@ RADE_EXPORT int rade_b200_tx_dev(rade_batch *b, RADE_COMP *d_tx_out, const float
   if (ofdm_mod_launch(b->tables, b->z_tx, (float2 *)d_tx_out, b->S, tx_side(b)) < 0) return -1;
   b->prof.end(K_OFDM_MOD);
   b->launches += 2;
+  if (tx_bpf_stage(b, (float2 *)d_tx_out, RADE_NMF, tx_side(b)) < 0) return -1;
+  return RADE_NMF;
+}
+// radae_tx(bypass_enc=True).do_radae_tx (radae_txe.py:122-132): the caller ran the core encoder and hands over the
+// 3 x 80 latents of one modem frame per stream; modulator, then the optional TX filter
+RADE_EXPORT int rade_b200_tx_z_dev(rade_batch *b, RADE_COMP *d_tx_out, const float *d_z) {
+  cudaSetDevice(b->device);        // the current device is per host thread
+  b->prof.begin(K_OFDM_MOD);
+  if (ofdm_mod_launch(b->tables, d_z, (float2 *)d_tx_out, b->S, b->stream) < 0) return -1;
+  b->prof.end(K_OFDM_MOD);
+  b->launches += 1;
+  if (tx_bpf_stage(b, (float2 *)d_tx_out, RADE_NMF, b->stream) < 0) return -1;
+  return RADE_NMF;
+}
+RADE_EXPORT int rade_b200_tx_z(rade_batch *b, RADE_COMP *tx_out, const float *z) {
+  cudaSetDevice(b->device);        // the current device is per host thread
+  const size_t S = b->S;
+  CUDA_CHECK(cudaMemcpyAsync(b->d_z, z, S * RADE_NZMF * RADE_LATENT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  if (rade_b200_tx_z_dev(b, (RADE_COMP *)b->d_tx, b->d_z) < 0) return -1;
+  CUDA_CHECK(cudaMemcpyAsync(tx_out, b->d_tx, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return RADE_NMF;
 }
 RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *features_in) {
@@ -304,7 +347,7 @@ RADE_EXPORT int rade_b200_tx(rade_batch *b, RADE_COMP *tx_out, const float *feat
   // cudaHostRegister), staged by the driver when they are pageable
   const size_t S = b->S;
   CUDA_CHECK(cudaMemcpyAsync(b->d_feat_in, features_in, S * RADE_NFEAT * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-  if (void *alias = pinned_alias(tx_out)) {            // modulator writes the samples straight into the caller's pinned buffer
+  if (void *alias = b->tx_bpf_en ? nullptr : pinned_alias(tx_out)) {     // modulator writes the samples straight into the caller's pinned buffer
     if (rade_b200_pipeline_fork(b) < 0 || rade_b200_tx_dev(b, (RADE_COMP *)alias, b->d_feat_in) < 0 || rade_b200_pipeline_join(b) < 0) return -1;
   } else {
     if (rade_b200_pipeline_fork(b) < 0 || rade_b200_tx_dev(b, (RADE_COMP *)b->d_tx, b->d_feat_in) < 0 || rade_b200_pipeline_join(b) < 0) return -1;
@@ -329,6 +372,7 @@ RADE_EXPORT int rade_b200_tx_eoo(rade_batch *b, RADE_COMP *tx_eoo_out) {
   if (eoo_launch(b->tables, b->eoo_bits, b->has_eoo_bits, b->d_tx_eoo, b->S, b->stream) < 0) return -1;
   b->prof.end(K_EOO);
   b->launches += 1;
+  if (tx_bpf_stage(b, b->d_tx_eoo, RADE_NEOO, b->stream) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(tx_eoo_out, b->d_tx_eoo, S * RADE_NEOO * sizeof(float2), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return RADE_NEOO;
@@ -467,6 +511,10 @@ RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx)
 // through the channel into the link FIFOs (the 960 tx samples per stream stay in shared memory)
 RADE_EXPORT int rade_b200_tx_channel_link_dev(rade_batch *b, const float *d_features_in) {
   cudaSetDevice(b->device);
+  if (b->tx_bpf_en) {      // the fused modulator+channel kernel has no filter stage: use tx_dev + channel_link_dev instead
+    fprintf(stderr, "libradae_b200: rade_b200_tx_channel_link_dev is not available while the TX band-pass filter is enabled\n");
+    return -1;
+  }
   const rade_b200_channel_cfg &c = b->chan_cfg;
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
   b->prof.begin(K_CORE_ENC);
@@ -639,7 +687,8 @@ RADE_EXPORT int rade_b200_profile_n_kernels(void) { return K_COUNT; }
 RADE_EXPORT const char *rade_b200_profile_kernel_name(int k) {
   static const char *names[K_COUNT] = {"core_encoder_kernel", "ofdm_mod_kernel", "eoo_kernel", "channel_stream_kernel",
                                        "link_push_kernel", "link_pop_kernel", "rx_bpf_kernel", "rx_detect_kernel",
-                                       "rx_track_kernel", "rx_demod_kernel", "rx_finish_kernel", "core_decoder_kernel"};
+                                       "rx_track_kernel", "rx_demod_kernel", "rx_finish_kernel", "core_decoder_kernel",
+                                       "tx_bpf_clip_kernel"};
   return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts) {

@@ -56,7 +56,50 @@ eoo_kernel(DspTables T, const float *__restrict__ bits, const int *__restrict__ 
   }
 }
 
+// Optional TX band-pass filter + unit-magnitude clip, radae_tx(txbpf_en=True): radae_txe.py:74-81 (same complex_bpf
+// object and band as the receive filter), :130-132 (modem frame) and :141-143 (EOO frame).  Applied in place to the
+// n = 960 or 1152 samples the modulator has just written; one CTA per stream.  complex_bpf.bpf (radae/dsp.py:63-102):
+// mix down with the running phase, 101 real taps over [memory, frame], mix up; the memory keeps Ntap+1 = 102 samples
+// (dsp.py:96), so every call after the first is delayed by two samples -- restated exactly as in rx_bpf_kernel.
+// clip(|y|, 0, 1) * exp(j angle(y)) == y * min(|y|, 1) / |y|.
+constexpr int TXBPF_THREADS = 288;
+__global__ void __launch_bounds__(TXBPF_THREADS)
+tx_bpf_clip_kernel(DspTables T, float2 *__restrict__ tx, size_t stride, int n, TxBpfState *__restrict__ st) {
+  __shared__ float2 X[RADE_BPF_MEM + RADE_NEOO + 2];
+  __shared__ float h[RADE_BPF_NTAP];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  TxBpfState &c = st[s];
+  float2 *x = tx + (size_t)s * stride;
+  const bool fresh = c.started == 0;                                 // zero-filled state == a new complex_bpf object
+  const float2 ph = fresh ? make_float2(1.f, 0.f) : c.phase;
+  const int off = fresh ? 2 : 0;                                     // 100 samples of memory on the first call, 102 afterwards
+  for (int i = tid; i < RADE_BPF_MEM; i += TXBPF_THREADS) X[i] = c.mem[i];
+  for (int i = tid; i < RADE_BPF_NTAP; i += TXBPF_THREADS) h[i] = T.bpf_h[i];
+  for (int i = tid; i < n; i += TXBPF_THREADS) X[RADE_BPF_MEM + i] = cmul(x[i], cmul(ph, T.bpf_exp[i]));     // mix down
+  for (int i = RADE_BPF_MEM + n + tid; i < RADE_BPF_MEM + RADE_NEOO + 2; i += TXBPF_THREADS) X[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < n; i += TXBPF_THREADS) {
+    float2 acc = make_float2(0.f, 0.f);
+    const float2 *w = X + i + off;
+    for (int k = 0; k < RADE_BPF_NTAP; k++) { acc.x = fmaf(h[k], w[k].x, acc.x); acc.y = fmaf(h[k], w[k].y, acc.y); }
+    const float2 u = cmul(ph, T.bpf_exp[i]);
+    const float2 y = cmul(acc, make_float2(u.x, -u.y));              // mix up
+    const float mag = hypotf(y.x, y.y);
+    const float g = mag > 0.f ? fminf(mag, 1.f) / mag : 0.f;
+    x[i] = make_float2(y.x * g, y.y * g);
+  }
+  for (int i = tid; i < RADE_BPF_MEM; i += TXBPF_THREADS) c.mem[i] = X[n + i];
+  if (tid == 0) { c.phase = cmul(ph, T.bpf_exp[n - 1]); c.started = 1; }
+}
+
 }  // namespace
+
+int tx_bpf_clip_launch(const DspTables &T, float2 *tx, size_t stride, int n, TxBpfState *st, int S, cudaStream_t stream) {
+  if (n < 1 || n > RADE_NEOO) return -1;
+  tx_bpf_clip_kernel<<<S, TXBPF_THREADS, 0, stream>>>(T, tx, stride, n, st);
+  CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream) {
   ofdm_mod_kernel<<<S, RADE_M, 0, stream>>>(T, z, tx, S);

@@ -101,7 +101,7 @@ struct DspTables {
   const float2 *Pmat;      // [30][2][3] LS projectors
   const float2 *eq_rot;    // [30] exp(-j w_c a)
   const float *bpf_h;      // [101]
-  const float2 *bpf_exp;   // [1120] exp(-j alpha (i+1)), float32 argument
+  const float2 *bpf_exp;   // [1152] exp(-j alpha (i+1)), float32 argument (rx reads [0,1120), the TX filter up to the EOO frame)
   const float2 *eoo_base;  // [1152] P E 0 0 0 E frame after the PA limiter
   const float *fcoarse;    // [40]
   float pilot_gain;
@@ -126,6 +126,13 @@ struct __align__(16) RxCtl {
   int valid_count, synced_count, n_check, bpf_first;
   int ring_head, candidate, endofover, valid_output;
   int uw_fail, ret, ran_sync, pad1;
+};
+
+// state of the optional TX band-pass filter (radae_tx(txbpf_en=True)); all zero == a new complex_bpf object
+struct TxBpfState {
+  float2 mem[RADE_BPF_MEM];
+  float2 phase;
+  int started, pad;
 };
 
 // per-stream channel-simulator state

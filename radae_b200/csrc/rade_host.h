@@ -58,6 +58,7 @@ struct RxBuffers {
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
 int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float2 *tx, int S, cudaStream_t stream);
+int tx_bpf_clip_launch(const DspTables &T, float2 *tx, size_t stride, int n, TxBpfState *st, int S, cudaStream_t stream);
 int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
                          int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
 int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
@@ -76,7 +77,7 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
 
 // ---- optional per-kernel timing with CUDA events on the context's stream (rade_b200_profile_*)
 enum KernelId { K_CORE_ENC = 0, K_OFDM_MOD, K_EOO, K_CHANNEL, K_LINK_PUSH, K_LINK_POP, K_RX_BPF, K_RX_DETECT, K_RX_TRACK,
-                K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_COUNT };
+                K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_TX_BPF, K_COUNT };
 struct Profiler {
   bool on = false;
   cudaStream_t stream = nullptr;

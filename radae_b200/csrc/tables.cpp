@@ -104,8 +104,8 @@ void dsp_tables_host(DspTablesHost &T) {
     float s = (float)std::sin((double)y) / y;                                              // np.sinc on float32
     T.bpf_h[i] = B * s;
   }
-  T.bpf_exp.resize(RADE_NIN_MAX);
-  for (int i = 0; i < RADE_NIN_MAX; i++) {
+  T.bpf_exp.resize(RADE_NEOO);                      // the receive filter reads [0, 1120), the TX filter up to the 1152-sample EOO frame
+  for (int i = 0; i < RADE_NEOO; i++) {
     float arg = (float)(-((double)alpha * (double)(i + 1)));                               // argument rounded to float32 (dsp.py:61)
     T.bpf_exp[i] = cexp32(arg);
   }

@@ -70,7 +70,7 @@ def test_dsp_tables_match_oracle(lib):
                             (5, c.Pmat, 1e-6), (6, c.eq_rot, 1e-7), (8, c.eoo_base, 1e-6)]:
         assert np.max(np.abs(cget(which, ref.size) - ref.ravel())) < tol, which
     f = od.ComplexBPF()
-    assert np.array_equal(cget(7, 1120), f.phase_vec_exp[:1120])
+    assert np.array_equal(cget(7, 1152), f.phase_vec_exp[:1152])     # receive filter reads [0,1120), TX filter up to the EOO frame
     h = np.zeros(101, np.float32); lib.rade_b200_debug_tables(16, h.ctypes.data, 101)
     assert np.max(np.abs(h - f.h)) < 1e-8
     k = np.zeros(4, np.float32); lib.rade_b200_debug_tables(18, k.ctypes.data, 4)

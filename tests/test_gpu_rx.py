@@ -293,3 +293,33 @@ def test_offair_recording_replicated_over_streams(golden):
     assert k == len(g["nin"])
     check_features(np.array(feats).reshape(-1, 432), g, "offair x96")
     b.close()
+
+
+@pytest.mark.parametrize("name", ["awgn_clean", "mpp_3dB"])
+def test_bypass_dec_receiver_hands_back_latents(golden, name):
+    """radae_rx(bypass_dec=True) (radae_rxe.py:318, the mode src/rade_api.c:476-506 runs in front of its own C decoder):
+    frames come back as 3 x 80 latents; framing identical to the golden trace, z_hat to 1e-5, and the stand-alone core
+    decoder applied to them reproduces the features of the ordinary receiver bit for bit"""
+    need_gpu()
+    from radae_b200 import radae_rx, RadeBatch
+    g = golden("rx_" + name)
+    _, feats_full, _ = run_single(g)
+    rx = radae_rx(v=0, bypass_dec=True)
+    assert rx.get_n_floats_out() == 240
+    o = 0; nins, rets, zs = [], [], []
+    floats = np.zeros(240, np.float32)
+    x = g["rx_in"]
+    while o + rx.get_nin() <= len(x):
+        nin = rx.get_nin()
+        ret = rx.do_radae_rx(x[o:o + nin], floats); o += nin
+        nins.append(nin); rets.append(ret)
+        if ret & 1: zs.append(floats.copy())
+    rx.close()
+    assert np.array_equal(np.array(nins), g["nin"]) and np.array_equal(np.array(rets), g["ret"])
+    zs = np.array(zs)
+    assert relrms(zs, g["z_hat"].reshape(zs.shape)) < 1e-5
+    b = RadeBatch(1)
+    out = b.core_decode(zs.reshape(1, -1, 80))[0].reshape(-1, 12, 21)
+    b.close()
+    api = np.zeros((out.shape[0], 12, 36), np.float32); api[:, :, :20] = out[:, :, :20]
+    assert np.array_equal(api.reshape(-1, 432), feats_full)

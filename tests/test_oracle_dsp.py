@@ -41,6 +41,19 @@ def test_bpf_chunked_vs_reference_including_memory_quirk(golden):
     assert relrms(np.concatenate(ys), g["y"]) < 1e-5
 
 
+def test_tx_bandpass_and_clip_vs_reference(golden):
+    """radae_tx(txbpf_en=True): six frames + EOO through one filter object (state carries), tools/make_golden_txbpf.py"""
+    g = golden("tx_bpf")
+    tx = od.RadaeTx(None, txbpf_en=True)
+    out = np.array([tx.do_radae_tx_from_z(z) for z in g["z"]])
+    assert relrms(out, g["tx"]) < 1e-5
+    tx.set_eoo_bits(g["eoo_bits"])
+    assert relrms(tx.do_eoo(), g["eoo"]) < 1e-5
+    assert np.abs(out).max() <= 1.0 + 1e-6
+    # the filter matters: the unfiltered frames of tx.npz (same z) are far away
+    assert relrms(golden("tx")["tx"], g["tx"]) > 0.1
+
+
 @pytest.mark.parametrize("name", SCENARIOS)
 def test_streaming_receiver_vs_reference(golden, name):
     g = golden("rx_" + name)
