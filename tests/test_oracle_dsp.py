@@ -5,7 +5,7 @@ import pytest
 from oracle import dsp as od
 from oracle.core import CoreOraclePort
 
-SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso"]
+SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso", "foff_test"]
 
 
 def relrms(a, b):
@@ -57,7 +57,9 @@ def test_tx_bandpass_and_clip_vs_reference(golden):
 @pytest.mark.parametrize("name", SCENARIOS)
 def test_streaming_receiver_vs_reference(golden, name):
     g = golden("rx_" + name)
-    rx = od.RadaeRx(CoreOraclePort(n_streams=1))
+    # foff_test: the RADE_FOFF_TEST mode of the C API (radae_rx(foff_err=10)): first sync is knocked 10 Hz off, the
+    # unique word fails, the receiver drops out and re-acquires
+    rx = od.RadaeRx(CoreOraclePort(n_streams=1), foff_err=10.0 if name == "foff_test" else 0.0)
     o = 0
     tr = {k: [] for k in ("nin", "ret", "state", "tmax", "fmax", "snr", "uw_errors")}
     zs, fs, eo = [], [], []

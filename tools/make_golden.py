@@ -64,6 +64,10 @@ def make_rx_input(scn, tx_frames, eoo):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="regenerate just this receiver scenario (e.g. foff_test); the other fixtures are left alone")
+    only = ap.parse_args().only
     radae = refenv.load()
     import torch
     sys.path.insert(0, refenv.REF)
@@ -75,6 +79,14 @@ def main():
         from radae import RADAE
     ck = "model19_check3/checkpoints/checkpoint_epoch_100.pth"
 
+    bits = np.sign(np.random.default_rng(65647).random(od.N_EOO_BITS) - 0.5).astype(np.float32)
+    if not only:
+        bits = make_static_fixtures(radae, radae_txe, RADAE, torch, ck)
+    make_rx_scenarios(radae_rxe, ck, bits, only)
+    os.chdir(cwd)
+
+
+def make_static_fixtures(radae, radae_txe, RADAE, torch, ck):
     # ---------------------------------------------------------------- core codec (a1, a2)
     S, T = 2, 24
     feats36 = synth_features(S, 4 * T, seed=1234)
@@ -145,6 +157,10 @@ def main():
         outs.append(np.array(bpf.bpf(sig[o:o + n])).astype(np.complex64)); o += n
     np.savez_compressed(os.path.join(GOLD, "bpf.npz"), x=sig, chunks=np.array(chunks), y=np.concatenate(outs))
 
+    return bits
+
+
+def make_rx_scenarios(radae_rxe, ck, bits, only=""):
     # ---------------------------------------------------------------- streaming receiver scenarios (a7-a11)
     scenarios = {
         "awgn_clean": dict(seed=11, EbNodB=20.0, freq_offset=13.0, lead=2 * od.NMF + 300, n_mf=16),
@@ -152,6 +168,9 @@ def main():
         "mpp_3dB":    dict(seed=13, EbNodB=6.0, freq_offset=-11.0, lead=od.NMF + 100, n_mf=24, multipath=True, gain=0.5),
         "slip_plus":  dict(seed=14, EbNodB=20.0, freq_offset=5.0, lead=od.NMF + 424, n_mf=36, resample=0.995),
         "slip_minus": dict(seed=15, EbNodB=20.0, freq_offset=-3.0, lead=od.NMF + 944, n_mf=36, resample=1.005),
+        # RADE_FOFF_TEST (src/rade_api.c:263-264 -> radae_rx(foff_err=10), radae_rxe.py:271-273): 10 Hz is added to fmax on
+        # the first sync, the decoder sees garbage, the unique word fails and the receiver has to drop sync and re-acquire
+        "foff_test":  dict(seed=16, EbNodB=10.0, freq_offset=7.0, lead=od.NMF + 200, n_mf=48, foff_err=10.0),
     }
     # a real off-air RADE V1 recording shipped with the reference (8 kHz s16); fed the way the
     # reference's ctest does: int16 -> (x, 0) complex, unscaled (int16tof32.py --zeropad, CMakeLists.txt:400-406)
@@ -161,6 +180,8 @@ def main():
         offair = np.frombuffer(w.readframes(12 * 8000), np.int16).copy()
     scenarios["offair_long_qso"] = dict(offair=True)
     for name, scn in scenarios.items():
+        if only and name != only:
+            continue
         if scn.get("offair"):
             rx_in = offair.astype(np.float32).astype(np.complex64)
         else:
@@ -171,7 +192,7 @@ def main():
             frames = [od.transmitter_one(z_all[i]) for i in range(n_mf)]
             rx_in = make_rx_input(scn, frames, od.eoo_frame(bits))
         with refenv.quiet():
-            rxr = radae_rxe.radae_rx(ck, bypass_dec=True, v=0)
+            rxr = radae_rxe.radae_rx(ck, bypass_dec=True, v=0, foff_err=scn.get("foff_err", 0))
         sched = RowSchedule()
         import radae.dsp as rdsp
         class _NP:                       # np proxy whose random.randint is our schedule
@@ -213,7 +234,6 @@ def main():
                             z_hat=np.array(zs, np.float32).reshape(-1, 240), features=np.array(feats_out, np.float32).reshape(-1, 432),
                             eoo=np.array(eoos, np.float32).reshape(-1, od.N_EOO_BITS),
                             **{k: np.array(v) for k, v in trace.items()})
-    os.chdir(cwd)
 
 
 if __name__ == "__main__":
