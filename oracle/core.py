@@ -76,14 +76,19 @@ class CoreOracleRef:
     def available(variant="int8"):
         return os.path.exists(os.path.join(HERE, "_ref", f"librade_ref_{variant}.so"))
 
-    def __init__(self, variant="int8", n_streams=1):
+    def __init__(self, variant="int8", n_streams=1, blob=None, input_dim=84, output_dim=84, bottleneck=3):
+        """blob: a DNNw weight file's bytes (e.g. the reference's bin/model05.bin, loaded the way src/test_rade_enc.c:50-66
+        does) instead of the compiled-in model19_check3 tables; input_dim / output_dim = 4 x (20 features [+ 1 aux symbol]);
+        bottleneck 1 applies tanh to z (src/rade_enc.c:107-113)"""
+        self.in_dim, self.out_dim, self.bottleneck = input_dim, output_dim, bottleneck
         self.lib = lib = _c.CDLL(os.path.join(HERE, "_ref", f"librade_ref_{variant}.so"))
         lib.ref_core_open.restype = _P
-        lib.ref_core_open.argtypes = [_P, _c.c_int, _c.c_int, _c.c_int]
+        lib.ref_core_open.argtypes = [_c.c_char_p, _c.c_int, _c.c_int, _c.c_int]
         lib.ref_core_encode.argtypes = [_P, _P, _c.c_int, _c.c_int, _P, _c.c_int, _P, _c.c_int, _c.c_int]
         lib.ref_core_decode.argtypes = [_P, _P, _c.c_int, _c.c_int, _P, _P, _c.c_int, _c.c_int]
         lib.ref_core_max_abs_acc.restype = _c.c_double
-        self.h = lib.ref_core_open(None, 0, 84, 84)
+        self._blob = bytes(blob) if blob is not None else None
+        self.h = lib.ref_core_open(self._blob, len(self._blob) if self._blob else 0, input_dim, output_dim)
         if not self.h:
             raise RuntimeError("ref_core_open failed")
         self.n = n_streams
@@ -99,14 +104,15 @@ class CoreOracleRef:
         f = np.ascontiguousarray(features, np.float32)
         S, T, _ = f.shape
         z = np.zeros((S, T, 80), np.float32)
-        self.lib.ref_core_encode(self.h, self.enc_state, S, T, f.ctypes.data, 84, z.ctypes.data, 3, nthreads)
+        assert f.shape[2] == self.in_dim
+        self.lib.ref_core_encode(self.h, self.enc_state, S, T, f.ctypes.data, self.in_dim, z.ctypes.data, self.bottleneck, nthreads)
         return z
 
     def decode(self, z, nthreads=1):
         zz = np.ascontiguousarray(z, np.float32)
         S, T, _ = zz.shape
-        f = np.zeros((S, T, 84), np.float32)
-        self.lib.ref_core_decode(self.h, self.dec_state, S, T, zz.ctypes.data, f.ctypes.data, 84, nthreads)
+        f = np.zeros((S, T, self.out_dim), np.float32)
+        self.lib.ref_core_decode(self.h, self.dec_state, S, T, zz.ctypes.data, f.ctypes.data, self.out_dim, nthreads)
         return f
 
     def max_abs_acc(self, reset=False):

@@ -57,3 +57,29 @@ def test_streams_are_independent_and_chunking_is_stateful():
     c = CoreOraclePort(n_streams=S)
     parts = [c.encode(x[:, i:i + 3]) for i in range(0, T, 3)]
     assert np.array_equal(a, np.concatenate(parts, axis=1))
+
+
+def test_model05_reference_c_path_within_the_reference_bar(golden):
+    """second codec configuration of the reference: model05 = 80-wide input / output, bottleneck 1 (tanh on z),
+    weights loaded from the reference's DNNw blob the way src/test_rade_enc.c does.  Golden: tools/make_golden_model05.py.
+    The reference's own ctests accept loss < 0.2 (c_encoder_model5 / c_decoder_model5, CMakeLists.txt:519-545)."""
+    g = golden("core_codec_model05")
+    assert float(g["loss_c_int8"]) < 0.2 and float(g["loss_py"]) < 0.2
+    assert abs(float(g["loss_c_int8"]) - float(g["loss_py"])) < 0.01
+    assert np.abs(g["z_c_int8"]).max() <= 1.0                                   # bottleneck 1: tanh-limited latents
+    assert np.sqrt(np.mean((g["z_c_int8"] - g["z_py"]) ** 2)) < 0.06
+
+
+MODEL05_BLOB = "/root/reference/bin/model05.bin"
+
+
+@pytest.mark.skipif(not (CoreOracleRef.available("int8") and __import__("os").path.exists(MODEL05_BLOB)),
+                    reason="needs oracle/_ref and the reference's bin/model05.bin (CPU container only)")
+def test_model05_blob_through_the_shim_reproduces_golden(golden):
+    g = golden("core_codec_model05")
+    x = np.ascontiguousarray(g["features36"][:, :, :20].reshape(2, -1, 80))
+    with open(MODEL05_BLOB, "rb") as f:
+        r = CoreOracleRef("int8", 2, blob=f.read(), input_dim=80, output_dim=80, bottleneck=1)
+    z = r.encode(x)
+    assert np.array_equal(z, g["z_c_int8"])
+    assert np.array_equal(r.decode(z), g["f_c_int8"])
