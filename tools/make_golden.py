@@ -55,12 +55,27 @@ def make_rx_input(scn, tx_frames, eoo):
     noise = ((rng.standard_normal(T) + 1j * rng.standard_normal(T)) / np.sqrt(2)).astype(np.complex64)
     sigma = od.ebno_sigma(scn["EbNodB"])
     rx = od.channel(tx, G1, G2, 16, 1.0, scn["freq_offset"], 0.3, sigma, noise, gain=scn.get("gain", 1.0))
+    if scn.get("df_dt"):
+        # linear frequency drift on top of the fixed offset (inference.py --df_dt, radae/radae.py:542-553): phase pi*df_dt*t^2
+        t = np.arange(T, dtype=np.float64) / od.FS
+        rx = (rx * np.exp(1j * np.pi * scn["df_dt"] * t * t)).astype(np.complex64)
     lead = scn["lead"]
     nl = ((rng.standard_normal(lead) + 1j * rng.standard_normal(lead)) / np.sqrt(2)).astype(np.complex64)
     tail = scn.get("tail", 2 * od.NMF)
     nt = ((rng.standard_normal(tail) + 1j * rng.standard_normal(tail)) / np.sqrt(2)).astype(np.complex64)
     g = np.float32(scn.get("gain", 1.0) * sigma)
     return np.concatenate([g * nl, rx, g * nt]).astype(np.complex64)
+
+
+def make_no_signal_input(scn):
+    """what the reference's acq_noise / acq_sine ctests feed (CMakeLists.txt:188-208): noise, optionally plus a carrier
+    at 1 kHz -- the receiver must never reach sync"""
+    rng = np.random.default_rng(scn["seed"])
+    T = scn["n_mf"] * od.NMF
+    x = ((rng.standard_normal(T) + 1j * rng.standard_normal(T)) / np.sqrt(2)).astype(np.complex64) * np.float32(scn["noise_rms"])
+    if scn.get("sine_amp"):
+        x = x + (scn["sine_amp"] * np.exp(2j * np.pi * scn["sine_freq"] * np.arange(T) / od.FS)).astype(np.complex64)
+    return x.astype(np.complex64)
 
 
 def main():
@@ -171,6 +186,12 @@ def make_rx_scenarios(radae_rxe, ck, bits, only=""):
         # RADE_FOFF_TEST (src/rade_api.c:263-264 -> radae_rx(foff_err=10), radae_rxe.py:271-273): 10 Hz is added to fmax on
         # the first sync, the decoder sees garbage, the unique word fails and the receiver has to drop sync and re-acquire
         "foff_test":  dict(seed=16, EbNodB=10.0, freq_offset=7.0, lead=od.NMF + 200, n_mf=48, foff_err=10.0),
+        # frequency drift (ctest radae_rx_dfdt, CMakeLists.txt:363-371, there 0.1 Hz/s over minutes; here 0.5 Hz/s over 6 s so
+        # that the tracked fmax visibly has to move) at the low-SNR operating point
+        "dfdt":       dict(seed=17, EbNodB=1.0, freq_offset=13.0, df_dt=0.5, lead=od.NMF + 700, n_mf=48),
+        # no signal present (ctests acq_noise / acq_sine, CMakeLists.txt:188-208): the receiver must stay out of sync
+        "noise_only": dict(seed=18, no_signal=True, noise_rms=0.7, n_mf=40),
+        "sine_noise": dict(seed=19, no_signal=True, noise_rms=0.5, sine_amp=1.0, sine_freq=1000.0, n_mf=40),
     }
     # a real off-air RADE V1 recording shipped with the reference (8 kHz s16); fed the way the
     # reference's ctest does: int16 -> (x, 0) complex, unscaled (int16tof32.py --zeropad, CMakeLists.txt:400-406)
@@ -184,6 +205,8 @@ def make_rx_scenarios(radae_rxe, ck, bits, only=""):
             continue
         if scn.get("offair"):
             rx_in = offair.astype(np.float32).astype(np.complex64)
+        elif scn.get("no_signal"):
+            rx_in = make_no_signal_input(scn)
         else:
             n_mf = scn["n_mf"]
             feats = synth_features(1, 12 * n_mf, seed=100 + scn["seed"])
