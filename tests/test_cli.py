@@ -1,0 +1,67 @@
+"""The streaming command-line entry points (python -m radae_b200.radae_txe / radae_rxe) mirror the reference's scripts
+(/root/reference/radae_txe.py:145-182, radae_rxe.py:332-378): same flags, same stdin / stdout record formats."""
+import io
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_cli(mod, args, data=b""):
+    env = dict(os.environ, PYTHONPATH=REPO)
+    return subprocess.run([sys.executable, "-m", mod] + args, input=data, capture_output=True, cwd=REPO, env=env, timeout=300)
+
+
+def test_cli_flags_match_the_reference_scripts():
+    tx = run_cli("radae_b200.radae_txe", ["--help"])
+    rx = run_cli("radae_b200.radae_rxe", ["--help"])
+    assert tx.returncode == 0 and rx.returncode == 0
+    for flag in ("--model_name", "--noauxdata", "--txbpf", "--bypass_enc", "--eoo_data_test"):
+        assert flag in tx.stdout.decode(), flag
+    for flag in ("--model_name", "--noauxdata", "-v", "--disable_unsync", "--no_stdout", "--foff_err", "--bypass_dec", "--eoo_data_test"):
+        assert flag in rx.stdout.decode(), flag
+
+
+def test_cli_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run_cli("radae_b200.radae_txe", [], np.zeros(432, np.float32).tobytes())
+    assert r.returncode != 0 and r.stdout == b""
+    assert b"no CPU fallback" in r.stderr
+
+
+def test_eoo_test_bits_are_the_reference_pattern(golden):
+    """both scripts of the reference seed default_rng(65647) (radae_txe.py:158-160, radae_rxe.py:366-368); the golden TX
+    fixture was generated from that very pattern"""
+    from radae_b200.radae_txe import eoo_test_bits
+    assert np.array_equal(eoo_test_bits(180), golden("tx")["eoo_bits"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
+                    reason="added after the round's GPU budget was spent; enable with RADE_B200_RUN_UNVALIDATED=1, drop the gate once green")
+def test_cli_pipe_tx_into_rx(golden):
+    """features -> radae_txe --eoo_data_test | radae_rxe --eoo_data_test: frames equal the in-process objects', EOO test passes"""
+    from gpu_util import need_gpu
+    need_gpu()
+    from radae_b200 import radae_tx
+    g = golden("tx")
+    feats = np.tile(g["features36"][0].reshape(-1, 432), (3, 1))          # 18 modem frames
+    tx = run_cli("radae_b200.radae_txe", ["--eoo_data_test"], feats.astype(np.float32).tobytes())
+    assert tx.returncode == 0, tx.stderr.decode()
+    iq = np.frombuffer(tx.stdout, np.complex64)
+    assert iq.size == feats.shape[0] * 960 + 2 * 1152
+    ref = radae_tx(); out = np.zeros(960, np.complex64)
+    for i in range(feats.shape[0]):
+        ref.do_radae_tx(feats[i], out)
+        assert np.array_equal(out, iq[i * 960:(i + 1) * 960]), i
+    ref.close()
+    rx = run_cli("radae_b200.radae_rxe", ["--eoo_data_test", "-v", "0"], tx.stdout)
+    assert rx.returncode == 0, rx.stderr.decode()
+    assert b"PASS" in rx.stderr
+    n = len(rx.stdout) // (432 * 4)
+    assert n >= feats.shape[0] - 6                                          # acquisition takes a few frames
