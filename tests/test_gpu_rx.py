@@ -353,9 +353,10 @@ def test_foff_test_flag_false_sync_and_reacquisition(golden):
 @pytest.mark.skipif(__import__("os").environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
                     reason="scenarios added after the round's GPU budget was spent; their oracle side is pinned against the "
                            "reference on CPU (test_oracle_dsp.py); enable with RADE_B200_RUN_UNVALIDATED=1, drop the gate once green")
-@pytest.mark.parametrize("name", ["dfdt", "noise_only", "sine_noise"])
+@pytest.mark.parametrize("name", ["dfdt", "noise_only", "sine_noise", "mpd_fading"])
 def test_more_reference_scenarios_single_stream(golden, name):
-    """frequency drift at 1 dB Eb/No (ctest radae_rx_dfdt) and the two must-not-acquire inputs (acq_noise, acq_sine)"""
+    """frequency drift at 1 dB Eb/No (ctest radae_rx_dfdt), the two must-not-acquire inputs (acq_noise, acq_sine) and fast
+    fading with a 4 ms delay spread (radae_rx_mpd: the two paths keep the candidate check bouncing for 4 s)"""
     need_gpu()
     g = golden("rx_" + name)
     tr, feats, eoos = run_single(g)

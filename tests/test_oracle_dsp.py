@@ -6,7 +6,7 @@ from oracle import dsp as od
 from oracle.core import CoreOraclePort
 
 SCENARIOS = ["awgn_clean", "awgn_1dB", "mpp_3dB", "slip_plus", "slip_minus", "offair_long_qso", "foff_test",
-             "dfdt", "noise_only", "sine_noise"]
+             "dfdt", "noise_only", "sine_noise", "mpd_fading"]
 
 
 def relrms(a, b):
