@@ -134,6 +134,7 @@ umma_probe(const int8_t *__restrict__ A_rm, const int8_t *__restrict__ B_rm, int
       if (lane == 0) { umma_i8(tmem, smem_desc(a0, LBO, SBO), smem_desc(b0, LBO, SBO), idesc, 0); umma_commit(&bar); }
       __syncwarp();
       mbar_wait(&bar, phase); phase ^= 1;
+      __syncwarp();                                      // tcgen05.ld is warp-collective (.sync.aligned)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int v[8];
       tmem_ld8(tmem, v);
