@@ -343,6 +343,20 @@ def run_gpu(args):
         cpu_base = {"value": rate, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
                     "note": "numpy DSP restatement + " + ("reference rade_enc.c/rade_dec.c on the nnet shim" if kind == "reference" else "C core port")}
 
+    try:
+        # the math-pipe figure SURVEY.md §8(d) asks for next to the HBM fraction: F/s x FLOP per F / peak, with the survey's own
+        # work table (enc+dec 1 838 720 MAC per F; full synced pipeline ~2.95 M MAC per F) against the fp32 CUDA-core peak of
+        # this device (SMs x 128 lanes x 2 flop x SM clock); per GPU, so it does not change with the number of ranks
+        props = torch.cuda.get_device_properties(local)
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak_tf = props.multi_processor_count * 128 * 2 * float(mhz) * 1e6 / 1e12
+        flop_per_F = 2 * (1838720 if codec_only else 2950000)
+        ach_tf = (value / world) * flop_per_F / 1e12
+        roofline["math"] = {"flop_per_frame": flop_per_F, "achieved_tflops": round(ach_tf, 2), "peak_tflops": round(peak_tf, 1),
+                            "frac": round(ach_tf / peak_tf, 4),
+                            "peak": "fp32 FMA peak of one GPU at the sampled SM clock; the codec's MACs actually run as int8 IMMA"}
+    except Exception:
+        pass
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
