@@ -71,7 +71,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
 // `iters` passes of 8 MMAs, cyc[1] = cycles of `chain` dependent single-MMA round trips
 __global__ void __launch_bounds__(128, 1)
 umma_probe(const int8_t *__restrict__ A_rm, const int8_t *__restrict__ B_rm, int N, int iters, int chain,
-           int *__restrict__ D, long long *__restrict__ cyc) {
+           int *__restrict__ D, long long *__restrict__ cyc, int swap_lbo_sbo) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sA = smem;                              // M * K_TOTAL
   uint8_t *sB = smem + M * K_TOTAL;                // N * K_TOTAL
@@ -79,6 +79,8 @@ umma_probe(const int8_t *__restrict__ A_rm, const int8_t *__restrict__ B_rm, int
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   constexpr uint32_t LBO = 128, SBO = K_TOTAL * 8;
+  // diagnostic: should the descriptor fields be the other way round on this toolchain / hardware, the host tries both
+  const uint32_t DL = swap_lbo_sbo ? SBO : LBO, DS = swap_lbo_sbo ? LBO : SBO;
 
   for (int i = tid; i < M * K_TOTAL; i += 128) { int r = i / K_TOTAL, b = i % K_TOTAL; sA[(r / 8) * SBO + (b / 16) * LBO + (r % 8) * 16 + b % 16] = A_rm[i]; }
   for (int i = tid; i < N * K_TOTAL; i += 128) { int r = i / K_TOTAL, b = i % K_TOTAL; sB[(r / 8) * SBO + (b / 16) * LBO + (r % 8) * 16 + b % 16] = B_rm[i]; }
@@ -103,7 +105,7 @@ umma_probe(const int8_t *__restrict__ A_rm, const int8_t *__restrict__ B_rm, int
       for (int it = 0; it < iters; it++)
 #pragma unroll
         for (int k = 0; k < K_TOTAL / K_MMA; k++)
-          umma_i8(tmem, smem_desc(a0 + k * 2 * LBO, LBO, SBO), smem_desc(b0 + k * 2 * LBO, LBO, SBO), idesc, (it | k) != 0);
+          umma_i8(tmem, smem_desc(a0 + k * 2 * LBO, DL, DS), smem_desc(b0 + k * 2 * LBO, DL, DS), idesc, (it | k) != 0);
       umma_commit(&bar);
     }
     __syncwarp();
@@ -131,7 +133,7 @@ umma_probe(const int8_t *__restrict__ A_rm, const int8_t *__restrict__ B_rm, int
     int sink = 0;
     long long t0 = clock64();
     for (int i = 0; i < chain; i++) {
-      if (lane == 0) { umma_i8(tmem, smem_desc(a0, LBO, SBO), smem_desc(b0, LBO, SBO), idesc, 0); umma_commit(&bar); }
+      if (lane == 0) { umma_i8(tmem, smem_desc(a0, DL, DS), smem_desc(b0, DL, DS), idesc, 0); umma_commit(&bar); }
       __syncwarp();
       mbar_wait(&bar, phase); phase ^= 1;
       __syncwarp();                                      // tcgen05.ld is warp-collective (.sync.aligned)
@@ -169,15 +171,20 @@ int main() {
       std::vector<int> hD(M * N);
       long long hC[2];
       // pass 1: iters = 1 for the exactness check (int32 would not overflow either way), pass 2: timing
-      umma_probe<<<grid, 128, (M + N) * K_TOTAL>>>(dA, dB, N, 1, 1, dD, dC);
-      CK(cudaDeviceSynchronize());
-      CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
-      long bad = 0;
-      for (int m = 0; m < M; m++) for (int n = 0; n < N; n++) {
-        int ref = 0; for (int k = 0; k < K_TOTAL; k++) ref += (int)hA[m * K_TOTAL + k] * (int)hB[n * K_TOTAL + k];
-        bad += ref != hD[m * N + n];
+      long bad = 0, bad_swapped = 0;
+      for (int swap = 1; swap >= 0; swap--) {             // ends with the documented field order
+        umma_probe<<<grid, 128, (M + N) * K_TOTAL>>>(dA, dB, N, 1, 1, dD, dC, swap);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+        long nb = 0;
+        for (int m = 0; m < M; m++) for (int n = 0; n < N; n++) {
+          int ref = 0; for (int k = 0; k < K_TOTAL; k++) ref += (int)hA[m * K_TOTAL + k] * (int)hB[n * K_TOTAL + k];
+          nb += ref != hD[m * N + n];
+        }
+        (swap ? bad_swapped : bad) = nb;
       }
-      umma_probe<<<grid, 128, (M + N) * K_TOTAL>>>(dA, dB, N, iters, chain, dD, dC);
+      if (bad && !bad_swapped) printf("  NOTE: exact only with LBO and SBO exchanged in the descriptors\n");
+      umma_probe<<<grid, 128, (M + N) * K_TOTAL>>>(dA, dB, N, iters, chain, dD, dC, 0);
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(hC, dC, 16, cudaMemcpyDeviceToHost));
       printf("M=128 N=%3d grid=%3d: %s (%ld mismatches)  %.2f cyc/MMA back to back (floor %d)  %.0f cyc per dependent link\n", N, grid,
