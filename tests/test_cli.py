@@ -65,3 +65,16 @@ def test_cli_pipe_tx_into_rx(golden):
     assert b"PASS" in rx.stderr
     n = len(rx.stdout) // (432 * 4)
     assert n >= feats.shape[0] - 6                                          # acquisition takes a few frames
+
+
+def test_mirror_classes_refuse_what_the_device_path_does_not_implement():
+    """unsupported reference options raise instead of silently doing something else (checked before any device is touched)"""
+    from radae_b200 import radae_tx, radae_rx
+    for kw in (dict(latent_dim=40), dict(auxdata=False), dict(bottleneck=1)):
+        with pytest.raises(NotImplementedError):
+            radae_tx(**kw)
+        with pytest.raises(NotImplementedError):
+            radae_rx(**kw)
+    for kw in (dict(bpf_en=False), dict(disable_unsync=True), dict(foff_err=3.0)):
+        with pytest.raises(NotImplementedError):
+            radae_rx(**kw)
