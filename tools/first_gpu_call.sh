@@ -9,9 +9,9 @@ echo "== gated GPU tests (foff_test, dfdt, noise_only, sine_noise, mpd_fading, C
 RADE_B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/first_call_pytest.log
 echo "== tcgen05 probes"
 cd tools/microbench
-for p in umma_i8_swapab umma_gru_layer umma_conv_layer umma_tf32_probe umma_tf32_refresh; do
+for p in umma_i8_swapab umma_gru_layer umma_conv_layer umma_gru_chain umma_tf32_probe umma_tf32_refresh; do
   extra=""
-  case $p in umma_gru_layer|umma_conv_layer) extra="-Xcompiler -ffp-contract=off";; esac
+  case $p in umma_gru_layer|umma_conv_layer|umma_gru_chain) extra="-Xcompiler -ffp-contract=off";; esac
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo $extra -o $p $p.cu 2>&1 | grep -i error
   timeout 60 ./$p 2>&1 | tee ../../gpurun_out/first_call_$p.log
 done
