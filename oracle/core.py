@@ -28,7 +28,9 @@ class CoreOraclePort:
     """Stateful multi-stream core encoder/decoder; features [S,T,84] <-> z [S,T,80]."""
     kind = "port"
 
-    def __init__(self, rdw_path=None, n_streams=1):
+    def __init__(self, rdw_path=None, n_streams=1, bottleneck=3):
+        """rdw_path: default model19_check3; an RDW of a model without the aux symbol (model05) makes the rows 80 wide;
+        bottleneck 1 applies tanh to z (src/rade_enc.c:107-113)"""
         path = os.path.join(HERE, "_ref", "libcore_oracle.so")
         if not os.path.exists(path):
             ensure_built()
@@ -40,6 +42,10 @@ class CoreOraclePort:
         self.h = lib.oracle_core_open((rdw_path or _rdw_default()).encode())
         if not self.h:
             raise RuntimeError("oracle_core_open failed")
+        lib.oracle_core_set_bottleneck.argtypes = [_P, _c.c_int]
+        lib.oracle_core_enc_in.argtypes = [_P]; lib.oracle_core_dec_out.argtypes = [_P]
+        lib.oracle_core_set_bottleneck(self.h, bottleneck)
+        self.in_dim, self.out_dim = lib.oracle_core_enc_in(self.h), lib.oracle_core_dec_out(self.h)
         self.n = n_streams
         self.reset()
 
@@ -50,7 +56,7 @@ class CoreOraclePort:
     def encode(self, features, nthreads=1, want_cat=False):
         f = np.ascontiguousarray(features, np.float32)
         S, T, _ = f.shape
-        assert S == self.n and f.shape[2] == 84
+        assert S == self.n and f.shape[2] == self.in_dim
         z = np.zeros((S, T, 80), np.float32)
         cat = np.zeros((S, T, 864), np.float32) if want_cat else None
         self.lib.oracle_core_encode(self.h, self.enc_state.ctypes.data, S, T, f.ctypes.data, z.ctypes.data,
@@ -61,7 +67,7 @@ class CoreOraclePort:
         zz = np.ascontiguousarray(z, np.float32)
         S, T, _ = zz.shape
         assert S == self.n and zz.shape[2] == 80
-        f = np.zeros((S, T, 84), np.float32)
+        f = np.zeros((S, T, self.out_dim), np.float32)
         cat = np.zeros((S, T, 736), np.float32) if want_cat else None
         self.lib.oracle_core_decode(self.h, self.dec_state.ctypes.data, S, T, zz.ctypes.data, f.ctypes.data,
                                     cat.ctypes.data if want_cat else None, nthreads)

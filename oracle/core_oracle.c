@@ -38,6 +38,8 @@ typedef struct { const int8_t *w8; const float *scale; const float *bias; const 
 
 typedef struct {
   unsigned char *blob;
+  int enc_in, dec_out;      /* 84 / 84 (model19_check3) or 80 / 80 (no aux symbol: the reference's model05) */
+  int bottleneck;           /* 3: linear latents, 1: tanh (src/rade_enc.c:107-113) */
   layer_t enc_dense1, enc_zdense, enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
   layer_t dec_dense1, dec_output, dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
 } model_t;
@@ -94,10 +96,16 @@ API void *oracle_core_open(const char *rdw_path)
   m->blob = (unsigned char*)malloc(len);
   if (fread(m->blob, 1, len, f) != (size_t)len || memcmp(m->blob, "RADEB200", 8) != 0) { fclose(f); return NULL; }
   fclose(f);
-  bad |= load_layer(m, &m->enc_dense1, "enc_dense1", ENC_IN, 64, 1);
+  {
+    uint32_t r = 0, c = 0;
+    m->enc_in = (find(m, "enc_dense1.wf", &r, &c) && r == 80) ? 80 : ENC_IN;
+    m->dec_out = (find(m, "dec_output.bias", &r, &c) && c == 80) ? 80 : DEC_OUT;
+    m->bottleneck = 3;
+  }
+  bad |= load_layer(m, &m->enc_dense1, "enc_dense1", m->enc_in, 64, 1);
   bad |= load_layer(m, &m->enc_zdense, "enc_zdense", ENC_CAT, ENC_Z, 1);
   bad |= load_layer(m, &m->dec_dense1, "dec_dense1", DEC_IN, 96, 1);
-  bad |= load_layer(m, &m->dec_output, "dec_output", DEC_CAT, DEC_OUT, 1);
+  bad |= load_layer(m, &m->dec_output, "dec_output", DEC_CAT, m->dec_out, 1);
   for (i=0;i<5;i++) {
     snprintf(nm, sizeof nm, "enc_gru%d_input", i+1);     bad |= load_layer(m, &m->enc_gru_in[i], nm, enc_k[i], 192, 0);
     snprintf(nm, sizeof nm, "enc_gru%d_recurrent", i+1); bad |= load_layer(m, &m->enc_gru_rec[i], nm, 64, 192, 0);
@@ -111,6 +119,9 @@ API void *oracle_core_open(const char *rdw_path)
   return m;
 }
 
+API void oracle_core_set_bottleneck(void *h, int bottleneck) { ((model_t*)h)->bottleneck = bottleneck; }
+API int oracle_core_enc_in(void *h) { return ((model_t*)h)->enc_in; }
+API int oracle_core_dec_out(void *h) { return ((model_t*)h)->dec_out; }
 API void oracle_core_close(void *h) { model_t *m = (model_t*)h; if (m) { free(m->blob); free(m); } }
 
 /* ---------- primitives (restating nnet_shim.c with unblocked weights) ---------- */
@@ -202,7 +213,8 @@ static void enc_step(const model_t *m, float *st, const float *feat, float *z, f
     conv_step(&m->enc_conv[i], cat + off, conv, cat, off, ENC_DIL[i]);
     conv += ENC_DIL[i]*off; off += 96;
   }
-  linear_f32(&m->enc_zdense, z, cat);                            /* bottleneck 3: linear (src/rade_enc.c:107-113) */
+  linear_f32(&m->enc_zdense, z, cat);                            /* bottleneck 3: linear, 1: tanh (src/rade_enc.c:107-113) */
+  if (m->bottleneck == 1) for (i=0;i<ENC_Z;i++) z[i] = tanh_rational(z[i]);
   if (cat_out) memcpy(cat_out, cat, sizeof cat);
 }
 
@@ -238,7 +250,7 @@ API void oracle_core_encode(void *h, float *states, int n_streams, int n_steps,
     int t;
     for (t=0;t<n_steps;t++) {
       size_t k = (size_t)s*n_steps + t;
-      enc_step(m, states + (size_t)s*oracle_enc_state_floats(), features + k*ENC_IN, z + k*ENC_Z, cat ? cat + k*ENC_CAT : NULL);
+      enc_step(m, states + (size_t)s*oracle_enc_state_floats(), features + k*m->enc_in, z + k*ENC_Z, cat ? cat + k*ENC_CAT : NULL);
     }
   }
 }
@@ -252,7 +264,7 @@ API void oracle_core_decode(void *h, float *states, int n_streams, int n_steps,
     int t;
     for (t=0;t<n_steps;t++) {
       size_t k = (size_t)s*n_steps + t;
-      dec_step(m, states + (size_t)s*oracle_dec_state_floats(), z + k*DEC_IN, features + k*DEC_OUT, cat ? cat + k*DEC_CAT : NULL);
+      dec_step(m, states + (size_t)s*oracle_dec_state_floats(), z + k*DEC_IN, features + k*m->dec_out, cat ? cat + k*DEC_CAT : NULL);
     }
   }
 }

@@ -80,6 +80,11 @@ def dnnw_to_arrays(buf):
     arrays = {}
     for name, nin, nout, kind in ALL_LAYERS:
         arrays[f"{name}.bias"] = raw[f"{name}_bias"][1].astype(np.float32)
+        # models without the auxiliary symbol (the reference's bin/model05.bin): 80 encoder inputs / decoder outputs
+        if name == "enc_dense1" and raw[f"{name}_weights_float"][1].size == 80 * nout:
+            nin = 80
+        if name == "dec_output" and arrays[f"{name}.bias"].size == 80:
+            nout = 80
         if kind == "f32":
             wf = raw[f"{name}_weights_float"][1]
             arrays[f"{name}.wf"] = wf.reshape(nin, nout).astype(np.float32)
@@ -130,3 +135,9 @@ def read_rdw(path_or_bytes):
 def default_weights_path():
     import os
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights", "model19_check3.rdw")
+
+
+def model05_weights_path():
+    """the reference's second shipped core codec (bin/model05.bin: no aux symbol, bottleneck 1), converted by tools/export_weights.py"""
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights", "model05.rdw")

@@ -83,3 +83,15 @@ def test_model05_blob_through_the_shim_reproduces_golden(golden):
     z = r.encode(x)
     assert np.array_equal(z, g["z_c_int8"])
     assert np.array_equal(r.decode(z), g["f_c_int8"])
+
+
+def test_port_runs_model05_bit_exact_vs_reference_golden(golden):
+    """the C port on radae_b200/weights/model05.rdw (80-wide rows, bottleneck 1) == the reference C sources on bin/model05.bin"""
+    from radae_b200 import rdw
+    g = golden("core_codec_model05")
+    x = np.ascontiguousarray(g["features36"][:, :, :20].reshape(2, -1, 80))
+    o = CoreOraclePort(rdw.model05_weights_path(), n_streams=2, bottleneck=1)
+    assert (o.in_dim, o.out_dim) == (80, 80)
+    z = o.encode(x)
+    assert np.array_equal(z, g["z_c_int8"])
+    assert np.array_equal(o.decode(z), g["f_c_int8"])

@@ -56,7 +56,11 @@ def derive_from_pth(ckpt_path):
 
     def glu(prefix, name):
         # weight_norm parametrisation: original0 = g [out,1], original1 = v [out,in]; w = g * v/||v|| per output row
-        gg, v = g(f"{prefix}.parametrizations.weight.original0"), g(f"{prefix}.parametrizations.weight.original1")
+        # (older checkpoints such as model05 still carry the pre-parametrisation names weight_g / weight_v)
+        if f"{prefix}.weight_g" in sd:
+            gg, v = g(f"{prefix}.weight_g"), g(f"{prefix}.weight_v")
+        else:
+            gg, v = g(f"{prefix}.parametrizations.weight.original0"), g(f"{prefix}.parametrizations.weight.original1")
         import torch as _t
         w = _t._weight_norm(_t.tensor(v), _t.tensor(gg), 0).numpy()
         lin_q(name, w.T, np.zeros(w.shape[0], np.float32))
@@ -96,7 +100,7 @@ def main():
                 worst = max(worst, d)
                 assert d <= 1e-6 * max(1.0, float(np.abs(a).max())), f"{k}: float mismatch {d}"
         print(f"verify-pth: {len(arrays)} arrays, int8 exact, worst float abs diff {worst:.3g}")
-    rdw.write_rdw(args.out, arrays)
+    rdw.write_rdw(args.out, arrays, model_name=os.path.splitext(os.path.basename(args.blob))[0])
     back = rdw.read_rdw(args.out)
     assert all(np.array_equal(back[k], arrays[k]) for k in arrays)
     print(f"wrote {args.out}: {len(arrays)} arrays, {os.path.getsize(args.out)} bytes")
