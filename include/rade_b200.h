@@ -19,7 +19,13 @@ extern "C" {
 typedef struct rade_batch rade_batch;
 
 /* weights: NULL/0 -> the RDW blob embedded in the library; else an RDW v1 or DNNw blob in host memory
- * (what a caller receives from the one-off ncclBroadcast at start-up).  device < 0 -> current device. */
+ * (what a caller receives from the one-off ncclBroadcast at start-up).  device < 0 -> current device.
+ * flags: the rade_api.h flags, plus RADE_B200_BOTTLENECK_1 for core-codec weights trained with bottleneck 1 (tanh on the
+ * latents, src/rade_enc.c:107-113): the reference's second shipped model, bin/model05.bin, as driven by
+ * `test_rade_enc 1 0 model05.bin` / `test_rade_dec 0 model05.bin` (CMakeLists.txt:519-545).  Such a model has no auxiliary
+ * symbol, so rade_b200_core_encode / _decode exchange 80-float rows with the host (rade_b200_core_dims); the modem entry
+ * points (rade_b200_tx / _rx ...) are defined for the RADE V1 waveform (model19_check3) only. */
+#define RADE_B200_BOTTLENECK_1 0x100
 RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, const void *weights, size_t weights_len);
 RADE_EXPORT void rade_b200_close(rade_batch *b);
 RADE_EXPORT int rade_b200_n_streams(rade_batch *b);
@@ -31,6 +37,9 @@ RADE_EXPORT int rade_b200_reset(rade_batch *b);                         /* all s
 
 /* --- core codec only (rade_core_encoder / rade_core_decoder, src/rade_core.h:42-49), n_steps 40 ms steps ---
  * features [S][n_steps][84] (4 x (20 features + aux)), z [S][n_steps][80] */
+/* row widths of the loaded model on the HOST side of rade_b200_core_encode / _decode: 84 / 84 (model19_check3) or 80 / 80
+ * (a model without the aux symbol); the _dev entry points always use 84-float rows (unused inputs zero, unused outputs 0) */
+RADE_EXPORT int rade_b200_core_dims(rade_batch *b, int *input_dim, int *output_dim);
 RADE_EXPORT int rade_b200_core_encode_dev(rade_batch *b, float *d_z, const float *d_features, int n_steps);
 RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, const float *d_z, int n_steps);
 RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *features, int n_steps);

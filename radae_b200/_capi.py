@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libradae_b200.so")
 
 NMF, NEOO, NIN_MAX, NFEAT, NEOO_BITS, LATENT, NZMF = 960, 1152, 1120, 432, 180, 80, 3
 RADE_USE_C_ENCODER, RADE_USE_C_DECODER, RADE_FOFF_TEST, RADE_VERBOSE_0 = 1, 2, 4, 8
+RADE_B200_BOTTLENECK_1 = 0x100
 
 
 class RxStatus(C.Structure):
@@ -42,6 +43,7 @@ SIGNATURES = {
     "rade_b200_n_streams": (_I, [_P]), "rade_b200_cuda_stream": (_P, [_P]), "rade_b200_synchronize": (_I, [_P]),
     "rade_b200_launch_count": (C.c_longlong, [_P]), "rade_b200_default_weights_blob": (_P, [C.POINTER(C.c_size_t)]),
     "rade_b200_reset": (_I, [_P]),
+    "rade_b200_core_dims": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "rade_b200_core_encode_dev": (_I, [_P, _P, _P, _I]), "rade_b200_core_decode_dev": (_I, [_P, _P, _P, _I]),
     "rade_b200_core_encode": (_I, [_P, _P, _P, _I]), "rade_b200_core_decode": (_I, [_P, _P, _P, _I]),
     "rade_b200_tx_dev": (_I, [_P, _P, _P]), "rade_b200_tx": (_I, [_P, _P, _P]),

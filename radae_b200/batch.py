@@ -58,10 +58,16 @@ class RadeBatch:
         _check(self.lib.rade_b200_reset(self.h), "reset")
 
     # ---- core codec (host arrays)
+    def core_dims(self):
+        """(input_dim, output_dim) of the loaded core codec on the host side: (84, 84), or (80, 80) for a model without the aux symbol"""
+        i, o = C.c_int(0), C.c_int(0)
+        _check(self.lib.rade_b200_core_dims(self.h, C.byref(i), C.byref(o)), "core_dims")
+        return i.value, o.value
+
     def core_encode(self, features):
         f, pf = _np(features, np.float32)
         S, T, K = f.shape
-        assert S == self.S and K == 84
+        assert S == self.S and K == self.core_dims()[0]
         z = np.empty((S, T, 80), np.float32)
         _check(self.lib.rade_b200_core_encode(self.h, z.ctypes.data, pf, T), "core_encode")
         return z
@@ -70,7 +76,7 @@ class RadeBatch:
         zz, pz = _np(z, np.float32)
         S, T, K = zz.shape
         assert S == self.S and K == 80
-        f = np.empty((S, T, 84), np.float32)
+        f = np.empty((S, T, self.core_dims()[1]), np.float32)
         _check(self.lib.rade_b200_core_decode(self.h, f.ctypes.data, pz, T), "core_decode")
         return f
 

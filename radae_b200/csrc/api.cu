@@ -143,6 +143,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
       cudaEventCreateWithFlags(&b->rx.ev_join, cudaEventDisableTiming) != cudaSuccess) { delete b; return nullptr; }
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
+  b->weights.dev.enc_z_tanh = (flags & RADE_B200_BOTTLENECK_1) ? 1 : 0;      // src/rade_enc.c:107-113
   DspTablesHost th; dsp_tables_host(th);
   if (dsp_tables_upload(th, &b->tables, b->allocs) < 0) { delete b; return nullptr; }
   const size_t S = n_streams;
@@ -259,11 +260,23 @@ RADE_EXPORT int rade_b200_core_decode_dev(rade_batch *b, float *d_features, cons
   b->launches += 1;
   return 0;
 }
+RADE_EXPORT int rade_b200_core_dims(rade_batch *b, int *input_dim, int *output_dim) {
+  if (input_dim) *input_dim = b->weights.input_dim;
+  if (output_dim) *output_dim = b->weights.output_dim;
+  return 0;
+}
 RADE_EXPORT int rade_b200_core_encode(rade_batch *b, float *z, const float *features, int n_steps) {
   cudaSetDevice(b->device);        // the current device is per host thread
-  const size_t nin = (size_t)b->S * n_steps * ENC_IN, nout = (size_t)b->S * n_steps * RADE_LATENT;
+  const size_t rows = (size_t)b->S * n_steps, nin = rows * ENC_IN, nout = rows * RADE_LATENT;
+  const int w = b->weights.input_dim;                 // caller's row width: 84, or 80 for a model without the aux symbol
   if (ensure_core_staging(b, nin) < 0) return -1;
-  CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, features, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  if (w == ENC_IN) {
+    CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, features, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  } else {                                            // widen to the kernels' 84-float rows, missing inputs = 0
+    CUDA_CHECK(cudaMemsetAsync(b->d_core_in, 0, nin * sizeof(float), b->stream));
+    CUDA_CHECK(cudaMemcpy2DAsync(b->d_core_in, ENC_IN * sizeof(float), features, w * sizeof(float), w * sizeof(float), rows,
+                                 cudaMemcpyHostToDevice, b->stream));
+  }
   if (rade_b200_core_encode_dev(b, b->d_core_out, b->d_core_in, n_steps) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(z, b->d_core_out, nout * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
@@ -275,7 +288,13 @@ RADE_EXPORT int rade_b200_core_decode(rade_batch *b, float *features, const floa
   if (ensure_core_staging(b, nout) < 0) return -1;
   CUDA_CHECK(cudaMemcpyAsync(b->d_core_in, z, nin * sizeof(float), cudaMemcpyHostToDevice, b->stream));
   if (rade_b200_core_decode_dev(b, b->d_core_out, b->d_core_in, n_steps) < 0) return -1;
-  CUDA_CHECK(cudaMemcpyAsync(features, b->d_core_out, nout * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  const int w = b->weights.output_dim;
+  if (w == DEC_OUT) {
+    CUDA_CHECK(cudaMemcpyAsync(features, b->d_core_out, nout * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+  } else {                                            // hand back the model's own 80-float rows
+    CUDA_CHECK(cudaMemcpy2DAsync(features, w * sizeof(float), b->d_core_out, DEC_OUT * sizeof(float), w * sizeof(float),
+                                 (size_t)b->S * n_steps, cudaMemcpyDeviceToHost, b->stream));
+  }
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return 0;
 }

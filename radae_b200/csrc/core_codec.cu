@@ -410,11 +410,13 @@ core_encoder_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const 
         bar_arrive(BAR_SEG_EMPTY + 0, NCT);
         off += ENC_CONV;
       }
-      // ---- z = zdense(cat) + b   (bottleneck 3: linear, src/rade_enc.c:107-113)
+      // ---- z = zdense(cat) + b   (bottleneck 3: linear; bottleneck 1: tanh -- src/rade_enc.c:107-113)
       if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / OPT) {
 #pragma unroll
-        for (int i = 0; i < OPT; i++)
-          z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
+        for (int i = 0; i < OPT; i++) {
+          const float v = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
+          z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = W.enc_z_tanh ? tanh_r(v) : v;
+        }
       }
     }
     return;

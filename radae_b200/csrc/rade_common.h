@@ -77,6 +77,7 @@ struct CoreWeightsDev {
   I8LayerDev enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
   CodecStreamDev enc_stream, dec_stream;
+  int enc_z_tanh;          // bottleneck 1 (model05): tanh on the latents, src/rade_enc.c:107-113; 0 for bottleneck 3
 };
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \

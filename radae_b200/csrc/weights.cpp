@@ -78,6 +78,10 @@ bool parse_dnnw(const unsigned char *buf, size_t len, ArrayMap &out) {
       auto it = raw.find(k);
       return (it != raw.end() && (size_t)it->second.size == bytes) ? it->second.p : nullptr;
     };
+    // models without the auxiliary symbol (model05, src/test_rade_enc.c:40): enc_dense1 has 80 inputs, dec_output 80 outputs;
+    // they are ingested as they are and widened with zeros by normalise_io_width() below
+    if (n == "enc_dense1" && !need(n + "_weights_float", 4 * (size_t)L.nin * L.nout)) L.nin = 80;
+    if (n == "dec_output" && !need(n + "_bias", 4 * (size_t)L.nout)) L.nout = 80;
     const unsigned char *b = need(n + "_bias", 4 * (size_t)L.nout);
     if (!b) return false;
     HostArray bias; bias.dtype = 0; bias.rows = 1; bias.cols = L.nout; bias.data.assign(b, b + 4 * (size_t)L.nout);
@@ -110,6 +114,25 @@ bool parse_dnnw(const unsigned char *buf, size_t len, ArrayMap &out) {
       HostArray s; s.dtype = 0; s.rows = 1; s.cols = L.nout; s.data.assign(sc, sc + 4 * (size_t)L.nout);
       out[n + ".scale"] = s;
     }
+  }
+  return true;
+}
+
+// enc_dense1.wf [80][64] -> [84][64] (zero rows), dec_output.wf [736][80] -> [736][84], dec_output.bias [80] -> [84] (zeros):
+// with zero weights the 84-wide kernels compute exactly what the 80-wide layers would (acc + 0 * x == acc)
+bool normalise_io_width(ArrayMap &arrays, int *input_dim, int *output_dim) {
+  *input_dim = 84; *output_dim = 84;
+  auto d1 = arrays.find("enc_dense1.wf");
+  if (d1 != arrays.end() && d1->second.rows == 80 && d1->second.cols == 64) {
+    d1->second.data.resize((size_t)84 * 64 * 4, 0); d1->second.rows = 84; *input_dim = 80;
+  }
+  auto ow = arrays.find("dec_output.wf"); auto ob = arrays.find("dec_output.bias");
+  if (ow != arrays.end() && ob != arrays.end() && ow->second.rows == 736 && ow->second.cols == 80 && ob->second.cols == 80) {
+    std::vector<unsigned char> wide((size_t)736 * 84 * 4, 0);
+    for (int r = 0; r < 736; r++) memcpy(&wide[(size_t)r * 84 * 4], &ow->second.data[(size_t)r * 80 * 4], 80 * 4);
+    ow->second.data.swap(wide); ow->second.cols = 84;
+    ob->second.data.resize(84 * 4, 0); ob->second.cols = 84;
+    *output_dim = 80;
   }
   return true;
 }
@@ -172,6 +195,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     fprintf(stderr, "libradae_b200: weight blob is neither RDW v1 nor a DNNw blob (%zu bytes)\n", len);
     return -1;
   }
+  normalise_io_width(arrays, &h->input_dim, &h->output_dim);
   std::vector<LayerSpec> specs; std::vector<std::string> names;
   layer_specs(specs, names);
   auto dev_copy = [&](const void *src, size_t bytes) -> void * {
@@ -212,6 +236,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     }
   }
   CoreWeightsDev &W = h->dev;
+  W.enc_z_tanh = 0;                      // set by the context from its flags (RADE_B200_BOTTLENECK_1)
   W.enc_dense1 = f32["enc_dense1"]; W.enc_zdense = f32["enc_zdense"]; W.dec_dense1 = f32["dec_dense1"]; W.dec_output = f32["dec_output"];
   for (int i = 0; i < 5; i++) {
     std::string n = std::to_string(i + 1);
