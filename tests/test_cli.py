@@ -42,8 +42,6 @@ def test_eoo_test_bits_are_the_reference_pattern(golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
-                    reason="added after the round's GPU budget was spent; enable with RADE_B200_RUN_UNVALIDATED=1, drop the gate once green")
 def test_cli_pipe_tx_into_rx(golden):
     """features -> radae_txe --eoo_data_test | radae_rxe --eoo_data_test: frames equal the in-process objects', EOO test passes"""
     from gpu_util import need_gpu

@@ -164,9 +164,6 @@ def test_config2_full_size_8192_streams_96_steps():
     b.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
-                    reason="model05 support was written after the round's GPU budget was spent (compiled, oracle side pinned on CPU); "
-                           "enable with RADE_B200_RUN_UNVALIDATED=1 and drop this gate once it has passed on a B200")
 @pytest.mark.parametrize("tile", [8, 16])
 def test_model05_bottleneck1_bit_exact(golden, tile, monkeypatch):
     """the reference's second codec configuration (ctests c_encoder_model5 / c_decoder_model5): 80-wide rows, tanh

@@ -325,10 +325,6 @@ def test_bypass_dec_receiver_hands_back_latents(golden, name):
     assert np.array_equal(api.reshape(-1, 432), feats_full)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
-                    reason="added after the round's GPU budget was spent: the oracle side is pinned against the reference on CPU "
-                           "(test_oracle_dsp.py::test_streaming_receiver_vs_reference[foff_test]); enable with "
-                           "RADE_B200_RUN_UNVALIDATED=1 and drop this gate once it has passed on a B200")
 def test_foff_test_flag_false_sync_and_reacquisition(golden):
     """RADE_FOFF_TEST (src/rade_api.c:263-264, src/radae_rx.c:19-20): 10 Hz added to fmax on the first sync ->
     unique-word failure -> back to search -> clean re-acquisition; trace must equal the reference's"""
@@ -350,9 +346,6 @@ def test_foff_test_flag_false_sync_and_reacquisition(golden):
     assert len(feats) == len(g["features"])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RADE_B200_RUN_UNVALIDATED") != "1",
-                    reason="scenarios added after the round's GPU budget was spent; their oracle side is pinned against the "
-                           "reference on CPU (test_oracle_dsp.py); enable with RADE_B200_RUN_UNVALIDATED=1, drop the gate once green")
 @pytest.mark.parametrize("name", ["dfdt", "noise_only", "sine_noise", "mpd_fading"])
 def test_more_reference_scenarios_single_stream(golden, name):
     """frequency drift at 1 dB Eb/No (ctest radae_rx_dfdt), the two must-not-acquire inputs (acq_noise, acq_sine) and fast
