@@ -290,6 +290,11 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     for (auto &kv : w8) p8[kv.first] = (const int8_t *)kv.second->data.data();
     for (auto &kv : wf) pf[kv.first] = (const float *)kv.second->data.data();
     build_streams(p8, pf, false, e, d, e_pro, d_pro);
+    if (core_codec_umma_enabled()) {             // the experimental tcgen05 encoder consumes its int8 chunks in the operand layout
+      StreamBuilder e2, d2; int ep2 = 0, dp2 = 0;
+      build_streams(p8, pf, true, e2, d2, ep2, dp2);
+      e = e2; e_pro = ep2;
+    }
   }
   if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
   auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out, int n_pro) -> int {
