@@ -293,7 +293,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     if (core_codec_umma_enabled()) {             // the experimental tcgen05 encoder consumes its int8 chunks in the operand layout
       StreamBuilder e2, d2; int ep2 = 0, dp2 = 0;
       build_streams(p8, pf, true, e2, d2, ep2, dp2);
-      e = e2; e_pro = ep2;
+      e = e2; e_pro = ep2; d = d2; d_pro = dp2;
     }
   }
   if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
