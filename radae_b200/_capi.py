@@ -68,6 +68,7 @@ SIGNATURES = {
     "rade_b200_hostlink_active": (_P, [_P]),
     # test hook
     "rade_b200_debug_tables": (_I, [_I, _P, _I]),
+    "rade_b200_debug_codec_stream": (C.c_longlong, [_I, _I, _P, C.c_longlong, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
 }
 
 _lib = None

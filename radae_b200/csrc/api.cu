@@ -751,6 +751,24 @@ RADE_EXPORT int rade_b200_debug_tables(int which, float *out, int cap_floats) {
   return (int)fv.size();
 }
 
+// debug/test hook (host only): the per-step weight stream of the encoder (which = 0) or decoder (1) built from the embedded
+// weights, int8 chunks either in the mma.sync fragment order (umma = 0, what the kernels consume today) or in the tcgen05
+// operand layout (umma = 1).  chunks_out receives (offset, bytes) pairs.  Returns the stream length in bytes
+// (call with cap_bytes = 0 to size the buffers; *n_chunks is always set) or -1.
+RADE_EXPORT long long rade_b200_debug_codec_stream(int which, int umma, unsigned char *bytes_out, long long cap_bytes,
+                                                   unsigned int *chunks_out, int cap_chunks, int *n_chunks, int *n_prologue) {
+  size_t len = 0;
+  const void *blob = rade_b200_default_weights_blob(&len);
+  std::vector<unsigned char> bytes; std::vector<ChunkDesc> chunks; int pro = 0;
+  if (core_weights_debug_stream((const unsigned char *)blob, len, which, umma, &bytes, &chunks, &pro) < 0) return -1;
+  if (n_chunks) *n_chunks = (int)chunks.size();
+  if (n_prologue) *n_prologue = pro;
+  if (bytes_out && cap_bytes >= (long long)bytes.size()) memcpy(bytes_out, bytes.data(), bytes.size());
+  if (chunks_out && cap_chunks >= (int)chunks.size())
+    for (size_t i = 0; i < chunks.size(); i++) { chunks_out[2 * i] = chunks[i].offset; chunks_out[2 * i + 1] = chunks[i].bytes; }
+  return (long long)bytes.size();
+}
+
 // ================================================================== rade_api.h: the reference's single-stream surface
 struct rade {
   rade_batch *b;

@@ -18,6 +18,9 @@ static inline __host__ __device__ int core_kbc(int NTL) { int k = CORE_STAGE_BYT
 // rows of a float layer (padded width noutp) per pipeline stage, multiple of 4
 static inline __host__ __device__ constexpr int core_f32_rpc(int noutp) { return (CORE_STAGE_BYTES / (noutp * 4)) & ~3; }
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h);
+int core_codec_umma_enabled();      // RADE_B200_CODEC_UMMA=1: experimental tcgen05 encoder + matching weight-stream format
+int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, int umma, std::vector<unsigned char> *bytes,
+                              std::vector<ChunkDesc> *chunks, int *n_prologue);
 void core_weights_free(CoreWeightsHolder *h);
 
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,

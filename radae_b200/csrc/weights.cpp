@@ -13,6 +13,7 @@
 #include <vector>
 #include "rade_common.h"
 #include "rade_host.h"
+#include "umma_layout.h"
 
 namespace {
 
@@ -151,6 +152,11 @@ struct StreamBuilder {
   std::vector<unsigned char> bytes;
   std::vector<ChunkDesc> chunks;
   bool ok = true;
+  bool umma = false;       // int8 chunks in the tcgen05 operand layout instead of the mma.sync fragment order
+  // tile_step / n_tiles: where the layer's M = 128 tiles start in the tcgen05 formulation (GRU: 0, units, 2 units; others: one tile)
+  void add_layer_i8(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles) {
+    if (umma) add_i8_umma(W8, N, K, kb_lo, kb_hi, tile_step, n_tiles); else add_i8(W8, N, K, kb_lo, kb_hi);
+  }
   void add(const void *p, size_t n) {
     if (n == 0 || n > CORE_STAGE_BYTES || (n & 15)) { ok = false; return; }
     ChunkDesc d; d.offset = (unsigned)bytes.size(); d.bytes = (unsigned)n;
@@ -175,6 +181,16 @@ struct StreamBuilder {
       add(t.data(), t.size() * 4);
     }
   }
+  // tcgen05 formulation: k-blocks [kb_lo, kb_hi) of ALL rows in the canonical K-major operand layout, as many
+  // k-blocks per chunk as a stage can hold for the rows the layer's M = 128 tiles may touch (tiles start at rows 0, tile_step, ...)
+  void add_i8_umma(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles) {
+    const int nk_max = umma_kblocks_per_stage(umma_span_rows(N, tile_step, n_tiles), CORE_STAGE_BYTES);
+    if (nk_max < 1) { ok = false; return; }
+    for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += nk_max) {
+      std::vector<uint8_t> c = umma_bake_chunk(W8, N, K, kb0, std::min(nk_max, kb_hi - kb0));
+      add(c.data(), c.size());
+    }
+  }
   // rows [j0, j0+nrows) of a float [K][NOUT] matrix, each row zero-padded to NOUTP floats, core_f32_rpc(NOUTP) rows per chunk
   void add_f32_rows(const float *Wf, int NOUT, int NOUTP, int j0, int nrows) {
     const int rpc = core_f32_rpc(NOUTP);
@@ -186,6 +202,53 @@ struct StreamBuilder {
     }
   }
 };
+
+// Host-only: the two per-step weight streams from row-major host matrices (p8: int8 [out][in], pf: float [in][out]).
+void build_streams(const std::map<std::string, const int8_t *> &p8, const std::map<std::string, const float *> &pf, bool umma,
+                   StreamBuilder &e, StreamBuilder &d, int &e_pro, int &d_pro) {
+  auto I8 = [&](const std::string &n) { return p8.at(n); };
+  auto F = [&](const std::string &n) { return pf.at(n); };
+  // Order = the kernels' consumption order.  dense1 is needed once up front (prologue) and then, for the NEXT step, just before
+  // the last conv layer, so that the F-warps can have the next step's first activation ready when the I-warps finish this one.
+  e.umma = d.umma = umma;
+  {
+    e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);
+    e_pro = (int)e.chunks.size();
+    e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, 0, 64);
+    int off = 64;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      e.add_layer_i8(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32, ENC_GRU, 3);
+      e.add_layer_i8(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2, ENC_GRU, 3);
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
+      off += ENC_GRU;
+      if (l == 4) e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);             // for the next step
+      e.add_layer_i8(I8("enc_conv" + n), 96, 2 * off, 0, off / 32, 0, 1);                    // tap 0 (oldest frame)
+      e.add_layer_i8(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32, 0, 1);         // tap 1 (current frame)
+      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
+      off += ENC_CONV;
+    }
+  }
+  {
+    d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);
+    d_pro = (int)d.chunks.size();
+    d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, 0, 96);
+    int off = 96;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      d.add_layer_i8(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32, DEC_GRU, 3);
+      d.add_layer_i8(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3, DEC_GRU, 3);
+      d.add_layer_i8(I8("dec_glu" + n), 96, 96, 0, 3, 0, 1);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
+      off += DEC_GRU;
+      if (l == 4) d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);             // for the next step
+      d.add_layer_i8(I8("dec_conv" + n), 32, 2 * off, 0, off / 32, 0, 1);
+      d.add_layer_i8(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32, 0, 1);
+      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
+      off += DEC_CONV;
+    }
+  }
+}
 
 }  // namespace
 
@@ -245,47 +308,17 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     W.dec_glu[i] = i8["dec_glu" + n]; W.dec_conv[i] = i8["dec_conv" + n];
   }
   // ---- per-step weight streams, in the kernels' consumption order (keep in lock-step with core_codec.cu)
-  auto I8 = [&](const std::string &n) { return (const int8_t *)w8[n]->data.data(); };
-  auto F = [&](const std::string &n) { return (const float *)wf[n]->data.data(); };
-  // Order = the kernels' consumption order.  dense1 is needed once up front (prologue) and then, for the NEXT step, just before
-  // the last conv layer, so that the F-warps can have the next step's first activation ready when the I-warps finish this one.
   StreamBuilder e, d;
   int e_pro = 0, d_pro = 0;
   {
-    e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);
-    e_pro = (int)e.chunks.size();
-    e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, 0, 64);
-    int off = 64;
-    for (int l = 0; l < 5; l++) {
-      std::string n = std::to_string(l + 1);
-      e.add_i8(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32);
-      e.add_i8(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2);
-      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
-      off += ENC_GRU;
-      if (l == 4) e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);             // for the next step
-      e.add_i8(I8("enc_conv" + n), 96, 2 * off, 0, off / 32);                    // tap 0 (oldest frame)
-      e.add_i8(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32);         // tap 1 (current frame)
-      e.add_f32_rows(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
-      off += ENC_CONV;
-    }
-  }
-  {
-    d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);
-    d_pro = (int)d.chunks.size();
-    d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, 0, 96);
-    int off = 96;
-    for (int l = 0; l < 5; l++) {
-      std::string n = std::to_string(l + 1);
-      d.add_i8(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32);
-      d.add_i8(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3);
-      d.add_i8(I8("dec_glu" + n), 96, 96, 0, 3);
-      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
-      off += DEC_GRU;
-      if (l == 4) d.add_f32_rows(F("dec_dense1"), 96, 96, 0, DEC_IN);             // for the next step
-      d.add_i8(I8("dec_conv" + n), 32, 2 * off, 0, off / 32);
-      d.add_i8(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32);
-      d.add_f32_rows(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
-      off += DEC_CONV;
+    std::map<std::string, const int8_t *> p8; std::map<std::string, const float *> pf;
+    for (auto &kv : w8) p8[kv.first] = (const int8_t *)kv.second->data.data();
+    for (auto &kv : wf) pf[kv.first] = (const float *)kv.second->data.data();
+    build_streams(p8, pf, false, e, d, e_pro, d_pro);
+    if (core_codec_umma_enabled()) {             // the experimental tcgen05 encoder consumes its int8 chunks in the operand layout
+      StreamBuilder e2, d2; int ep2 = 0, dp2 = 0;
+      build_streams(p8, pf, true, e2, d2, ep2, dp2);
+      e = e2; e_pro = ep2; d = d2; d_pro = dp2;
     }
   }
   if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
@@ -300,5 +333,25 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   if (core_codec_set_chunk_table(0, e.chunks.data(), (int)e.chunks.size()) < 0 ||
       core_codec_set_chunk_table(1, d.chunks.data(), (int)d.chunks.size()) < 0) return -1;
   h->enc_chunks_per_step = W.enc_stream.n_chunks; h->dec_chunks_per_step = W.dec_stream.n_chunks;
+  return 0;
+}
+
+// Debug / test hook (no device involved): the weight stream of one codec as the host builds it, in either int8 chunk format.
+// which: 0 encoder, 1 decoder.  Returns 0 and fills bytes / chunks / n_prologue, or -1.
+int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, int umma, std::vector<unsigned char> *bytes,
+                              std::vector<ChunkDesc> *chunks, int *n_prologue) {
+  ArrayMap arrays;
+  if (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays)) return -1;
+  std::map<std::string, const int8_t *> p8; std::map<std::string, const float *> pf;
+  for (auto &kv : arrays) {
+    const std::string &k = kv.first;
+    if (k.size() > 3 && k.compare(k.size() - 3, 3, ".w8") == 0) p8[k.substr(0, k.size() - 3)] = (const int8_t *)kv.second.data.data();
+    if (k.size() > 3 && k.compare(k.size() - 3, 3, ".wf") == 0) pf[k.substr(0, k.size() - 3)] = (const float *)kv.second.data.data();
+  }
+  StreamBuilder e, d; int e_pro = 0, d_pro = 0;
+  try { build_streams(p8, pf, umma != 0, e, d, e_pro, d_pro); } catch (...) { return -1; }
+  if (!e.ok || !d.ok) return -1;
+  StreamBuilder &sb = which ? d : e;
+  *bytes = sb.bytes; *chunks = sb.chunks; *n_prologue = which ? d_pro : e_pro;
   return 0;
 }

@@ -3,7 +3,7 @@
 //   g++ -O2 -std=c++17 -o test_umma_layout test_umma_layout.cpp && ./test_umma_layout
 #include <cstdio>
 #include <cstdlib>
-#include "umma_layout.h"
+#include "../../radae_b200/csrc/umma_layout.h"
 
 static int check_layer(const char *name, int n_rows, int K, int tile_step, int n_tiles, int n_streams) {
   const int STAGE = 32768;
