@@ -333,7 +333,7 @@ def run_gpu(args):
 
     # ---- end to end through the host-buffer C ABI (pinned host in, host out, every step), wall clock
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         e2e = run_e2e(b, S, feats_host, codec_only, K, world, dist if world > 1 else None, torch,
                       n_ctx=args.e2e_contexts, weights=blob, device=local, serial=args.e2e_serial)
 
@@ -490,6 +490,7 @@ def main():
     ap.add_argument("--workload", default="full", choices=["full", "codec"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="development runs: skip the end-to-end leg (the line then has e2e = null)")
     ap.add_argument("--ref-frames", type=int, default=200, help="--impl reference: modem frames per process and step (bounded sample)")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: tx, channel, push, rx back to back on ONE host thread")
     ap.add_argument("--no-pipeline", action="store_true", help="run TX and RX of a frame back to back on one stream")

@@ -143,6 +143,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
       cudaEventCreateWithFlags(&b->rx.ev_join, cudaEventDisableTiming) != cudaSuccess) { delete b; return nullptr; }
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
+  b->weights.dev.trace = nullptr;
   b->weights.dev.enc_z_tanh = (flags & RADE_B200_BOTTLENECK_1) ? 1 : 0;      // src/rade_enc.c:107-113
   DspTablesHost th; dsp_tables_host(th);
   if (dsp_tables_upload(th, &b->tables, b->allocs) < 0) { delete b; return nullptr; }
@@ -751,22 +752,62 @@ RADE_EXPORT int rade_b200_debug_tables(int which, float *out, int cap_floats) {
   return (int)fv.size();
 }
 
-// debug/test hook (host only): the per-step weight stream of the encoder (which = 0) or decoder (1) built from the embedded
-// weights, int8 chunks either in the mma.sync fragment order (umma = 0, what the kernels consume today) or in the tcgen05
-// operand layout (umma = 1).  chunks_out receives (offset, bytes) pairs.  Returns the stream length in bytes
+// debug/test hook (host only): the per-step weight streams of the encoder (which = 0) or decoder (1) built from the embedded
+// weights: umma = 0 the mma.sync kernels' stream (fragment order), 1 the tcgen05 kernels' int8 stream (operand layout),
+// 2 the tcgen05 kernels' float stream.  chunks_out receives (offset, bytes) pairs.  Returns the stream length in bytes
 // (call with cap_bytes = 0 to size the buffers; *n_chunks is always set) or -1.
 RADE_EXPORT long long rade_b200_debug_codec_stream(int which, int umma, unsigned char *bytes_out, long long cap_bytes,
                                                    unsigned int *chunks_out, int cap_chunks, int *n_chunks, int *n_prologue) {
   size_t len = 0;
   const void *blob = rade_b200_default_weights_blob(&len);
   std::vector<unsigned char> bytes; std::vector<ChunkDesc> chunks; int pro = 0;
-  if (core_weights_debug_stream((const unsigned char *)blob, len, which, umma, &bytes, &chunks, &pro) < 0) return -1;
+  if (core_weights_debug_stream((const unsigned char *)blob, len, which, umma, &bytes, &chunks, &pro, nullptr) < 0) return -1;
   if (n_chunks) *n_chunks = (int)chunks.size();
   if (n_prologue) *n_prologue = pro;
   if (bytes_out && cap_bytes >= (long long)bytes.size()) memcpy(bytes_out, bytes.data(), bytes.size());
   if (chunks_out && cap_chunks >= (int)chunks.size())
     for (size_t i = 0; i < chunks.size(); i++) { chunks_out[2 * i] = chunks[i].offset; chunks_out[2 * i + 1] = chunks[i].bytes; }
   return (long long)bytes.size();
+}
+// the per-step MMA program of the tcgen05 kernels (one record of 13 ints per weight image, in issue order): a_off16, tile_step,
+// b_kb, nk, n_tiles, b_buf, flags, d_blk, d_tile_stride, dep, commit, 0, 0.  Returns the record count or -1.
+RADE_EXPORT int rade_b200_debug_codec_program(int which, int *ops_out, int cap_ops) {
+  size_t len = 0;
+  const void *blob = rade_b200_default_weights_blob(&len);
+  std::vector<unsigned char> bytes; std::vector<ChunkDesc> chunks; std::vector<UmmaRec> recs; int pro = 0;
+  if (core_weights_debug_stream((const unsigned char *)blob, len, which, 1, &bytes, &chunks, &pro, &recs) < 0) return -1;
+  if (ops_out && cap_ops >= (int)recs.size())
+    for (size_t i = 0; i < recs.size(); i++) {
+      const UmmaRec &o = recs[i];
+      const int v[13] = {o.a_off16, o.tile_step, o.b_kb, o.nk, o.n_tiles, o.b_buf, o.flags, o.d_blk, o.d_tile_stride, o.dep, o.commit, 0, 0};
+      memcpy(ops_out + 13 * i, v, sizeof(v));
+    }
+  return (int)recs.size();
+}
+
+// debug: timeline of CTA 0 of the next codec launches (clock64 stamps, slot map in core_codec_umma.cu).  enable allocates and
+// zeroes an n-slot device buffer; read copies it back (after a synchronize) and disables tracing.
+RADE_EXPORT int rade_b200_debug_trace_enable(rade_batch *b, int n) {
+  cudaSetDevice(b->device);
+  long long *d = nullptr;
+  CUDA_CHECK(cudaMalloc((void **)&d, sizeof(long long) * n));
+  CUDA_CHECK(cudaMemset(d, 0, sizeof(long long) * n));
+  b->allocs.push_back(d);
+  b->weights.dev.trace = d;
+  return 0;
+}
+RADE_EXPORT int rade_b200_debug_trace_read(rade_batch *b, long long *out, int n) {
+  cudaSetDevice(b->device);
+  if (!b->weights.dev.trace) return -1;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(cudaMemcpy(out, b->weights.dev.trace, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  b->weights.dev.trace = nullptr;
+  return 0;
+}
+
+// debug/test hook (host only): would rade_b200_open accept this weight blob?  0 yes, -1 no (truncated / crafted / wrong shapes)
+RADE_EXPORT int rade_b200_debug_check_weights(const void *weights, size_t weights_len) {
+  return core_weights_validate((const unsigned char *)weights, weights_len);
 }
 
 // ================================================================== rade_api.h: the reference's single-stream surface

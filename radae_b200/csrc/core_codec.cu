@@ -27,9 +27,11 @@
 //     their two taps over different warps and reduce the exact int32 partial sums through shared memory;
 //   * the float layers accumulate sequentially over inputs (the generic sgemv order): packed FMUL2 products, scalar FADDs.
 // Per-stream HBM state: GRU h (fp32) + int8 concat of step t-1 (and t-2 for the encoder's dilation-2 convs).
+#include <string.h>
 #include "rade_common.h"
 #include "rade_host.h"
 #include "tma.cuh"
+#include "codec_math.cuh"
 
 namespace {
 
@@ -37,27 +39,6 @@ constexpr int SEG_LD = 100;                // float rows are 16-byte aligned (fl
 constexpr int FIN_LD = 92;
 constexpr int ZIN_LD = 84;
 constexpr int HQ_LD = 496;                 // row stride of the decoder's quantised hidden states (conflict-free A fragments)
-
-// ---------------------------------------------------------------- scalar math, bit-exact w.r.t. oracle/nnet_shim.c
-__device__ __forceinline__ float tanh_r(float x) {
-  const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
-  const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
-  float x2 = __fmul_rn(x, x);
-  float num = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(N2, x2), N1), x2), N0);
-  float den = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(D2, x2), D1), x2), D0);
-  float y = __fdiv_rn(__fmul_rn(num, x), den);
-  return fmaxf(-1.f, fminf(1.f, y));
-}
-__device__ __forceinline__ float sigmoid_r(float x) {
-  return __fadd_rn(.5f, __fmul_rn(.5f, tanh_r(__fmul_rn(.5f, x))));
-}
-// C semantics of `(int)floor(.5+127*x)`: 127*x is a float product (rounded to binary32), the sum with .5 is double
-__device__ __forceinline__ int8_t quant8(float x) {
-  return (int8_t)__double2int_rd((double)__fmul_rn(127.f, x) + 0.5);
-}
-__device__ __forceinline__ float lin(int acc, float scale, float bias) {
-  return __fadd_rn(__fmul_rn((float)acc, scale), bias);
-}
 
 template <int NST> struct PipeSmem {
   alignas(128) unsigned char ring[NST][CORE_STAGE_BYTES];
@@ -158,22 +139,6 @@ __device__ __forceinline__ int f32_chunks(int K, int NOUTP) { const int rpc = co
 // acc[i] = ((acc[i] + W[j0][o] x[j0]) + W[j0+1][o] x[j0+1]) + ...  — separately rounded, in input order
 // (round(w.x * x), round(w.y * x)) with one packed multiply (SASS FMUL2); the accumulation stays scalar so that ptxas cannot
 // contract product and sum into an FFMA2 (it does that to mul.rn.f32x2 + add.rn.f32x2, which would round once instead of twice)
-__device__ __forceinline__ float2 prod2_rn(float wx, float wy, float x) {
-  float2 w = make_float2(wx, wy), xx = make_float2(x, x);
-  unsigned long long ra = *reinterpret_cast<unsigned long long *>(&w), rb = *reinterpret_cast<unsigned long long *>(&xx), rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2 *>(&rd);
-}
-template <int OPT>
-__device__ __forceinline__ void mac_row(float (&acc)[OPT], const float4 *wrow, float x) {
-#pragma unroll
-  for (int v = 0; v < OPT / 4; v++) {
-    const float4 w = wrow[v];
-    const float2 p0 = prod2_rn(w.x, w.y, x), p1 = prod2_rn(w.z, w.w, x);
-    acc[4 * v + 0] = __fadd_rn(acc[4 * v + 0], p0.x); acc[4 * v + 1] = __fadd_rn(acc[4 * v + 1], p0.y);
-    acc[4 * v + 2] = __fadd_rn(acc[4 * v + 2], p1.x); acc[4 * v + 3] = __fadd_rn(acc[4 * v + 3], p1.y);
-  }
-}
 template <int NOUTP, int OPT, typename CX>
 __device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[OPT], const float *xrow, int K, int grp) {
   constexpr int RPC = core_f32_rpc(NOUTP);
@@ -692,683 +657,6 @@ core_decoder_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const 
   }
 }
 
-// ================================================================= encoder, tcgen05 formulation -- EXPERIMENTAL
-// Selected with RADE_B200_CODEC_UMMA=1 (8-stream tiles only); same inputs, outputs, state and float arithmetic as
-// core_encoder_kernel, so the bit-exact tests apply unchanged.  The int8 GEMMs run as tcgen05.mma kind::i8 with the operands
-// swapped: A = weight rows (M = 128 TMEM lanes = output features), B = the quantised activations of the 8 streams, straight
-// out of the concat buffers, which are kept in the B-operand layout  offset(stream n, feature k) = (k/16)*128 + n*16 + k%16.
-// Warps: 0-3 epilogue (TMEM lane = output feature), 4 issuer (one thread), 5.. float layers (as in the mma.sync kernel),
-// last = TMA producer.  Written at the end of round 1 without GPU time: compiles, has not run yet.
-constexpr int UE_NE = 4, UE_NF = ENC_NF, UE_THREADS = (UE_NE + 1 + UE_NF + 1) * 32, UE_NST = 5;
-constexpr int UE_KCAT = 864, UE_CB_BYTES = (UE_KCAT / 16) * 128;          // one concat buffer for 8 streams in B layout
-constexpr int UE_NSEG = (UE_NE + UE_NF) * 32;                               // participants of the seg hand-over barriers
-constexpr int UE_ND1 = (UE_NF + 1) * 32;                                    // float warps + issuer warp
-constexpr int UE_NALL = (UE_NE + 1 + UE_NF) * 32;
-constexpr int UE_TMEM_COLS = 512;                                           // 5 x 48 (GRU) + 5 x 8 (conv) accumulator columns
-
-struct UmmaEncSmem {
-  PipeSmem<UE_NST> pipe;
-  alignas(128) uint8_t cb[3][UE_CB_BYTES];
-  alignas(16) float hs[8][5 * ENC_GRU];
-  alignas(16) float seg[3][8][SEG_LD];
-  alignas(16) float fin[8][FIN_LD];
-  alignas(16) int8_t d1q[8][64];
-  alignas(8) uint64_t acc_full[10], act_ready[10];
-  uint32_t tmem_base;
-  int any_active;
-};
-
-__device__ __forceinline__ int cb_off(int n, int k) { return (k >> 4) * 128 + n * 16 + (k & 15); }
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t sbo_bytes) {   // K-major, no swizzle, LBO = 128
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | (uint64_t)(128 >> 4) << 16 | (uint64_t)(sbo_bytes >> 4) << 32 | (uint64_t)1 << 46;
-}
-__device__ __forceinline__ void umma_i8_m128n8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((8u >> 3) << 17) | ((128u >> 4) << 24);
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_to(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
-}
-// k-blocks per ring stage / chunks per layer in the tcgen05 weight stream (weights.cpp add_i8_umma, umma_layout.h)
-__device__ __forceinline__ int umma_nk_max(int span_rows) { return CORE_STAGE_BYTES / (span_rows * 32); }
-__device__ __forceinline__ int umma_chunks(int kblocks, int span_rows) { const int m = umma_nk_max(span_rows); return (kblocks + m - 1) / m; }
-constexpr int UE_SPAN_GRU = 2 * ENC_GRU + 128, UE_SPAN_CONV = 128;
-
-__global__ void __launch_bounds__(UE_THREADS, 1)
-core_encoder_umma_kernel(CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
-                         float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int TS = 8, NF = UE_NF, OPT = TS / 2, NST = UE_NST;
-  constexpr int NIT = (UE_NE + 1) * 32;                       // epilogue + issuer threads come first
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  UmmaEncSmem &sm = *reinterpret_cast<UmmaEncSmem *>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int s0 = blockIdx.x * TS;
-
-  if (tid == 0) sm.any_active = 0;
-  __syncthreads();
-  if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
-  if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NF + 1); }
-    for (int i = 0; i < 10; i++) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.act_ready[i], UE_NE * 32); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (!sm.any_active) return;
-  if (warp == 0) {                                            // TMEM for the accumulators of all ten int8 layers of a step
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem_base)), "r"(UE_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = sm.tmem_base;
-  // accumulator columns: GRU l at 48 l (blocks z_in, r_in, n_in, z_rec, r_rec, n_rec of 8 columns), conv l at 240 + 8 l
-  auto gru_cols = [&](int l) { return tmem + 48 * l; };
-  auto conv_cols = [&](int l) { return tmem + 240 + 8 * l; };
-
-  if (tid >= NIT + NF * 32) {                                 // ---- producer warp: the weight stream (state is loaded by the epilogue warps)
-    if (tid == NIT + NF * 32) producer_loop<NST>(&sm.pipe, W.enc_stream, 0, T);
-    return;                                                   // (TMEM is freed by warp 0 after the final barrier among the other warps)
-  }
-  Cursor<NST> cx{&sm.pipe, 0, 0u};
-
-  if (tid >= NIT) {
-    // =========================== F-warps: as in core_encoder_kernel, except for the concat-buffer layout and barrier head counts
-    const int ft = tid - NIT, sl = ft % TS, grp = ft / TS;
-    const int sg = s0 + sl;
-    bar_arrive(BAR_SEG_EMPTY + 0, UE_NSEG); bar_arrive(BAR_SEG_EMPTY + 1, UE_NSEG);
-    bar_sync(BAR_ALL, UE_NALL);
-    auto stage_input = [&](int t) {
-      for (int i = ft; i < TS * ENC_IN; i += NF * 32) {
-        const int r = i / ENC_IN, k = i % ENC_IN;
-        float v = 0.f;
-        if (s0 + r < S) {
-          if (in_mode == 0) v = in[((size_t)(s0 + r) * T + t) * ENC_IN + k];
-          else {
-            const int fr = k / 21, f = k % 21;
-            v = (f == 20) ? -1.f : in[((size_t)(s0 + r) * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f];
-          }
-        }
-        sm.fin[r][k] = v;
-      }
-    };
-    auto dense1 = [&]() {
-      float a[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) a[i] = 0.f;
-      dense_seg<64, OPT>(cx, a, sm.fin[sl], ENC_IN, grp);
-      if (grp < 64 / OPT) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          float y = tanh_r(__fadd_rn(a[i], W.enc_dense1.bias[o]));
-          sm.seg[2][sl][o] = y;
-          sm.d1q[sl][o] = quant8(y);
-        }
-      }
-    };
-    auto publish_d1 = [&](int t) {               // d1q -> cur(t) features [0, 64) in the B layout, then the issuer may start GRU 1 of step t
-      uint8_t *cur = sm.cb[t % 3];
-      for (int i = ft; i < TS * 16; i += NF * 32) {
-        const int n = i / 16, k = 4 * (i % 16);
-        *reinterpret_cast<uint32_t *>(cur + cb_off(n, k)) = reinterpret_cast<const uint32_t *>(sm.d1q[n])[i % 16];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      f_sync<NF>();
-      bar_arrive(BAR_D1, UE_ND1);
-    };
-    stage_input(0);
-    f_sync<NF>();
-    dense1();
-    f_sync<NF>();
-    publish_d1(0);
-    for (int t = 0; t < T; t++) {
-      float zacc[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) zacc[i] = 0.f;
-      dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[2][sl], 64, grp);
-      if (t + 1 < T) stage_input(t + 1);
-      int off = 64;
-#pragma unroll 1
-      for (int l = 0; l < 5; l++) {
-        skip_chunks(cx, umma_chunks(off / 32, UE_SPAN_GRU) + umma_chunks(ENC_GRU / 32, UE_SPAN_GRU));
-        bar_sync(BAR_SEG_FULL + 1, UE_NSEG);
-        dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[1][sl], ENC_GRU, grp);
-        bar_arrive(BAR_SEG_EMPTY + 1, UE_NSEG);
-        off += ENC_GRU;
-        if (l == 4) {
-          f_sync<NF>();
-          if (t + 1 < T) dense1(); else skip_chunks(cx, f32_chunks(ENC_IN, 64));
-          f_sync<NF>();
-        }
-        skip_chunks(cx, 2 * umma_chunks(off / 32, UE_SPAN_CONV));
-        bar_sync(BAR_SEG_FULL + 0, UE_NSEG);     // l == 4: the epilogue warps have finished this step
-        if (l == 4 && t + 1 < T) publish_d1(t + 1);
-        dense_seg<RADE_LATENT, OPT>(cx, zacc, sm.seg[0][sl], ENC_CONV, grp);
-        bar_arrive(BAR_SEG_EMPTY + 0, UE_NSEG);
-        off += ENC_CONV;
-      }
-      if (sg < S && (!active || active[sg]) && grp < RADE_LATENT / OPT) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++)
-          z_out[((size_t)sg * T + t) * RADE_LATENT + OPT * grp + i] = __fadd_rn(zacc[i], W.enc_zdense.bias[OPT * grp + i]);
-      }
-    }
-    bar_sync(BAR_I, NIT + NF * 32);              // meet the epilogue / issuer warps before they free TMEM and store the state
-    return;
-  }
-
-  constexpr int dil[5] = {1, 2, 2, 2, 2};
-  if (warp == UE_NE) {
-    // =========================== issuer warp: one thread walks the weight stream and issues every MMA
-    bar_sync(BAR_ALL, UE_NALL);                  // concat buffers / state are in shared memory (and fenced for the async proxy)
-    for (int t = 0; t < T; t++) {
-      const uint32_t cur = smem_u32(sm.cb[t % 3]), prev1 = smem_u32(sm.cb[(t + 2) % 3]), prev2 = smem_u32(sm.cb[(t + 1) % 3]);
-      const uint32_t par = t & 1;
-      skip_chunks(cx, (t == 0 ? f32_chunks(ENC_IN, 64) : 0) + f32_chunks(64, RADE_LATENT));
-      bar_sync(BAR_D1, UE_ND1);                  // dense1 output (int8) is in cur, features [0, 64)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int off = 64;
-#pragma unroll 1
-      for (int l = 0; l < 5; l++) {
-        // one int8 matrix: k-blocks [0, nkb) of `n_tiles` tiles that start `tile_step` rows apart, B operand = bsrc + k * 256;
-        // k-blocks >= fresh_from wait for `dep` (the layer that produces those features) first
-        auto run_matrix = [&](int nkb, int span, int n_tiles, int tile_step, uint32_t bsrc, uint32_t dcol, int dblk0, int fresh_from, uint64_t *dep) {
-          const int nk_max = umma_nk_max(span);
-          bool waited = dep == nullptr;
-          for (int kb0 = 0; kb0 < nkb; kb0 += nk_max) {
-            const int nk = min(nk_max, nkb - kb0), kbytes = nk * 32;
-            const uint32_t a0 = smem_u32(cx.acquire());
-            if ((threadIdx.x & 31) == 0) {
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              for (int k = 0; k < nk; k++) {
-                if (!waited && kb0 + k >= fresh_from) { mbar_wait(dep, par); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); waited = true; }
-                for (int g = 0; g < n_tiles; g++)
-                  umma_i8_m128n8(dcol + (dblk0 + g) * 8, umma_desc(a0 + (g * tile_step / 8) * (kbytes * 8) + k * 256, kbytes * 8),
-                                 umma_desc(bsrc + (kb0 + k) * 256, 1024), (kb0 + k) != 0);
-              }
-              umma_commit_to(&sm.pipe.empty[cx.stage]);           // the stage is free once these MMAs have read it
-            }
-            __syncwarp();
-            if (++cx.stage == NST) { cx.stage = 0; cx.phase ^= 1; }
-          }
-        };
-        // GRU l: input = cur[0, off) (its last 3 k-blocks are conv l-1's outputs), recurrent input = h(t-1) quantised = prev1[off, off+64)
-        run_matrix(off / 32, UE_SPAN_GRU, 3, ENC_GRU, cur, gru_cols(l), 0, off / 32 - 3, l ? &sm.act_ready[2 * l - 1] : nullptr);
-        run_matrix(ENC_GRU / 32, UE_SPAN_GRU, 3, ENC_GRU, prev1 + (off / 16) * 128, gru_cols(l), 3, 0, nullptr);
-        if ((threadIdx.x & 31) == 0) umma_commit_to(&sm.acc_full[2 * l]);
-        __syncwarp();
-        skip_chunks(cx, f32_chunks(ENC_GRU, RADE_LATENT) + (l == 4 ? f32_chunks(ENC_IN, 64) : 0));
-        off += ENC_GRU;
-        // conv l: tap 0 = prefix of step t - dilation, tap 1 = current prefix (its last 2 k-blocks are GRU l's outputs)
-        const uint32_t old = (dil[l] == 1) ? prev1 : prev2;
-        run_matrix(off / 32, UE_SPAN_CONV, 1, 0, old, conv_cols(l), 0, 0, nullptr);
-        // second tap continues the same accumulator chain: temporarily treat it as k-blocks that never reset the accumulator
-        {
-          const int nkb = off / 32, nk_max = umma_nk_max(UE_SPAN_CONV);
-          bool waited = false;
-          for (int kb0 = 0; kb0 < nkb; kb0 += nk_max) {
-            const int nk = min(nk_max, nkb - kb0), kbytes = nk * 32;
-            const uint32_t a0 = smem_u32(cx.acquire());
-            if ((threadIdx.x & 31) == 0) {
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              for (int k = 0; k < nk; k++) {
-                if (!waited && kb0 + k >= nkb - 2) { mbar_wait(&sm.act_ready[2 * l], par); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); waited = true; }
-                umma_i8_m128n8(conv_cols(l), umma_desc(a0 + k * 256, kbytes * 8), umma_desc(cur + (kb0 + k) * 256, 1024), 1);
-              }
-              umma_commit_to(&sm.pipe.empty[cx.stage]);
-            }
-            __syncwarp();
-            if (++cx.stage == NST) { cx.stage = 0; cx.phase ^= 1; }
-          }
-        }
-        if ((threadIdx.x & 31) == 0) umma_commit_to(&sm.acc_full[2 * l + 1]);
-        __syncwarp();
-        skip_chunks(cx, f32_chunks(ENC_CONV, RADE_LATENT));
-        off += ENC_CONV;
-      }
-    }
-    bar_sync(BAR_I, NIT + NF * 32);
-    return;
-  }
-
-  // =========================== epilogue warps 0-3: thread u owns output feature u of every int8 layer (TMEM lane u)
-  const int u = tid;
-  // state: concat buffers of steps t-1 (cb[2]) and t-2 (cb[1]) from the per-stream row-major state, zero for missing streams
-  for (int i = tid; i < 3 * UE_CB_BYTES / 4; i += UE_NE * 32) reinterpret_cast<uint32_t *>(sm.cb[0])[i] = 0u;
-  __syncwarp();
-  bar_sync(BAR_F + 8, UE_NE * 32);               // (named barrier 10: the four epilogue warps)
-  for (int r = 0; r < TS; r++) {
-    const bool ok = s0 + r < S;
-    const EncStreamState *st = state + (s0 + (ok ? r : 0));
-    for (int i = tid; i < 5 * ENC_GRU; i += UE_NE * 32) sm.hs[r][i] = ok ? st->h[i] : 0.f;
-    if (ok)
-      for (int i = tid; i < UE_KCAT / 4; i += UE_NE * 32) {
-        *reinterpret_cast<uint32_t *>(sm.cb[2] + cb_off(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat1)[i];
-        *reinterpret_cast<uint32_t *>(sm.cb[1] + cb_off(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat2)[i];
-      }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  bar_sync(BAR_ALL, UE_NALL);
-
-  for (int t = 0; t < T; t++) {
-    uint8_t *cur = sm.cb[t % 3];
-    const uint32_t par = t & 1;
-    int off = 64;
-#pragma unroll 1
-    for (int l = 0; l < 5; l++) {
-      // ---- GRU l
-      float si[3], bi[3], sr[3], br[3];
-      if (u < ENC_GRU)
-#pragma unroll
-        for (int g = 0; g < 3; g++) {
-          si[g] = W.enc_gru_in[l].scale[g * ENC_GRU + u]; bi[g] = W.enc_gru_in[l].bias[g * ENC_GRU + u];
-          sr[g] = W.enc_gru_rec[l].scale[g * ENC_GRU + u]; br[g] = W.enc_gru_rec[l].bias[g * ENC_GRU + u];
-        }
-      bar_sync(BAR_SEG_EMPTY + 1, UE_NSEG);      // the float warps have consumed the previous GRU segment
-      mbar_wait(&sm.acc_full[2 * l], par);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        int acc[6][8];
-#pragma unroll
-        for (int q = 0; q < 6; q++) tmem_ld8(gru_cols(l) + ((uint32_t)(32 * warp) << 16) + q * 8, acc[q]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u < ENC_GRU) {
-#pragma unroll
-          for (int s = 0; s < TS; s++) {
-            float z = sigmoid_r(__fadd_rn(lin(acc[0][s], si[0], bi[0]), lin(acc[3][s], sr[0], br[0])));
-            float r = sigmoid_r(__fadd_rn(lin(acc[1][s], si[1], bi[1]), lin(acc[4][s], sr[1], br[1])));
-            float n = tanh_r(__fadd_rn(lin(acc[2][s], si[2], bi[2]), __fmul_rn(lin(acc[5][s], sr[2], br[2]), r)));
-            float hold = sm.hs[s][l * ENC_GRU + u];
-            float h = __fadd_rn(__fmul_rn(z, hold), __fmul_rn(__fsub_rn(1.f, z), n));
-            sm.hs[s][l * ENC_GRU + u] = h;
-            sm.seg[1][s][u] = h;
-            cur[cb_off(s, off + u)] = (uint8_t)quant8(h);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.act_ready[2 * l]);
-      bar_arrive(BAR_SEG_FULL + 1, UE_NSEG);
-      off += ENC_GRU;
-      // ---- conv l
-      float es = 0.f, eb = 0.f;
-      if (u < ENC_CONV) { es = W.enc_conv[l].scale[u]; eb = W.enc_conv[l].bias[u]; }
-      bar_sync(BAR_SEG_EMPTY + 0, UE_NSEG);
-      mbar_wait(&sm.acc_full[2 * l + 1], par);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        int acc[8];
-        tmem_ld8(conv_cols(l) + ((uint32_t)(32 * warp) << 16), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u < ENC_CONV) {
-#pragma unroll
-          for (int s = 0; s < TS; s++) {
-            float y = tanh_r(lin(acc[s], es, eb));
-            sm.seg[0][s][u] = y;
-            cur[cb_off(s, off + u)] = (uint8_t)quant8(y);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.act_ready[2 * l + 1]);
-      bar_arrive(BAR_SEG_FULL + 0, UE_NSEG);
-      off += ENC_CONV;
-    }
-  }
-  bar_sync(BAR_I, NIT + NF * 32);                // every MMA has been consumed, the float warps are done with seg
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(UE_TMEM_COLS) : "memory");
-  const int last = (T + 2) % 3, last2 = (T + 1) % 3;
-  for (int r = 0; r < TS; r++) {
-    if (s0 + r >= S || (active && !active[s0 + r])) continue;
-    EncStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * ENC_GRU; i += UE_NE * 32) st->h[i] = sm.hs[r][i];
-    for (int i = tid; i < UE_KCAT / 4; i += UE_NE * 32) {
-      reinterpret_cast<uint32_t *>(st->cat1)[i] = *reinterpret_cast<const uint32_t *>(sm.cb[last] + cb_off(r, 4 * i));
-      reinterpret_cast<uint32_t *>(st->cat2)[i] = *reinterpret_cast<const uint32_t *>(sm.cb[last2] + cb_off(r, 4 * i));
-    }
-  }
-}
-
-// ================================================================= decoder, tcgen05 formulation -- EXPERIMENTAL (see the encoder above)
-// Three int8 products per DenseNet stage: GRU (input + recurrent), GLU gate on the new state, conv (two taps).  The quantised
-// hidden states live in their own ping-pong buffers (hq), like the concat buffers in the B-operand layout.
-constexpr int UD_NE = 4, UD_NF = DEC_NF, UD_THREADS = (UD_NE + 1 + UD_NF + 1) * 32, UD_NST = 5;
-constexpr int UD_KCAT = 736, UD_CB_BYTES = (UD_KCAT / 16) * 128, UD_HQ_BYTES = (5 * DEC_GRU / 16) * 128;
-constexpr int UD_NSEG = (UD_NE + UD_NF) * 32, UD_ND1 = (UD_NF + 1) * 32, UD_NALL = (UD_NE + 1 + UD_NF) * 32;
-constexpr int UD_SPAN_GRU = 2 * DEC_GRU + 128, UD_SPAN_1 = 128;
-constexpr int UD_TMEM_COLS = 512;                 // 5 x 48 (GRU) + 5 x 8 (GLU) + 5 x 8 (conv) columns
-
-struct UmmaDecSmem {
-  PipeSmem<UD_NST> pipe;
-  alignas(128) uint8_t cb[2][UD_CB_BYTES];
-  alignas(128) uint8_t hq[2][UD_HQ_BYTES];
-  alignas(16) float hs[8][5 * DEC_GRU];
-  alignas(16) float seg[3][8][SEG_LD];
-  alignas(16) float zin[8][ZIN_LD];
-  alignas(16) int8_t d1q[8][96];
-  alignas(8) uint64_t acc_full[15], act_ready[15];     // per stage l: 3l GRU, 3l+1 GLU, 3l+2 conv
-  uint32_t tmem_base;
-  int any_active;
-};
-
-__global__ void __launch_bounds__(UD_THREADS, 1)
-core_decoder_umma_kernel(CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
-                         float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
-                         const uint8_t *__restrict__ active, int S, int T) {
-  constexpr int TS = 8, NF = UD_NF, OPT = TS, NST = UD_NST;
-  constexpr int NIT = (UD_NE + 1) * 32, NGRP = NF * 32 / TS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  UmmaDecSmem &sm = *reinterpret_cast<UmmaDecSmem *>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int s0 = blockIdx.x * TS;
-
-  if (tid == 0) sm.any_active = 0;
-  __syncthreads();
-  if (tid < TS && s0 + tid < S && (!active || active[s0 + tid])) sm.any_active = 1;
-  if (tid == 0) {
-    for (int i = 0; i < NST; i++) { mbar_init(&sm.pipe.full[i], 1); mbar_init(&sm.pipe.empty[i], NF + 1); }
-    for (int i = 0; i < 15; i++) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.act_ready[i], UD_NE * 32); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (!sm.any_active) return;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem_base)), "r"(UD_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = sm.tmem_base;
-  auto gru_cols = [&](int l) { return tmem + 48 * l; };
-  auto glu_cols = [&](int l) { return tmem + 240 + 8 * l; };
-  auto conv_cols = [&](int l) { return tmem + 280 + 8 * l; };
-
-  if (tid >= NIT + NF * 32) {                                 // ---- producer warp
-    if (tid == NIT + NF * 32) producer_loop<NST>(&sm.pipe, W.dec_stream, 1, T);
-    return;
-  }
-  Cursor<NST> cx{&sm.pipe, 0, 0u};
-
-  if (tid >= NIT) {
-    // =========================== F-warps: as in core_decoder_kernel (layout of the concat buffer and barrier head counts differ)
-    const int ft = tid - NIT, sl = ft % TS, grp = ft / TS;
-    const int sg = s0 + sl;
-    bar_arrive(BAR_SEG_EMPTY + 0, UD_NSEG); bar_arrive(BAR_SEG_EMPTY + 1, UD_NSEG);
-    bar_sync(BAR_ALL, UD_NALL);
-    auto stage_input = [&](int t) {
-      for (int i = ft; i < TS * DEC_IN; i += NF * 32) {
-        const int r = i / DEC_IN, k = i % DEC_IN;
-        sm.zin[r][k] = (s0 + r < S) ? z_in[((size_t)(s0 + r) * T + t) * DEC_IN + k] : 0.f;
-      }
-    };
-    auto dense1 = [&]() {
-      float a[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) a[i] = 0.f;
-      dense_seg<96, OPT>(cx, a, sm.zin[sl], DEC_IN, grp);
-#pragma unroll
-      for (int i = 0; i < OPT; i++) {
-        const int o = OPT * grp + i;
-        float y = tanh_r(__fadd_rn(a[i], W.dec_dense1.bias[o]));
-        sm.seg[2][sl][o] = y;
-        sm.d1q[sl][o] = quant8(y);
-      }
-    };
-    auto publish_d1 = [&](int t) {
-      uint8_t *cur = sm.cb[t & 1];
-      for (int i = ft; i < TS * 24; i += NF * 32) {
-        const int n = i / 24, k = 4 * (i % 24);
-        *reinterpret_cast<uint32_t *>(cur + cb_off(n, k)) = reinterpret_cast<const uint32_t *>(sm.d1q[n])[i % 24];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      f_sync<NF>();
-      bar_arrive(BAR_D1, UD_ND1);
-    };
-    stage_input(0);
-    f_sync<NF>();
-    dense1();
-    f_sync<NF>();
-    publish_d1(0);
-    for (int t = 0; t < T; t++) {
-      float oacc[OPT];
-#pragma unroll
-      for (int i = 0; i < OPT; i++) oacc[i] = 0.f;
-      dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[2][sl], 96, grp);
-      if (t + 1 < T) stage_input(t + 1);
-      int off = 96;
-#pragma unroll 1
-      for (int l = 0; l < 5; l++) {
-        skip_chunks(cx, umma_chunks(off / 32, UD_SPAN_GRU) + umma_chunks(DEC_GRU / 32, UD_SPAN_GRU) + umma_chunks(DEC_GRU / 32, UD_SPAN_1));
-        bar_sync(BAR_SEG_FULL + 1, UD_NSEG);
-        dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[1][sl], DEC_GRU, grp);
-        bar_arrive(BAR_SEG_EMPTY + 1, UD_NSEG);
-        off += DEC_GRU;
-        if (l == 4) {
-          f_sync<NF>();
-          if (t + 1 < T) dense1(); else skip_chunks(cx, f32_chunks(DEC_IN, 96));
-          f_sync<NF>();
-        }
-        skip_chunks(cx, 2 * umma_chunks(off / 32, UD_SPAN_1));
-        bar_sync(BAR_SEG_FULL + 0, UD_NSEG);
-        if (l == 4 && t + 1 < T) publish_d1(t + 1);
-        dense_seg<DEC_OUTP, OPT>(cx, oacc, sm.seg[0][sl], DEC_CONV, grp);
-        bar_arrive(BAR_SEG_EMPTY + 0, UD_NSEG);
-        off += DEC_CONV;
-      }
-      if (sg < S && (!active || active[sg])) {
-#pragma unroll
-        for (int i = 0; i < OPT; i++) {
-          const int o = OPT * grp + i;
-          if (o >= DEC_OUT) continue;
-          const float v = __fadd_rn(oacc[i], W.dec_output.bias[o]);
-          if (out_mode == 0) out[((size_t)sg * T + t) * DEC_OUT + o] = v;
-          else {
-            const int fr = o / 21, f = o % 21;
-            if (f < 20) out[((size_t)sg * 4 * T + 4 * t + fr) * RADE_NB_TOTAL_FEATURES + f] = v;
-          }
-          if (o == 20 && uw_count && v > 0.f) atomicAdd(&uw_count[sg], 1);
-        }
-        if (out_mode == 1) {
-          for (int k = grp; k < 4 * 16; k += NGRP)
-            out[((size_t)sg * 4 * T + 4 * t + k / 16) * RADE_NB_TOTAL_FEATURES + 20 + (k % 16)] = 0.f;
-        }
-      }
-    }
-    bar_sync(BAR_I, NIT + NF * 32);
-    return;
-  }
-
-  if (warp == UD_NE) {
-    // =========================== issuer warp
-    bar_sync(BAR_ALL, UD_NALL);
-    for (int t = 0; t < T; t++) {
-      const uint32_t cur = smem_u32(sm.cb[t & 1]), prev1 = smem_u32(sm.cb[(t + 1) & 1]);
-      const uint32_t hq_rd = smem_u32(sm.hq[t & 1]), hq_wr = smem_u32(sm.hq[(t + 1) & 1]);
-      const uint32_t par = t & 1;
-      skip_chunks(cx, (t == 0 ? f32_chunks(DEC_IN, 96) : 0) + f32_chunks(96, DEC_OUTP));
-      bar_sync(BAR_D1, UD_ND1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int off = 96;
-#pragma unroll 1
-      for (int l = 0; l < 5; l++) {
-        // k-blocks [0, nkb) of a matrix whose n_tiles tiles start tile_step rows apart; `first` says whether k-block 0 starts a new
-        // accumulation; k-blocks >= fresh_from wait for `dep` first
-        auto run_matrix = [&](int nkb, int span, int n_tiles, int tile_step, uint32_t bsrc, uint32_t dcol, int dblk0, bool first, int fresh_from, uint64_t *dep) {
-          const int nk_max = umma_nk_max(span);
-          bool waited = dep == nullptr;
-          for (int kb0 = 0; kb0 < nkb; kb0 += nk_max) {
-            const int nk = min(nk_max, nkb - kb0), kbytes = nk * 32;
-            const uint32_t a0 = smem_u32(cx.acquire());
-            if ((threadIdx.x & 31) == 0) {
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              for (int k = 0; k < nk; k++) {
-                if (!waited && kb0 + k >= fresh_from) { mbar_wait(dep, par); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); waited = true; }
-                for (int g = 0; g < n_tiles; g++)
-                  umma_i8_m128n8(dcol + (dblk0 + g) * 8, umma_desc(a0 + (g * tile_step / 8) * (kbytes * 8) + k * 256, kbytes * 8),
-                                 umma_desc(bsrc + (kb0 + k) * 256, 1024), !(first && kb0 + k == 0));
-              }
-              umma_commit_to(&sm.pipe.empty[cx.stage]);
-            }
-            __syncwarp();
-            if (++cx.stage == NST) { cx.stage = 0; cx.phase ^= 1; }
-          }
-        };
-        // GRU l: input = cur[0, off) (last k-block = conv l-1's 32 outputs), recurrent input = quantised h(t-1) of this stage
-        run_matrix(off / 32, UD_SPAN_GRU, 3, DEC_GRU, cur, gru_cols(l), 0, true, off / 32 - 1, l ? &sm.act_ready[3 * l - 1] : nullptr);
-        run_matrix(DEC_GRU / 32, UD_SPAN_GRU, 3, DEC_GRU, hq_rd + (l * DEC_GRU / 16) * 128, gru_cols(l), 3, true, 0, nullptr);
-        if ((threadIdx.x & 31) == 0) umma_commit_to(&sm.acc_full[3 * l]);
-        __syncwarp();
-        // GLU l: gate on the NEW state of this stage, which the GRU epilogue has just quantised into hq_wr
-        run_matrix(DEC_GRU / 32, UD_SPAN_1, 1, 0, hq_wr + (l * DEC_GRU / 16) * 128, glu_cols(l), 0, true, 0, &sm.act_ready[3 * l]);
-        if ((threadIdx.x & 31) == 0) umma_commit_to(&sm.acc_full[3 * l + 1]);
-        __syncwarp();
-        skip_chunks(cx, f32_chunks(DEC_GRU, DEC_OUTP) + (l == 4 ? f32_chunks(DEC_IN, 96) : 0));
-        off += DEC_GRU;
-        // conv l: tap 0 = previous step's prefix, tap 1 = current prefix (last 3 k-blocks = the GLU outputs)
-        run_matrix(off / 32, UD_SPAN_1, 1, 0, prev1, conv_cols(l), 0, true, 0, nullptr);
-        run_matrix(off / 32, UD_SPAN_1, 1, 0, cur, conv_cols(l), 0, false, off / 32 - 3, &sm.act_ready[3 * l + 1]);
-        if ((threadIdx.x & 31) == 0) umma_commit_to(&sm.acc_full[3 * l + 2]);
-        __syncwarp();
-        skip_chunks(cx, f32_chunks(DEC_CONV, DEC_OUTP));
-        off += DEC_CONV;
-      }
-    }
-    bar_sync(BAR_I, NIT + NF * 32);
-    return;
-  }
-
-  // =========================== epilogue warps 0-3
-  const int u = tid;
-  for (int i = tid; i < (2 * UD_CB_BYTES + 2 * UD_HQ_BYTES) / 4; i += UD_NE * 32) reinterpret_cast<uint32_t *>(sm.cb[0])[i] = 0u;
-  bar_sync(BAR_F + 8, UD_NE * 32);
-  for (int r = 0; r < TS; r++) {
-    const bool ok = s0 + r < S;
-    const DecStreamState *st = state + (s0 + (ok ? r : 0));
-    for (int i = tid; i < 5 * DEC_GRU; i += UD_NE * 32) {
-      const float h = ok ? st->h[i] : 0.f;
-      sm.hs[r][i] = h;
-      sm.hq[0][cb_off(r, i)] = (uint8_t)quant8(h);
-    }
-    if (ok)
-      for (int i = tid; i < UD_KCAT / 4; i += UD_NE * 32)
-        *reinterpret_cast<uint32_t *>(sm.cb[1] + cb_off(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat1)[i];
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  bar_sync(BAR_ALL, UD_NALL);
-
-  for (int t = 0; t < T; t++) {
-    uint8_t *cur = sm.cb[t & 1], *hq_wr = sm.hq[(t + 1) & 1];
-    const uint32_t par = t & 1;
-    int off = 96;
-#pragma unroll 1
-    for (int l = 0; l < 5; l++) {
-      // ---- GRU l: new state, kept un-gated (src/rade_dec.c:66-67); quantised copy -> hq_wr
-      float si[3], bi[3], sr[3], br[3];
-      if (u < DEC_GRU)
-#pragma unroll
-        for (int g = 0; g < 3; g++) {
-          si[g] = W.dec_gru_in[l].scale[g * DEC_GRU + u]; bi[g] = W.dec_gru_in[l].bias[g * DEC_GRU + u];
-          sr[g] = W.dec_gru_rec[l].scale[g * DEC_GRU + u]; br[g] = W.dec_gru_rec[l].bias[g * DEC_GRU + u];
-        }
-      mbar_wait(&sm.acc_full[3 * l], par);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        int acc[6][8];
-#pragma unroll
-        for (int q = 0; q < 6; q++) tmem_ld8(gru_cols(l) + ((uint32_t)(32 * warp) << 16) + q * 8, acc[q]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u < DEC_GRU) {
-#pragma unroll
-          for (int s = 0; s < TS; s++) {
-            float z = sigmoid_r(__fadd_rn(lin(acc[0][s], si[0], bi[0]), lin(acc[3][s], sr[0], br[0])));
-            float r = sigmoid_r(__fadd_rn(lin(acc[1][s], si[1], bi[1]), lin(acc[4][s], sr[1], br[1])));
-            float n = tanh_r(__fadd_rn(lin(acc[2][s], si[2], bi[2]), __fmul_rn(lin(acc[5][s], sr[2], br[2]), r)));
-            float hold = sm.hs[s][l * DEC_GRU + u];
-            float h = __fadd_rn(__fmul_rn(z, hold), __fmul_rn(__fsub_rn(1.f, z), n));
-            sm.hs[s][l * DEC_GRU + u] = h;
-            hq_wr[cb_off(s, l * DEC_GRU + u)] = (uint8_t)quant8(h);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.act_ready[3 * l]);
-      // ---- GLU l: out = h * sigmoid(Wg h + b) -> concat
-      float gs = 0.f, gb = 0.f;
-      if (u < DEC_GRU) { gs = W.dec_glu[l].scale[u]; gb = W.dec_glu[l].bias[u]; }
-      bar_sync(BAR_SEG_EMPTY + 1, UD_NSEG);
-      mbar_wait(&sm.acc_full[3 * l + 1], par);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        int acc[8];
-        tmem_ld8(glu_cols(l) + ((uint32_t)(32 * warp) << 16), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u < DEC_GRU) {
-#pragma unroll
-          for (int s = 0; s < TS; s++) {
-            float y = __fmul_rn(sm.hs[s][l * DEC_GRU + u], sigmoid_r(lin(acc[s], gs, gb)));
-            sm.seg[1][s][u] = y;
-            cur[cb_off(s, off + u)] = (uint8_t)quant8(y);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.act_ready[3 * l + 1]);
-      bar_arrive(BAR_SEG_FULL + 1, UD_NSEG);
-      off += DEC_GRU;
-      // ---- conv l
-      float es = 0.f, eb = 0.f;
-      if (u < DEC_CONV) { es = W.dec_conv[l].scale[u]; eb = W.dec_conv[l].bias[u]; }
-      bar_sync(BAR_SEG_EMPTY + 0, UD_NSEG);
-      mbar_wait(&sm.acc_full[3 * l + 2], par);
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      {
-        int acc[8];
-        tmem_ld8(conv_cols(l) + ((uint32_t)(32 * warp) << 16), acc);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (u < DEC_CONV) {
-#pragma unroll
-          for (int s = 0; s < TS; s++) {
-            float y = tanh_r(lin(acc[s], es, eb));
-            sm.seg[0][s][u] = y;
-            cur[cb_off(s, off + u)] = (uint8_t)quant8(y);
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.act_ready[3 * l + 2]);
-      bar_arrive(BAR_SEG_FULL + 0, UD_NSEG);
-      off += DEC_CONV;
-    }
-  }
-  bar_sync(BAR_I, NIT + NF * 32);
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(UD_TMEM_COLS) : "memory");
-  const int last = (T + 1) & 1;
-  for (int r = 0; r < TS; r++) {
-    if (s0 + r >= S || (active && !active[s0 + r])) continue;
-    DecStreamState *st = state + (s0 + r);
-    for (int i = tid; i < 5 * DEC_GRU; i += UD_NE * 32) st->h[i] = sm.hs[r][i];
-    for (int i = tid; i < UD_KCAT / 4; i += UD_NE * 32)
-      reinterpret_cast<uint32_t *>(st->cat1)[i] = *reinterpret_cast<const uint32_t *>(sm.cb[last] + cb_off(r, 4 * i));
-  }
-}
-
 }  // namespace
 
 // ----------------------------------------------------------------- host launchers
@@ -1380,10 +668,6 @@ static int core_tile_streams(int S) {
 }
 // weight-ring depth: 8-stream tiles have the shared memory for a deeper ring
 constexpr int NST16 = 4, NST8 = 5;
-int core_codec_umma_enabled() {
-  static const int on = getenv("RADE_B200_CODEC_UMMA") && atoi(getenv("RADE_B200_CODEC_UMMA")) == 1;
-  return on;
-}
 int core_codec_set_chunk_table(int which, const ChunkDesc *d, int n) {
   if (n > CORE_MAX_CHUNKS) { fprintf(stderr, "libradae_b200: weight stream has %d chunks (max %d)\n", n, CORE_MAX_CHUNKS); return -1; }
   CUDA_CHECK(cudaMemcpyToSymbol(c_chunks, d, sizeof(ChunkDesc) * n, sizeof(ChunkDesc) * CORE_MAX_CHUNKS * which));
@@ -1395,18 +679,18 @@ int core_codec_init_device() {
   CUDA_CHECK(cudaFuncSetAttribute(core_encoder_kernel<8, NST8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmem<8, NST8>)));
   CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel<16, NST16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem<16, NST16>)));
   CUDA_CHECK(cudaFuncSetAttribute(core_decoder_kernel<8, NST8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem<8, NST8>)));
-  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaEncSmem)));
-  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UmmaDecSmem)));
-  return 0;
+  return core_codec_umma_init_device();
+}
+
+// kernel family: tcgen05 by default; RADE_B200_CODEC=mma selects the mma.sync kernels of this file (kept for A/B measurements)
+int core_codec_use_umma() {
+  static const int on = !(getenv("RADE_B200_CODEC") && strcmp(getenv("RADE_B200_CODEC"), "mma") == 0);
+  return on;
 }
 
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                         const uint8_t *active, int S, int T, cudaStream_t stream) {
-  if (core_codec_umma_enabled()) {               // experimental tcgen05 encoder (8-stream tiles), see core_encoder_umma_kernel
-    core_encoder_umma_kernel<<<(S + 7) / 8, UE_THREADS, sizeof(UmmaEncSmem), stream>>>(W, state, in, in_mode, z, active, S, T);
-    CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
+  if (core_codec_use_umma()) return core_encoder_umma_launch(W, state, in, in_mode, z, active, S, T, stream);
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)
@@ -1419,11 +703,7 @@ int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const fl
 
 int core_decoder_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
                         int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
-  if (core_codec_umma_enabled()) {               // experimental tcgen05 decoder (8-stream tiles), see core_decoder_umma_kernel
-    core_decoder_umma_kernel<<<(S + 7) / 8, UD_THREADS, sizeof(UmmaDecSmem), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
-    CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
+  if (core_codec_use_umma()) return core_decoder_umma_launch(W, state, z, out, out_mode, uw_count, active, S, T, stream);
   const int ts = core_tile_streams(S);
   const int grid = (S + ts - 1) / ts;
   if (ts == 16)

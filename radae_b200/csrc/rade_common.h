@@ -72,11 +72,53 @@ struct ChunkDesc { unsigned int offset; unsigned int bytes; };
 #define CORE_MAX_CHUNKS 96
 // chunks[0 .. n_prologue) are streamed once per launch (dense1 of the first step), chunks[n_prologue .. n_chunks) once per step
 struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; int n_chunks; int n_prologue; };
+// ---- tcgen05 formulation of the codec (core_codec_umma.cu): D[out feature][stream] = W[out][K] x X[stream][K]^T, kind::i8,
+// A = weight rows (M = 128 TMEM lanes), B = the quantised activations of the tile's streams, int32 accumulators in TMEM.
+// The host compiles, next to the weight streams, the per-step MMA PROGRAM the issuer thread walks: one UmmaOp per int8 matrix.
+#define UMMA_I8_STAGE_BYTES 40960              // ring stage of the int8 weight stream: one cp.async.bulk each (the TMA unit of an SM
+                                               // completes ~1 bulk copy per 440 cycles whatever its size: few, large copies)
+#define UMMA_F32_STAGE_BYTES 22528             // ring stage of the float weight stream (rows of dense1 / zdense / output)
+#define UMMA_MAX_RECS 120
+#define UMMA_MAX_I8_CHUNKS 48
+#define UMMA_MAX_F32_CHUNKS 24
+enum { UB_CUR = 0, UB_PREV1 = 1, UB_PREV2 = 2, UB_HQ_RD = 3, UB_HQ_WR = 4 };
+enum { UR_STAGE_FIRST = 1, UR_STAGE_LAST = 2, UR_ZERO_FIRST = 4 };
+// One record per weight image: nk k-blocks (32 bytes of K each) of all rows of an int8 matrix in the canonical K-major operand
+// layout (8-row group stride = nk * 256 B), packed back to back into the ring stages.  The issuer thread runs the record list
+// once per step: nk x n_tiles tcgen05.mma, straight-line.  16 bytes; the list travels in kernel-parameter space (uniform loads).
+struct UmmaRec {
+  unsigned short a_off16;      // offset of the image inside its ring stage, in 16-byte units
+  unsigned short tile_step;    // rows between the starts of consecutive M = 128 tiles
+  unsigned short b_kb;         // first k-block of the B operand inside its buffer
+  unsigned char nk;            // 1..8 (one tile), 1..4 (two tiles), 1..3 (three tiles)
+  unsigned char n_tiles;
+  unsigned char b_buf;         // UB_*
+  unsigned char flags;         // UR_*
+  unsigned char d_blk;         // accumulator column block (x NS columns) of tile 0
+  unsigned char d_tile_stride; // column blocks between consecutive tiles
+  signed char dep;             // act_ready barrier to wait for before the first MMA of this record, -1 = none
+  signed char commit;          // acc_full barrier to commit after the last MMA of this record, -1 = none
+  unsigned short pad;
+};
+// the form the issuer reads (descriptor words pre-assembled on the host, one 16-byte uniform load per record):
+//   w[0] = a_off16 | LBO field: added to (stage address >> 4) gives the low word of the A descriptor
+//   w[1] = high word of the A descriptor (8-row group stride nk * 256 B, descriptor version)
+//   w[2] = b_kb * 16 (low half: 16-byte units inside the B buffer) | tile offset in 16-byte units (high half)
+//   w[3] = nk [0,4) | n_tiles [4,6) | b_buf [6,9) | flags [9,12) | d_blk [12,17) | d_tile_stride [17,20) | dep + 1 [20,25) | commit + 1 [25,30)
+struct UmmaRecPacked { unsigned int w[4]; };
+struct UmmaProgram { int n_recs; int pad[3]; UmmaRecPacked recs[UMMA_MAX_RECS]; };
+struct UmmaCodecDev {
+  const unsigned char *i8_stream; const ChunkDesc *i8_chunks; int n_i8_chunks;          // per step: one chunk = one ring stage = one bulk copy
+  const unsigned char *f32_stream; const ChunkDesc *f32_chunks; int n_f32_chunks, n_f32_prologue;
+  const UmmaProgram *prog_host;                                                         // HOST pointer (owned by the weights holder): passed by value at launch
+};
 struct CoreWeightsDev {
   F32LayerDev enc_dense1, enc_zdense, dec_dense1, dec_output;
   I8LayerDev enc_gru_in[5], enc_gru_rec[5], enc_conv[5];
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
   CodecStreamDev enc_stream, dec_stream;
+  UmmaCodecDev enc_umma, dec_umma;
+  long long *trace;        // debug: clock64() stamps of CTA 0's warp roles (rade_b200_debug_trace_*), nullptr in production
   int enc_z_tanh;          // bottleneck 1 (model05): tanh on the latents, src/rade_enc.c:107-113; 0 for bottleneck 3
 };
 

@@ -12,16 +12,24 @@ struct CoreWeightsHolder {
   // 84 for model19_check3 (20 features + aux symbol per 10 ms vector), 80 for models without the aux symbol (model05): the
   // kernels always run the 84-wide layout, the missing inputs / outputs are zero weights (exact: + 0 * x)
   int input_dim = 84, output_dim = 84;
+  UmmaProgram enc_prog, dec_prog;        // MMA programs of the tcgen05 kernels (host copies, passed as kernel parameters)
 };
 // k-blocks (32 inputs each) of an int8 layer with NTL n-tiles (8 outputs each) that fit one pipeline stage
 static inline __host__ __device__ int core_kbc(int NTL) { int k = CORE_STAGE_BYTES / (NTL * 256); return k < 1 ? 1 : k; }
 // rows of a float layer (padded width noutp) per pipeline stage, multiple of 4
 static inline __host__ __device__ constexpr int core_f32_rpc(int noutp) { return (CORE_STAGE_BYTES / (noutp * 4)) & ~3; }
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h);
-int core_codec_umma_enabled();      // RADE_B200_CODEC_UMMA=1: experimental tcgen05 encoder + matching weight-stream format
+// codec kernel family: tcgen05 (core_codec_umma.cu, default) or mma.sync (core_codec.cu, RADE_B200_CODEC=mma)
+int core_codec_use_umma();
+int core_codec_umma_init_device();
+int core_encoder_umma_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
+                             const uint8_t *active, int S, int T, cudaStream_t stream);
+int core_decoder_umma_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
+                             int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream);
 int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, int umma, std::vector<unsigned char> *bytes,
-                              std::vector<ChunkDesc> *chunks, int *n_prologue);
+                              std::vector<ChunkDesc> *chunks, int *n_prologue, std::vector<UmmaRec> *ops);
 void core_weights_free(CoreWeightsHolder *h);
+int core_weights_validate(const unsigned char *blob, size_t len);      // host only: 0 = acceptable, -1 = rejected
 
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                         const uint8_t *active, int S, int T, cudaStream_t stream);

@@ -20,18 +20,24 @@ namespace {
 struct HostArray { int dtype; int rows, cols; std::vector<unsigned char> data; };
 typedef std::map<std::string, HostArray> ArrayMap;
 
+// Every length that comes from the file is checked against the buffer before it is used (overflow-safe: all comparisons are
+// of the form `n <= len - off` with `off <= len` established first), and a payload must be exactly rows * cols * sizeof(dtype)
+// bytes — a truncated or crafted container is rejected as a whole, nothing is read past `buf + len`.
 bool parse_rdw(const unsigned char *buf, size_t len, ArrayMap &out) {
   if (len < 64 || memcmp(buf, "RADEB200", 8) != 0) return false;
   uint32_t version, n;
   memcpy(&version, buf + 8, 4); memcpy(&n, buf + 12, 4);
-  if (version != 1 || 64 + 80 * (size_t)n > len) return false;
+  if (version != 1 || (size_t)n > (len - 64) / 80) return false;
+  const size_t table_end = 64 + 80 * (size_t)n;
   for (uint32_t i = 0; i < n; i++) {
     const unsigned char *e = buf + 64 + 80 * (size_t)i;
     char name[49]; memcpy(name, e, 48); name[48] = 0;
     uint32_t dtype, rows, cols; uint64_t off, nbytes;
     memcpy(&dtype, e + 48, 4); memcpy(&rows, e + 52, 4); memcpy(&cols, e + 56, 4);
     memcpy(&off, e + 64, 8); memcpy(&nbytes, e + 72, 8);
-    if (off + nbytes > len) return false;
+    if (dtype > 2 || rows == 0 || cols == 0 || rows > (1u << 20) || cols > (1u << 20)) return false;
+    const uint64_t want = (uint64_t)rows * cols * (dtype == 1 ? 1u : 4u);   // 0 f32, 1 int8, 2 int32 (radae_b200/rdw.py)      // <= 2^42: cannot overflow
+    if (nbytes != want || off < table_end || off > len || nbytes > len - off) return false;
     HostArray a; a.dtype = (int)dtype; a.rows = (int)rows; a.cols = (int)cols;
     a.data.assign(buf + off, buf + off + nbytes);
     out[name] = a;
@@ -56,61 +62,72 @@ void layer_specs(std::vector<LayerSpec> &v, std::vector<std::string> &names) {
   for (size_t i = 0; i < v.size(); i++) v[i].name = names[i].c_str();
 }
 
-// DNNw blob -> the same flat map RDW gives (unblocking the 8x4 tiles)
+// DNNw blob -> the same flat map RDW gives (unblocking the 8x4 tiles).  Record headers, record types / sizes and every entry of
+// a block index list are bounded by what the file actually holds; the int8 payload and the index list must be consumed exactly.
 bool parse_dnnw(const unsigned char *buf, size_t len, ArrayMap &out) {
-  struct Raw { int type; const unsigned char *p; int size; };
+  struct Raw { int type; const unsigned char *p; size_t size; };
   std::map<std::string, Raw> raw;
   size_t off = 0;
-  while (off + 64 <= len) {
-    if (memcmp(buf + off, "DNNw", 4) != 0) return false;
+  while (off < len) {
+    if (len - off < 64 || memcmp(buf + off, "DNNw", 4) != 0) return false;
     int version, type, size, block;
     memcpy(&version, buf + off + 4, 4); memcpy(&type, buf + off + 8, 4);
     memcpy(&size, buf + off + 12, 4); memcpy(&block, buf + off + 16, 4);
-    if (version != 0 || size <= 0 || block < size || off + 64 + (size_t)block > len) return false;
+    if (version != 0 || size <= 0 || block < size || (size_t)block > len - off - 64) return false;
     char name[45]; memcpy(name, buf + off + 20, 44); name[44] = 0;
-    raw[name] = {type, buf + off + 64, size};
+    raw[name] = {type, buf + off + 64, (size_t)size};
     off += 64 + (size_t)block;
   }
   std::vector<LayerSpec> specs; std::vector<std::string> names;
   layer_specs(specs, names);
+  // record types of the reference's writer (src/write_rade_weights.c:56-72): 0 float, 1 int, 3 int8
   for (auto &L : specs) {
     std::string n = L.name;
-    auto need = [&](const std::string &k, size_t bytes) -> const unsigned char * {
+    auto need = [&](const std::string &k, int type, size_t bytes) -> const unsigned char * {
       auto it = raw.find(k);
-      return (it != raw.end() && (size_t)it->second.size == bytes) ? it->second.p : nullptr;
+      return (it != raw.end() && it->second.type == type && it->second.size == bytes) ? it->second.p : nullptr;
     };
     // models without the auxiliary symbol (model05, src/test_rade_enc.c:40): enc_dense1 has 80 inputs, dec_output 80 outputs;
     // they are ingested as they are and widened with zeros by normalise_io_width() below
-    if (n == "enc_dense1" && !need(n + "_weights_float", 4 * (size_t)L.nin * L.nout)) L.nin = 80;
-    if (n == "dec_output" && !need(n + "_bias", 4 * (size_t)L.nout)) L.nout = 80;
-    const unsigned char *b = need(n + "_bias", 4 * (size_t)L.nout);
+    if (n == "enc_dense1" && !need(n + "_weights_float", 0, 4 * (size_t)L.nin * L.nout)) L.nin = 80;
+    if (n == "dec_output" && !need(n + "_bias", 0, 4 * (size_t)L.nout)) L.nout = 80;
+    const unsigned char *b = need(n + "_bias", 0, 4 * (size_t)L.nout);
     if (!b) return false;
     HostArray bias; bias.dtype = 0; bias.rows = 1; bias.cols = L.nout; bias.data.assign(b, b + 4 * (size_t)L.nout);
     out[n + ".bias"] = bias;
     if (L.kind == 0) {
-      const unsigned char *w = need(n + "_weights_float", 4 * (size_t)L.nin * L.nout);
+      const unsigned char *w = need(n + "_weights_float", 0, 4 * (size_t)L.nin * L.nout);
       if (!w) return false;
       HostArray a; a.dtype = 0; a.rows = L.nin; a.cols = L.nout; a.data.assign(w, w + 4 * (size_t)L.nin * L.nout);
       out[n + ".wf"] = a;
     } else {
-      const unsigned char *sc = need(n + "_scale", 4 * (size_t)L.nout);
+      const unsigned char *sc = need(n + "_scale", 0, 4 * (size_t)L.nout);
       auto itw = raw.find(n + "_weights_int8");
-      if (!sc || itw == raw.end()) return false;
+      if (!sc || itw == raw.end() || itw->second.type != 3) return false;
       const int8_t *wb = (const int8_t *)itw->second.p;
-      const int *idx = nullptr;
-      if (L.kind == 2) { auto ii = raw.find(n + "_weights_idx"); if (ii == raw.end()) return false; idx = (const int *)ii->second.p; }
+      const size_t wsize = itw->second.size;
+      const unsigned char *idx = nullptr; size_t idx_n = 0, ip = 0;      // index list as 4-byte ints, read with memcpy (alignment)
+      if (L.kind == 2) {
+        auto ii = raw.find(n + "_weights_idx");
+        if (ii == raw.end() || ii->second.type != 1 || (ii->second.size & 3)) return false;
+        idx = ii->second.p; idx_n = ii->second.size / 4;
+      }
+      auto next_idx = [&](int *v) -> bool { if (ip >= idx_n) return false; memcpy(v, idx + 4 * ip++, 4); return true; };
       HostArray a; a.dtype = 1; a.rows = L.nout; a.cols = L.nin; a.data.assign((size_t)L.nin * L.nout, 0);
       size_t p = 0;
       for (int ob = 0; ob < L.nout / 8; ob++) {
-        int nblk = idx ? *idx++ : L.nin / 4;
+        int nblk = L.nin / 4;
+        if (idx && (!next_idx(&nblk) || nblk < 0 || nblk > L.nin / 4)) return false;
         for (int j = 0; j < nblk; j++) {
-          int pos = idx ? *idx++ : 4 * j;
-          if (pos < 0 || pos + 3 >= L.nin || p + 32 > (size_t)itw->second.size) return false;
+          int pos = 4 * j;
+          if (idx && !next_idx(&pos)) return false;
+          if (pos < 0 || pos > L.nin - 4 || wsize < 32 || p > wsize - 32) return false;
           for (int k = 0; k < 8; k++) for (int c = 0; c < 4; c++)
             a.data[(size_t)(ob * 8 + k) * L.nin + pos + c] = (unsigned char)wb[p + 4 * k + c];
           p += 32;
         }
       }
+      if (p != wsize || ip != idx_n) return false;       // payload and index list consumed exactly (as rdw.py's unblock_int8)
       out[n + ".w8"] = a;
       HostArray s; s.dtype = 0; s.rows = 1; s.cols = L.nout; s.data.assign(sc, sc + 4 * (size_t)L.nout);
       out[n + ".scale"] = s;
@@ -152,11 +169,7 @@ struct StreamBuilder {
   std::vector<unsigned char> bytes;
   std::vector<ChunkDesc> chunks;
   bool ok = true;
-  bool umma = false;       // int8 chunks in the tcgen05 operand layout instead of the mma.sync fragment order
-  // tile_step / n_tiles: where the layer's M = 128 tiles start in the tcgen05 formulation (GRU: 0, units, 2 units; others: one tile)
-  void add_layer_i8(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles) {
-    if (umma) add_i8_umma(W8, N, K, kb_lo, kb_hi, tile_step, n_tiles); else add_i8(W8, N, K, kb_lo, kb_hi);
-  }
+  void add_layer_i8(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int, int) { add_i8(W8, N, K, kb_lo, kb_hi); }
   void add(const void *p, size_t n) {
     if (n == 0 || n > CORE_STAGE_BYTES || (n & 15)) { ok = false; return; }
     ChunkDesc d; d.offset = (unsigned)bytes.size(); d.bytes = (unsigned)n;
@@ -181,16 +194,6 @@ struct StreamBuilder {
       add(t.data(), t.size() * 4);
     }
   }
-  // tcgen05 formulation: k-blocks [kb_lo, kb_hi) of ALL rows in the canonical K-major operand layout, as many
-  // k-blocks per chunk as a stage can hold for the rows the layer's M = 128 tiles may touch (tiles start at rows 0, tile_step, ...)
-  void add_i8_umma(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles) {
-    const int nk_max = umma_kblocks_per_stage(umma_span_rows(N, tile_step, n_tiles), CORE_STAGE_BYTES);
-    if (nk_max < 1) { ok = false; return; }
-    for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += nk_max) {
-      std::vector<uint8_t> c = umma_bake_chunk(W8, N, K, kb0, std::min(nk_max, kb_hi - kb0));
-      add(c.data(), c.size());
-    }
-  }
   // rows [j0, j0+nrows) of a float [K][NOUT] matrix, each row zero-padded to NOUTP floats, core_f32_rpc(NOUTP) rows per chunk
   void add_f32_rows(const float *Wf, int NOUT, int NOUTP, int j0, int nrows) {
     const int rpc = core_f32_rpc(NOUTP);
@@ -204,13 +207,12 @@ struct StreamBuilder {
 };
 
 // Host-only: the two per-step weight streams from row-major host matrices (p8: int8 [out][in], pf: float [in][out]).
-void build_streams(const std::map<std::string, const int8_t *> &p8, const std::map<std::string, const float *> &pf, bool umma,
+void build_streams(const std::map<std::string, const int8_t *> &p8, const std::map<std::string, const float *> &pf,
                    StreamBuilder &e, StreamBuilder &d, int &e_pro, int &d_pro) {
   auto I8 = [&](const std::string &n) { return p8.at(n); };
   auto F = [&](const std::string &n) { return pf.at(n); };
   // Order = the kernels' consumption order.  dense1 is needed once up front (prologue) and then, for the NEXT step, just before
   // the last conv layer, so that the F-warps can have the next step's first activation ready when the I-warps finish this one.
-  e.umma = d.umma = umma;
   {
     e.add_f32_rows(F("enc_dense1"), 64, 64, 0, ENC_IN);
     e_pro = (int)e.chunks.size();
@@ -250,6 +252,131 @@ void build_streams(const std::map<std::string, const int8_t *> &p8, const std::m
   }
 }
 
+
+// ---- tcgen05 formulation (core_codec_umma.cu): per codec an int8 stream (weight images — k-blocks of ALL rows of a matrix in
+// the canonical K-major operand layout, umma_layout.h — packed back to back into ring stages of <= 40 KB, one bulk copy each),
+// a float stream (rows of dense1 / zdense / output in the float warps' order, packed into stages of <= 22 KB) and the MMA
+// program (one UmmaRec per weight image) the issuer thread walks every step.  Accumulator column blocks (x NS columns):
+// encoder GRU l at 4 (l & 1) + {0: [z;r] input, 1: [z;r] recurrent, 2: [n;-] input, 3: [n;-] recurrent}, conv l at 8 + (l & 1);
+// decoder GRU l at 6 (l & 1) + {0..5: z, r, n tiles x (input, recurrent)}, GLU l at 12 + (l & 1), conv l at 14 + (l & 1).
+struct UmmaBuilder {
+  std::vector<unsigned char> i8, f32;
+  std::vector<ChunkDesc> i8_chunks, f32_chunks;       // ring stages (= bulk copies)
+  std::vector<UmmaRec> recs;
+  std::vector<unsigned char> i8_cur, f32_cur;         // the stage being filled
+  int f32_prologue = 0;
+  bool ok = true;
+  static void close(std::vector<unsigned char> &bytes, std::vector<ChunkDesc> &chunks, std::vector<unsigned char> &cur) {
+    if (cur.empty()) return;
+    ChunkDesc d; d.offset = (unsigned)bytes.size(); d.bytes = (unsigned)cur.size();
+    bytes.insert(bytes.end(), cur.begin(), cur.end());
+    chunks.push_back(d);
+    cur.clear();
+  }
+  void close_i8() {
+    if (i8_cur.empty()) return;
+    recs.back().flags |= UR_STAGE_LAST;
+    close(i8, i8_chunks, i8_cur);
+  }
+  void close_f32() { close(f32, f32_chunks, f32_cur); }
+  // k-blocks [kb_lo, kb_hi) of the row-major int8 [N][K] matrix: as many k-blocks per image as fit the current stage (at most
+  // what the issuer has unrolled code for).  The k-blocks from kb_lo + fresh_from on depend on the layer before (act_ready[dep])
+  // and start an image of their own, so that no image straddles the dependency.
+  void add_op(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles, int b_buf, int b_kb0, int d_blk,
+              int d_tile_stride, int zero_first, int dep, int fresh_from, int commit) {
+    if (dep >= 0 && fresh_from > 0 && kb_lo + fresh_from < kb_hi) {
+      add_op(W8, N, K, kb_lo, kb_lo + fresh_from, tile_step, n_tiles, b_buf, b_kb0, d_blk, d_tile_stride, zero_first, -1, 0, -1);
+      add_op(W8, N, K, kb_lo + fresh_from, kb_hi, tile_step, n_tiles, b_buf, b_kb0 + fresh_from, d_blk, d_tile_stride, 0, dep, 0, commit);
+      return;
+    }
+    static const int unrolled[3] = {8, 4, 3};
+    if (n_tiles < 1 || n_tiles > 3 || N * 32 > UMMA_I8_STAGE_BYTES) { ok = false; return; }
+    for (int kb = kb_lo; kb < kb_hi;) {
+      const int space = UMMA_I8_STAGE_BYTES - (int)i8_cur.size();
+      int nk = std::min(std::min(unrolled[n_tiles - 1], kb_hi - kb), space / (N * 32));
+      if (nk < 1) { close_i8(); continue; }
+      UmmaRec r; memset(&r, 0, sizeof(r));
+      r.a_off16 = (unsigned short)(i8_cur.size() / 16); r.tile_step = (unsigned short)tile_step;
+      r.b_kb = (unsigned short)(b_kb0 + (kb - kb_lo)); r.nk = (unsigned char)nk; r.n_tiles = (unsigned char)n_tiles;
+      r.b_buf = (unsigned char)b_buf; r.d_blk = (unsigned char)d_blk; r.d_tile_stride = (unsigned char)d_tile_stride;
+      r.flags = (unsigned char)((i8_cur.empty() ? UR_STAGE_FIRST : 0) | ((zero_first && kb == kb_lo) ? UR_ZERO_FIRST : 0));
+      r.dep = (signed char)(kb == kb_lo ? dep : -1);
+      r.commit = (signed char)(kb + nk == kb_hi ? commit : -1);
+      std::vector<uint8_t> c = umma_bake_chunk(W8, N, K, kb, nk);
+      i8_cur.insert(i8_cur.end(), c.begin(), c.end());
+      recs.push_back(r);
+      kb += nk;
+    }
+  }
+  // rows [j0, j0 + nrows) of a float [K][NOUT] matrix, each zero-padded to NOUTP floats; a stage always holds a multiple of 4 rows
+  // of a segment (the float warps read the activations four at a time)
+  void add_f32(const float *Wf, int NOUT, int NOUTP, int j0, int nrows) {
+    const int rb = NOUTP * 4;
+    for (int r0 = 0; r0 < nrows;) {
+      const int space = UMMA_F32_STAGE_BYTES - (int)f32_cur.size();
+      const int n = std::min(nrows - r0, space / rb) & ~3;
+      if (n < 4) { if (f32_cur.empty()) { ok = false; return; } close_f32(); continue; }
+      std::vector<float> t((size_t)n * NOUTP, 0.f);
+      for (int r = 0; r < n; r++) memcpy(&t[(size_t)r * NOUTP], Wf + (size_t)(j0 + r0 + r) * NOUT, NOUT * sizeof(float));
+      const unsigned char *p = (const unsigned char *)t.data();
+      f32_cur.insert(f32_cur.end(), p, p + (size_t)n * rb);
+      r0 += n;
+    }
+  }
+};
+
+void build_umma(const std::map<std::string, const int8_t *> &p8, const std::map<std::string, const float *> &pf, UmmaBuilder &e, UmmaBuilder &d) {
+  auto I8 = [&](const std::string &n) { return p8.at(n); };
+  auto F = [&](const std::string &n) { return pf.at(n); };
+  static const int enc_dil[5] = {1, 2, 2, 2, 2};
+  {
+    e.add_f32(F("enc_dense1"), 64, 64, 0, ENC_IN);                         // prologue: dense1 of step 0
+    e.close_f32();
+    e.f32_prologue = (int)e.f32_chunks.size();
+    e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, 0, 64);           // concat segment 0 = dense1 output
+    e.add_f32(F("enc_dense1"), 64, 64, 0, ENC_IN);                         // dense1 of the next step
+    int off = 64;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      const int gs = (l & 1) * 4, cs = 8 + (l & 1);
+      // GRU: tiles [z; r] (rows 0..127) and [n; -] (rows 128..); fresh input = conv l-1's 96 outputs (3 k-blocks)
+      e.add_op(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32, 128, 2, UB_CUR, 0, gs, 2, 1, l ? 2 * (l - 1) + 1 : -1, l ? off / 32 - 3 : 0, -1);
+      e.add_op(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2, 128, 2, UB_PREV1, off / 32, gs + 1, 2, 1, -1, 0, 2 * l);
+      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
+      off += ENC_GRU;
+      // conv (k = 2): tap 0 = concat prefix of step t - dilation, tap 1 = current prefix whose last 2 k-blocks are GRU l's outputs
+      e.add_op(I8("enc_conv" + n), 96, 2 * off, 0, off / 32, 0, 1, enc_dil[l] == 1 ? UB_PREV1 : UB_PREV2, 0, cs, 0, 1, -1, 0, -1);
+      e.add_op(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32, 0, 1, UB_CUR, 0, cs, 0, 0, 2 * l, off / 32 - 2, 2 * l + 1);
+      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
+      off += ENC_CONV;
+    }
+    e.close_i8(); e.close_f32();
+  }
+  {
+    d.add_f32(F("dec_dense1"), 96, 96, 0, DEC_IN);
+    d.close_f32();
+    d.f32_prologue = (int)d.f32_chunks.size();
+    d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, 0, 96);
+    d.add_f32(F("dec_dense1"), 96, 96, 0, DEC_IN);
+    int off = 96;
+    for (int l = 0; l < 5; l++) {
+      std::string n = std::to_string(l + 1);
+      const int gs = (l & 1) * 6, us = 12 + (l & 1), cs = 14 + (l & 1);
+      // GRU: three overlapping tiles starting at rows 0, 96, 192 (z, r, n of unit u in TMEM lane u); fresh input = conv l-1 (1 k-block)
+      d.add_op(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32, DEC_GRU, 3, UB_CUR, 0, gs, 2, 1, l ? 3 * (l - 1) + 2 : -1, l ? off / 32 - 1 : 0, -1);
+      d.add_op(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3, DEC_GRU, 3, UB_HQ_RD, 3 * l, gs + 1, 2, 1, -1, 0, 3 * l);
+      d.add_op(I8("dec_glu" + n), 96, 96, 0, 3, 0, 1, UB_HQ_WR, 3 * l, us, 0, 1, 3 * l, 0, 3 * l + 1);
+      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
+      off += DEC_GRU;
+      d.add_op(I8("dec_conv" + n), 32, 2 * off, 0, off / 32, 0, 1, UB_PREV1, 0, cs, 0, 1, -1, 0, -1);
+      d.add_op(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32, 0, 1, UB_CUR, 0, cs, 0, 0, 3 * l + 1, off / 32 - 3, 3 * l + 2);
+      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
+      off += DEC_CONV;
+    }
+    d.close_i8(); d.close_f32();
+  }
+}
+
 }  // namespace
 
 int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder *h) {
@@ -275,7 +402,8 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     std::string n = L.name;
     auto get = [&](const std::string &k, int dtype, int rows, int cols) -> const HostArray * {
       auto it = arrays.find(k);
-      if (it == arrays.end() || it->second.dtype != dtype || it->second.rows != rows || it->second.cols != cols) return nullptr;
+      if (it == arrays.end() || it->second.dtype != dtype || it->second.rows != rows || it->second.cols != cols ||
+          it->second.data.size() != (size_t)rows * cols * (dtype == 1 ? 1 : 4)) return nullptr;
       return &it->second;
     };
     const HostArray *b = get(n + ".bias", 0, 1, L.nout);
@@ -309,19 +437,46 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   }
   // ---- per-step weight streams, in the kernels' consumption order (keep in lock-step with core_codec.cu)
   StreamBuilder e, d;
+  UmmaBuilder ue, ud;
   int e_pro = 0, d_pro = 0;
   {
     std::map<std::string, const int8_t *> p8; std::map<std::string, const float *> pf;
     for (auto &kv : w8) p8[kv.first] = (const int8_t *)kv.second->data.data();
     for (auto &kv : wf) pf[kv.first] = (const float *)kv.second->data.data();
-    build_streams(p8, pf, false, e, d, e_pro, d_pro);
-    if (core_codec_umma_enabled()) {             // the experimental tcgen05 encoder consumes its int8 chunks in the operand layout
-      StreamBuilder e2, d2; int ep2 = 0, dp2 = 0;
-      build_streams(p8, pf, true, e2, d2, ep2, dp2);
-      e = e2; e_pro = ep2; d = d2; d_pro = dp2;
-    }
+    build_streams(p8, pf, e, d, e_pro, d_pro);
+    build_umma(p8, pf, ue, ud);
   }
-  if (!e.ok || !d.ok) { fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1; }
+  if (!e.ok || !d.ok || !ue.ok || !ud.ok || ue.recs.size() > UMMA_MAX_RECS || ud.recs.size() > UMMA_MAX_RECS ||
+      ue.i8_chunks.size() > UMMA_MAX_I8_CHUNKS || ud.i8_chunks.size() > UMMA_MAX_I8_CHUNKS ||
+      ue.f32_chunks.size() > UMMA_MAX_F32_CHUNKS || ud.f32_chunks.size() > UMMA_MAX_F32_CHUNKS) {
+    fprintf(stderr, "libradae_b200: internal error building the weight streams\n"); return -1;
+  }
+  auto up_umma = [&](UmmaBuilder &ub, UmmaCodecDev &out) -> int {
+    out.i8_stream = (const unsigned char *)dev_copy(ub.i8.data(), ub.i8.size());
+    out.i8_chunks = (const ChunkDesc *)dev_copy(ub.i8_chunks.data(), ub.i8_chunks.size() * sizeof(ChunkDesc));
+    out.n_i8_chunks = (int)ub.i8_chunks.size();
+    out.f32_stream = (const unsigned char *)dev_copy(ub.f32.data(), ub.f32.size());
+    out.f32_chunks = (const ChunkDesc *)dev_copy(ub.f32_chunks.data(), ub.f32_chunks.size() * sizeof(ChunkDesc));
+    out.n_f32_chunks = (int)ub.f32_chunks.size(); out.n_f32_prologue = ub.f32_prologue;
+    return (out.i8_stream && out.i8_chunks && out.f32_stream && out.f32_chunks) ? 0 : -1;
+  };
+  auto set_prog = [&](UmmaBuilder &ub, UmmaProgram &P, UmmaCodecDev &out) {
+    memset(&P, 0, sizeof(P));
+    P.n_recs = (int)ub.recs.size();
+    for (size_t i = 0; i < ub.recs.size(); i++) {
+      const UmmaRec &r = ub.recs[i];
+      const unsigned asbo = (unsigned)r.nk * 256u;
+      UmmaRecPacked &p = P.recs[i];
+      p.w[0] = (unsigned)r.a_off16 | ((128u >> 4) << 16);
+      p.w[1] = (asbo >> 4) | (1u << 14);
+      p.w[2] = ((unsigned)r.b_kb * 16u) | ((((unsigned)(r.tile_step >> 3) * asbo) >> 4) << 16);
+      p.w[3] = (unsigned)r.nk | (unsigned)r.n_tiles << 4 | (unsigned)r.b_buf << 6 | (unsigned)r.flags << 9 | (unsigned)r.d_blk << 12 |
+               (unsigned)r.d_tile_stride << 17 | (unsigned)(r.dep + 1) << 20 | (unsigned)(r.commit + 1) << 25;
+    }
+    out.prog_host = &P;
+  };
+  if (up_umma(ue, W.enc_umma) < 0 || up_umma(ud, W.dec_umma) < 0) return -1;
+  set_prog(ue, h->enc_prog, W.enc_umma); set_prog(ud, h->dec_prog, W.dec_umma);
   auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out, int n_pro) -> int {
     out.n_prologue = n_pro;
     out.stream = (const unsigned char *)dev_copy(sb.bytes.data(), sb.bytes.size());
@@ -336,10 +491,33 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
   return 0;
 }
 
+// Host-only validation of a weight blob (no device involved): container parse + every array the layer table needs present with
+// the right dtype and shape.  0 = core_weights_upload would accept it, -1 = rejected.  (rade_b200_debug_check_weights)
+int core_weights_validate(const unsigned char *blob, size_t len) {
+  ArrayMap arrays;
+  if (!blob || (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays))) return -1;
+  int in_dim, out_dim;
+  normalise_io_width(arrays, &in_dim, &out_dim);
+  std::vector<LayerSpec> specs; std::vector<std::string> names;
+  layer_specs(specs, names);
+  auto ok = [&](const std::string &k, int dtype, int rows, int cols) {
+    auto it = arrays.find(k);
+    return it != arrays.end() && it->second.dtype == dtype && it->second.rows == rows && it->second.cols == cols &&
+           it->second.data.size() == (size_t)rows * cols * (dtype == 1 ? 1 : 4);
+  };
+  for (auto &L : specs) {
+    std::string n = L.name;
+    if (!ok(n + ".bias", 0, 1, L.nout)) return -1;
+    if (L.kind == 0) { if (!ok(n + ".wf", 0, L.nin, L.nout)) return -1; }
+    else if (!ok(n + ".w8", 1, L.nout, L.nin) || !ok(n + ".scale", 0, 1, L.nout)) return -1;
+  }
+  return 0;
+}
+
 // Debug / test hook (no device involved): the weight stream of one codec as the host builds it, in either int8 chunk format.
 // which: 0 encoder, 1 decoder.  Returns 0 and fills bytes / chunks / n_prologue, or -1.
 int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, int umma, std::vector<unsigned char> *bytes,
-                              std::vector<ChunkDesc> *chunks, int *n_prologue) {
+                              std::vector<ChunkDesc> *chunks, int *n_prologue, std::vector<UmmaRec> *ops) {
   ArrayMap arrays;
   if (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays)) return -1;
   std::map<std::string, const int8_t *> p8; std::map<std::string, const float *> pf;
@@ -348,8 +526,18 @@ int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, 
     if (k.size() > 3 && k.compare(k.size() - 3, 3, ".w8") == 0) p8[k.substr(0, k.size() - 3)] = (const int8_t *)kv.second.data.data();
     if (k.size() > 3 && k.compare(k.size() - 3, 3, ".wf") == 0) pf[k.substr(0, k.size() - 3)] = (const float *)kv.second.data.data();
   }
+  if (umma) {                                  // 1: int8 stream, 2: float stream of the tcgen05 formulation
+    UmmaBuilder ue, ud;
+    try { build_umma(p8, pf, ue, ud); } catch (...) { return -1; }
+    if (!ue.ok || !ud.ok) return -1;
+    UmmaBuilder &ub = which ? ud : ue;
+    if (umma == 1) { *bytes = ub.i8; *chunks = ub.i8_chunks; *n_prologue = 0; }
+    else { *bytes = ub.f32; *chunks = ub.f32_chunks; *n_prologue = ub.f32_prologue; }
+    if (ops) *ops = ub.recs;
+    return 0;
+  }
   StreamBuilder e, d; int e_pro = 0, d_pro = 0;
-  try { build_streams(p8, pf, umma != 0, e, d, e_pro, d_pro); } catch (...) { return -1; }
+  try { build_streams(p8, pf, e, d, e_pro, d_pro); } catch (...) { return -1; }
   if (!e.ok || !d.ok) return -1;
   StreamBuilder &sb = which ? d : e;
   *bytes = sb.bytes; *chunks = sb.chunks; *n_prologue = which ? d_pro : e_pro;

@@ -92,8 +92,52 @@ def test_product_does_not_import_the_oracle():
     code = "import sys, radae_b200, radae_b200.batch, radae_b200.streaming, radae_b200.rdw; " \
            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'product imports oracle'"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=REPO)
+    # ... and no source file of the product imports, links, dlopens or executes anything under oracle/ (comments may cite it)
+    import re
+    forbidden = re.compile(r"^\s*(import|from)\s+oracle\b|oracle/_ref|librade_ref|libcore_oracle|core_oracle\.c|nnet_shim\.c\s*\"|"
+                           r"CDLL\([^)]*oracle|dlopen\([^)]*oracle|-loracle", re.M)
+    n_files = 0
     for root, _, files in os.walk(os.path.join(REPO, "radae_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".h")):
-                assert "oracle" not in open(os.path.join(root, f)).read().replace("oracle/", "").replace("the oracle", "").replace("C oracle", "").replace("oracle's", "") \
-                    or True
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".S")):
+                n_files += 1
+                m = forbidden.search(open(os.path.join(root, f)).read())
+                assert m is None, (f, m.group(0))
+    assert n_files > 15
+
+
+def test_weight_blobs_are_validated_before_use(lib):
+    """rade_open(model_file) / rade_b200_open(weights, len) take caller-supplied bytes — truncated or crafted
+    containers must be rejected as a whole (host-only hook, the same parser rade_b200_open uses)"""
+    import struct
+    from radae_b200 import rdw
+    chk = lambda b: lib.rade_b200_debug_check_weights(bytes(b), len(b))
+    good = open(rdw.default_weights_path(), "rb").read()
+    assert chk(good) == 0
+    assert chk(open(rdw.model05_weights_path(), "rb").read()) == 0
+    assert chk(good[:len(good) // 2]) == -1 and chk(good[:70]) == -1 and chk(b"RADEB200") == -1 and chk(b"") == -1
+    n = struct.unpack_from("<I", good, 12)[0]
+    for i in (0, n // 2, n - 1):                       # payload shorter than rows x cols, offset overflow, offset into the table
+        e = 64 + 80 * i
+        nm, dt, rows, cols, _, off, nbytes = struct.unpack_from("<48sIIIIQQ", good, e)
+        for patch in ((off, nbytes - 16), (2 ** 64 - 8, nbytes), (len(good) - 4, nbytes), (64, nbytes)):
+            bad = bytearray(good); struct.pack_into("<QQ", bad, e + 64, *patch)
+            assert chk(bad) == -1, (i, patch)
+        bad = bytearray(good); struct.pack_into("<I", bad, e + 52, rows + 1)
+        assert chk(bad) == -1
+    blob_path = "/root/reference/bin/model19_check3.bin"
+    if os.path.exists(blob_path):                      # the reference's DNNw blob (not on the GPU box: CPU suite only)
+        blob = open(blob_path, "rb").read()
+        assert chk(blob) == 0
+        assert chk(blob[:-64]) == -1 and chk(blob[:len(blob) // 3]) == -1
+        # an index list that claims more blocks than the file holds, or points outside the matrix
+        off = 0
+        while off < len(blob):
+            size, block = struct.unpack_from("<ii", blob, off + 12)
+            name = blob[off + 20:off + 64].split(b"\0")[0]
+            if name.endswith(b"_weights_idx"):
+                bad = bytearray(blob); struct.pack_into("<i", bad, off + 64, 10 ** 6); assert chk(bad) == -1
+                bad = bytearray(blob); struct.pack_into("<i", bad, off + 68, 10 ** 6); assert chk(bad) == -1
+                bad = bytearray(blob); struct.pack_into("<i", bad, off + 12, size - 4); assert chk(bad) == -1
+                break
+            off += 64 + block

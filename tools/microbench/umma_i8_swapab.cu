@@ -172,7 +172,7 @@ int main() {
       long long hC[2];
       // pass 1: iters = 1 for the exactness check (int32 would not overflow either way), pass 2: timing
       long bad = 0, bad_swapped = 0;
-      for (int swap = 1; swap >= 0; swap--) {             // ends with the documented field order
+      for (int swap = 0; swap >= 0; swap--) {             // the documented field order (the exchanged one reads outside shared memory: round-2 run)
         umma_probe<<<grid, 128, (M + N) * K_TOTAL>>>(dA, dB, N, 1, 1, dD, dC, swap);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
