@@ -144,6 +144,8 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   b->weights.dev.trace = nullptr;
+  b->weights.dev.float_fma = 0;            // measurement switch only (tools/gpu_fma_ab.sh sets it through RADE_B200_DEBUG_FLOAT_FMA): never on in the product
+  if (getenv("RADE_B200_DEBUG_FLOAT_FMA") && atoi(getenv("RADE_B200_DEBUG_FLOAT_FMA")) == 1) b->weights.dev.float_fma = 1;
   b->weights.dev.enc_z_tanh = (flags & RADE_B200_BOTTLENECK_1) ? 1 : 0;      // src/rade_enc.c:107-113
   DspTablesHost th; dsp_tables_host(th);
   if (dsp_tables_upload(th, &b->tables, b->allocs) < 0) { delete b; return nullptr; }

@@ -16,8 +16,9 @@
 //   E  8 epilogue warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (= output features), column half w / 4 (= streams); float
 //      epilogue in the oracle's rounding order straight from tcgen05.ld registers, appends the quantised outputs to the concat
 //      buffer (byte stores + fence.proxy.async) and the float outputs to a 4-deep segment ring for the float warps;
-//   I  issuer: ONE thread walks the per-step MMA program the host compiled (UmmaOp list), waits for a weight chunk, issues its
-//      MMAs, releases the ring stage with tcgen05.commit; only the last 1-3 k-blocks of a layer depend on the previous layer's
+//   I  issuer: ONE elected thread runs the per-step MMA program — fixed at compile time (umma_program.h) and unrolled into
+//      straight-line tcgen05.mma with immediate descriptor offsets — waits for a weight stage, issues its MMAs, releases the
+//      stage with tcgen05.commit; only the last 1-3 k-blocks of a layer depend on the previous layer's
 //      output, so all other k-blocks are issued ahead while the epilogue of the previous layer is still running;
 //   F  float warps: dense1 (one step ahead, written straight into the next step's concat buffer) and the wide zdense / output
 //      layer, accumulated segment by segment in concat order (= the reference's sequential summation order) from their own ring;
@@ -32,6 +33,7 @@
 #include "rade_host.h"
 #include "tma.cuh"
 #include "codec_math.cuh"
+#include "umma_program.h"
 
 namespace {
 
@@ -143,15 +145,29 @@ template <int NST, int STAGE> struct FloatCursor {
 // Float thread = (4 consecutive outputs, RS streams): acc[r][i] += sum_j W[j][4 grp + i] x_r[j] over the next K rows (NOUTP floats
 // each) of the float stream, sequentially in j.  One LDS.128 of weights serves RS streams: the float layers are bound by the
 // shared-memory port (every weight used to be delivered once per stream), not by arithmetic.
-template <int RS> __device__ __forceinline__ void mac4(float (&acc)[RS][4], const float4 w, const float (&x)[RS]) {
+// FMA = false: product and sum separately rounded (the generic C sgemv of the reference, bit for bit).  FMA = true: one fused
+// multiply-add per MAC (what the reference computes when opus is built with its AVX2 / NEON sgemv): 1/3 of the FP32-pipe time.
+__device__ __forceinline__ float2 fma2_rn(float wx, float wy, float x, float ax, float ay) {
+  float2 w = make_float2(wx, wy), xx = make_float2(x, x), a = make_float2(ax, ay);
+  unsigned long long rw = *reinterpret_cast<unsigned long long *>(&w), rx = *reinterpret_cast<unsigned long long *>(&xx),
+                     ra = *reinterpret_cast<unsigned long long *>(&a), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rw), "l"(rx), "l"(ra));
+  return *reinterpret_cast<float2 *>(&rd);
+}
+template <int RS, bool FMA> __device__ __forceinline__ void mac4(float (&acc)[RS][4], const float4 w, const float (&x)[RS]) {
 #pragma unroll
   for (int r = 0; r < RS; r++) {
-    const float2 p0 = prod2_rn(w.x, w.y, x[r]), p1 = prod2_rn(w.z, w.w, x[r]);
-    acc[r][0] = __fadd_rn(acc[r][0], p0.x); acc[r][1] = __fadd_rn(acc[r][1], p0.y);
-    acc[r][2] = __fadd_rn(acc[r][2], p1.x); acc[r][3] = __fadd_rn(acc[r][3], p1.y);
+    if constexpr (FMA) {
+      const float2 a0 = fma2_rn(w.x, w.y, x[r], acc[r][0], acc[r][1]), a1 = fma2_rn(w.z, w.w, x[r], acc[r][2], acc[r][3]);
+      acc[r][0] = a0.x; acc[r][1] = a0.y; acc[r][2] = a1.x; acc[r][3] = a1.y;
+    } else {
+      const float2 p0 = prod2_rn(w.x, w.y, x[r]), p1 = prod2_rn(w.z, w.w, x[r]);
+      acc[r][0] = __fadd_rn(acc[r][0], p0.x); acc[r][1] = __fadd_rn(acc[r][1], p0.y);
+      acc[r][2] = __fadd_rn(acc[r][2], p1.x); acc[r][3] = __fadd_rn(acc[r][3], p1.y);
+    }
   }
 }
-template <int NOUTP, int RS, typename CX>
+template <int NOUTP, int RS, bool FMA = false, typename CX>
 __device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[RS][4], const float *x0, int ldx, int K, int grp, bool act) {
   for (int r0 = 0; r0 < K;) {
     if (cx.left == 0) cx.next_stage();
@@ -166,16 +182,16 @@ __device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[RS][4], const flo
         float x[RS];
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].x;
-        mac4<RS>(acc, W4[(j + 0) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 0) * (NOUTP / 4)], x);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].y;
-        mac4<RS>(acc, W4[(j + 1) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 1) * (NOUTP / 4)], x);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].z;
-        mac4<RS>(acc, W4[(j + 2) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 2) * (NOUTP / 4)], x);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].w;
-        mac4<RS>(acc, W4[(j + 3) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 3) * (NOUTP / 4)], x);
       }
     }
     cx.consumed(n * NOUTP * 4);
@@ -191,87 +207,52 @@ template <int NOUTP, typename CX> __device__ __forceinline__ void skip_seg(CX &c
   }
 }
 
-// ---------------------------------------------------------------- issuer: walks the host-compiled MMA program
-// The WHOLE warp runs this loop on warp-uniform values (program in kernel-parameter space, loop counters, shared-memory
-// addresses), so the descriptor arithmetic stays on the uniform datapath; only the tcgen05 instructions themselves are issued by
-// one elected lane.  (A first version ran the loop inside `if (lane == 0)`: the compiler then moves every descriptor through
-// R2UR waterfall code, ~25 dependent instructions = 380 cycles per MMA, 8 x the tensor core's own 47, measured with
-// tools/microbench/umma_issue_rate.cu.)
+// ---------------------------------------------------------------- issuer: the compile-time MMA program as straight-line code
+// ONE elected thread issues everything.  The record list (umma_program.h) is unrolled by template recursion: per record a block
+// of nk x n_tiles tcgen05.mma whose descriptors are `base register + immediate`, plus the waits and commits the record carries.
+// History of this loop, measured on the B200 (tools/microbench/umma_issue_loop.cu, tools/codec_trace.py): descriptors computed
+// inside `if (lane == 0)` -> R2UR waterfall code, 380 cycles per MMA; warp-uniform loop with `if (leader)` per MMA -> 100;
+// elect.sync + unrolled chunks interpreted from a run-time record list -> 30 per MMA but ~480 per record; the tensor core itself
+// needs 47-52 per MMA (M = 128, N = 8, kind::i8: bound by the 4 KB operand fetch, not by the 16 cycles of math).
 struct IssuerBufs { uint32_t lo[5]; uint32_t hi_cat, hi_hq; };     // low descriptor words (address + LBO) of the five B buffers
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | ((128u >> 4) << 16); }       // start address, LBO = 128
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }                  // SBO, descriptor version 1
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }        // SBO, descriptor version 1
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return (uint64_t)hi << 32 | lo; }
-// one ring chunk = NK k-blocks x TILES tiles of straight-line MMAs (tools/microbench/umma_issue_loop.cu: 54 cycles per MMA unrolled,
-// 84-100 with a runtime loop around each MMA); only the very first MMA of a matrix may overwrite the accumulator
-template <int NS, int NK, int TILES>
-__device__ __forceinline__ void issue_chunk(uint32_t d0, uint32_t dstep, uint32_t a_lo, uint32_t a_hi, uint32_t tile_off, uint32_t b_lo,
-                                            uint32_t b_hi, uint32_t acc_first) {
+template <typename I8Ring> struct IssueCtx {
+  I8Ring cx; IssuerBufs B; uint32_t tmem, stage_lo, par; uint64_t *act_ready, *acc_full; long long *trace; int t;
+};
+template <int NS, bool ENC, int I, typename CTX>
+__device__ __forceinline__ void issue_rec(CTX &c) {
+  constexpr UmmaRecC r = ENC ? kUmmaEncProg.r[I] : kUmmaDecProg.r[I];
+  long long *const trace = c.trace;
+  if constexpr ((r.flags & UR_STAGE_FIRST) != 0) { c.stage_lo = (smem_u32(c.cx.acquire()) & 0x3FFFF) >> 4; tc_fence_after(); }
+  if constexpr (r.dep >= 0) {                                      // this image consumes the outputs of the layer before
+    TR((c.t * 128 + I) * 2);
+    mbar_wait(&c.act_ready[r.dep], c.par); tc_fence_after();
+    TR((c.t * 128 + I) * 2 + 1);
+  }
+  constexpr uint32_t asbo = (uint32_t)r.nk * 256u;                 // 8-row group stride of the image: kbytes * 8
+  constexpr uint32_t a_hi = desc_hi(asbo);
+  constexpr uint32_t tile_off = ((uint32_t)(r.tile_step >> 3) * asbo) >> 4;      // descriptor units (16 B) between tiles
+  const uint32_t a_lo = c.stage_lo + ((uint32_t)r.a_off16 | ((128u >> 4) << 16));
+  const uint32_t b_lo = c.B.lo[r.b_buf] + (uint32_t)r.b_kb * 16u;
+  const uint32_t b_hi = r.b_buf >= UB_HQ_RD ? c.B.hi_hq : c.B.hi_cat;
 #pragma unroll
-  for (int k = 0; k < NK; k++) {
+  for (int k = 0; k < r.nk; k++) {
 #pragma unroll
-    for (int g = 0; g < TILES; g++)
-      umma_i8<NS>(d0 + g * dstep, desc64(a_lo + k * 16 + g * tile_off, a_hi), desc64(b_lo + k * 16, b_hi), k == 0 ? acc_first : 1u);
+    for (int g = 0; g < r.n_tiles; g++)
+      umma_i8<NS>(c.tmem + (uint32_t)(r.d_blk + g * r.d_tile_stride) * NS, desc64(a_lo + k * 16 + g * tile_off, a_hi),
+                  desc64(b_lo + k * 16, b_hi), (k == 0 && (r.flags & UR_ZERO_FIRST)) ? 0u : 1u);
   }
+  if constexpr ((r.flags & UR_STAGE_LAST) != 0) { umma_commit(&c.cx.r->empty[c.cx.stage]); c.cx.advance(); }   // stage free once these MMAs have read it
+  if constexpr (r.commit >= 0) { umma_commit(&c.acc_full[r.commit]); TR(1024 + c.t * 16 + r.commit); }
 }
-template <int NS, int TILES>
-__device__ __forceinline__ void issue_chunk_nk(int nk, uint32_t d0, uint32_t dstep, uint32_t a_lo, uint32_t a_hi, uint32_t tile_off,
-                                               uint32_t b_lo, uint32_t b_hi, uint32_t acc_first) {
-  switch (nk) {
-    case 1: issue_chunk<NS, 1, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 2: issue_chunk<NS, 2, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 3: issue_chunk<NS, 3, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 4: if constexpr (TILES <= 2) issue_chunk<NS, 4, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 5: if constexpr (TILES == 1) issue_chunk<NS, 5, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 6: if constexpr (TILES == 1) issue_chunk<NS, 6, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 7: if constexpr (TILES == 1) issue_chunk<NS, 7, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    case 8: if constexpr (TILES == 1) issue_chunk<NS, 8, TILES>(d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first); break;
-    default: break;
-  }
-}
-template <int NS, bool TRACE, typename I8Ring>
-__device__ __forceinline__ void issuer_step(I8Ring &cx, const UmmaProgram &P, const IssuerBufs &B, uint32_t tmem,
-                                            uint64_t *act_ready, uint64_t *acc_full, uint32_t par, bool leader, long long *trace, int t) {
-  uint32_t stage_lo = 0;
-  long long t_acq = 0, t_iss = 0;
-  const int n_recs = P.n_recs;
-  uint4 nxt = *reinterpret_cast<const uint4 *>(P.recs[0].w);
-  for (int i = 0; i < n_recs; i++) {
-    const uint4 rec = nxt;
-    if (i + 1 < n_recs) nxt = *reinterpret_cast<const uint4 *>(P.recs[i + 1].w);   // the next record is on its way while this one issues
-    const uint32_t ctl = rec.w;
-    const int nk = ctl & 15, n_tiles = (ctl >> 4) & 3, b_buf = (ctl >> 6) & 7, flags = (ctl >> 9) & 7;
-    const int dep = (int)((ctl >> 20) & 31) - 1, commit = (int)((ctl >> 25) & 31) - 1;
-    if (flags & UR_STAGE_FIRST) {
-      long long ta = 0;
-      if (TRACE) ta = clock64();
-      stage_lo = (smem_u32(cx.acquire()) & 0x3FFFF) >> 4; tc_fence_after();
-      if (TRACE) t_acq += clock64() - ta;
-    }
-    if (dep >= 0) {                                                // this image consumes the outputs of the layer before
-      if (TRACE && leader) TR((t * 128 + i) * 2);
-      mbar_wait(&act_ready[dep], par); tc_fence_after();
-      if (TRACE && leader) TR((t * 128 + i) * 2 + 1);
-    }
-    const uint32_t b_lo = (b_buf == UB_CUR ? B.lo[0] : b_buf == UB_PREV1 ? B.lo[1] : b_buf == UB_PREV2 ? B.lo[2] : b_buf == UB_HQ_RD ? B.lo[3] : B.lo[4]) +
-                          (rec.z & 0xffffu);
-    const uint32_t b_hi = b_buf >= UB_HQ_RD ? B.hi_hq : B.hi_cat;
-    const uint32_t d0 = tmem + ((ctl >> 12) & 31) * NS, dstep = ((ctl >> 17) & 7) * NS;
-    const uint32_t a_lo = stage_lo + rec.x, a_hi = rec.y, tile_off = rec.z >> 16;
-    const uint32_t acc_first = (flags & UR_ZERO_FIRST) ? 0u : 1u;
-    long long ti = 0;
-    if (TRACE) ti = clock64();
-    if (leader) {
-      if (n_tiles == 1) issue_chunk_nk<NS, 1>(nk, d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first);
-      else if (n_tiles == 2) issue_chunk_nk<NS, 2>(nk, d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first);
-      else issue_chunk_nk<NS, 3>(nk, d0, dstep, a_lo, a_hi, tile_off, b_lo, b_hi, acc_first);
-      if (flags & UR_STAGE_LAST) umma_commit(&cx.r->empty[cx.stage]);            // the stage is free once these MMAs have read it
-      if (commit >= 0) { umma_commit(&acc_full[commit]); if (TRACE) TR(1024 + t * 16 + commit); }
-    }
-    if (TRACE) { const long long d = clock64() - ti; t_iss += d; if (trace && blockIdx.x == 0) trace[8192 + t * 128 + i] = d; }
-    if (flags & UR_STAGE_LAST) cx.advance();
-  }
-  if (TRACE && leader && trace && blockIdx.x == 0) { trace[1536 + t * 4] = t_acq; trace[1536 + t * 4 + 1] = t_iss; }
-}
+template <int NS, bool ENC, int I, int N> struct IssueAll {
+  template <typename CTX> static __device__ __forceinline__ void run(CTX &c) { issue_rec<NS, ENC, I>(c); IssueAll<NS, ENC, I + 1, N>::run(c); }
+};
+template <int NS, bool ENC, int N> struct IssueAll<NS, ENC, N, N> {
+  template <typename CTX> static __device__ __forceinline__ void run(CTX &) {}
+};
 
 // ================================================================= encoder
 template <int NS> struct EncCfg {
@@ -302,7 +283,7 @@ template <int NS> struct EncSmemU {
 
 template <int NS>
 __global__ void __launch_bounds__(EncCfg<NS>::THREADS, 1)
-core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_constant__ UmmaProgram P, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
+core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
                          float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
   typedef EncCfg<NS> C;
   constexpr int NC = C::NC, RSF = C::RSF, NSP = NS / RSF, NF = C::NF, KB = C::KB, NCB = C::NCB;
@@ -401,7 +382,8 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
       float zacc[RSF][4];
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) zacc[r][i] = 0.f;
-      dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on);
+      if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on);
+      else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on);
       nb_sync(NB_F, NF * 32);                    // everybody is done with d1f and fin of this step
       if (t + 1 < T) { stage_input(t + 1); nb_sync(NB_F, NF * 32); dense1(t + 1); }
       else skip_seg<64>(cx, ENC_IN);
@@ -410,7 +392,8 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
         const int slot = nseg % NSEG;
         mbar_wait(&sm.seg_full[slot], (nseg / NSEG) & 1);
         if (ft == 0) TR(4096 + (t * 16 + j) * 2);
-        dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on);
+        if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on);
+        else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on);
         __syncwarp();
         if (ft == 0) TR(4096 + (t * 16 + j) * 2 + 1);
         if (lane == 0) mbar_arrive(&sm.seg_empty[slot]);
@@ -435,19 +418,19 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
   // ---------------------------------------------------------------- issuer warp
   if (warp == NF + NE + 2) {
     nb_sync(NB_MAIN, N_MAIN);
-    const bool leader = true;
-    if (elect_one()) {                           // ONE thread runs the whole issue loop (no reconvergence points inside)
-    RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> cx{&sm.i8, 0, 0u};
-    IssuerBufs B;
-    B.lo[3] = B.lo[4] = 0; B.hi_cat = B.hi_hq = desc_hi(KB * 8);
-    for (int t = 0; t < T; t++) {
-      B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
-      B.lo[2] = desc_lo(smem_u32(sm.cb[(t + NCB - 2) % NCB]));
-      mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);          // dense1 output (int8) is in cur, features [0, 64)
-      tc_fence_after();
-      if (trace) issuer_step<NS, true>(cx, P, B, tmem, sm.act_ready, sm.acc_full, t & 1, leader, trace, t);
-      else issuer_step<NS, false>(cx, P, B, tmem, sm.act_ready, sm.acc_full, t & 1, leader, trace, t);
-    }
+    if (elect_one()) {                           // ONE thread runs the whole issue program (no reconvergence points inside)
+      typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
+      IssueCtx<Ring> c;
+      c.cx = Ring{&sm.i8, 0, 0u}; c.tmem = tmem; c.stage_lo = 0; c.act_ready = sm.act_ready; c.acc_full = sm.acc_full; c.trace = trace;
+      c.B.lo[3] = c.B.lo[4] = 0; c.B.hi_cat = c.B.hi_hq = desc_hi(KB * 8);
+      for (int t = 0; t < T; t++) {
+        c.B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); c.B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
+        c.B.lo[2] = desc_lo(smem_u32(sm.cb[(t + NCB - 2) % NCB]));
+        c.par = t & 1; c.t = t;
+        mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);        // dense1 output (int8) is in cur, features [0, 64)
+        tc_fence_after();
+        IssueAll<NS, true, 0, kUmmaEncProg.n>::run(c);
+      }
     }
     __syncwarp();
     nb_sync(NB_MAIN, N_MAIN);
@@ -616,7 +599,7 @@ template <int NS> struct DecSmemU {
 // uw_count (optional): += number of steps whose first aux symbol (feature 20) is > 0 (src/rade_api.c:502-505)
 template <int NS>
 __global__ void __launch_bounds__(DecCfg<NS>::THREADS, 1)
-core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_constant__ UmmaProgram P, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
+core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamState *__restrict__ state, const float *__restrict__ z_in,
                          float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
                          const uint8_t *__restrict__ active, int S, int T) {
   typedef DecCfg<NS> C;
@@ -703,7 +686,8 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
       float oacc[RSF][4];
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) oacc[r][i] = 0.f;
-      dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on);
+      if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on);
+      else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on);
       nb_sync(NB_F, NF * 32);
       if (t + 1 < T) { stage_input(t + 1); nb_sync(NB_F, NF * 32); dense1(t + 1); }
       else skip_seg<96>(cx, DEC_IN);
@@ -712,7 +696,8 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
         const int slot = nseg % NSEG;
         mbar_wait(&sm.seg_full[slot], (nseg / NSEG) & 1);
         if (ft == 0) TR(4096 + (t * 16 + j) * 2);
-        dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on);
+        if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on);
+        else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on);
         __syncwarp();
         if (ft == 0) TR(4096 + (t * 16 + j) * 2 + 1);
         if (lane == 0) mbar_arrive(&sm.seg_empty[slot]);
@@ -747,19 +732,19 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, const __grid_
 
   if (warp == NF + NE + 2) {                     // ---- issuer
     nb_sync(NB_MAIN, N_MAIN);
-    const bool leader = true;
     if (elect_one()) {
-    RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> cx{&sm.i8, 0, 0u};
-    IssuerBufs B;
-    B.lo[2] = 0; B.hi_cat = desc_hi(KB * 8); B.hi_hq = desc_hi(KH * 8);
-    for (int t = 0; t < T; t++) {
-      B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
-      B.lo[3] = desc_lo(smem_u32(sm.hq[t & 1])); B.lo[4] = desc_lo(smem_u32(sm.hq[(t + 1) & 1]));
-      mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);
-      tc_fence_after();
-      if (trace) issuer_step<NS, true>(cx, P, B, tmem, sm.act_ready, sm.acc_full, t & 1, leader, trace, t);
-      else issuer_step<NS, false>(cx, P, B, tmem, sm.act_ready, sm.acc_full, t & 1, leader, trace, t);
-    }
+      typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
+      IssueCtx<Ring> c;
+      c.cx = Ring{&sm.i8, 0, 0u}; c.tmem = tmem; c.stage_lo = 0; c.act_ready = sm.act_ready; c.acc_full = sm.acc_full; c.trace = trace;
+      c.B.lo[2] = 0; c.B.hi_cat = desc_hi(KB * 8); c.B.hi_hq = desc_hi(KH * 8);
+      for (int t = 0; t < T; t++) {
+        c.B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); c.B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
+        c.B.lo[3] = desc_lo(smem_u32(sm.hq[t & 1])); c.B.lo[4] = desc_lo(smem_u32(sm.hq[(t + 1) & 1]));
+        c.par = t & 1; c.t = t;
+        mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);
+        tc_fence_after();
+        IssueAll<NS, false, 0, kUmmaDecProg.n>::run(c);
+      }
     }
     __syncwarp();
     nb_sync(NB_MAIN, N_MAIN);
@@ -926,14 +911,14 @@ int core_codec_umma_init_device() {
 int core_encoder_umma_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                              const uint8_t *active, int S, int T, cudaStream_t stream) {
   const int grid = umma_grid(S, 8, g_n_sm);
-  core_encoder_umma_kernel<8><<<grid, EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, *W.enc_umma.prog_host, state, in, in_mode, z, active, S, T);
+  core_encoder_umma_kernel<8><<<grid, EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 int core_decoder_umma_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
                              int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
   const int grid = umma_grid(S, 8, g_n_sm);
-  core_decoder_umma_kernel<8><<<grid, DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, *W.dec_umma.prog_host, state, z, out, out_mode, uw_count, active, S, T);
+  core_decoder_umma_kernel<8><<<grid, DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

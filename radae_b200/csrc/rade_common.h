@@ -84,8 +84,8 @@ struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; in
 enum { UB_CUR = 0, UB_PREV1 = 1, UB_PREV2 = 2, UB_HQ_RD = 3, UB_HQ_WR = 4 };
 enum { UR_STAGE_FIRST = 1, UR_STAGE_LAST = 2, UR_ZERO_FIRST = 4 };
 // One record per weight image: nk k-blocks (32 bytes of K each) of all rows of an int8 matrix in the canonical K-major operand
-// layout (8-row group stride = nk * 256 B), packed back to back into the ring stages.  The issuer thread runs the record list
-// once per step: nk x n_tiles tcgen05.mma, straight-line.  16 bytes; the list travels in kernel-parameter space (uniform loads).
+// layout (8-row group stride = nk * 256 B), packed back to back into the ring stages.  The list is fixed at compile time
+// (umma_program.h); this run-time form exists for the debug hook and the CPU emulation test of the program.
 struct UmmaRec {
   unsigned short a_off16;      // offset of the image inside its ring stage, in 16-byte units
   unsigned short tile_step;    // rows between the starts of consecutive M = 128 tiles
@@ -100,17 +100,9 @@ struct UmmaRec {
   signed char commit;          // acc_full barrier to commit after the last MMA of this record, -1 = none
   unsigned short pad;
 };
-// the form the issuer reads (descriptor words pre-assembled on the host, one 16-byte uniform load per record):
-//   w[0] = a_off16 | LBO field: added to (stage address >> 4) gives the low word of the A descriptor
-//   w[1] = high word of the A descriptor (8-row group stride nk * 256 B, descriptor version)
-//   w[2] = b_kb * 16 (low half: 16-byte units inside the B buffer) | tile offset in 16-byte units (high half)
-//   w[3] = nk [0,4) | n_tiles [4,6) | b_buf [6,9) | flags [9,12) | d_blk [12,17) | d_tile_stride [17,20) | dep + 1 [20,25) | commit + 1 [25,30)
-struct UmmaRecPacked { unsigned int w[4]; };
-struct UmmaProgram { int n_recs; int pad[3]; UmmaRecPacked recs[UMMA_MAX_RECS]; };
 struct UmmaCodecDev {
   const unsigned char *i8_stream; const ChunkDesc *i8_chunks; int n_i8_chunks;          // per step: one chunk = one ring stage = one bulk copy
   const unsigned char *f32_stream; const ChunkDesc *f32_chunks; int n_f32_chunks, n_f32_prologue;
-  const UmmaProgram *prog_host;                                                         // HOST pointer (owned by the weights holder): passed by value at launch
 };
 struct CoreWeightsDev {
   F32LayerDev enc_dense1, enc_zdense, dec_dense1, dec_output;
@@ -118,6 +110,7 @@ struct CoreWeightsDev {
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
   CodecStreamDev enc_stream, dec_stream;
   UmmaCodecDev enc_umma, dec_umma;
+  int float_fma;           // MEASUREMENT ONLY (RADE_B200_DEBUG_FLOAT_FMA=1): wide float layers with fused multiply-add — not bit-exact, 9 % faster encoder
   long long *trace;        // debug: clock64() stamps of CTA 0's warp roles (rade_b200_debug_trace_*), nullptr in production
   int enc_z_tanh;          // bottleneck 1 (model05): tanh on the latents, src/rade_enc.c:107-113; 0 for bottleneck 3
 };

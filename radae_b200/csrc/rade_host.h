@@ -12,7 +12,6 @@ struct CoreWeightsHolder {
   // 84 for model19_check3 (20 features + aux symbol per 10 ms vector), 80 for models without the aux symbol (model05): the
   // kernels always run the 84-wide layout, the missing inputs / outputs are zero weights (exact: + 0 * x)
   int input_dim = 84, output_dim = 84;
-  UmmaProgram enc_prog, dec_prog;        // MMA programs of the tcgen05 kernels (host copies, passed as kernel parameters)
 };
 // k-blocks (32 inputs each) of an int8 layer with NTL n-tiles (8 outputs each) that fit one pipeline stage
 static inline __host__ __device__ int core_kbc(int NTL) { int k = CORE_STAGE_BYTES / (NTL * 256); return k < 1 ? 1 : k; }

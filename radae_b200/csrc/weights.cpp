@@ -14,6 +14,7 @@
 #include "rade_common.h"
 #include "rade_host.h"
 #include "umma_layout.h"
+#include "umma_program.h"
 
 namespace {
 
@@ -255,58 +256,46 @@ void build_streams(const std::map<std::string, const int8_t *> &p8, const std::m
 
 // ---- tcgen05 formulation (core_codec_umma.cu): per codec an int8 stream (weight images — k-blocks of ALL rows of a matrix in
 // the canonical K-major operand layout, umma_layout.h — packed back to back into ring stages of <= 40 KB, one bulk copy each),
-// a float stream (rows of dense1 / zdense / output in the float warps' order, packed into stages of <= 22 KB) and the MMA
-// program (one UmmaRec per weight image) the issuer thread walks every step.  Accumulator column blocks (x NS columns):
-// encoder GRU l at 4 (l & 1) + {0: [z;r] input, 1: [z;r] recurrent, 2: [n;-] input, 3: [n;-] recurrent}, conv l at 8 + (l & 1);
-// decoder GRU l at 6 (l & 1) + {0..5: z, r, n tiles x (input, recurrent)}, GLU l at 12 + (l & 1), conv l at 14 + (l & 1).
+// laid out exactly as the compile-time MMA program says (umma_program.h: the device code is generated from the same table), and
+// a float stream (rows of dense1 / zdense / output in the float warps' order, packed into stages of <= 22 KB).
 struct UmmaBuilder {
   std::vector<unsigned char> i8, f32;
   std::vector<ChunkDesc> i8_chunks, f32_chunks;       // ring stages (= bulk copies)
-  std::vector<UmmaRec> recs;
-  std::vector<unsigned char> i8_cur, f32_cur;         // the stage being filled
+  std::vector<UmmaRec> recs;                          // the program in the debug hook's format
+  std::vector<unsigned char> f32_cur;                 // the float stage being filled
   int f32_prologue = 0;
   bool ok = true;
-  static void close(std::vector<unsigned char> &bytes, std::vector<ChunkDesc> &chunks, std::vector<unsigned char> &cur) {
-    if (cur.empty()) return;
-    ChunkDesc d; d.offset = (unsigned)bytes.size(); d.bytes = (unsigned)cur.size();
-    bytes.insert(bytes.end(), cur.begin(), cur.end());
-    chunks.push_back(d);
-    cur.clear();
+  void close_f32() {
+    if (f32_cur.empty()) return;
+    ChunkDesc d; d.offset = (unsigned)f32.size(); d.bytes = (unsigned)f32_cur.size();
+    f32.insert(f32.end(), f32_cur.begin(), f32_cur.end());
+    f32_chunks.push_back(d);
+    f32_cur.clear();
   }
-  void close_i8() {
-    if (i8_cur.empty()) return;
-    recs.back().flags |= UR_STAGE_LAST;
-    close(i8, i8_chunks, i8_cur);
-  }
-  void close_f32() { close(f32, f32_chunks, f32_cur); }
-  // k-blocks [kb_lo, kb_hi) of the row-major int8 [N][K] matrix: as many k-blocks per image as fit the current stage (at most
-  // what the issuer has unrolled code for).  The k-blocks from kb_lo + fresh_from on depend on the layer before (act_ready[dep])
-  // and start an image of their own, so that no image straddles the dependency.
-  void add_op(const int8_t *W8, int N, int K, int kb_lo, int kb_hi, int tile_step, int n_tiles, int b_buf, int b_kb0, int d_blk,
-              int d_tile_stride, int zero_first, int dep, int fresh_from, int commit) {
-    if (dep >= 0 && fresh_from > 0 && kb_lo + fresh_from < kb_hi) {
-      add_op(W8, N, K, kb_lo, kb_lo + fresh_from, tile_step, n_tiles, b_buf, b_kb0, d_blk, d_tile_stride, zero_first, -1, 0, -1);
-      add_op(W8, N, K, kb_lo + fresh_from, kb_hi, tile_step, n_tiles, b_buf, b_kb0 + fresh_from, d_blk, d_tile_stride, 0, dep, 0, commit);
-      return;
+  // the int8 stream of one codec from its compile-time program
+  void bake_i8(const UmmaProgC &P, const std::map<int, const int8_t *> &mats) {
+    int stage = 0;
+    std::vector<unsigned char> cur;
+    for (int i = 0; i < P.n; i++) {
+      const UmmaRecC &r = P.r[i];
+      auto it = mats.find(r.mat);
+      if (it == mats.end() || (size_t)r.a_off16 * 16 != cur.size()) { ok = false; return; }
+      std::vector<uint8_t> c = umma_bake_chunk(it->second, r.n_rows, r.K, r.kb, r.nk);
+      cur.insert(cur.end(), c.begin(), c.end());
+      UmmaRec o; memset(&o, 0, sizeof(o));
+      o.a_off16 = (unsigned short)r.a_off16; o.tile_step = (unsigned short)r.tile_step; o.b_kb = (unsigned short)r.b_kb;
+      o.nk = (unsigned char)r.nk; o.n_tiles = (unsigned char)r.n_tiles; o.b_buf = (unsigned char)r.b_buf; o.flags = (unsigned char)r.flags;
+      o.d_blk = (unsigned char)r.d_blk; o.d_tile_stride = (unsigned char)r.d_tile_stride; o.dep = (signed char)r.dep; o.commit = (signed char)r.commit;
+      recs.push_back(o);
+      if (r.flags & UR_STAGE_LAST) {
+        if (stage >= P.n_stages || (int)cur.size() != P.stage_bytes[stage] || cur.size() > UMMA_I8_STAGE_BYTES) { ok = false; return; }
+        ChunkDesc d; d.offset = (unsigned)i8.size(); d.bytes = (unsigned)cur.size();
+        i8.insert(i8.end(), cur.begin(), cur.end());
+        i8_chunks.push_back(d);
+        cur.clear(); stage++;
+      }
     }
-    static const int unrolled[3] = {8, 4, 3};
-    if (n_tiles < 1 || n_tiles > 3 || N * 32 > UMMA_I8_STAGE_BYTES) { ok = false; return; }
-    for (int kb = kb_lo; kb < kb_hi;) {
-      const int space = UMMA_I8_STAGE_BYTES - (int)i8_cur.size();
-      int nk = std::min(std::min(unrolled[n_tiles - 1], kb_hi - kb), space / (N * 32));
-      if (nk < 1) { close_i8(); continue; }
-      UmmaRec r; memset(&r, 0, sizeof(r));
-      r.a_off16 = (unsigned short)(i8_cur.size() / 16); r.tile_step = (unsigned short)tile_step;
-      r.b_kb = (unsigned short)(b_kb0 + (kb - kb_lo)); r.nk = (unsigned char)nk; r.n_tiles = (unsigned char)n_tiles;
-      r.b_buf = (unsigned char)b_buf; r.d_blk = (unsigned char)d_blk; r.d_tile_stride = (unsigned char)d_tile_stride;
-      r.flags = (unsigned char)((i8_cur.empty() ? UR_STAGE_FIRST : 0) | ((zero_first && kb == kb_lo) ? UR_ZERO_FIRST : 0));
-      r.dep = (signed char)(kb == kb_lo ? dep : -1);
-      r.commit = (signed char)(kb + nk == kb_hi ? commit : -1);
-      std::vector<uint8_t> c = umma_bake_chunk(W8, N, K, kb, nk);
-      i8_cur.insert(i8_cur.end(), c.begin(), c.end());
-      recs.push_back(r);
-      kb += nk;
-    }
+    if (!cur.empty() || stage != P.n_stages) ok = false;
   }
   // rows [j0, j0 + nrows) of a float [K][NOUT] matrix, each zero-padded to NOUTP floats; a stage always holds a multiple of 4 rows
   // of a segment (the float warps read the activations four at a time)
@@ -326,9 +315,17 @@ struct UmmaBuilder {
 };
 
 void build_umma(const std::map<std::string, const int8_t *> &p8, const std::map<std::string, const float *> &pf, UmmaBuilder &e, UmmaBuilder &d) {
-  auto I8 = [&](const std::string &n) { return p8.at(n); };
   auto F = [&](const std::string &n) { return pf.at(n); };
-  static const int enc_dil[5] = {1, 2, 2, 2, 2};
+  std::map<int, const int8_t *> mats;
+  for (int l = 0; l < 5; l++) {
+    std::string n = std::to_string(l + 1);
+    mats[UM_ENC_GRU_IN + l] = p8.at("enc_gru" + n + "_input"); mats[UM_ENC_GRU_REC + l] = p8.at("enc_gru" + n + "_recurrent");
+    mats[UM_ENC_CONV + l] = p8.at("enc_conv" + n);
+    mats[UM_DEC_GRU_IN + l] = p8.at("dec_gru" + n + "_input"); mats[UM_DEC_GRU_REC + l] = p8.at("dec_gru" + n + "_recurrent");
+    mats[UM_DEC_GLU + l] = p8.at("dec_glu" + n); mats[UM_DEC_CONV + l] = p8.at("dec_conv" + n);
+  }
+  e.bake_i8(kUmmaEncProg, mats);
+  d.bake_i8(kUmmaDecProg, mats);
   {
     e.add_f32(F("enc_dense1"), 64, 64, 0, ENC_IN);                         // prologue: dense1 of step 0
     e.close_f32();
@@ -337,20 +334,10 @@ void build_umma(const std::map<std::string, const int8_t *> &p8, const std::map<
     e.add_f32(F("enc_dense1"), 64, 64, 0, ENC_IN);                         // dense1 of the next step
     int off = 64;
     for (int l = 0; l < 5; l++) {
-      std::string n = std::to_string(l + 1);
-      const int gs = (l & 1) * 4, cs = 8 + (l & 1);
-      // GRU: tiles [z; r] (rows 0..127) and [n; -] (rows 128..); fresh input = conv l-1's 96 outputs (3 k-blocks)
-      e.add_op(I8("enc_gru" + n + "_input"), 192, off, 0, off / 32, 128, 2, UB_CUR, 0, gs, 2, 1, l ? 2 * (l - 1) + 1 : -1, l ? off / 32 - 3 : 0, -1);
-      e.add_op(I8("enc_gru" + n + "_recurrent"), 192, 64, 0, 2, 128, 2, UB_PREV1, off / 32, gs + 1, 2, 1, -1, 0, 2 * l);
-      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU);
-      off += ENC_GRU;
-      // conv (k = 2): tap 0 = concat prefix of step t - dilation, tap 1 = current prefix whose last 2 k-blocks are GRU l's outputs
-      e.add_op(I8("enc_conv" + n), 96, 2 * off, 0, off / 32, 0, 1, enc_dil[l] == 1 ? UB_PREV1 : UB_PREV2, 0, cs, 0, 1, -1, 0, -1);
-      e.add_op(I8("enc_conv" + n), 96, 2 * off, off / 32, 2 * off / 32, 0, 1, UB_CUR, 0, cs, 0, 0, 2 * l, off / 32 - 2, 2 * l + 1);
-      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV);
-      off += ENC_CONV;
+      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_GRU); off += ENC_GRU;
+      e.add_f32(F("enc_zdense"), RADE_LATENT, RADE_LATENT, off, ENC_CONV); off += ENC_CONV;
     }
-    e.close_i8(); e.close_f32();
+    e.close_f32();
   }
   {
     d.add_f32(F("dec_dense1"), 96, 96, 0, DEC_IN);
@@ -360,20 +347,10 @@ void build_umma(const std::map<std::string, const int8_t *> &p8, const std::map<
     d.add_f32(F("dec_dense1"), 96, 96, 0, DEC_IN);
     int off = 96;
     for (int l = 0; l < 5; l++) {
-      std::string n = std::to_string(l + 1);
-      const int gs = (l & 1) * 6, us = 12 + (l & 1), cs = 14 + (l & 1);
-      // GRU: three overlapping tiles starting at rows 0, 96, 192 (z, r, n of unit u in TMEM lane u); fresh input = conv l-1 (1 k-block)
-      d.add_op(I8("dec_gru" + n + "_input"), 288, off, 0, off / 32, DEC_GRU, 3, UB_CUR, 0, gs, 2, 1, l ? 3 * (l - 1) + 2 : -1, l ? off / 32 - 1 : 0, -1);
-      d.add_op(I8("dec_gru" + n + "_recurrent"), 288, 96, 0, 3, DEC_GRU, 3, UB_HQ_RD, 3 * l, gs + 1, 2, 1, -1, 0, 3 * l);
-      d.add_op(I8("dec_glu" + n), 96, 96, 0, 3, 0, 1, UB_HQ_WR, 3 * l, us, 0, 1, 3 * l, 0, 3 * l + 1);
-      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU);
-      off += DEC_GRU;
-      d.add_op(I8("dec_conv" + n), 32, 2 * off, 0, off / 32, 0, 1, UB_PREV1, 0, cs, 0, 1, -1, 0, -1);
-      d.add_op(I8("dec_conv" + n), 32, 2 * off, off / 32, 2 * off / 32, 0, 1, UB_CUR, 0, cs, 0, 0, 3 * l + 1, off / 32 - 3, 3 * l + 2);
-      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV);
-      off += DEC_CONV;
+      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_GRU); off += DEC_GRU;
+      d.add_f32(F("dec_output"), DEC_OUT, DEC_OUTP, off, DEC_CONV); off += DEC_CONV;
     }
-    d.close_i8(); d.close_f32();
+    d.close_f32();
   }
 }
 
@@ -460,23 +437,7 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
     out.n_f32_chunks = (int)ub.f32_chunks.size(); out.n_f32_prologue = ub.f32_prologue;
     return (out.i8_stream && out.i8_chunks && out.f32_stream && out.f32_chunks) ? 0 : -1;
   };
-  auto set_prog = [&](UmmaBuilder &ub, UmmaProgram &P, UmmaCodecDev &out) {
-    memset(&P, 0, sizeof(P));
-    P.n_recs = (int)ub.recs.size();
-    for (size_t i = 0; i < ub.recs.size(); i++) {
-      const UmmaRec &r = ub.recs[i];
-      const unsigned asbo = (unsigned)r.nk * 256u;
-      UmmaRecPacked &p = P.recs[i];
-      p.w[0] = (unsigned)r.a_off16 | ((128u >> 4) << 16);
-      p.w[1] = (asbo >> 4) | (1u << 14);
-      p.w[2] = ((unsigned)r.b_kb * 16u) | ((((unsigned)(r.tile_step >> 3) * asbo) >> 4) << 16);
-      p.w[3] = (unsigned)r.nk | (unsigned)r.n_tiles << 4 | (unsigned)r.b_buf << 6 | (unsigned)r.flags << 9 | (unsigned)r.d_blk << 12 |
-               (unsigned)r.d_tile_stride << 17 | (unsigned)(r.dep + 1) << 20 | (unsigned)(r.commit + 1) << 25;
-    }
-    out.prog_host = &P;
-  };
   if (up_umma(ue, W.enc_umma) < 0 || up_umma(ud, W.dec_umma) < 0) return -1;
-  set_prog(ue, h->enc_prog, W.enc_umma); set_prog(ud, h->dec_prog, W.dec_umma);
   auto up_stream = [&](StreamBuilder &sb, CodecStreamDev &out, int n_pro) -> int {
     out.n_prologue = n_pro;
     out.stream = (const unsigned char *)dev_copy(sb.bytes.data(), sb.bytes.size());

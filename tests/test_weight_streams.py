@@ -151,7 +151,7 @@ def run_program(recs, buf, chunks, bufs, n_blocks, rng, stop_after_commit=None):
         if rec["dep"] >= 0:
             events.append(("wait", rec["dep"]))
         nk, tiles = rec["nk"], rec["n_tiles"]
-        assert 1 <= nk <= (8, 4, 3)[tiles - 1]
+        assert 1 <= nk <= 8 and 1 <= tiles <= 3
         B = bufs[rec["b_buf"]]
         asbo = nk * 256
         a0 = base + rec["a_off16"] * 16

@@ -38,13 +38,6 @@ for t in range(T):
         if recs[i][9] >= 0:
             a, d = rel(tr[(t * 128 + i) * 2]), rel(tr[(t * 128 + i) * 2 + 1])
             print(f"  I rec{i:3d} waits for layer {recs[i][9]:2d}: reached {a:7d}, satisfied {d:7d} (idle {d - a})")
-    print(f"  I cycles waiting for weight stages: {int(tr[1536 + t * 4])}, cycles inside the MMA issue code: {int(tr[1536 + t * 4 + 1])}")
-    durs = [(int(recs[i][3]) * int(recs[i][4]), int(tr[8192 + t * 128 + i])) for i in range(n_recs)]
-    print("  I per record (MMAs, cycles in issue code):", durs)
-    import numpy as _np
-    A = _np.array([[1, m] for m, _ in durs], float); y = _np.array([d for _, d in durs], float)
-    coef = _np.linalg.lstsq(A, y, rcond=None)[0]
-    print(f"  I fit: {coef[0]:.0f} cycles per record + {coef[1]:.1f} cycles per MMA")
     print("  I accumulator commits:", [rel(tr[1024 + t * 16 + l]) for l in range(nlayers)])
     for l in range(nlayers):
         a, d = rel(tr[2048 + (t * 16 + l) * 2]), rel(tr[2048 + (t * 16 + l) * 2 + 1])
