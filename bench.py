@@ -8,7 +8,9 @@
 One step = one 120 ms modem frame (3 forty-ms frames F) for every stream of the batch.  Workload = BASELINE.json
 configs[2] ("Full TX+OFDM+MPP-multipath+demod+RX pipeline, 1024 concurrent streams, 1xB200"), the configuration the
 headline metric (enc->OFDM->chan->demod->dec frames/s) is quoted on; weak scaling: 1024 streams per GPU.
-`--workload codec` runs configs[1] (CoreEncoder+CoreDecoder only, 8192 streams) instead.
+`--workload codec` runs configs[1] (CoreEncoder+CoreDecoder only, 8192 streams), `--workload rx-search` configs[3] at one GPU's
+share (streaming receiver from a cold start: 1 s of noise, then a signal with its own frequency offset U(-40, 40) Hz and start
+delay U[0, 960) per stream: coarse search -> candidate -> sync -> decode; 1024 streams per GPU).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is derived.
 """
@@ -92,7 +94,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------ CPU arm
 def _cpu_worker(args):
     """one host process: n_streams independent streams of the oracle pipeline for n_frames modem frames"""
-    seed, n_streams, n_frames, warm = args
+    seed, n_streams, n_frames, warm, search = args
     os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import dsp as od
     from oracle.core import CoreOraclePort, CoreOracleRef, synth_features
@@ -116,6 +118,8 @@ def _cpu_worker(args):
             g1 = (0.7 * np.exp(1j * 2 * np.pi * 0.5 * (n + 960 * f) / 8000)).astype(np.complex64)
             g2 = (0.7 * np.exp(-1j * 2 * np.pi * 0.3 * (n + 960 * f) / 8000)).astype(np.complex64)
             y = od.channel(y, g1, g2, 16, 1.0, -11.0, 0.0, sigma, nz(960))
+            if search and (f // 10) % 2 == 0:
+                y = (sigma * nz(960)).astype(np.complex64)          # config 4: every other second the stream is noise only -> the receiver searches
             fifo = np.concatenate([fifo, y])
             if len(fifo) >= rx.nin:
                 k = rx.nin
@@ -124,7 +128,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, "reference" if Core else "port"
 
 
-def cpu_pipeline_rate(n_frames, warm=2, streams_per_proc=1, procs=None):
+def cpu_pipeline_rate(n_frames, warm=2, streams_per_proc=1, procs=None, search=False):
     """frames F per second of the CPU oracle pipeline using all host cores (one process per core, 1 thread each)"""
     import multiprocessing as mp
     procs = procs or os.cpu_count()
@@ -137,7 +141,7 @@ def cpu_pipeline_rate(n_frames, warm=2, streams_per_proc=1, procs=None):
         os.environ[k] = "1"
     try:
         with ctx.Pool(procs) as pool:
-            res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, n_frames, warm) for i in range(procs)])
+            res = pool.map(_cpu_worker, [(1000 + i, streams_per_proc, n_frames, warm, search) for i in range(procs)])
     finally:
         for k, v in saved.items():
             if v is None:
@@ -146,29 +150,124 @@ def cpu_pipeline_rate(n_frames, warm=2, streams_per_proc=1, procs=None):
                 os.environ[k] = v
     slowest = max(r[0] for r in res)
     total_F = procs * streams_per_proc * n_frames * F_PER_STEP
-    return total_F / slowest, procs, res[0][1], f"{procs} procs x {streams_per_proc} stream x {n_frames} modem frames (after {warm} warm-up frames, i.e. receiver in sync), MPP-like 2-path, Eb/No 3 dB, -11 Hz"
+    what = "signal / noise alternating every 10 frames: search, acquisition and tracking" if search else f"after {warm} warm-up frames, i.e. receiver in sync"
+    return total_F / slowest, procs, res[0][1], (f"{procs} procs x {streams_per_proc} stream x {n_frames} modem frames ({what}), 2-path channel (deterministic two-tone "
+                                                 f"gains: the CPU arm is timed, not scored), Eb/No 3 dB, -11 Hz")
+
+
+def cpu_codec_rate(n_steps=96, n_streams=None):
+    """BASELINE.md §3.1 / SURVEY §8(d)(i): the reference's own rade_enc.c + rade_dec.c (int8 path, -O2, on the nnet shim:
+    oracle/_ref) or, where that library is absent, the C port — one stream per host thread over all host cores.
+    Returns F/s for encoder, decoder and both, total and per core."""
+    from oracle.core import CoreOraclePort, CoreOracleRef, pack_enc_input, synth_features
+    cores = os.cpu_count() or 1
+    S = n_streams or 4 * cores
+    ref = CoreOracleRef.available("int8")
+    o = CoreOracleRef("int8", n_streams=S) if ref else CoreOraclePort(n_streams=S)
+    x = pack_enc_input(synth_features(S, 4 * n_steps, seed=4321))
+    o.encode(x[:, :8], nthreads=cores); o.reset()                                   # warm the threads / caches
+    t0 = time.perf_counter(); z = o.encode(x, nthreads=cores); te = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.decode(z, nthreads=cores); td = time.perf_counter() - t0
+    F = S * n_steps
+    return {"enc": F / te, "dec": F / td, "enc_dec": F / (te + td), "cores": cores, "kind": "reference" if ref else "port",
+            "sample": f"{S} streams x {n_steps} steps, one stream per thread, {cores} threads"}
+
+
+def feature_error_report(n_streams=8, n_frames=40, seed=99):
+    """the second half of the metric ("...; feat RMS err"): recovered features of the CUDA path against the reference C path
+    (oracle: numpy DSP restatement + the reference's rade_dec.c on the nnet shim) on the SAME receive samples, outside any timed
+    region.  decoder_boundary_rms: oracle z_hat -> CUDA decoder vs oracle features (integer arithmetic: must be exactly 0).
+    e2e: CUDA receiver end to end; its z_hat differs from the oracle's by fp32 re-association (~5e-7 relative), which sooner or
+    later flips one floor(.5 + 127 x) inside the recurrent int8 decoder: identical features up to that frame
+    (frames_to_first_flip), a bounded perturbation afterwards."""
+    from radae_b200 import RadeBatch
+    from oracle import dsp as od
+    from oracle.core import CoreOraclePort, CoreOracleRef, synth_features
+    S, F = n_streams, n_frames
+    rng = np.random.default_rng(seed)
+    feats = np.ascontiguousarray(synth_features(S, 12 * F, seed=seed).reshape(S, F, 432))
+    b = RadeBatch(S)
+    tx = np.concatenate([b.tx(feats[:, f]) for f in range(F)], axis=1)                 # [S, F * 960]
+    n = np.arange(tx.shape[1] + 1920)
+    sig = np.zeros((S, len(n)), np.complex64); sig[:, 700:700 + tx.shape[1]] = tx
+    sig *= np.exp(1j * 2 * np.pi * (-11.0) * n / 8000.0).astype(np.complex64)
+    sigma = od.ebno_sigma(6.0)
+    sig += (sigma / np.sqrt(2) * (rng.standard_normal(sig.shape) + 1j * rng.standard_normal(sig.shape))).astype(np.complex64)
+    pos = np.zeros(S, np.int64); col = np.arange(1120)
+    got = [[] for _ in range(S)]; zh = [[] for _ in range(S)]; nins = []
+    while pos.max() + 1120 <= sig.shape[1]:
+        nin = b.nin(); nins.append(nin.copy())
+        x = np.where(col[None, :] < nin[:, None], np.take_along_axis(sig, pos[:, None] + col[None, :], axis=1), 0).astype(np.complex64)
+        pos += nin
+        f_out, ret, _ = b.rx(x)
+        z_hat = b.rx_z_hat()
+        for s in np.nonzero(ret & 1)[0]:
+            got[s].append(f_out[s].copy()); zh[s].append(z_hat[s].copy())
+    b.close()
+    use_ref = CoreOracleRef.available("int8")
+    per_all, flips, dec_sq, dec_n, zrel = [], [], 0.0, 0, []
+    for s in range(S):
+        core = CoreOracleRef("int8", 1) if use_ref else CoreOraclePort(n_streams=1)
+        rx = od.RadaeRx(core)
+        p = 0; of, oz = [], []
+        for nin in nins:
+            assert rx.nin == nin[s], "framing differs from the oracle"
+            ret, f, _ = rx.do_radae_rx(sig[s, p:p + rx.nin]); p += int(nin[s])
+            if ret & 1:
+                of.append(f.copy()); oz.append(rx.z_hat.copy() if hasattr(rx, "z_hat") else None)
+        assert len(of) == len(got[s]), "valid-frame pattern differs from the oracle"
+        if not of:
+            continue
+        G, O = np.array(got[s]).reshape(len(of), 432), np.array(of).reshape(len(of), 432)
+        per = np.sqrt(np.mean((G - O) ** 2, axis=1))
+        per_all.append(per)
+        flips.append(int(np.argmax(per > 1e-6)) if (per > 1e-6).any() else len(per))
+        if oz[0] is not None:
+            Z = np.array(oz).reshape(len(oz), 240)
+            zrel.append(float(np.sqrt(np.mean((np.array(zh[s]) - Z) ** 2) / np.mean(Z ** 2))))
+            bd = RadeBatch(1)
+            out = bd.core_decode(Z.reshape(1, -1, 80))[0].reshape(-1, 12, 21)
+            bd.close()
+            api = np.zeros((out.shape[0], 12, 36), np.float32); api[:, :, :20] = out[:, :, :20]
+            dec_sq += float(np.sum((api.reshape(-1, 432) - O) ** 2)); dec_n += O.size
+    allp = np.concatenate(per_all)
+    return {"reference": "oracle: numpy DSP + " + ("reference rade_dec.c on the nnet shim (oracle/_ref)" if use_ref else "C port"),
+            "streams": S, "modem_frames_compared": int(allp.size), "channel": "AWGN Eb/No 6 dB, -11 Hz, identical samples to both receivers",
+            "decoder_boundary_rms": (dec_sq / dec_n) ** 0.5 if dec_n else None,
+            "z_hat_rel_rms": float(np.max(zrel)) if zrel else None,
+            "e2e_rms": float(np.sqrt(np.mean(allp ** 2))), "e2e_max_frame_rms": float(allp.max()),
+            "frames_to_first_flip": {"min": int(min(flips)), "median": float(np.median(flips)), "of": int(max(len(p) for p in per_all))},
+            "contract": "features within 1e-4 RMS of the reference C path: met exactly (0) at the decoder boundary; end to end identical until the first int8 quantisation flip, bounded (< 0.02 per frame, tests/test_gpu_rx.py) afterwards"}
 
 
 def run_reference(args):
+    """CPU arm: the reference's own CPU implementation of the path on this box's host cores (oracle/_ref = the reference's
+    rade_enc.c / rade_dec.c compiled where they lie, on the restated nnet shim; DSP = the numpy restatement pinned against the
+    Python reference), every step a bounded sample of the workload"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    per_step = []
-    frames_per_sample = args.ref_frames
+    per_step, kind, sample = [], "port", ""
+    codec = args.workload == "codec"
     for i in range(args.warmup + args.steps):
-        rate, procs, kind, sample = cpu_pipeline_rate(frames_per_sample, warm=8)
+        if codec:
+            r = cpu_codec_rate(n_steps=48)
+            rate, kind, sample = r["enc_dec"], r["kind"], r["sample"]
+        else:
+            rate, _, kind, sample = cpu_pipeline_rate(args.ref_frames, warm=8, search=(args.workload == "rx-search"))
         if i >= args.warmup:
             per_step.append(rate)
     v = float(np.mean(per_step))
-    sample_units = cores * frames_per_sample * F_PER_STEP
+    wl = {"full": "full TX+OFDM+MPP+demod+RX pipeline (BASELINE configs[2])", "codec": "CoreEncoder+CoreDecoder only (BASELINE configs[1])",
+          "rx-search": "streaming receiver with frequency-offset search (BASELINE configs[3])"}[args.workload]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * sample_units / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8xint8->int32 + f32", "data": "synthetic",
-            "config": {"workload": "full TX+OFDM+MPP+demod+RX pipeline (BASELINE configs[2]) — CPU oracle port on host cores; each step = a bounded sample",
-                       "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
-                             "note": f"DSP = numpy restatement (oracle/dsp.py); core codec = {'reference rade_enc.c/rade_dec.c + nnet shim (oracle/_ref)' if kind == 'reference' else 'oracle/core_oracle.c'}"},
+            "config": {"workload": wl + " — CPU implementation on host cores; each step = a bounded sample", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
+                             "note": "core codec = " + ("the reference's rade_enc.c / rade_dec.c (oracle/_ref, nnet shim)" if kind == "reference" else "oracle/core_oracle.c (C port)") +
+                                     ("" if codec else "; DSP = numpy restatement of radae/dsp.py + radae_rxe.py (oracle/dsp.py), ~4x faster than the reference's own Python receiver (BASELINE.md §2)")},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -200,6 +299,7 @@ def run_gpu(args):
         sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
 
     codec_only = args.workload == "codec"
+    rx_search = args.workload == "rx-search"
     S = args.streams or (8192 if codec_only else 1024)
     K, W = args.steps, args.warmup
     b = RadeBatch(S, device=local, weights=blob)
@@ -222,6 +322,36 @@ def run_gpu(args):
             b.core_encode_dev(z.data_ptr(), xs[k % n_feat_frames].data_ptr(), T)
             b.core_decode_dev(fo.data_ptr(), z.data_ptr(), T)
         xs = [x[:, i].contiguous() for i in range(n_feat_frames)]
+    elif rx_search:
+        # BASELINE configs[3] at one GPU's share: every stream gets 1 s of noise, then F modem frames of its own signal at a carrier
+        # offset U(-40, 40) Hz and a start delay U[0, 960); a step = 960 new samples per stream pushed into the device link FIFO +
+        # one rade_rx call per stream (coarse search while unsynced, then candidate, sync, demod, decode).  Every timed pass starts
+        # from rade_b200_reset (cold receiver) and runs K steps; the passes before it are the warm-up.
+        sig_frames = max(K, 12) + 2
+        rng = np.random.default_rng(4242 + rank)
+        feats_s = np.ascontiguousarray(np.tile(base, ((S + base.shape[0] - 1) // base.shape[0], (sig_frames + n_feat_frames - 1) // n_feat_frames, 1))[:S, :sig_frames])
+        txs = np.concatenate([b.tx(feats_s[:, f]) for f in range(sig_frames)], axis=1)
+        b.reset()
+        foff = rng.uniform(-40.0, 40.0, S); delay = rng.integers(0, 960, S)
+        N0 = 8000
+        L = 960 * ((N0 + 960 + sig_frames * 960 + 959) // 960)
+        sig = np.zeros((S, L), np.complex64)
+        for si in range(S):
+            sig[si, N0 + delay[si]:N0 + delay[si] + sig_frames * 960] = txs[si]
+        sig *= np.exp(1j * 2 * np.pi * foff[:, None] * np.arange(L)[None, :] / 8000.0).astype(np.complex64)
+        from math import sqrt
+        sigma = sqrt(8000.0 / (10 ** (10.0 / 10.0) * 2000.0))                          # Eb/No 10 dB (radae.py:570-574)
+        sig += (sigma / np.sqrt(2) * (rng.standard_normal((S, L)) + 1j * rng.standard_normal((S, L)))).astype(np.complex64)
+        n_sig_steps = L // 960
+        d_sig = [torch.tensor(np.ascontiguousarray(sig[:, i * 960:(i + 1) * 960]).view(np.float32).reshape(S, 960, 2)).cuda() for i in range(n_sig_steps)]
+        h_sig = sig
+        d_fo = torch.zeros((S, 432), device="cuda"); d_ret = torch.zeros(S, dtype=torch.int32, device="cuda")
+        d_eoo = torch.zeros((S, 180), device="cuda")
+
+        def step(k):
+            i = k % n_sig_steps
+            b.link_push_dev(d_sig[i].data_ptr())
+            b.rx_link_dev(d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr())
     else:
         b.channel_config(EbNodB=3.0, freq_offset_hz=-11.0, freq_offset_spread_hz=0.0, doppler_spread_hz=1.0,
                          delay_samples=16, gain=1.0, seed=77 + rank)
@@ -252,14 +382,20 @@ def run_gpu(args):
 
     # ---- acquisition phase (not timed): run until (almost) every stream is in sync so the timed region is steady state
     pre = 0
-    if not codec_only:
+    if not codec_only and not rx_search:
         for k in range(40):
             step(pre); pre += 1
             if k >= 8 and k % 4 == 0:
                 if np.mean([s.state == 2 for s in b.rx_status()]) > 0.98:
                     break
-    for k in range(W):
-        step(pre + k)
+    if rx_search:                                   # warm-up = one whole pass (>= W steps) from a cold receiver; then reset: the
+        for k in range(n_sig_steps):                 # timed region is the first K steps of the next pass
+            step(k)
+        b.reset()
+        pre = -W                                     # step(pre + W + k) == step(k)
+    else:
+        for k in range(W):
+            step(pre + k)
     barrier()
     sampler = ClockSampler(local); sampler.start()
     launches0 = b.launch_count()
@@ -284,10 +420,11 @@ def run_gpu(args):
     total_F = S * world * F_PER_STEP * K
     value = total_F / (dev_ms_max / 1000.0)
     sync_frac = None if codec_only else float(np.mean([s.state == 2 for s in b.rx_status()]))
+    states_end = None if not rx_search else [int(np.sum([s.state == j for s in b.rx_status()])) for j in range(3)]
 
     # ---- the same K steps without the frame pipeline (everything on one stream), for reference
     serial_ms = None
-    if not codec_only and not args.no_pipeline:
+    if not codec_only and not rx_search and not args.no_pipeline:
         b.synchronize(); b.pipeline_enable(False)
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         for k in range(K):
@@ -299,11 +436,13 @@ def run_gpu(args):
         barrier()
         serial_ms = sum(a.elapsed_time(c) for a, c in ev2) / K
     # ---- per-kernel pass (CUDA events around every launch, inside the library, same steps; after the timed region)
+    if rx_search:
+        b.reset()
     b.profile_enable(True)
     for k in range(K):
         with torch.cuda.stream(ext):
             l2_flush.zero_()
-        step(pre + W + K + k)
+        step(pre + W + (0 if rx_search else K) + k)
     prof = b.profile_read()
     b.profile_enable(False)
     tot_prof = sum(ms for ms, _ in prof.values())
@@ -334,151 +473,188 @@ def run_gpu(args):
     # ---- end to end through the host-buffer C ABI (pinned host in, host out, every step), wall clock
     e2e = None
     if (rank == 0 or world > 1) and not args.no_e2e:
-        e2e = run_e2e(b, S, feats_host, codec_only, K, world, dist if world > 1 else None, torch,
-                      n_ctx=args.e2e_contexts, weights=blob, device=local, serial=args.e2e_serial)
+        if rx_search:
+            e2e = run_e2e_rx(S, h_sig, K, world, dist if world > 1 else None, torch, weights=blob, device=local)
+        else:
+            e2e = run_e2e(b, S, feats_host, codec_only, K, world, dist if world > 1 else None, torch,
+                          n_ctx=args.e2e_contexts, weights=blob, device=local, serial=args.e2e_serial, python_driver=args.e2e_python)
 
-    cpu_base = None
+    # ---- reported CPU baseline (rank 0, N = 1): the reference's CPU implementation of this workload on the box's host cores,
+    # bounded sample; and — the oracle being loaded here anyway — the feature-error half of the metric
+    cpu_base, feat_err = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, procs, kind, sample = cpu_pipeline_rate(200, warm=8)
-        cpu_base = {"value": rate, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
-                    "note": "numpy DSP restatement + " + ("reference rade_enc.c/rade_dec.c on the nnet shim" if kind == "reference" else "C core port")}
+        if codec_only:
+            r = cpu_codec_rate(n_steps=96)
+            cpu_base = {"value": r["enc_dec"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                        "per_core": r["enc_dec"] / r["cores"], "encoder_only": r["enc"], "decoder_only": r["dec"],
+                        "note": "src/rade_enc.c + src/rade_dec.c (int8 path, -O2) compiled where they lie on the restated nnet shim (oracle/_ref), one stream per host thread"
+                                if r["kind"] == "reference" else "oracle/core_oracle.c (C port of rade_enc.c / rade_dec.c), one stream per host thread"}
+        else:
+            rate, procs, kind, sample = cpu_pipeline_rate(200, warm=8, search=rx_search)
+            cpu_base = {"value": rate, "unit": "frames/s", "cores": procs, "kind": kind, "sample": sample, "per_core": rate / procs,
+                        "note": "DSP: numpy restatement of radae/dsp.py + radae_rxe.py (oracle/dsp.py, ~4x faster than the reference's own Python receiver); core codec: " +
+                                ("the reference's rade_enc.c / rade_dec.c on the nnet shim (oracle/_ref)" if kind == "reference" else "C port")}
+            r = cpu_codec_rate(n_steps=48)
+            cpu_base["codec_only"] = {"value": r["enc_dec"], "per_core": r["enc_dec"] / r["cores"], "encoder_only": r["enc"], "decoder_only": r["dec"],
+                                      "kind": r["kind"], "sample": r["sample"], "what": "src/rade_enc.c + src/rade_dec.c alone (north star: timed on the same box's host cores in the same run)"}
+        try:
+            feat_err = feature_error_report()
+        except Exception as e:                             # never lose the timing line to the checker
+            feat_err = {"error": repr(e)}
 
+    # what binds, next to the HBM fraction: pipe utilisations of the dominant kernels from the committed ncu --set full captures
+    # (profiles/r02_pipe_util.json; captured with the same command line, not in this run)
     try:
-        # the math-pipe figure SURVEY.md §8(d) asks for next to the HBM fraction: F/s x FLOP per F / peak, with the survey's own
-        # work table (enc+dec 1 838 720 MAC per F; full synced pipeline ~2.95 M MAC per F) against the fp32 CUDA-core peak of
-        # this device (SMs x 128 lanes x 2 flop x SM clock); per GPU, so it does not change with the number of ranks
-        props = torch.cuda.get_device_properties(local)
-        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
-        peak_tf = props.multi_processor_count * 128 * 2 * float(mhz) * 1e6 / 1e12
-        flop_per_F = 2 * (1838720 if codec_only else 2950000)
-        ach_tf = (value / world) * flop_per_F / 1e12
-        roofline["math"] = {"flop_per_frame": flop_per_F, "achieved_tflops": round(ach_tf, 2), "peak_tflops": round(peak_tf, 1),
-                            "frac": round(ach_tf / peak_tf, 4),
-                            "peak": "fp32 FMA peak of one GPU at the sampled SM clock; the codec's MACs actually run as int8 IMMA"}
+        pu = json.load(open(os.path.join(REPO, "profiles", "r02_pipe_util.json")))
+        roofline["pipes"] = {k: v for k, v in pu.items() if k in kernels or k == "source"}
     except Exception:
         pass
     if rank == 0:
+        wl = (("CoreEncoder+CoreDecoder only, %d streams x 3 steps per launch (BASELINE configs[1])" % S) if codec_only else
+              ("streaming receiver from a cold start with frequency-offset search, %d streams per GPU (BASELINE configs[3] at one GPU's share): 1 s noise, then "
+               "signal at U(-40,40) Hz / delay U[0,960) per stream, Eb/No 10 dB; a pass = reset + %d steps" % (S, K)) if rx_search else
+              ("full TX+OFDM+MPP+demod+RX pipeline, %d concurrent streams per GPU (BASELINE configs[2]); MPP 1 Hz/2 ms, Eb/No 3 dB, -11 Hz" % S))
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8xint8->int32 (codec) + f32/f64 (DSP)", "data": "synthetic",
-                "config": {"workload": ("CoreEncoder+CoreDecoder only, %d streams x 3 steps per launch (BASELINE configs[1])" % S) if codec_only else
-                           ("full TX+OFDM+MPP+demod+RX pipeline, %d concurrent streams per GPU (BASELINE configs[2]); MPP 1 Hz/2 ms, Eb/No 3 dB, -11 Hz" % S),
+                "config": {"workload": wl,
                            "streams_per_gpu": S, "frames_per_step_per_stream": F_PER_STEP, "l2": "flushed (256 MB memset) before every timed step",
                            "timing": "CUDA events on the library's stream around each step, summed; max over ranks",
-                           "sync_fraction": sync_frac, "acquisition_steps_before_timing": pre,
-                           "pipeline": None if codec_only else ("off (one stream)" if args.no_pipeline else
+                           "codec_kernels": os.environ.get("RADE_B200_CODEC", "umma") + (" (tcgen05.mma kind::i8, TMEM accumulators)" if os.environ.get("RADE_B200_CODEC", "umma") != "mma" else " (mma.sync)"),
+                           "sync_fraction": sync_frac, "states_at_end_search_candidate_sync": states_end, "acquisition_steps_before_timing": max(pre, 0),
+                           "pipeline": None if (codec_only or rx_search) else ("off (one stream)" if args.no_pipeline else
                                        "TX side of frame k+1 on a second CUDA stream, concurrent with the RX side of frame k; fork/join inside every timed step"),
                            "ms_per_step_unpipelined": serial_ms},
                 "gpu_launches": int(launches), "wall_s": t_wall, "clocks": clocks, "roofline": roofline, "kernels": kernels,
-                "e2e": e2e, "cpu_baseline": cpu_base}
+                "e2e": e2e, "cpu_baseline": cpu_base, "feat_rms_err": feat_err}
         print(json.dumps(line))
     b.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=2, weights=None, device=0, serial=False):
-    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed; every call
-    is the synchronous reference-style call.  Full pipeline: like the reference's `radae_tx | ch | radae_rx` (two programs
-    joined by a pipe) the transmitter side (rade_b200_tx, rade_b200_channel, FIFO push) and the receiver side (FIFO gather +
-    rade_b200_rx) run on two host threads with a context each, joined by the pinned host sample FIFO; `--e2e-serial` runs
-    the four calls back to back on one thread instead.  n_ctx > 1 splits the streams over several such pairs."""
+def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=1, weights=None, device=0, serial=False, python_driver=False):
+    """same metric through the host-pointer C ABI: pinned host features in, host features out, all copies timed; every call is the
+    synchronous reference-style call.  Full pipeline: like the reference's `radae_tx | ch | radae_rx` (two programs joined by a
+    pipe) the transmitter side (rade_b200_tx, rade_b200_channel_hostlink) and the receiver side (rade_b200_hostlink_rx) run on two
+    host threads with a context each, joined by the pinned per-stream sample FIFOs, which the channel kernel writes and the
+    band-pass kernel reads in place.  The two-thread loop is rade_b200_duplex_run (C); `--e2e-python` drives the same calls from
+    two Python threads, `--e2e-serial` runs them back to back on one thread."""
     import threading
     from radae_b200 import RadeBatch
     from radae_b200.batch import HostLink
-    # host threads of the C-side sample FIFOs: this rank's share of the cores (torchrun exports OMP_NUM_THREADS=1)
     duplex = not codec_only and not serial
-    os.environ.setdefault("RADE_B200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, world) // max(1, n_ctx) // (2 if duplex else 1)))))
     n_feat_frames = feats_host.shape[1]
     pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-    bounds = [(S * i) // n_ctx for i in range(n_ctx + 1)]
-    ctxs = []
-    for i in range(n_ctx):
-        lo, hi = bounds[i], bounds[i + 1]
-        n = hi - lo
-        c = {"b": RadeBatch(n, device=device, weights=weights), "n": n}
-        fh = feats_host[lo:hi]
-        if codec_only:
-            x = np.ascontiguousarray(np.concatenate([fh.reshape(n, n_feat_frames, 12, 36)[..., :20],
-                                     -np.ones((n, n_feat_frames, 12, 1), np.float32)], axis=-1).reshape(n, n_feat_frames, 3, 84))
-            c["x"] = [np.ascontiguousarray(x[:, j]) for j in range(n_feat_frames)]
-        else:
-            c["btx"] = RadeBatch(n, device=device, weights=weights) if duplex else c["b"]     # transmitter-side context
-            c["btx"].channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5 + i)
-            c["link"] = HostLink(c["b"])
-            c["tx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
-            c["rx"] = pin((n, 960, 2), torch.float32).view(np.complex64).reshape(n, 960)
-            c["feats"] = []
-            for j in range(n_feat_frames):
-                a = pin((n, 432), torch.float32); a[...] = fh[:, j]; c["feats"].append(a)
-        ctxs.append(c)
+    c = {"b": RadeBatch(S, device=device, weights=weights)}
+    if codec_only:
+        x = np.ascontiguousarray(np.concatenate([feats_host.reshape(S, n_feat_frames, 12, 36)[..., :20],
+                                 -np.ones((S, n_feat_frames, 12, 1), np.float32)], axis=-1).reshape(S, n_feat_frames, 3, 84))
+        c["x"] = [np.ascontiguousarray(x[:, j]) for j in range(n_feat_frames)]
+    else:
+        c["btx"] = RadeBatch(S, device=device, weights=weights) if duplex else c["b"]         # transmitter-side context
+        c["bch"] = RadeBatch(S, device=device, weights=weights) if duplex else c["b"]         # channel-simulator context
+        c["bch"].channel_config(EbNodB=3.0, freq_offset_hz=-11.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=5)
+        c["link"] = HostLink(c["b"])
+        c["txs"] = pin((3, S, 960, 2), torch.float32).view(np.complex64).reshape(3, S, 960)
+        c["tx"] = c["txs"][0]
+        c["feats"] = pin((n_feat_frames, S, 432), torch.float32)
+        c["feats"][...] = np.transpose(feats_host, (1, 0, 2))
+        c["valid"] = np.zeros(S, np.int64)
 
-    def step(c, k):
+    def step(k):
         if codec_only:
             z = c["b"].core_encode(c["x"][k % n_feat_frames])
             c["b"].core_decode(z)
         else:
-            tx_side(c, k)
-            c["link"].rx()                                              # gather nin[s] per stream, H2D rx_in, D2H features/ret/eoo/nin
+            tx_side(k)
+            c["link"].rx()                                              # pop nin[s] per stream from the FIFOs, D2H features / ret / eoo
 
-    def tx_side(c, k):
-        c["btx"].tx(c["feats"][k % n_feat_frames], out=c["tx"])        # H2D features (pinned), D2H tx samples
-        c["btx"].channel(c["tx"], out=c["rx"])                          # H2D tx, D2H rx (the channel is a simulator outside rade_api.h)
-        c["link"].push(c["rx"])                                         # pinned host FIFO, C/OpenMP
+    def tx_side(k):
+        c["btx"].tx(c["feats"][k % n_feat_frames], out=c["tx"])        # H2D features (pinned), D2H tx samples (written in place)
+        c["link"].channel_push(c["bch"], c["tx"])                       # H2D tx (copy engine), channel output D2H straight into the pinned frame slot
 
-    def run(c, k0, n):
+    def run(k0, n):
         if not duplex:
             for k in range(k0, k0 + n):
-                step(c, k)
-            return
-        # two host threads joined by the sample FIFO; the transmitter may run at most two frames ahead of the receiver
-        filled, space = threading.Semaphore(0), threading.Semaphore(2)
+                step(k)
+        elif not python_driver:
+            c["link"].duplex_run(c["btx"], c["bch"], c["feats"], n, c["txs"], valid_frames=c["valid"])
+        else:                       # two Python threads joined by the FIFO; the transmitter may run at most two frames ahead
+            filled, space = threading.Semaphore(0), threading.Semaphore(2)
 
-        def producer():
+            def producer():
+                for k in range(k0, k0 + n):
+                    space.acquire(); tx_side(k); filled.release()
+            th = threading.Thread(target=producer); th.start()
             for k in range(k0, k0 + n):
-                space.acquire(); tx_side(c, k); filled.release()
-        th = threading.Thread(target=producer); th.start()
-        for k in range(k0, k0 + n):
-            filled.acquire(); c["link"].rx(); space.release()
-        th.join()
-
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=n_ctx)                      # persistent host threads, one per context
-
-    def run_all(k0, n):
-        if n_ctx == 1:
-            run(ctxs[0], k0, n)
-        else:
-            list(pool.map(lambda c: run(c, k0, n), ctxs))
+                filled.acquire(); c["link"].rx(); space.release()
+            th.join()
 
     if codec_only:
         h2d = S * (3 * 84 * 4 + 3 * 80 * 4); d2h = S * (3 * 80 * 4 + 3 * 84 * 4)
     else:
-        h2d = S * (432 * 4 + 960 * 8 + 1120 * 8 + 1); d2h = S * (960 * 8 + 960 * 8 + 432 * 4 + 4 + 180 * 4 + 4)
-    run_all(0, 12 if not codec_only else 2)                           # warm-up incl. acquisition
+        # features in, tx samples up to the channel, channel output up to the receiver | tx samples out, channel output into the
+        # frame slot, features + return codes + active flags out
+        h2d = S * (432 * 4 + 960 * 8 + 960 * 8); d2h = S * (960 * 8 + 960 * 8 + 432 * 4 + 4 + 1)
+    run(0, 14 if not codec_only else 2)                               # warm-up incl. acquisition
+    if not codec_only:
+        c["valid"][:] = 0
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    run_all(100, K)
-    for c in ctxs:
-        c["b"].synchronize()
-        if "btx" in c: c["btx"].synchronize()
+    run(100, K)
+    c["b"].synchronize()
+    if "btx" in c: c["btx"].synchronize(); c["bch"].synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
-    pool.shutdown()
-    for c in ctxs:
-        if "link" in c: c["link"].close()
-        if c.get("btx") is not None and c["btx"] is not c["b"]: c["btx"].close()
-        c["b"].close()
-    return {"value": S * world * F_PER_STEP * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": K, "contexts": n_ctx, "host_threads": n_ctx * (2 if duplex else 1),
-            "timing": ("host wall clock around K modem frames per stream; transmitter side (rade_b200_tx, rade_b200_channel, FIFO push) and "
-                       "receiver side (FIFO gather, rade_b200_rx) on two host threads joined by the pinned host FIFO, like radae_tx | ch | radae_rx; "
-                       "every call synchronous; max over ranks") if duplex else
-                      "host wall clock around K synchronous steps (tx, channel, push, rx back to back on one host thread), pinned buffers, host FIFO in C; max over ranks"}
+    out = {"value": S * world * F_PER_STEP * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": K, "host_threads": 3 if duplex else 1}
+    if not codec_only:
+        out["valid_output_fraction"] = float(c["valid"].mean() / K) if (duplex and not python_driver) else None
+        out["frames_dropped_on_full_fifos"] = int(c["link"].dropped())
+        out["timing"] = ("host wall clock around ONE rade_b200_duplex_run call for K modem frames per stream: rade_b200_tx, rade_b200_channel_hostlink and "
+                         "rade_b200_hostlink_rx on three host threads in C with a context each, joined by pinned tx buffers and the pinned frame slots of the link, "
+                         "like radae_tx | ch | radae_rx; every call synchronous, every sample crosses PCIe four times; max over ranks") if (duplex and not python_driver) else \
+                        ("host wall clock; two Python threads around the same synchronous calls" if duplex else
+                         "host wall clock around K synchronous steps (tx, channel, rx back to back on one host thread), pinned buffers; max over ranks")
+        c["link"].close()
+        if c["btx"] is not c["b"]: c["btx"].close(); c["bch"].close()
+    c["b"].close()
+    return out
+
+
+def run_e2e_rx(S, sig, K, world, dist, torch, weights=None, device=0):
+    """rx-search end to end: 960 new receive samples per stream per step from pinned host memory -> rade_b200_hostlink_push
+    (host FIFO) -> rade_b200_hostlink_rx (features, return codes back to the host), cold receiver, K steps, wall clock"""
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import HostLink
+    b = RadeBatch(S, device=device, weights=weights)
+    link = HostLink(b)
+    n_steps = sig.shape[1] // 960
+    frames = [torch.from_numpy(np.ascontiguousarray(sig[:, i * 960:(i + 1) * 960])).pin_memory().numpy() for i in range(min(n_steps, K + 2))]
+    for i in range(2):
+        link.push(frames[i]); link.rx()
+    b.reset(); link.close(); link = HostLink(b)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        link.push(frames[k % len(frames)])
+        link.rx()
+    b.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    link.close(); b.close()
+    return {"value": S * world * F_PER_STEP * K / dt, "unit": "frames/s", "h2d_bytes_per_step": int(S * (960 * 8 + 16)), "d2h_bytes_per_step": int(S * (432 * 4 + 4 + 1 + 8)),
+            "steps": K, "host_threads": 1,
+            "timing": "host wall clock around K x (rade_b200_hostlink_push of 960 samples per stream from pinned host memory, rade_b200_hostlink_rx), cold receiver; max over ranks"}
 
 
 def main():
@@ -487,14 +663,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "codec"])
+    ap.add_argument("--workload", default="full", choices=["full", "codec", "rx-search"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default 1024 full / 8192 codec)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="development runs: skip the end-to-end leg (the line then has e2e = null)")
     ap.add_argument("--ref-frames", type=int, default=200, help="--impl reference: modem frames per process and step (bounded sample)")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg: tx, channel, push, rx back to back on ONE host thread")
     ap.add_argument("--no-pipeline", action="store_true", help="run TX and RX of a frame back to back on one stream")
-    ap.add_argument("--e2e-contexts", type=int, default=1, help="host threads / contexts serving the streams in the e2e leg")
+    ap.add_argument("--e2e-contexts", type=int, default=1, help="(unused; kept for old command lines)")
+    ap.add_argument("--e2e-python", action="store_true", help="e2e leg: drive the duplex loop from two Python threads instead of rade_b200_duplex_run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

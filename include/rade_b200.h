@@ -138,15 +138,34 @@ RADE_EXPORT int rade_b200_profile_n_kernels(void);
 RADE_EXPORT const char *rade_b200_profile_kernel_name(int k);
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts);
 
-/* --- host-side sample link: per-stream FIFOs in pinned host memory in front of rade_b200_rx.
- * push: samples [S][960] appended per stream.  rx: every stream with >= nin[s] samples queued is advanced by exactly
- * one rade_rx call (the others are left untouched, `active` = 0); outputs as rade_b200_rx. --- */
+/* --- host-side sample link in front of rade_b200_rx: a ring of 4 modem-frame slots [S][960] in pinned host
+ * memory that producers fill, per-stream sample rings on the device that the receiver consumes; queued frames go up with the
+ * copy engine, issued ahead so that they overlap the previous call's kernels.
+ * push: samples [S][960] from an ordinary host array (host memcpy); returns 0, or S when the frame was DROPPED because all slots
+ * were full.  channel_hostlink: tx [S][960] (host) -> channel simulator of `bch` (any context on the same device with the same
+ * S) -> the next slot, written in place by the kernel; returns like push.  rx: every stream with >= nin[s] samples queued is
+ * advanced by exactly one rade_rx call (the others are left untouched, `active` = 0); outputs as rade_b200_rx.
+ * One producer and one consumer per link (they may be different host threads with a context each). --- */
 typedef struct rade_b200_hostlink rade_b200_hostlink;
-RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples);
+RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples /* ignored */);
 RADE_EXPORT void rade_b200_hostlink_close(rade_b200_hostlink *h);
 RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples);
+RADE_EXPORT int rade_b200_channel_hostlink(rade_batch *bch, rade_b200_hostlink *h, const RADE_COMP *tx);
 RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out, int *ret, float *eoo_out);
 RADE_EXPORT const unsigned char *rade_b200_hostlink_active(rade_b200_hostlink *h);
+RADE_EXPORT long long rade_b200_hostlink_dropped(rade_b200_hostlink *h);
+/* pinned (page-locked) host memory for the arrays handed to the host-pointer entry points: only pinned arrays are moved by the copy
+ * engines asynchronously, pageable ones are staged by the driver */
+RADE_EXPORT void *rade_b200_host_alloc(size_t bytes);
+RADE_EXPORT void rade_b200_host_free(void *p);
+/* the reference's `radae_tx | ch | radae_rx` pipe (src/radae_tx.c:14-55, src/radae_rx.c:14-58) for S streams as one C call: three
+ * host threads with a context each — rade_b200_tx on `btx`, rade_b200_channel_hostlink on `bch`, rade_b200_hostlink_rx (the calling
+ * thread) on the link's receiver context; every call is the synchronous host-buffer call, the pipes are the tx buffers and the link.
+ * features_in: n_in frames of [S][432] (cycled over); tx_bufs: n_tx_bufs (2..4) x [S][960] (pinned memory is written in place by the
+ * modulator); features_out [S][432] / ret [S]: the receiver's outputs for the last frame; valid_frames [S] (optional): += calls
+ * that returned features.  With bch == btx transmitter and channel share one thread. */
+RADE_EXPORT int rade_b200_duplex_run(rade_batch *btx, rade_batch *bch, rade_b200_hostlink *link, const float *features_in, int n_in,
+                                     int n_frames, RADE_COMP *tx_bufs, int n_tx_bufs, float *features_out, int *ret, long long *valid_frames);
 
 /* --- host-buffer channel call (for end-to-end measurements through host memory): tx, rx [S][960] --- */
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx);

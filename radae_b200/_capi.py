@@ -65,7 +65,10 @@ SIGNATURES = {
     "rade_b200_channel": (_I, [_P, _P, _P]),
     "rade_b200_hostlink_open": (_P, [_P, _I]), "rade_b200_hostlink_close": (None, [_P]),
     "rade_b200_hostlink_push": (_I, [_P, _P]), "rade_b200_hostlink_rx": (_I, [_P, _P, _P, _P]),
-    "rade_b200_hostlink_active": (_P, [_P]),
+    "rade_b200_hostlink_active": (_P, [_P]), "rade_b200_hostlink_dropped": (C.c_longlong, [_P]),
+    "rade_b200_channel_hostlink": (_I, [_P, _P, _P]),
+    "rade_b200_host_alloc": (_P, [C.c_size_t]), "rade_b200_host_free": (None, [_P]),
+    "rade_b200_duplex_run": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P]),
     # test hook
     "rade_b200_debug_tables": (_I, [_I, _P, _I]),
     "rade_b200_debug_codec_stream": (C.c_longlong, [_I, _I, _P, C.c_longlong, _P, _I, C.POINTER(_I), C.POINTER(_I)]),

@@ -15,6 +15,17 @@ def _np(a, dtype):
     return a, a.ctypes.data
 
 
+def pinned_empty(shape, dtype):
+    """numpy array in pinned host memory (rade_b200_host_alloc); the memory lives as long as the array (never freed: small, few)"""
+    lib = capi.lib()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.rade_b200_host_alloc(max(n, 16))
+    if not p:
+        raise RuntimeError("rade_b200_host_alloc failed")
+    buf = (C.c_char * max(n, 16)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 def _check(rc, what):
     if rc is None or rc < 0:
         raise RuntimeError(f"libradae_b200: {what} failed (see stderr for the CUDA error)")
@@ -239,18 +250,39 @@ class HostLink:
         if not self.h:
             raise RuntimeError("rade_b200_hostlink_open failed")
         S = batch.S
-        self.features = np.zeros((S, NFEAT), np.float32)
-        self.ret = np.zeros(S, np.int32)
-        self.eoo = np.zeros((S, NEOO_BITS), np.float32)
+        self.features = pinned_empty((S, NFEAT), np.float32)          # pinned: the D2H copies run on the copy engine
+        self.ret = pinned_empty((S,), np.int32)
+        self.eoo = pinned_empty((S, NEOO_BITS), np.float32)
 
     def push(self, samples):
+        """returns the number of streams whose frame was dropped because their FIFO was full"""
         x, px = _np(samples, np.complex64)
         assert x.shape == (self.b.S, NMF)
-        _check(self.lib.rade_b200_hostlink_push(self.h, px), "hostlink_push")
+        return _check(self.lib.rade_b200_hostlink_push(self.h, px), "hostlink_push")
+
+    def channel_push(self, bch, tx):
+        """tx [S][960] -> channel simulator of context `bch` -> the next frame slot (kernel writes in place); 0 or S (dropped)"""
+        t, pt = _np(tx, np.complex64)
+        assert t.shape == (self.b.S, NMF)
+        return _check(self.lib.rade_b200_channel_hostlink(bch.h, self.h, pt), "channel_hostlink")
+
+    def duplex_run(self, btx, bch, features_in, n_frames, tx_bufs, valid_frames=None):
+        """the reference's radae_tx | ch | radae_rx pipe for S streams, driven from C (three host threads, synchronous calls)"""
+        f, pf = _np(features_in, np.float32)
+        assert f.ndim == 3 and f.shape[1:] == (self.b.S, NFEAT)
+        assert tx_bufs.dtype == np.complex64 and tx_bufs.ndim == 3 and tx_bufs.shape[1:] == (self.b.S, NMF) and tx_bufs.flags.c_contiguous
+        vp = valid_frames.ctypes.data if valid_frames is not None else None
+        _check(self.lib.rade_b200_duplex_run(btx.h, bch.h, self.h, pf, f.shape[0], int(n_frames), tx_bufs.ctypes.data, tx_bufs.shape[0],
+                                             self.features.ctypes.data, self.ret.ctypes.data, vp), "duplex_run")
+        return self.features, self.ret
 
     def rx(self):
         _check(self.lib.rade_b200_hostlink_rx(self.h, self.features.ctypes.data, self.ret.ctypes.data, self.eoo.ctypes.data), "hostlink_rx")
         return self.features, self.ret, self.eoo
+
+    def dropped(self):
+        """frames refused by push() so far because a FIFO was full"""
+        return int(self.lib.rade_b200_hostlink_dropped(self.h))
 
     def close(self):
         if self.h:

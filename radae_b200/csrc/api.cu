@@ -30,7 +30,7 @@ struct rade_batch {
   RxBuffers rx;
   ChanState *chan_state;
   rade_b200_channel_cfg chan_cfg;
-  float2 *link_ring; long long *link_wr, *link_rd;
+  float2 *link_ring; long long *link_wr, *link_rd; int *link_overflow;    // device loop-back FIFOs; frames dropped because a FIFO was full
   // transmitter
   float *z_tx;                // [S][240]
   float *eoo_bits; int *has_eoo_bits;
@@ -69,6 +69,9 @@ int reset_state(rade_batch *b) {
   CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->link_wr, 0, sizeof(long long) * S, b->stream));
   CUDA_CHECK(cudaMemsetAsync(b->link_rd, 0, sizeof(long long) * S, b->stream));
+  CUDA_CHECK(cudaMemsetAsync(b->link_overflow, 0, sizeof(int), b->stream));
+  for (auto &g : b->step_graphs) cudaGraphExecDestroy(g.exec);      // captured graphs hold the old state's arguments
+  b->step_graphs.clear();
   CUDA_CHECK(cudaMemsetAsync(b->has_eoo_bits, 0, sizeof(int) * S, b->stream));
   if (b->tx_bpf) CUDA_CHECK(cudaMemsetAsync(b->tx_bpf, 0, sizeof(TxBpfState) * S, b->stream));
   const double foff_err = (b->flags & RADE_FOFF_TEST) ? 10.0 : 0.0;     // src/rade_api.c:263-264
@@ -80,13 +83,14 @@ int reset_state(rade_batch *b) {
   return 0;
 }
 
-// Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host buffer, or nullptr for pageable memory.
-// With an alias the big sample buffers are read / written by the kernels directly over PCIe (no staging copy, the
-// transfer overlaps the compute of the other CTAs); pageable buffers take the cudaMemcpyAsync path.
-// RADE_B200_ZERO_COPY: 1 (default) kernels read and write pinned buffers in place; 2 writes in place, reads staged through
-// the H2D copy engine; 0 everything staged through cudaMemcpyAsync
+// Device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host buffer, or nullptr.
+// RADE_B200_ZERO_COPY: 0 (default) every host array is staged through cudaMemcpyAsync — the copy engines move 7.9 MB in 0.15 ms
+// either way without occupying an SM; 1: kernels read and write pinned buffers in place over PCIe (round 1's default: a kernel
+// that writes in place reaches 48 GB/s but holds its SMs for the whole transfer, a kernel that reads in place gets 19-27 GB/s —
+// with transmitter, channel and receiver contexts sharing one GPU that serialised them, tools/e2e_breakdown.py); 2: writes in
+// place, reads staged.
 int zero_copy_mode() {
-  static const int mode = getenv("RADE_B200_ZERO_COPY") ? atoi(getenv("RADE_B200_ZERO_COPY")) : 1;
+  static const int mode = getenv("RADE_B200_ZERO_COPY") ? atoi(getenv("RADE_B200_ZERO_COPY")) : 0;
   return mode;
 }
 void *pinned_alias(const void *p, bool for_read = false) {
@@ -169,6 +173,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   bad |= dalloc(b, &b->link_ring, S * LINK_CAP);
   bad |= dalloc(b, &b->link_wr, S);
   bad |= dalloc(b, &b->link_rd, S);
+  bad |= dalloc(b, &b->link_overflow, (size_t)1);
   bad |= dalloc(b, &b->z_tx, S * 240);
   bad |= dalloc(b, &b->eoo_bits, S * RADE_NEOO_BITS);
   bad |= dalloc(b, &b->has_eoo_bits, S);
@@ -493,6 +498,8 @@ RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_
   if (cfg->delay_samples < 0 || cfg->delay_samples > 64) return -1;
   b->chan_cfg = *cfg;
   CUDA_CHECK(cudaMemsetAsync(b->chan_state, 0, sizeof(ChanState) * b->S, b->stream));
+  for (auto &g : b->step_graphs) cudaGraphExecDestroy(g.exec);      // the channel parameters are baked into captured graphs
+  b->step_graphs.clear();
   return 0;
 }
 RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx) {
@@ -501,7 +508,7 @@ RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));       // radae.py:570-574, Rb = 80/0.04
   b->prof.begin(K_CHANNEL);
   if (channel_stream_launch(b->tables, nullptr, (float2 *)d_rx, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz,
-                            c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, nullptr, nullptr, b->stream) < 0) return -1;
+                            c.freq_offset_spread_hz, c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, nullptr, nullptr, nullptr, nullptr, b->stream) < 0) return -1;
   b->prof.end(K_CHANNEL);
   b->launches += 1;
   return 0;
@@ -524,7 +531,7 @@ RADE_EXPORT int rade_b200_channel_link_dev(rade_batch *b, const RADE_COMP *d_tx)
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
   b->prof.begin(K_CHANNEL);
   if (channel_stream_launch(b->tables, nullptr, nullptr, (const float2 *)d_tx, b->chan_state, b->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
-                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, tx_side(b)) < 0) return -1;
+                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, b->link_rd, b->link_overflow, tx_side(b)) < 0) return -1;
   b->prof.end(K_CHANNEL);
   b->launches += 1;
   return 0;
@@ -543,7 +550,7 @@ RADE_EXPORT int rade_b200_tx_channel_link_dev(rade_batch *b, const float *d_feat
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, tx_side(b)) < 0) return -1;
   b->prof.end(K_CORE_ENC); b->prof.begin(K_CHANNEL);
   if (channel_stream_launch(b->tables, b->z_tx, nullptr, nullptr, b->chan_state, b->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
-                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, tx_side(b)) < 0) return -1;
+                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, b->link_rd, b->link_overflow, tx_side(b)) < 0) return -1;
   b->prof.end(K_CHANNEL);
   b->launches += 2;
   return 0;
@@ -607,7 +614,7 @@ RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_featur
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {
   cudaSetDevice(b->device);        // the current device is per host thread
   b->prof.begin(K_LINK_PUSH);
-  if (link_push_launch(b->link_ring, b->link_wr, (const float2 *)d_samples, b->S, b->stream) < 0) return -1;
+  if (link_push_launch(b->link_ring, b->link_wr, b->link_rd, b->link_overflow, (const float2 *)d_samples, b->S, b->stream) < 0) return -1;
   b->prof.end(K_LINK_PUSH);
   b->launches += 1;
   return 0;
@@ -621,85 +628,226 @@ RADE_EXPORT int rade_b200_link_pop_dev(rade_batch *b, RADE_COMP *d_rx_in, unsign
   return 0;
 }
 
-// ---- host-side sample link (batched host I/O around the C ABI): per-stream FIFOs in pinned host memory
-// between whatever produces receive samples and rade_b200_rx, which wants nin[s] in {800, 960, 1120} fresh samples per
-// stream per call.  push appends 960 samples per stream; rx gathers nin[s] samples for every stream that has them
-// (OpenMP over streams), marks the others inactive, runs rade_b200_rx and refreshes nin[] in the same round trip.
+// ---- host-side sample link (batched host I/O around the C ABI) between whatever produces receive samples
+// and rade_b200_rx, which wants nin[s] in {800, 960, 1120} fresh samples per stream per call.
+// Host side: a ring of HL_SLOTS modem-frame slots [S][960] in pinned memory (what a producer fills: rade_b200_hostlink_push by
+// host memcpy, rade_b200_channel_hostlink by letting the channel kernel write its output there in place).  Device side: the
+// receiver context's per-stream sample rings (the loop-back link).  rade_b200_hostlink_rx moves queued frames host -> device
+// with the COPY ENGINE (one contiguous 7.9 MB cudaMemcpyAsync per frame of 1024 streams, issued ahead on its own stream so it
+// overlaps the previous call's kernels), appends them to the per-stream rings on the device and runs the receiver on the rings.
+// (Measured, tools/e2e_breakdown.py: a kernel READING pinned host memory in place gets 19-27 GB/s over PCIe — the band-pass
+// kernel took 0.41 ms instead of 0.025 — while the copy engine moves the same bytes in 0.155 ms; kernel WRITES in place reach
+// 48 GB/s, which is why producers on the device still write their frames straight into the host slots.)
+// Single producer / single consumer per link; they may be different host threads with a context each.
+#define HL_SLOTS 4
 struct rade_b200_hostlink {
-  rade_batch *b; int cap; int nthreads;
-  float2 *fifo; volatile long long *wr, *rd; int *nin;      // single producer (push) / single consumer (rx) per stream: the two
-                                                            // may run on different host threads
-  float2 *rx_in; unsigned char *active;
+  rade_batch *b; int nthreads;
+  float2 *frames, *d_frames;                                 // pinned [HL_SLOTS][S][960] + its device alias
+  volatile long long pushed, popped;                         // frames queued by the producer / released by the consumer
+  long long staged, appended, rx_calls;                      // consumer side: frames whose H2D copy was issued / appended to the device rings
+  float2 *d_stage[2];                                        // device staging of a frame
+  cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_appended[2];
+  unsigned char *active;                                     // pinned: which streams the last rx call advanced
+  long long dropped;                                         // frames refused because all slots were full
 };
 RADE_EXPORT rade_b200_hostlink *rade_b200_hostlink_open(rade_batch *b, int capacity_samples) {
   cudaSetDevice(b->device);
-  if (capacity_samples < 2 * RADE_NIN_MAX) capacity_samples = 4096;
+  (void)capacity_samples;                                    // fixed: HL_SLOTS frames on the host, 4096 samples per stream on the device
   rade_b200_hostlink *h = new rade_b200_hostlink();
-  h->b = b; h->cap = capacity_samples;
-  // OpenMP team for the per-stream FIFO copies: RADE_B200_HOST_THREADS, else OpenMP's default (launchers such as torchrun
-  // export OMP_NUM_THREADS=1, which would serialise 16 MB of copies per modem frame of 1024 streams)
+  memset((void *)h, 0, sizeof(*h));
+  h->b = b;
+  // OpenMP team of rade_b200_hostlink_push: RADE_B200_HOST_THREADS, else OpenMP's default (launchers such as torchrun export
+  // OMP_NUM_THREADS=1, which would serialise 8 MB of copies per modem frame of 1024 streams)
   h->nthreads = getenv("RADE_B200_HOST_THREADS") ? atoi(getenv("RADE_B200_HOST_THREADS")) : 0;
   if (h->nthreads < 1) h->nthreads = 0;
-  const size_t S = b->S;
-  bool ok = cudaMallocHost((void **)&h->fifo, S * h->cap * sizeof(float2)) == cudaSuccess &&
-            cudaMallocHost((void **)&h->rx_in, S * RADE_NIN_MAX * sizeof(float2)) == cudaSuccess &&
-            cudaMallocHost((void **)&h->active, S) == cudaSuccess && cudaMallocHost((void **)&h->nin, S * sizeof(int)) == cudaSuccess;
-  if (!ok) { fprintf(stderr, "libradae_b200: cannot allocate pinned host FIFOs\n"); delete h; return nullptr; }
-  h->wr = new long long[S](); h->rd = new long long[S]();
-  memset(h->rx_in, 0, S * RADE_NIN_MAX * sizeof(float2));
-  for (size_t s = 0; s < S; s++) h->nin[s] = RADE_NMF;
+  const size_t S = b->S, fb = S * RADE_NMF * sizeof(float2);
+  const unsigned fl = cudaHostAllocMapped | cudaHostAllocPortable;
+  bool ok = cudaHostAlloc((void **)&h->frames, HL_SLOTS * fb, fl) == cudaSuccess &&
+            cudaHostGetDevicePointer((void **)&h->d_frames, h->frames, 0) == cudaSuccess &&
+            cudaHostAlloc((void **)&h->active, S, fl) == cudaSuccess &&
+            cudaMalloc((void **)&h->d_stage[0], fb) == cudaSuccess && cudaMalloc((void **)&h->d_stage[1], fb) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; i++)
+    ok = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_appended[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { fprintf(stderr, "libradae_b200: cannot allocate the host sample link\n"); rade_b200_hostlink_close(h); return nullptr; }
+  memset(h->frames, 0, HL_SLOTS * fb); memset(h->active, 0, S);
   return h;
 }
 RADE_EXPORT void rade_b200_hostlink_close(rade_b200_hostlink *h) {
   if (!h) return;
-  cudaFreeHost(h->fifo); cudaFreeHost(h->rx_in); cudaFreeHost(h->active); cudaFreeHost(h->nin);
-  delete[] const_cast<long long *>(h->wr); delete[] const_cast<long long *>(h->rd); delete h;
-}
-RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples) {
-  const int S = h->b->S, cap = h->cap;
-#pragma omp parallel for schedule(static) num_threads(h->nthreads ? h->nthreads : omp_get_max_threads())
-  for (int s = 0; s < S; s++) {
-    if (h->wr[s] - h->rd[s] + RADE_NMF > cap) continue;            // full: drop (the consumer is not keeping up)
-    const float2 *src = (const float2 *)samples + (size_t)s * RADE_NMF;
-    float2 *dst = h->fifo + (size_t)s * cap;
-    const int w = (int)(h->wr[s] % cap), first = (cap - w < RADE_NMF) ? cap - w : RADE_NMF;
-    memcpy(dst + w, src, first * sizeof(float2));
-    if (first < RADE_NMF) memcpy(dst, src + first, (RADE_NMF - first) * sizeof(float2));
-    h->wr[s] = h->wr[s] + RADE_NMF;
+  cudaSetDevice(h->b->device);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_appended[i]) cudaEventDestroy(h->ev_appended[i]);
+    if (h->d_stage[i]) cudaFree(h->d_stage[i]);
   }
+  if (h->frames) cudaFreeHost(h->frames);
+  if (h->active) cudaFreeHost(h->active);
+  delete h;
+}
+// samples [S][960] in ordinary host memory -> the next frame slot (host memcpy, OpenMP over streams).  Returns the number of
+// streams whose frame was DROPPED because all slots were full (0 = queued, S = dropped), < 0 on error.
+RADE_EXPORT int rade_b200_hostlink_push(rade_b200_hostlink *h, const RADE_COMP *samples) {
+  const int S = h->b->S;
+  if (h->pushed - h->popped >= HL_SLOTS) { h->dropped += S; return S; }       // the consumer is not keeping up
+  float2 *dst = h->frames + (size_t)(h->pushed % HL_SLOTS) * S * RADE_NMF;
+#pragma omp parallel for schedule(static) num_threads(h->nthreads ? h->nthreads : omp_get_max_threads())
+  for (int s = 0; s < S; s++) memcpy(dst + (size_t)s * RADE_NMF, (const float2 *)samples + (size_t)s * RADE_NMF, RADE_NMF * sizeof(float2));
+  __sync_synchronize();
+  h->pushed = h->pushed + 1;
   return 0;
 }
+// transmit samples tx [S][960] (host) -> channel simulator of context `bch` (any context on the link's device with the same S; its
+// channel configuration and state are used) -> the next frame slot: tx goes up with the copy engine, the channel kernel writes
+// its output straight into the pinned slot.  Returns 0, or S when the frame was dropped because all slots were full; < 0 on error.
+RADE_EXPORT int rade_b200_channel_hostlink(rade_batch *bch, rade_b200_hostlink *h, const RADE_COMP *tx) {
+  cudaSetDevice(bch->device);
+  if (bch->S != h->b->S || bch->device != h->b->device) { fprintf(stderr, "libradae_b200: channel_hostlink: contexts do not match\n"); return -1; }
+  const size_t S = bch->S;
+  if (h->pushed - h->popped >= HL_SLOTS) { h->dropped += (long long)S; return (int)S; }
+  const rade_b200_channel_cfg &c = bch->chan_cfg;
+  const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
+  CUDA_CHECK(cudaMemcpyAsync(bch->d_tx, tx, S * RADE_NMF * sizeof(float2), cudaMemcpyHostToDevice, bch->stream));
+  const size_t slot_off = (size_t)(h->pushed % HL_SLOTS) * S * RADE_NMF;
+  float2 *out = zero_copy_mode() ? h->d_frames + slot_off : bch->d_rx_in;      // in place over PCIe, or device buffer + copy engine
+  bch->prof.begin(K_CHANNEL);
+  if (channel_stream_launch(bch->tables, nullptr, out, bch->d_tx, bch->chan_state, bch->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
+                            c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, nullptr, nullptr, nullptr, nullptr, bch->stream) < 0) return -1;
+  bch->prof.end(K_CHANNEL);
+  bch->launches += 1;
+  if (!zero_copy_mode()) CUDA_CHECK(cudaMemcpyAsync(h->frames + slot_off, bch->d_rx_in, S * RADE_NMF * sizeof(float2), cudaMemcpyDeviceToHost, bch->stream));
+  CUDA_CHECK(cudaStreamSynchronize(bch->stream));
+  __sync_synchronize();
+  h->pushed = h->pushed + 1;
+  return 0;
+}
+// every stream with >= nin[s] samples queued is advanced by exactly one rade_rx call (the others are left untouched, `active` = 0)
 RADE_EXPORT int rade_b200_hostlink_rx(rade_b200_hostlink *h, float *features_out, int *ret, float *eoo_out) {
   rade_batch *b = h->b;
   cudaSetDevice(b->device);
-  const int S = b->S, cap = h->cap;
-#pragma omp parallel for schedule(static) num_threads(h->nthreads ? h->nthreads : omp_get_max_threads())
-  for (int s = 0; s < S; s++) {
-    const int n = h->nin[s];
-    const bool ok = h->wr[s] - h->rd[s] >= n;
-    h->active[s] = ok ? 1 : 0;
-    if (!ok) continue;
-    const float2 *src = h->fifo + (size_t)s * cap;
-    float2 *dst = h->rx_in + (size_t)s * RADE_NIN_MAX;
-    const int r = (int)(h->rd[s] % cap), first = (cap - r < n) ? cap - r : n;
-    memcpy(dst, src + r, first * sizeof(float2));
-    if (first < n) memcpy(dst + first, src, (n - first) * sizeof(float2));
-    h->rd[s] = h->rd[s] + n;
+  const size_t Sz = b->S, fb = Sz * RADE_NMF * sizeof(float2);
+  const long long pushed = h->pushed;
+  __sync_synchronize();
+  // (1) host -> device copies of every queued frame not yet on its way (at most two in flight: two staging buffers)
+  while (h->staged < pushed && h->staged - h->appended < 2) {
+    const int sb = (int)(h->staged & 1);
+    if (h->staged >= 2) CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_appended[sb], 0));   // the staging buffer has been consumed
+    CUDA_CHECK(cudaMemcpyAsync(h->d_stage[sb], h->frames + (size_t)(h->staged % HL_SLOTS) * Sz * RADE_NMF, fb, cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_CHECK(cudaEventRecord(h->ev_copied[sb], h->copy_stream));
+    h->staged++;
   }
-  const size_t Sz = S;
-  // the gathered samples sit in our own pinned buffer: the band-pass kernel reads them in place over PCIe
-  const void *rx_alias = pinned_alias(h->rx_in, true);
-  if (!rx_alias) { CUDA_CHECK(cudaMemcpyAsync(b->d_rx_in, h->rx_in, Sz * RADE_NIN_MAX * sizeof(float2), cudaMemcpyHostToDevice, b->stream)); rx_alias = b->d_rx_in; }
-  CUDA_CHECK(cudaMemcpyAsync(b->d_active, h->active, Sz, cudaMemcpyHostToDevice, b->stream));
-  if (rade_b200_rx_dev(b, b->d_feat_out, b->d_ret, nullptr, (const RADE_COMP *)rx_alias, b->d_active) < 0) return -1;
+  // (2) append ONE staged frame per call to the per-stream device rings (what a call consumes on average); the frames behind it
+  // are already on their way up, so the next call finds its frame on the device
+  long long newly = 0;
+  while (h->appended < h->staged && h->appended < h->rx_calls + 1) {
+    const int sb = (int)(h->appended & 1);
+    CUDA_CHECK(cudaStreamWaitEvent(b->stream, h->ev_copied[sb], 0));
+    b->prof.begin(K_LINK_PUSH);
+    if (link_push_launch(b->link_ring, b->link_wr, b->link_rd, b->link_overflow, h->d_stage[sb], b->S, b->stream) < 0) return -1;
+    b->prof.end(K_LINK_PUSH);
+    CUDA_CHECK(cudaEventRecord(h->ev_appended[sb], b->stream));
+    b->launches += 1;
+    h->appended++; newly++;
+  }
+  // (3) the receiver on the rings
+  const int reset_dec = (b->flags & RADE_USE_C_DECODER) ? 0 : 1;
+  LinkSrc ls = {b->link_ring, b->link_wr, b->link_rd, b->d_active};
+  int n = rx_dsp_launch(b->tables, b->rx, nullptr, nullptr, &ls, b->S, 1, reset_dec, b->d_ret, b->stream, &b->prof);
+  if (n < 0) return -1;
+  b->prof.begin(K_CORE_DEC);
+  if (core_decoder_launch(b->weights.dev, b->rx.dec_state, b->rx.z_hat, b->d_feat_out, 1, b->rx.uw_errors, b->rx.dec_active,
+                          b->S, RADE_NZMF, b->stream) < 0) return -1;
+  b->prof.end(K_CORE_DEC);
+  b->launches += n + 1;
   CUDA_CHECK(cudaMemcpyAsync(features_out, b->d_feat_out, Sz * RADE_NFEAT * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaMemcpyAsync(ret, b->d_ret, Sz * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   if (eoo_out) CUDA_CHECK(cudaMemcpyAsync(eoo_out, b->rx.eoo, Sz * RADE_NEOO_BITS * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-  CUDA_CHECK(cudaMemcpyAsync(h->nin, b->rx.nin, Sz * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h->active, b->d_active, Sz, cudaMemcpyDeviceToHost, b->stream));
   CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  h->rx_calls++;
+  __sync_synchronize();
+  h->popped = h->appended;                                   // their copies have completed: the producer may reuse those slots
   return 0;
 }
+// pinned host memory for callers without a CUDA runtime of their own (C hosts, ctypes): buffers handed to the host-pointer entry
+// points are copied by the copy engines asynchronously only when they are pinned — a pageable array is staged by the driver
+RADE_EXPORT void *rade_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  memset(p, 0, bytes);
+  return p;
+}
+RADE_EXPORT void rade_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 RADE_EXPORT const unsigned char *rade_b200_hostlink_active(rade_b200_hostlink *h) { return h->active; }
+RADE_EXPORT long long rade_b200_hostlink_dropped(rade_b200_hostlink *h) { return h->dropped; }
+
+// ---- the reference's `radae_tx | ch | radae_rx` pipe (three programs joined by pipes: src/radae_tx.c:14-55, the channel
+// simulator, src/radae_rx.c:14-58) for S streams as ONE C call: three host threads, one context each — rade_b200_tx on `btx`,
+// rade_b200_channel_hostlink on `bch`, rade_b200_hostlink_rx (the calling thread) on the link's receiver context — every call the
+// synchronous host-buffer call a C host would make itself; the pipes are the n_tx_bufs pinned tx buffers and the link.
+// features_in: n_in frames of [S][432] (cycled over); tx_bufs: n_tx_bufs (2..4) x [S][960], pinned memory is written in place;
+// features_out [S][432] / ret [S]: the receiver's outputs for the LAST frame; valid_frames [S] (optional): += calls that returned
+// features.  bch may equal btx: transmitter and channel then share a thread (two stages).
+}  // extern "C"
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <chrono>
+namespace {
+struct Sem {
+  std::mutex m; std::condition_variable cv; int n;
+  explicit Sem(int v) : n(v) {}
+  void post() { { std::lock_guard<std::mutex> l(m); n++; } cv.notify_one(); }
+  void wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return n > 0; }); n--; }
+};
+}  // namespace
+extern "C" {
+RADE_EXPORT int rade_b200_duplex_run(rade_batch *btx, rade_batch *bch, rade_b200_hostlink *link, const float *features_in, int n_in,
+                                     int n_frames, RADE_COMP *tx_bufs, int n_tx_bufs, float *features_out, int *ret, long long *valid_frames) {
+  if (!btx || !bch || !link || !features_in || n_in < 1 || n_frames < 0 || !tx_bufs || n_tx_bufs < 1 || !features_out || !ret) return -1;
+  if (n_tx_bufs > 4) n_tx_bufs = 4;
+  const size_t S = btx->S;
+  const bool three = bch != btx && n_tx_bufs >= 2;
+  Sem tx_free(three ? n_tx_bufs : 1), tx_full(0), frames_free(HL_SLOTS - 1), frames_full(0);
+  int tx_rc = 0, ch_rc = 0;
+  auto tx_stage = [&](int k) {
+    RADE_COMP *buf = tx_bufs + (size_t)(three ? k % n_tx_bufs : 0) * S * RADE_NMF;
+    if (tx_rc == 0 && rade_b200_tx(btx, buf, features_in + (size_t)(k % n_in) * S * RADE_NFEAT) < 0) tx_rc = -1;
+  };
+  auto ch_stage = [&](int k) {
+    RADE_COMP *buf = tx_bufs + (size_t)(three ? k % n_tx_bufs : 0) * S * RADE_NMF;
+    if (ch_rc == 0 && tx_rc == 0) { const int r = rade_b200_channel_hostlink(bch, link, buf); if (r != 0) ch_rc = r < 0 ? -1 : -2; }
+  };
+  std::thread t_tx, t_ch;
+  if (three) {
+    t_tx = std::thread([&] { for (int k = 0; k < n_frames; k++) { tx_free.wait(); tx_stage(k); tx_full.post(); } });
+    t_ch = std::thread([&] { for (int k = 0; k < n_frames; k++) { tx_full.wait(); frames_free.wait(); ch_stage(k); tx_free.post(); frames_full.post(); } });
+  } else {
+    t_ch = std::thread([&] { for (int k = 0; k < n_frames; k++) { frames_free.wait(); tx_stage(k); ch_stage(k); frames_full.post(); } });
+  }
+  int rc = 0;
+  const bool trace = getenv("RADE_B200_DUPLEX_TRACE") != nullptr;
+  double t_wait = 0, t_rx = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  for (int k = 0; k < n_frames; k++) {
+    const double t0 = now();
+    frames_full.wait();
+    const double t1 = now();
+    if (rc == 0 && rade_b200_hostlink_rx(link, features_out, ret, nullptr) < 0) rc = -1;
+    t_wait += t1 - t0; t_rx += now() - t1;
+    if (rc == 0 && valid_frames)
+      for (size_t s = 0; s < S; s++) valid_frames[s] += (ret[s] & 1);
+    frames_free.post();
+  }
+  if (three) t_tx.join();
+  t_ch.join();
+  if (trace && n_frames > 0)
+    fprintf(stderr, "rade_b200_duplex_run: receiver thread per frame: %.3f ms waiting for a frame, %.3f ms in rade_b200_hostlink_rx\n",
+            1e3 * t_wait / n_frames, 1e3 * t_rx / n_frames);
+  return (rc < 0 || tx_rc < 0 || ch_rc < 0) ? -1 : 0;
+}
 
 // ---- per-kernel timing (CUDA events on the context's stream).  enable=1 starts recording an event pair around every
 // kernel launch; rade_b200_profile_read synchronises, returns per-kernel-class total milliseconds and launch counts

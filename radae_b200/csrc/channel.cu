@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256)
 channel_stream_kernel(DspTables T, const float *__restrict__ z_mod, float2 *__restrict__ rx, const float2 *__restrict__ tx,
                       ChanState *__restrict__ st, int S,
                       float sigma, float freq0, float freq_spread, float doppler, int d, float gain, unsigned long long seed,
-                      float2 *__restrict__ link_ring, long long *__restrict__ link_wr) {
+                      float2 *__restrict__ link_ring, long long *__restrict__ link_wr, const long long *__restrict__ link_rd,
+                      int *__restrict__ link_overflow) {
   __shared__ float2 stx[64 + RADE_NMF];
   __shared__ float2 g[4];                       // G1(t0), G1(t0+960), G2(t0), G2(t0+960)
   __shared__ float2 sym[RADE_NS + 1][RADE_NC];
@@ -114,6 +115,8 @@ channel_stream_kernel(DspTables T, const float *__restrict__ z_mod, float2 *__re
   float2 *out = link_ring ? link_ring + (size_t)s * LINK_CAP : rx + (size_t)s * RADE_NMF;
   const long long lw = link_ring ? link_wr[s] : 0;
   const int omask = link_ring ? LINK_CAP - 1 : 0x7fffffff;
+  // a full FIFO (the receiver is not keeping up) drops the frame instead of overwriting unread samples, and says so
+  const bool full = link_ring && link_rd && lw - link_rd[s] + RADE_NMF > LINK_CAP;
   for (int i = tid; i < RADE_NMF; i += blockDim.x) {
     const float a = (float)i * (1.f / RADE_NMF);
     const float2 g1 = make_float2(g[0].x + a * (g[1].x - g[0].x), g[0].y + a * (g[1].y - g[0].y));
@@ -123,7 +126,7 @@ channel_stream_kernel(DspTables T, const float *__restrict__ z_mod, float2 *__re
     mp.x += e.x; mp.y += e.y;
     const float2 v = cmul(mp, make_float2((float)cs, (float)sn));
     const float2 nz = cnormal(seed, s, (unsigned long long)(t0 + i), 0xA11CEu);
-    out[(int)((lw + i) & omask)] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
+    if (!full) out[(int)((lw + i) & omask)] = make_float2(gain * (v.x + sigma * nz.x), gain * (v.y + sigma * nz.y));
     const double c2 = cs * cb - sn * sb, s2 = sn * cb + cs * sb;
     cs = c2; sn = s2;
   }
@@ -131,14 +134,16 @@ channel_stream_kernel(DspTables T, const float *__restrict__ z_mod, float2 *__re
   for (int i = tid; i < 64; i += blockDim.x) cs_.delay[i] = stx[RADE_NMF + i];
   if (link_ring) __threadfence();               // samples before the write pointer: the receiver may be running concurrently
   __syncthreads();
-  if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); if (link_ring) link_wr[s] = lw + RADE_NMF; }
+  if (tid == 0) { cs_.t = t0 + RADE_NMF; cs_.phase = fmod(ph0 + dphi * RADE_NMF, 2.0 * M_PI); if (link_ring && !full) link_wr[s] = lw + RADE_NMF; if (full && link_overflow) atomicAdd(link_overflow, 1); }
 }
 
 // ---------------------------------------------------------------- loop-back link (per-stream FIFO)
 
-__global__ void link_push_kernel(float2 *__restrict__ ring, long long *__restrict__ wr, const float2 *__restrict__ in, int S) {
+__global__ void link_push_kernel(float2 *__restrict__ ring, long long *__restrict__ wr, const long long *__restrict__ rd, int *__restrict__ overflow,
+                                 const float2 *__restrict__ in, int S) {
   const int s = blockIdx.x;
   const long long w = wr[s];
+  if (rd && w - rd[s] + RADE_NMF > LINK_CAP) { if (threadIdx.x == 0 && overflow) atomicAdd(overflow, 1); return; }   // full: drop, flag
   for (int i = threadIdx.x; i < RADE_NMF; i += blockDim.x)
     ring[(size_t)s * LINK_CAP + ((w + i) & (LINK_CAP - 1))] = in[(size_t)s * RADE_NMF + i];
   __syncthreads();
@@ -170,15 +175,16 @@ int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const f
 
 int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
                           float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
-                          cudaStream_t stream) {
+                          const long long *link_rd, int *link_overflow, cudaStream_t stream) {
   if (d < 0 || d > 64) return -1;
-  channel_stream_kernel<<<S, 256, 0, stream>>>(T, z_mod, rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed, link_ring, link_wr);
+  channel_stream_kernel<<<S, 256, 0, stream>>>(T, z_mod, rx, tx, st, S, sigma, freq0, freq_spread, doppler, d, gain, seed, link_ring, link_wr, link_rd,
+                                               link_overflow);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream) {
-  link_push_kernel<<<S, 256, 0, stream>>>(ring, wr, in, S);
+int link_push_launch(float2 *ring, long long *wr, const long long *rd, int *overflow, const float2 *in, int S, cudaStream_t stream) {
+  link_push_kernel<<<S, 256, 0, stream>>>(ring, wr, rd, overflow, in, S);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -427,6 +427,10 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
         c.B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); c.B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
         c.B.lo[2] = desc_lo(smem_u32(sm.cb[(t + NCB - 2) % NCB]));
         c.par = t & 1; c.t = t;
+        // accumulator columns are reused by layer parity; within a step every overwrite is ordered behind the epilogue that last
+        // read the columns by the layer dependencies, EXCEPT the first conv of a step (no dependency of its own) against the last
+        // conv epilogue of the step before: wait for that epilogue here (found as run-to-run differences in frame 1 of the CLI test)
+        if (t > 0) { mbar_wait(&sm.act_ready[9], (t - 1) & 1); tc_fence_after(); }
         mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);        // dense1 output (int8) is in cur, features [0, 64)
         tc_fence_after();
         IssueAll<NS, true, 0, kUmmaEncProg.n>::run(c);
@@ -741,6 +745,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
         c.B.lo[0] = desc_lo(smem_u32(sm.cb[t % NCB])); c.B.lo[1] = desc_lo(smem_u32(sm.cb[(t + NCB - 1) % NCB]));
         c.B.lo[3] = desc_lo(smem_u32(sm.hq[t & 1])); c.B.lo[4] = desc_lo(smem_u32(sm.hq[(t + 1) & 1]));
         c.par = t & 1; c.t = t;
+        if (t > 0) { mbar_wait(&sm.act_ready[14], (t - 1) & 1); tc_fence_after(); }      // as in the encoder (here the GLU dependency already orders it)
         mbar_wait(&sm.d1_ready[t & 1], (t >> 1) & 1);
         tc_fence_after();
         IssueAll<NS, false, 0, kUmmaDecProg.n>::run(c);

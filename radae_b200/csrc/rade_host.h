@@ -76,8 +76,8 @@ int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const f
                          int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
 int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
                           float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
-                          cudaStream_t stream);
-int link_push_launch(float2 *ring, long long *wr, const float2 *in, int S, cudaStream_t stream);
+                          const long long *link_rd, int *link_overflow, cudaStream_t stream);
+int link_push_launch(float2 *ring, long long *wr, const long long *rd, int *overflow, const float2 *in, int S, cudaStream_t stream);
 int link_pop_launch(const float2 *ring, const long long *wr, long long *rd, const RxCtl *ctl, float2 *out,
                     unsigned char *active, int S, cudaStream_t stream);
 int rx_init_launch(RxCtl *ctl, int *uw_errors, int S, double foff_err, cudaStream_t stream);

@@ -177,6 +177,65 @@ def test_hostlink_fifo_feeds_the_same_call_sequence(golden):
     link.close(); b.close()
 
 
+def test_channel_into_host_fifo_and_c_duplex_driver_equal_the_call_sequence():
+    """rade_b200_channel_hostlink (the channel kernel writes its output straight into the pinned frame slot, the copy engine brings
+    it to the receiver's device rings) and rade_b200_duplex_run (the radae_tx | ch | radae_rx pipe driven from three C threads with
+    a context each — or two, when transmitter and channel share one) must give, bit for bit, what the plain call sequence
+    tx -> channel -> hostlink_push -> hostlink_rx gives"""
+    torch = need_gpu()
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import HostLink
+    from oracle.core import synth_features
+    S, F = 37, 16
+    feats = np.ascontiguousarray(synth_features(S, 12 * F, seed=5).reshape(S, F, 432))
+    cfg = dict(EbNodB=8.0, freq_offset_hz=-11.0, freq_offset_spread_hz=15.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=21)
+    runs = []
+    for mode in ("calls", "fused", "duplex3", "duplex2"):
+        brx = RadeBatch(S); btx = RadeBatch(S); btx.channel_config(**cfg)
+        bch = RadeBatch(S) if mode == "duplex3" else btx
+        bch.channel_config(**cfg)
+        link = HostLink(brx)
+        fo, ro, valid = [], [], np.zeros(S, np.int64)
+        if mode.startswith("duplex"):
+            fin = torch.empty((F, S, 432), dtype=torch.float32).pin_memory().numpy(); fin[...] = np.transpose(feats, (1, 0, 2))
+            txs = torch.empty((3, S, 960, 2), dtype=torch.float32).pin_memory().numpy().view(np.complex64).reshape(3, S, 960)
+            f, r = link.duplex_run(btx, bch, fin, F, txs, valid_frames=valid)
+            fo.append(f.copy()); ro.append(r.copy())
+        else:
+            for k in range(F):
+                tx = btx.tx(feats[:, k])
+                if mode == "calls":
+                    assert link.push(btx.channel(tx)) == 0
+                else:
+                    assert link.channel_push(btx, tx) == 0
+                f, r, _ = link.rx()
+                fo.append(f.copy()); ro.append(r.copy()); valid += r & 1
+        assert link.dropped() == 0
+        runs.append((fo, ro, valid.copy()))
+        link.close(); brx.close(); btx.close()
+        if bch is not btx: bch.close()
+    (f0, r0, v0), (f1, r1, v1), (f2, r2, v2), (f3, r3, v3) = runs
+    assert np.median(v0) >= F - 6                      # most streams decode from the fifth frame on (fading: a few take longer)
+    assert all(np.array_equal(a, b) for a, b in zip(r0, r1)) and all(np.array_equal(a, b) for a, b in zip(f0, f1))
+    for f, r, v in ((f2, r2, v2), (f3, r3, v3)):
+        assert np.array_equal(v0, v) and np.array_equal(r0[-1], r[-1]) and np.array_equal(f0[-1], f[-1])
+
+
+def test_full_link_fifo_drops_the_frame_and_says_so():
+    """a producer that outruns the receiver must not overwrite unread samples silently"""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import HostLink
+    S = 3
+    b = RadeBatch(S); link = HostLink(b)
+    x = np.zeros((S, 960), np.complex64)
+    dropped = [link.push(x) for _ in range(6)]          # four frame slots
+    assert dropped[:4] == [0, 0, 0, 0] and dropped[4] == S and dropped[5] == S and link.dropped() == 2 * S
+    link.rx()                                            # moves queued frames to the device rings: their slots are free again
+    assert link.push(x) == 0
+    link.close(); b.close()
+
+
 def test_fused_loopback_equals_copy_kernels():
     """rade_b200_channel_link_dev + rade_b200_rx_link_dev (channel writes into the link FIFOs, the band-pass kernel pops
     from them) must give exactly what channel_dev -> link_push_dev -> link_pop_dev -> rx_dev gives"""
