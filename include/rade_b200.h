@@ -111,6 +111,11 @@ typedef struct {
 RADE_EXPORT int rade_b200_channel_config(rade_batch *b, const rade_b200_channel_cfg *cfg);
 RADE_EXPORT int rade_b200_channel_dev(rade_batch *b, RADE_COMP *d_rx, const RADE_COMP *d_tx);
 
+/* ... with the reference's frequency drift df_dt in Hz/s (radae.py:546-550): phase[k] = phase0 + 2 pi / Fs (f (k + 1) + df_dt k (k + 1) / (2 Fs)) */
+RADE_EXPORT int rade_b200_channel_apply_drift(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
+                                              const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float df_dt,
+                                              float phase0, float sigma, float gain);
+
 /* --- loop-back link between channel output and receiver input (per-stream sample FIFO on the device): the
  * receiver consumes nin[s] in {800, 960, 1120} samples per call while the transmitter produces 960 --- */
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples /* [S][960] */);
@@ -169,6 +174,24 @@ RADE_EXPORT int rade_b200_duplex_run(rade_batch *btx, rade_batch *bch, rade_b200
 
 /* --- host-buffer channel call (for end-to-end measurements through host memory): tx, rx [S][960] --- */
 RADE_EXPORT int rade_b200_channel(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx);
+
+/* --- several GPUs from ONE C host (replaces "single context only", src/rade_api.h:87): n_streams are split
+ * into contiguous blocks, one context per device, every call is routed by block with one host thread per device.  The weights
+ * are the only data every device needs: the host blob goes to each device once at open (across processes: one NCCL broadcast
+ * of the blob before rade_b200_open, radae_b200/multigpu.py); there is no per-frame exchange between devices.
+ * device_mask: bit i = CUDA device i, 0 = every visible device.  rade_b200_open_devices takes an explicit device list (a device
+ * may appear more than once: several contexts on one GPU).  Arrays are those of the single-device calls with S = n_streams. */
+typedef struct rade_multi rade_multi;
+RADE_EXPORT rade_multi *rade_b200_open_multi(int n_streams, unsigned long long device_mask, int flags, const void *weights, size_t weights_len);
+RADE_EXPORT rade_multi *rade_b200_open_devices(int n_streams, const int *devices, int n_devices, int flags, const void *weights, size_t weights_len);
+RADE_EXPORT void rade_b200_close_multi(rade_multi *m);
+RADE_EXPORT int rade_b200_multi_n_devices(rade_multi *m);
+RADE_EXPORT int rade_b200_multi_n_streams(rade_multi *m);
+RADE_EXPORT rade_batch *rade_b200_multi_context(rade_multi *m, int i, int *first_stream, int *n_streams);   /* the i-th device's context */
+RADE_EXPORT int rade_b200_multi_tx(rade_multi *m, RADE_COMP *tx_out, const float *features_in);
+RADE_EXPORT int rade_b200_multi_nin(rade_multi *m, int *nin);
+RADE_EXPORT int rade_b200_multi_rx(rade_multi *m, float *features_out, int *ret, float *eoo_out, const RADE_COMP *rx_in, const unsigned char *active);
+RADE_EXPORT int rade_b200_multi_rx_get_status(rade_multi *m, rade_b200_rx_status *status);
 
 #ifdef __cplusplus
 }

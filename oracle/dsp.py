@@ -520,12 +520,26 @@ def ebno_sigma(EbNodB):
     return math.sqrt(FS / (10 ** (EbNodB / 10) * (LATENT / 0.04)))
 
 
-def channel(tx, G1, G2, d, mp_gain, freq_offset, phase0, sigma, noise, gain=1.0):
+def mp_gain_of(tx, G1, G2, d):
+    """the reference's power normalisation through the multipath model (radae.py:536-539), for ONE stream (the reference takes
+    the means over its whole batch tensor; the batched implementations here normalise per stream)"""
+    tx = np.asarray(tx, np.complex64)
+    mp = (tx * G1).astype(np.complex64)
+    if d:
+        mp[d:] += (tx[:-d] * G2[:-d]).astype(np.complex64)
+    else:
+        mp += (tx * G2).astype(np.complex64)
+    return float(np.sqrt(np.mean(np.abs(tx) ** 2) / np.mean(np.abs(mp) ** 2)))
+
+
+def channel(tx, G1, G2, d, mp_gain, freq_offset, phase0, sigma, noise, gain=1.0, df_dt=0.0):
     """tx [T] c64; G1,G2 [T] c64 path gains; delay d samples; noise [T] c64 unit-variance complex normal.
-    rx = gain*( mp_gain*(tx*G1 + shift_d(tx*G2)) * exp(j*(phase0 + 2*pi*f/Fs*(n+1))) + sigma*noise )"""
+    rx = gain*( mp_gain*(tx*G1 + shift_d(tx*G2)) * exp(j*(phase0 + cumsum(omega))) + sigma*noise ),
+    omega[n] = 2*pi*(freq_offset + df_dt*n/Fs)/Fs (radae.py:546-550); pinned by tests/golden/channel.npz (RADAE.forward itself)"""
     tx = np.asarray(tx, np.complex64)
     mp = (tx * G1).astype(np.complex64)
     mp[d:] += (tx[:-d] * G2[:-d]).astype(np.complex64) if d else (tx * G2).astype(np.complex64)
-    n = np.arange(1, len(tx) + 1)
-    lin = np.exp(1j * (phase0 + 2 * np.pi * freq_offset / FS * n)).astype(np.complex64)
+    n = np.arange(len(tx), dtype=np.float64)
+    ph = phase0 + 2 * np.pi / FS * (freq_offset * (n + 1) + df_dt * n * (n + 1) / (2 * FS))
+    lin = np.exp(1j * ph).astype(np.complex64)
     return (np.float32(gain) * (np.float32(mp_gain) * mp * lin + np.float32(sigma) * noise)).astype(np.complex64)

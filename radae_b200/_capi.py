@@ -55,6 +55,7 @@ SIGNATURES = {
     "rade_b200_rx_get_status": (_I, [_P, _P]), "rade_b200_rx_get_z_hat": (_I, [_P, _P]),
     "rade_b200_channel_apply_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F]),
     "rade_b200_channel_apply": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F]),
+    "rade_b200_channel_apply_drift": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F]),
     "rade_b200_channel_config": (_I, [_P, C.POINTER(ChannelCfg)]), "rade_b200_channel_dev": (_I, [_P, _P, _P]),
     "rade_b200_link_push_dev": (_I, [_P, _P]), "rade_b200_channel_link_dev": (_I, [_P, _P]),
     "rade_b200_rx_link_dev": (_I, [_P, _P, _P, _P]), "rade_b200_tx_channel_link_dev": (_I, [_P, _P]),
@@ -68,6 +69,12 @@ SIGNATURES = {
     "rade_b200_hostlink_active": (_P, [_P]), "rade_b200_hostlink_dropped": (C.c_longlong, [_P]),
     "rade_b200_channel_hostlink": (_I, [_P, _P, _P]),
     "rade_b200_host_alloc": (_P, [C.c_size_t]), "rade_b200_host_free": (None, [_P]),
+    "rade_b200_open_multi": (_P, [_I, C.c_ulonglong, _I, C.c_char_p, C.c_size_t]),
+    "rade_b200_open_devices": (_P, [_I, C.POINTER(_I), _I, _I, C.c_char_p, C.c_size_t]),
+    "rade_b200_close_multi": (None, [_P]), "rade_b200_multi_n_devices": (_I, [_P]), "rade_b200_multi_n_streams": (_I, [_P]),
+    "rade_b200_multi_context": (_P, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "rade_b200_multi_tx": (_I, [_P, _P, _P]), "rade_b200_multi_nin": (_I, [_P, _P]),
+    "rade_b200_multi_rx": (_I, [_P, _P, _P, _P, _P, _P]), "rade_b200_multi_rx_get_status": (_I, [_P, _P]),
     "rade_b200_duplex_run": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P]),
     # test hook
     "rade_b200_debug_tables": (_I, [_I, _P, _I]),

@@ -203,15 +203,15 @@ class RadeBatch:
     def rx_link_dev(self, d_features_out, d_ret, d_eoo_out):
         _check(self.lib.rade_b200_rx_link_dev(self.h, d_features_out, d_ret, d_eoo_out), "rx_link_dev")
 
-    def channel_apply(self, tx, G1, G2, noise, delay=16, mp_gain=1.0, freq_offset_hz=0.0, phase0=0.0, sigma=0.0, gain=1.0):
+    def channel_apply(self, tx, G1, G2, noise, delay=16, mp_gain=1.0, freq_offset_hz=0.0, phase0=0.0, sigma=0.0, gain=1.0, df_dt=0.0):
         """explicit channel on host arrays [S][n] complex64 (RADAE.forward rate-Fs branch, radae/radae.py:529-599):
         G1, G2 e.g. from a fading file (radae_b200.gfile.read_g), noise unit-variance complex normal"""
         arrs = [np.ascontiguousarray(a, np.complex64) for a in (tx, G1, G2, noise)]
         S, n = arrs[0].shape
         assert S == self.S and all(a.shape == (S, n) for a in arrs)
         out = np.empty((S, n), np.complex64)
-        _check(self.lib.rade_b200_channel_apply(self.h, out.ctypes.data, *[a.ctypes.data for a in arrs], n, delay, mp_gain,
-                                                freq_offset_hz, phase0, sigma, gain), "channel_apply")
+        _check(self.lib.rade_b200_channel_apply_drift(self.h, out.ctypes.data, *[a.ctypes.data for a in arrs], n, delay, mp_gain,
+                                                      freq_offset_hz, df_dt, phase0, sigma, gain), "channel_apply")
         return out
 
     def link_push_dev(self, d_samples):
@@ -287,3 +287,61 @@ class HostLink:
     def close(self):
         if self.h:
             self.lib.rade_b200_hostlink_close(self.h); self.h = None
+
+
+class RadeMulti:
+    """S streams over several GPUs from one process (rade_b200_open_multi / rade_b200_open_devices): contiguous blocks of
+    streams per device, calls routed by block with one host thread per device; arrays as RadeBatch's with S = n_streams."""
+
+    def __init__(self, n_streams, devices=None, device_mask=0, flags=capi.RADE_USE_C_ENCODER | capi.RADE_USE_C_DECODER | capi.RADE_VERBOSE_0,
+                 weights=None):
+        self.lib = capi.lib()
+        self.S = int(n_streams)
+        buf, n = (None, 0)
+        if weights is not None:
+            self._w = bytes(weights); buf, n = C.c_char_p(self._w), len(self._w)
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            self.h = self.lib.rade_b200_open_devices(self.S, arr, len(devices), flags, buf, n)
+        else:
+            self.h = self.lib.rade_b200_open_multi(self.S, device_mask, flags, buf, n)
+        if not self.h:
+            raise RuntimeError("rade_b200_open_multi failed: no usable sm_100 CUDA device, bad device list or bad weights")
+
+    @property
+    def n_devices(self):
+        return int(self.lib.rade_b200_multi_n_devices(self.h))
+
+    def blocks(self):
+        out = []
+        for i in range(self.n_devices):
+            f, c = C.c_int(0), C.c_int(0)
+            self.lib.rade_b200_multi_context(self.h, i, C.byref(f), C.byref(c))
+            out.append((f.value, c.value))
+        return out
+
+    def tx(self, features_in):
+        f, pf = _np(features_in, np.float32)
+        assert f.size == self.S * NFEAT
+        out = np.empty((self.S, NMF), np.complex64)
+        _check(self.lib.rade_b200_multi_tx(self.h, out.ctypes.data, pf), "multi_tx")
+        return out
+
+    def nin(self):
+        n = np.zeros(self.S, np.int32)
+        _check(self.lib.rade_b200_multi_nin(self.h, n.ctypes.data), "multi_nin")
+        return n
+
+    def rx(self, rx_in, active=None):
+        x, px = _np(rx_in, np.complex64)
+        assert x.shape == (self.S, NIN_MAX)
+        f = np.zeros((self.S, NFEAT), np.float32); ret = np.zeros(self.S, np.int32); eoo = np.zeros((self.S, NEOO_BITS), np.float32)
+        pa = None
+        if active is not None:
+            a, pa = _np(active, np.uint8)
+        _check(self.lib.rade_b200_multi_rx(self.h, f.ctypes.data, ret.ctypes.data, eoo.ctypes.data, px, pa), "multi_rx")
+        return f, ret, eoo
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rade_b200_close_multi(self.h); self.h = None

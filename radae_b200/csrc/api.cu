@@ -470,15 +470,24 @@ RADE_EXPORT int rade_b200_channel_apply_dev(rade_batch *b, RADE_COMP *d_rx, cons
                                             float mp_gain, float freq_offset_hz, float phase0, float sigma, float gain) {
   cudaSetDevice(b->device);        // the current device is per host thread
   if (channel_apply_launch((float2 *)d_rx, (const float2 *)d_tx, (const float2 *)d_G1, (const float2 *)d_G2, (const float2 *)d_noise,
-                           b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) return -1;
+                           b->S, n, delay, mp_gain, freq_offset_hz, 0.f, phase0, sigma, gain, b->stream) < 0) return -1;
   b->launches += 1;
   return 0;
 }
 // host-pointer form of the explicit channel: tx, G1, G2, noise are [S][n] complex64 host arrays (G from a fading file,
 // radae_b200/gfile.py), rx [S][n] comes back
+RADE_EXPORT int rade_b200_channel_apply_drift(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
+                                              const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float df_dt,
+                                              float phase0, float sigma, float gain);
 RADE_EXPORT int rade_b200_channel_apply(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
                                         const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float phase0,
                                         float sigma, float gain) {
+  return rade_b200_channel_apply_drift(b, rx, tx, G1, G2, noise, n, delay, mp_gain, freq_offset_hz, 0.f, phase0, sigma, gain);
+}
+// ... with a frequency drift df_dt (Hz/s): phase = phase0 + cumsum(2 pi (f + df_dt i / Fs) / Fs), radae.py:546-550
+RADE_EXPORT int rade_b200_channel_apply_drift(rade_batch *b, RADE_COMP *rx, const RADE_COMP *tx, const RADE_COMP *G1, const RADE_COMP *G2,
+                                              const RADE_COMP *noise, int n, int delay, float mp_gain, float freq_offset_hz, float df_dt,
+                                              float phase0, float sigma, float gain) {
   cudaSetDevice(b->device);
   const size_t bytes = (size_t)b->S * n * sizeof(float2);
   float2 *d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -486,7 +495,7 @@ RADE_EXPORT int rade_b200_channel_apply(rade_batch *b, RADE_COMP *rx, const RADE
   int rc = 0;
   for (int i = 0; i < 5 && rc == 0; i++) if (cudaMalloc((void **)&d[i], bytes) != cudaSuccess) rc = -1;
   for (int i = 0; i < 4 && rc == 0; i++) if (cudaMemcpyAsync(d[i], src[i], bytes, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
-  if (rc == 0 && channel_apply_launch(d[4], d[0], d[1], d[2], d[3], b->S, n, delay, mp_gain, freq_offset_hz, phase0, sigma, gain, b->stream) < 0) rc = -1;
+  if (rc == 0 && channel_apply_launch(d[4], d[0], d[1], d[2], d[3], b->S, n, delay, mp_gain, freq_offset_hz, df_dt, phase0, sigma, gain, b->stream) < 0) rc = -1;
   if (rc == 0 && cudaMemcpyAsync(rx, d[4], bytes, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
   if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
   for (int i = 0; i < 5; i++) if (d[i]) cudaFree(d[i]);
@@ -960,6 +969,89 @@ RADE_EXPORT int rade_b200_debug_check_weights(const void *weights, size_t weight
   return core_weights_validate((const unsigned char *)weights, weights_len);
 }
 
+// ================================================================== several GPUs from ONE C host
+// The reference API is "single context only" (src/rade_api.h:87); streams are independent, so n_streams are split into
+// contiguous blocks, one rade_batch per device, and every call is routed by block with one host thread per device.  The only
+// data every device needs are the weights: the caller's host blob goes to each device once at open (inside one process that
+// is a host -> device upload per GPU; across processes it is the one NCCL broadcast of the blob before rade_b200_open, see
+// radae_b200/multigpu.py).  No per-frame exchange between devices.
+struct rade_multi {
+  int S, n;
+  std::vector<rade_batch *> ctx;
+  std::vector<int> first, count;
+};
+RADE_EXPORT rade_multi *rade_b200_open_devices(int n_streams, const int *devices, int n_devices, int flags, const void *weights, size_t weights_len) {
+  if (n_streams <= 0 || !devices || n_devices <= 0 || n_devices > 64 || n_streams < n_devices) return nullptr;
+  rade_multi *m = new rade_multi();
+  m->S = n_streams; m->n = n_devices;
+  for (int i = 0; i < n_devices; i++) {
+    const int lo = (int)((long long)n_streams * i / n_devices), hi = (int)((long long)n_streams * (i + 1) / n_devices);
+    rade_batch *b = rade_b200_open(hi - lo, devices[i], flags, weights, weights_len);
+    if (!b) { for (rade_batch *c : m->ctx) rade_b200_close(c); delete m; return nullptr; }
+    m->ctx.push_back(b); m->first.push_back(lo); m->count.push_back(hi - lo);
+  }
+  return m;
+}
+// device_mask: bit i = CUDA device i (0 = every visible device)
+RADE_EXPORT rade_multi *rade_b200_open_multi(int n_streams, unsigned long long device_mask, int flags, const void *weights, size_t weights_len) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "libradae_b200: no CUDA device available — this library has no CPU fallback\n");
+    return nullptr;
+  }
+  std::vector<int> devs;
+  for (int i = 0; i < ndev && i < 64; i++) if (!device_mask || (device_mask >> i) & 1) devs.push_back(i);
+  if (devs.empty()) { fprintf(stderr, "libradae_b200: device mask 0x%llx selects no visible device\n", device_mask); return nullptr; }
+  return rade_b200_open_devices(n_streams, devs.data(), (int)devs.size(), flags, weights, weights_len);
+}
+RADE_EXPORT void rade_b200_close_multi(rade_multi *m) {
+  if (!m) return;
+  for (rade_batch *c : m->ctx) rade_b200_close(c);
+  delete m;
+}
+RADE_EXPORT int rade_b200_multi_n_devices(rade_multi *m) { return m->n; }
+RADE_EXPORT int rade_b200_multi_n_streams(rade_multi *m) { return m->S; }
+RADE_EXPORT rade_batch *rade_b200_multi_context(rade_multi *m, int i, int *first_stream, int *n_streams) {
+  if (i < 0 || i >= m->n) return nullptr;
+  if (first_stream) *first_stream = m->first[i];
+  if (n_streams) *n_streams = m->count[i];
+  return m->ctx[i];
+}
+}  // extern "C"
+namespace {
+// run f(i) for every device on its own host thread (the calls are synchronous: this is what overlaps the devices)
+template <typename F> int multi_each(rade_multi *m, F f) {
+  std::vector<int> rc(m->n, 0);
+  std::vector<std::thread> th;
+  for (int i = 1; i < m->n; i++) th.emplace_back([&, i] { rc[i] = f(i); });
+  rc[0] = f(0);
+  for (auto &t : th) t.join();
+  for (int r : rc) if (r < 0) return -1;
+  return 0;
+}
+}  // namespace
+extern "C" {
+// rade_tx / rade_nin / rade_rx for all S streams: arrays as in the single-device calls ([S][432], [S][960], [S][1120], [S] ...)
+RADE_EXPORT int rade_b200_multi_tx(rade_multi *m, RADE_COMP *tx_out, const float *features_in) {
+  const int rc = multi_each(m, [&](int i) {
+    return rade_b200_tx(m->ctx[i], tx_out + (size_t)m->first[i] * RADE_NMF, features_in + (size_t)m->first[i] * RADE_NFEAT);
+  });
+  return rc < 0 ? -1 : RADE_NMF;
+}
+RADE_EXPORT int rade_b200_multi_nin(rade_multi *m, int *nin) {
+  return multi_each(m, [&](int i) { return rade_b200_nin(m->ctx[i], nin + m->first[i]); });
+}
+RADE_EXPORT int rade_b200_multi_rx(rade_multi *m, float *features_out, int *ret, float *eoo_out, const RADE_COMP *rx_in, const unsigned char *active) {
+  return multi_each(m, [&](int i) {
+    const size_t o = m->first[i];
+    return rade_b200_rx(m->ctx[i], features_out + o * RADE_NFEAT, ret + o, eoo_out ? eoo_out + o * RADE_NEOO_BITS : nullptr,
+                        rx_in + o * RADE_NIN_MAX, active ? active + o : nullptr);
+  });
+}
+RADE_EXPORT int rade_b200_multi_rx_get_status(rade_multi *m, rade_b200_rx_status *status) {
+  return multi_each(m, [&](int i) { return rade_b200_rx_get_status(m->ctx[i], status + m->first[i]); });
+}
+
 // ================================================================== rade_api.h: the reference's single-stream surface
 struct rade {
   rade_batch *b;
@@ -982,6 +1074,18 @@ RADE_EXPORT struct rade *rade_open(char model_file[], int flags) {
       if (n > 8) { blob.resize(n); if (fread(blob.data(), 1, n, f) != (size_t)n) blob.clear(); }
       fclose(f);
       if (blob.size() > 8 && memcmp(blob.data(), "RADEB200", 8) != 0 && memcmp(blob.data(), "DNNw", 4) != 0) blob.clear();
+    }
+  }
+  if (!blob.empty()) {
+    // a file with the right magic is used only if it is a complete RADE V1 model (a truncated file, or the reference's
+    // model05 — no auxiliary symbol, bottleneck 1: a core-codec test model, not a V1 waveform — used to end in exit(1) with a
+    // misleading message); anything else falls back to the embedded weights, as rade_api.h promises
+    int in_dim = 0, out_dim = 0;
+    const int ok = core_weights_validate(blob.data(), blob.size(), &in_dim, &out_dim);
+    if (ok < 0 || in_dim != ENC_IN || out_dim != DEC_OUT) {
+      fprintf(stderr, "libradae_b200: %s is %s; using the embedded model19_check3 weights\n", model_file,
+              ok < 0 ? "not a complete RDW / DNNw weight file" : "not a RADE V1 model (no auxiliary symbol: rade_b200_core_encode / _decode can run it, the modem cannot)");
+      blob.clear();
     }
   }
   if (!(flags & RADE_VERBOSE_0))

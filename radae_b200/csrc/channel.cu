@@ -43,14 +43,16 @@ __device__ __forceinline__ float2 cnormal(unsigned long long seed, uint32_t stre
 // explicit form used by the parity tests: every random quantity supplied by the caller
 __global__ void channel_apply_kernel(float2 *__restrict__ rx, const float2 *__restrict__ tx, const float2 *__restrict__ G1,
                                      const float2 *__restrict__ G2, const float2 *__restrict__ noise, int S, int n, int d,
-                                     float mp_gain, float freq, float phase0, float sigma, float gain) {
+                                     float mp_gain, float freq, float df_dt, float phase0, float sigma, float gain) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)S * n) return;
   const int k = (int)(i % n);
   float2 mp = cmul(tx[i], G1[i]);
   if (k >= d) { float2 e = cmul(tx[i - d], G2[i - d]); mp.x += e.x; mp.y += e.y; }
   double sn, cs;
-  sincos((double)phase0 + 2.0 * M_PI * (double)freq / RADE_FS * (double)(k + 1), &sn, &cs);
+  // cumsum of omega[i] = 2 pi (f + df_dt i / Fs) / Fs over i = 0..k (radae.py:546-550): f (k + 1) + df_dt k (k + 1) / (2 Fs)
+  const double kk = (double)(k + 1);
+  sincos((double)phase0 + 2.0 * M_PI / RADE_FS * ((double)freq * kk + (double)df_dt * (double)k * kk / (2.0 * RADE_FS)), &sn, &cs);
   float2 v = cmul(make_float2(mp_gain * mp.x, mp_gain * mp.y), make_float2((float)cs, (float)sn));
   rx[i] = make_float2(gain * (v.x + sigma * noise[i].x), gain * (v.y + sigma * noise[i].y));
 }
@@ -166,9 +168,9 @@ __global__ void link_pop_kernel(const float2 *__restrict__ ring, const long long
 }  // namespace
 
 int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
-                         int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream) {
+                         int d, float mp_gain, float freq, float df_dt, float phase0, float sigma, float gain, cudaStream_t stream) {
   const size_t total = (size_t)S * n;
-  channel_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(rx, tx, G1, G2, noise, S, n, d, mp_gain, freq, phase0, sigma, gain);
+  channel_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(rx, tx, G1, G2, noise, S, n, d, mp_gain, freq, df_dt, phase0, sigma, gain);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

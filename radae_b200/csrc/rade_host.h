@@ -28,7 +28,7 @@ int core_decoder_umma_launch(const CoreWeightsDev &W, DecStreamState *state, con
 int core_weights_debug_stream(const unsigned char *blob, size_t len, int which, int umma, std::vector<unsigned char> *bytes,
                               std::vector<ChunkDesc> *chunks, int *n_prologue, std::vector<UmmaRec> *ops);
 void core_weights_free(CoreWeightsHolder *h);
-int core_weights_validate(const unsigned char *blob, size_t len);      // host only: 0 = acceptable, -1 = rejected
+int core_weights_validate(const unsigned char *blob, size_t len, int *input_dim = nullptr, int *output_dim = nullptr);   // host only: 0 = acceptable, -1 = rejected
 
 int core_encoder_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                         const uint8_t *active, int S, int T, cudaStream_t stream);
@@ -73,7 +73,7 @@ int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaS
 int eoo_launch(const DspTables &T, const float *bits, const int *has_bits, float2 *tx, int S, cudaStream_t stream);
 int tx_bpf_clip_launch(const DspTables &T, float2 *tx, size_t stride, int n, TxBpfState *st, int S, cudaStream_t stream);
 int channel_apply_launch(float2 *rx, const float2 *tx, const float2 *G1, const float2 *G2, const float2 *noise, int S, int n,
-                         int d, float mp_gain, float freq, float phase0, float sigma, float gain, cudaStream_t stream);
+                         int d, float mp_gain, float freq, float df_dt, float phase0, float sigma, float gain, cudaStream_t stream);
 int channel_stream_launch(const DspTables &T, const float *z_mod, float2 *rx, const float2 *tx, ChanState *st, int S, float sigma, float freq0, float freq_spread,
                           float doppler, int d, float gain, unsigned long long seed, float2 *link_ring, long long *link_wr,
                           const long long *link_rd, int *link_overflow, cudaStream_t stream);

@@ -454,11 +454,13 @@ int core_weights_upload(const unsigned char *blob, size_t len, CoreWeightsHolder
 
 // Host-only validation of a weight blob (no device involved): container parse + every array the layer table needs present with
 // the right dtype and shape.  0 = core_weights_upload would accept it, -1 = rejected.  (rade_b200_debug_check_weights)
-int core_weights_validate(const unsigned char *blob, size_t len) {
+int core_weights_validate(const unsigned char *blob, size_t len, int *input_dim, int *output_dim) {
   ArrayMap arrays;
   if (!blob || (!parse_rdw(blob, len, arrays) && !parse_dnnw(blob, len, arrays))) return -1;
   int in_dim, out_dim;
   normalise_io_width(arrays, &in_dim, &out_dim);
+  if (input_dim) *input_dim = in_dim;
+  if (output_dim) *output_dim = out_dim;
   std::vector<LayerSpec> specs; std::vector<std::string> names;
   layer_specs(specs, names);
   auto ok = [&](const std::string &k, int dtype, int rows, int cols) {

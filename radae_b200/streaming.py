@@ -104,14 +104,19 @@ class radae_rx:
     sum_uw_errors() from the caller is accepted and ignored instead of counted twice."""
 
     def __init__(self, model_name=None, latent_dim=80, auxdata=True, bottleneck=3, bpf_en=True, v=2,
-                 disable_unsync=False, foff_err=0, bypass_dec=False, eoo_data_test=False):
+                 disable_unsync=False, foff_err=0, bypass_dec=False, eoo_data_test=False, reset_decoder_on_sync=None):
         if latent_dim != 80 or not auxdata or bottleneck != 3 or not bpf_en:
             raise NotImplementedError("libradae_b200 implements the RADE V1 waveform: latent_dim=80, auxdata, bottleneck=3, bpf_en")
         if disable_unsync:
             raise NotImplementedError("disable_unsync is a reference test mode that rade_api.h does not expose")
         if foff_err not in (0, 0.0, 10, 10.0):
             raise NotImplementedError("foff_err: rade_api.h only exposes RADE_FOFF_TEST (= 10 Hz, src/rade_api.c:263-264)")
-        flags = _FLAGS
+        # The reference class owns its decoder and clears its state on every candidate -> sync transition (radae_rxe.py:263);
+        # only the C API with RADE_USE_C_DECODER (bypass_dec + rade_dec.c outside the class, src/rade_api.c:494-506) never does.
+        # reset_decoder_on_sync: None = follow the reference (reset unless bypass_dec), or force either behaviour.
+        if reset_decoder_on_sync is None:
+            reset_decoder_on_sync = not bypass_dec
+        flags = _FLAGS if not reset_decoder_on_sync else (_FLAGS & ~capi.RADE_USE_C_DECODER)
         if foff_err:
             flags |= capi.RADE_FOFF_TEST
         self.bypass_dec = bool(bypass_dec)

@@ -79,3 +79,23 @@ def test_channel_apply_host_with_fading_file(tmp_path):
     ref = np.array([od.channel(tx[s], g1[s], g2[s], d, 1.0, -11.0, 0.0, sigma, nz[s]) for s in range(S)])
     assert relrms(got, ref) < 1e-5
     b.close()
+
+
+def test_channel_apply_vs_reference_forward_fixture(golden):
+    """the CUDA explicit channel (rade_b200_channel_apply_drift through the host-pointer C ABI) against the rate-Fs channel of the
+    reference's RADAE.forward itself (tests/golden/channel.npz, tools/make_golden_channel.py): multipath + power normalisation,
+    frequency offset with drift, phase offset, AWGN with the reference's noise draw, gain; <= 1e-5 relative RMS"""
+    need_gpu()
+    from radae_b200 import RadeBatch
+    g = golden("channel")
+    b = RadeBatch(1)
+    for name in g["names"]:
+        EbNodB, f0, df_dt, ph0, gain, d = g[f"{name}_params"]
+        tx, G, noise = g[f"{name}_tx"], g[f"{name}_G"], g[f"{name}_noise"]
+        mpg = od.mp_gain_of(tx, G[:, 0], G[:, 1], int(d))
+        rx = b.channel_apply(tx[None], G[None, :, 0], G[None, :, 1], noise[None], delay=int(d), mp_gain=mpg, freq_offset_hz=float(f0),
+                             phase0=float(ph0), sigma=od.ebno_sigma(EbNodB), gain=float(gain), df_dt=float(df_dt))[0]
+        ref = g[f"{name}_rx"]
+        err = np.sqrt(np.mean(np.abs(rx - ref) ** 2) / np.mean(np.abs(ref) ** 2))
+        assert err < 1e-5, (name, err)
+    b.close()

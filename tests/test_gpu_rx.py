@@ -39,7 +39,7 @@ def check_features(feats, g, name=""):
 
 def run_single(g):
     from radae_b200 import radae_rx
-    rx = radae_rx(v=0)
+    rx = radae_rx(v=0, reset_decoder_on_sync=False)      # the golden traces are the C-API path (bypass_dec + rade_dec.c: no reset)
     o = 0
     tr = {k: [] for k in ("nin", "ret", "sync")}
     feats, eoos = [], []
@@ -403,6 +403,42 @@ def test_foff_test_flag_false_sync_and_reacquisition(golden):
     assert np.array_equal(np.array(nins), g["nin"]) and np.array_equal(np.array(rets), g["ret"])
     assert np.array_equal(np.array(syncs), (g["state"] == 2).astype(int))
     assert len(feats) == len(g["features"])
+
+
+def test_streaming_class_resets_the_decoder_on_resync(golden):
+    """radae_rxe.radae_rx (non-bypass) clears the core decoder state on every candidate -> sync transition
+    (radae_rxe.py:263); the C API with RADE_USE_C_DECODER does not (src/rade_api.c:494-506).  On the RADE_FOFF_TEST trace (false
+    sync, unique-word failure, re-acquisition) the mirror class must produce the features of the oracle WITH the reset after the
+    second sync, the C-API semantics those WITHOUT (= the golden fixture)."""
+    need_gpu()
+    from radae_b200 import radae_rx
+    from oracle import dsp as od
+    from oracle.core import CoreOracleRef, CoreOraclePort
+    g = golden("rx_foff_test")
+    x = g["rx_in"]
+    def run(**kw):
+        rx = radae_rx(v=0, foff_err=10, **kw)
+        o = 0; feats = []; floats = np.zeros(432, np.float32)
+        while o + rx.get_nin() <= len(x):
+            nin = rx.get_nin()
+            if rx.do_radae_rx(x[o:o + nin], floats) & 1: feats.append(floats.copy())
+            o += nin
+        rx.close()
+        return np.array(feats)
+    f_reset, f_capi = run(), run(reset_decoder_on_sync=False)
+    core = CoreOraclePort(n_streams=1)                   # (bit-identical to the reference C sources; its state is a numpy array the oracle can clear)
+    orx = od.RadaeRx(core, foff_err=10.0, reset_dec_on_sync=True)
+    o = 0; of = []
+    while o + orx.nin <= len(x):
+        nin = orx.nin
+        ret, f, _ = orx.do_radae_rx(x[o:o + nin]); o += nin
+        if ret & 1: of.append(np.asarray(f, np.float32).reshape(-1))
+    of = np.array(of)
+    assert f_reset.shape == of.shape == f_capi.shape == g["features"].shape
+    per = lambda a, b: np.sqrt(np.mean((a - b) ** 2, axis=1))
+    assert per(f_reset, of).max() < 0.02 and np.median(per(f_reset, of)) < 1e-6
+    assert per(f_capi, g["features"]).max() < 0.02 and np.median(per(f_capi, g["features"])) < 1e-6
+    assert per(f_reset, f_capi).max() > 0.05                 # the two semantics really differ once the receiver has re-acquired
 
 
 @pytest.mark.parametrize("name", ["dfdt", "noise_only", "sine_noise", "mpd_fading"])

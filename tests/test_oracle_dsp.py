@@ -93,3 +93,20 @@ def test_arange_restatement_matches_numpy():
         assert np.array_equal(od.arange_like_numpy(f - 1, f + 1, 0.1), np.arange(f - 1, f + 1, 0.1))
     for f in np.arange(-50, 50, 2.5):
         assert np.array_equal(od.arange_like_numpy(f - 10, f + 10, 0.25), np.arange(f - 10, f + 10, 0.25))
+
+
+def test_channel_oracle_vs_reference_forward(golden):
+    """oracle.dsp.channel / ebno_sigma / mp_gain_of against the rate-Fs channel of RADAE.forward itself
+    (radae/radae.py:529-599; fixture: tools/make_golden_channel.py): two-path multipath with the power normalisation, frequency
+    offset with drift (cumsum phase), phase offset, AWGN with the reference's own noise draw, gain"""
+    g = golden("channel")
+    for name in g["names"]:
+        EbNodB, f0, df_dt, ph0, gain, d = g[f"{name}_params"]
+        tx, G, noise = g[f"{name}_tx"], g[f"{name}_G"], g[f"{name}_noise"]
+        sigma = od.ebno_sigma(EbNodB)
+        assert abs(sigma - float(g[f"{name}_sigma"])) < 1e-6 * sigma
+        mpg = od.mp_gain_of(tx, G[:, 0], G[:, 1], int(d))
+        rx = od.channel(tx, G[:, 0], G[:, 1], int(d), mpg, f0, ph0, sigma, noise, gain=gain, df_dt=df_dt)
+        ref = g[f"{name}_rx"]
+        err = np.sqrt(np.mean(np.abs(rx - ref) ** 2) / np.mean(np.abs(ref) ** 2))
+        assert err < 2e-6, (name, err)          # float32 phase accumulation (torch.cumsum) vs the closed form

@@ -69,7 +69,7 @@ def test_c_hosts_pipe_tx_into_rx_on_device(tmp_path, golden):
     eoo = np.zeros(1152, np.complex64); t.do_eoo(eoo); sig.append(eoo); sig.append(np.zeros(2000, np.complex64))
     sig = np.concatenate(sig)
     assert np.array_equal(sig[:len(tx)], tx)
-    r = radae_rx(v=0); o = 0; ref = []; fl = np.zeros(432, np.float32)
+    r = radae_rx(v=0, reset_decoder_on_sync=False); o = 0; ref = []; fl = np.zeros(432, np.float32)      # the C host runs rade_rx with the C decoder: no reset
     while o + r.get_nin() <= len(sig):
         n = r.get_nin(); ret = r.do_radae_rx(sig[o:o + n], fl); o += n
         if ret & 1: ref.append(fl.copy())
