@@ -132,6 +132,12 @@ RADE_EXPORT int rade_b200_pipeline_join(rade_batch *b);
    pipeline is enabled); with RADE_B200_GRAPH=1 in the environment it is replayed as a single CUDA graph launch per step */
 RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_features_next /* [S][432] */, float *d_features_out,
                                             int *d_ret, float *d_eoo_out);
+/* the same pipeline for n_frames modem frames with HOST buffers at both ends: per frame S x 432 input features go up from (pinned) host
+   memory, S x 432 recovered features and S return codes come back; the modem samples stay on the device.  Uploads / downloads run on
+   their own streams, double-buffered, and overlap the kernels of the neighbouring frames.  features_in: n_in frames of [S][432], cycled
+   over; features_out [S][432] / ret [S]: overwritten every frame; valid_frames [S] (optional): += frames that returned features. */
+RADE_EXPORT int rade_b200_loopback_run(rade_batch *b, const float *features_in, int n_in, int n_frames, float *features_out, int *ret,
+                                       long long *valid_frames);
 /* core encoder, then one kernel that modulates the frame and sends it through the channel into the link FIFOs */
 RADE_EXPORT int rade_b200_tx_channel_link_dev(rade_batch *b, const float *d_features_in /* [S][432] */);
 RADE_EXPORT int rade_b200_rx_link_dev(rade_batch *b, float *d_features_out, int *d_ret, float *d_eoo_out);

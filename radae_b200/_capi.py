@@ -68,6 +68,7 @@ SIGNATURES = {
     "rade_b200_hostlink_push": (_I, [_P, _P]), "rade_b200_hostlink_rx": (_I, [_P, _P, _P, _P]),
     "rade_b200_hostlink_active": (_P, [_P]), "rade_b200_hostlink_dropped": (C.c_longlong, [_P]),
     "rade_b200_channel_hostlink": (_I, [_P, _P, _P]),
+    "rade_b200_loopback_run": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "rade_b200_host_alloc": (_P, [C.c_size_t]), "rade_b200_host_free": (None, [_P]),
     "rade_b200_open_multi": (_P, [_I, C.c_ulonglong, _I, C.c_char_p, C.c_size_t]),
     "rade_b200_open_devices": (_P, [_I, C.POINTER(_I), _I, _I, C.c_char_p, C.c_size_t]),

@@ -182,6 +182,14 @@ class RadeBatch:
         _check(self.lib.rade_b200_channel_apply_dev(self.h, d_rx, d_tx, d_G1, d_G2, d_noise, n, delay, mp_gain, freq,
                                                     phase0, sigma, gain), "channel_apply_dev")
 
+    def loopback_run(self, features_in, n_frames, features_out, ret, valid_frames=None):
+        """features -> encoder -> modulator -> channel -> receiver -> decoder -> features for n_frames modem frames, host arrays at
+        both ends (features_in [n_in][S][432] cycled over; features_out [S][432], ret [S] int32 overwritten every frame)"""
+        f, pf = _np(features_in, np.float32)
+        assert f.ndim == 3 and f.shape[1:] == (self.S, NFEAT) and features_out.dtype == np.float32 and ret.dtype == np.int32
+        vp = valid_frames.ctypes.data if valid_frames is not None else None
+        _check(self.lib.rade_b200_loopback_run(self.h, pf, f.shape[0], int(n_frames), features_out.ctypes.data, ret.ctypes.data, vp), "loopback_run")
+
     def loopback_step_dev(self, d_features_next, d_features_out, d_ret, d_eoo_out):
         _check(self.lib.rade_b200_loopback_step_dev(self.h, d_features_next, d_features_out, d_ret, d_eoo_out), "loopback_step_dev")
 

@@ -41,6 +41,8 @@ struct rade_batch {
   int *d_ret; unsigned char *d_active;
   // pinned host staging
   float *h_feat; float2 *h_cplx; int *h_int;
+  // rade_b200_loopback_run: double-buffered device staging + copy streams
+  float *lb_fin[2], *lb_fout[2]; int *lb_ret[2]; cudaStream_t lb_h2d, lb_d2h; cudaEvent_t lb_ev_in[2], lb_ev_step[2], lb_ev_out[2];
 };
 
 namespace {
@@ -139,6 +141,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   b->S = n_streams; b->device = device; b->flags = flags; b->launches = 0; b->core_cap = 0;
   b->tx_stream = nullptr; b->pipelined = 0;
   b->d_core_in = b->d_core_out = nullptr;
+  b->lb_fin[0] = nullptr; b->lb_h2d = b->lb_d2h = nullptr;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { delete b; return nullptr; }
   b->prof.stream = b->stream;
   if (core_codec_init_device() < 0 || rx_dsp_init_device() < 0) { delete b; return nullptr; }
@@ -206,6 +209,10 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   if (b->h_feat) cudaFreeHost(b->h_feat);
   if (b->h_cplx) cudaFreeHost(b->h_cplx);
   if (b->h_int) cudaFreeHost(b->h_int);
+  if (b->lb_h2d) {
+    cudaStreamDestroy(b->lb_h2d); cudaStreamDestroy(b->lb_d2h);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(b->lb_ev_in[i]); cudaEventDestroy(b->lb_ev_step[i]); cudaEventDestroy(b->lb_ev_out[i]); }
+  }
   for (auto &g : b->step_graphs) cudaGraphExecDestroy(g.exec);
   cudaStreamDestroy(b->stream);
   if (b->tx_stream) { cudaStreamDestroy(b->tx_stream); cudaEventDestroy(b->ev_txfork); cudaEventDestroy(b->ev_txjoin); }
@@ -618,6 +625,55 @@ RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_featur
   }
   CUDA_CHECK(cudaGraphLaunch(exec, b->stream));
   b->launches += 8;
+  return 0;
+}
+// The whole loop-back pipeline (features -> core encoder -> OFDM modulator -> HF channel -> receiver -> core decoder -> features)
+// for n_frames modem frames with HOST buffers at both ends: per frame the S x 432 input features go up from (pinned) host memory,
+// the S x 432 recovered features and S return codes come back; the modem samples stay on the device (this is the call for a
+// simulation on one machine — the three-program pipe of the reference moves every sample through host memory four times,
+// rade_b200_duplex_run).  Copies run on their own streams, double-buffered, so the upload of frame k + 1 and the download of
+// frame k - 1 overlap the kernels of frame k.  features_in: n_in frames of [S][432], cycled over; features_out [S][432] / ret [S]:
+// overwritten every frame (the last frame's values remain; rows of streams whose ret lacks RADE_B200_VALID are unspecified);
+// valid_frames [S] (optional): += frames that returned features.
+RADE_EXPORT int rade_b200_loopback_run(rade_batch *b, const float *features_in, int n_in, int n_frames, float *features_out, int *ret,
+                                       long long *valid_frames) {
+  if (!b || !features_in || n_in < 1 || n_frames < 0 || !features_out || !ret) return -1;
+  cudaSetDevice(b->device);
+  const size_t S = b->S, fb = S * RADE_NFEAT * sizeof(float);
+  if (!b->lb_h2d) {
+    for (int i = 0; i < 2; i++) {
+      if (dalloc(b, &b->lb_fin[i], S * RADE_NFEAT) < 0 || dalloc(b, &b->lb_fout[i], S * RADE_NFEAT) < 0 || dalloc(b, &b->lb_ret[i], S) < 0) return -1;
+      CUDA_CHECK(cudaEventCreateWithFlags(&b->lb_ev_in[i], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&b->lb_ev_step[i], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&b->lb_ev_out[i], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaStreamCreateWithFlags(&b->lb_h2d, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&b->lb_d2h, cudaStreamNonBlocking));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
+  for (int k = 0; k < n_frames; k++) {
+    const int sl = k & 1;
+    if (k >= 2) CUDA_CHECK(cudaStreamWaitEvent(b->lb_h2d, b->lb_ev_step[sl], 0));            // frame k - 2 has consumed this input buffer
+    CUDA_CHECK(cudaMemcpyAsync(b->lb_fin[sl], features_in + (size_t)(k % n_in) * S * RADE_NFEAT, fb, cudaMemcpyHostToDevice, b->lb_h2d));
+    CUDA_CHECK(cudaEventRecord(b->lb_ev_in[sl], b->lb_h2d));
+    CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->lb_ev_in[sl], 0));
+    if (k >= 2) CUDA_CHECK(cudaStreamWaitEvent(b->stream, b->lb_ev_out[sl], 0));              // its outputs have left this output buffer
+    if (rade_b200_loopback_step_dev(b, b->lb_fin[sl], b->lb_fout[sl], b->lb_ret[sl], nullptr) < 0) return -1;
+    CUDA_CHECK(cudaEventRecord(b->lb_ev_step[sl], b->stream));
+    if (k >= 1) {                                                                           // frame k - 1 is on the host: count it
+      CUDA_CHECK(cudaEventSynchronize(b->lb_ev_out[sl ^ 1]));
+      if (valid_frames) for (size_t s = 0; s < S; s++) valid_frames[s] += (ret[s] & 1);
+    }
+    CUDA_CHECK(cudaStreamWaitEvent(b->lb_d2h, b->lb_ev_step[sl], 0));
+    CUDA_CHECK(cudaMemcpyAsync(features_out, b->lb_fout[sl], fb, cudaMemcpyDeviceToHost, b->lb_d2h));
+    CUDA_CHECK(cudaMemcpyAsync(ret, b->lb_ret[sl], S * sizeof(int), cudaMemcpyDeviceToHost, b->lb_d2h));
+    CUDA_CHECK(cudaEventRecord(b->lb_ev_out[sl], b->lb_d2h));
+  }
+  if (n_frames > 0) {
+    CUDA_CHECK(cudaEventSynchronize(b->lb_ev_out[(n_frames - 1) & 1]));
+    if (valid_frames) for (size_t s = 0; s < S; s++) valid_frames[s] += (ret[s] & 1);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(b->stream));
   return 0;
 }
 RADE_EXPORT int rade_b200_link_push_dev(rade_batch *b, const RADE_COMP *d_samples) {

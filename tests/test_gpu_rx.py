@@ -221,6 +221,42 @@ def test_channel_into_host_fifo_and_c_duplex_driver_equal_the_call_sequence():
         assert np.array_equal(v0, v) and np.array_equal(r0[-1], r[-1]) and np.array_equal(f0[-1], f[-1])
 
 
+def test_host_buffer_loopback_run_equals_device_steps():
+    """rade_b200_loopback_run (host features in, host features out every frame, double-buffered copy streams) must produce exactly
+    what the same number of rade_b200_loopback_step_dev calls on device buffers produces"""
+    torch = need_gpu()
+    from radae_b200 import RadeBatch
+    from radae_b200.batch import pinned_empty
+    from oracle.core import synth_features
+    S, F = 29, 15
+    feats = np.ascontiguousarray(np.transpose(synth_features(S, 12 * 4, seed=12).reshape(S, 4, 432), (1, 0, 2)))     # [4][S][432], cycled
+    cfg = dict(EbNodB=8.0, freq_offset_hz=9.0, freq_offset_spread_hz=5.0, doppler_spread_hz=1.0, delay_samples=16, gain=1.0, seed=3)
+    outs = []
+    for mode in ("dev", "host", "dev_pipelined", "host_pipelined"):       # pipelined: the transmitter of frame k + 1 runs beside the receiver of frame k
+        b = RadeBatch(S); b.channel_config(**cfg)
+        if mode.endswith("pipelined"):
+            b.pipeline_enable(True)
+        if mode.startswith("dev"):
+            d_in = [torch.tensor(feats[i]).cuda() for i in range(4)]
+            d_fo = torch.zeros((S, 432), device="cuda"); d_ret = torch.zeros(S, dtype=torch.int32, device="cuda"); d_eoo = torch.zeros((S, 180), device="cuda")
+            valid = np.zeros(S, np.int64)
+            for k in range(F):
+                b.loopback_step_dev(d_in[k % 4].data_ptr(), d_fo.data_ptr(), d_ret.data_ptr(), d_eoo.data_ptr()); b.synchronize()
+                valid += d_ret.cpu().numpy() & 1
+            outs.append((d_fo.cpu().numpy(), d_ret.cpu().numpy(), valid))
+        else:
+            fo = pinned_empty((S, 432), np.float32); ro = pinned_empty((S,), np.int32); valid = np.zeros(S, np.int64)
+            b.loopback_run(feats, F, fo, ro, valid_frames=valid)
+            outs.append((fo.copy(), ro.copy(), valid))
+        b.close()
+    for dev, host in ((outs[0], outs[1]), (outs[2], outs[3])):
+        ok = (dev[1] & 1) != 0                 # rows of streams without the valid flag are unspecified (stale buffer contents)
+        assert ok.sum() >= S // 2
+        assert np.array_equal(host[1], dev[1]) and np.array_equal(host[2], dev[2])
+        assert np.array_equal(host[0][ok], dev[0][ok])
+    assert np.median(outs[0][2]) >= F - 7
+
+
 def test_full_link_fifo_drops_the_frame_and_says_so():
     """a producer that outruns the receiver must not overwrite unread samples silently"""
     need_gpu()
