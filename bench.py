@@ -33,8 +33,9 @@ KERNEL_BYTES = {
     "link_pop_kernel": 7680 + 7680,
     "rx_bpf_kernel": 7680 + 7680 + 2 * 816,
     "rx_detect_kernel": 16896 + 7680,                   # ring read once, row sums written
-    "rx_track_kernel": 16896 + 7680 + 384,              # ring read once, row sums read + 48x2 refreshed
-    "rx_demod_kernel": 9216 + 960,
+    "rx_refresh_kernel": 16896 + 384,                   # ring read once, 48 x 2 row sums written
+    "rx_track_kernel": 2 * 1472 + 4 * 1280 + 64,        # two 184-sample refine windows, four spot windows, results
+    "rx_demod_kernel": 9216 + 960 + 7680 + 64,          # symbols in, z_hat out, row sums + refine results read by the state machine
     "rx_finish_kernel": 7680 + 256,
     "core_decoder_kernel": 960 + 1728 + 2 * 2672,
 }

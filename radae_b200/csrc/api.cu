@@ -146,11 +146,14 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   b->prof.stream = b->stream;
   if (core_codec_init_device() < 0 || rx_dsp_init_device() < 0) { delete b; return nullptr; }
   if (cudaStreamCreateWithFlags(&b->rx.side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&b->rx.side2_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->rx.ev_join2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->rx.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&b->rx.ev_join, cudaEventDisableTiming) != cudaSuccess) { delete b; return nullptr; }
   if (!weights) { weights = rade_b200_default_weights_blob(&weights_len); }
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   b->weights.dev.trace = nullptr;
+  b->weights.dev.one = 1.0f;
   b->weights.dev.float_fma = 0;            // measurement switch only (tools/gpu_fma_ab.sh sets it through RADE_B200_DEBUG_FLOAT_FMA): never on in the product
   if (getenv("RADE_B200_DEBUG_FLOAT_FMA") && atoi(getenv("RADE_B200_DEBUG_FLOAT_FMA")) == 1) b->weights.dev.float_fma = 1;
   b->weights.dev.enc_z_tanh = (flags & RADE_B200_BOTTLENECK_1) ? 1 : 0;      // src/rade_enc.c:107-113
@@ -171,6 +174,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   bad |= dalloc(b, &b->rx.nin, S);
   bad |= dalloc(b, &b->rx.search_list, S);
   bad |= dalloc(b, &b->rx.track_list, S);
+  { double *p = nullptr; bad |= dalloc(b, &p, (size_t)S * 8); b->rx.track_tmp = p; }      // TrackTmp = 64 bytes
   bad |= dalloc(b, &b->rx.counters, 8);
   bad |= dalloc(b, &b->chan_state, S);
   bad |= dalloc(b, &b->link_ring, S * LINK_CAP);
@@ -203,6 +207,7 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   cudaSetDevice(b->device);
   cudaStreamSynchronize(b->stream);
   if (b->rx.side_stream) cudaStreamSynchronize(b->rx.side_stream);
+  if (b->rx.side2_stream) cudaStreamSynchronize(b->rx.side2_stream);
   for (void *p : b->allocs) cudaFree(p);
   core_weights_free(&b->weights);
   if (b->d_core_in) { cudaFree(b->d_core_in); cudaFree(b->d_core_out); }
@@ -216,6 +221,7 @@ RADE_EXPORT void rade_b200_close(rade_batch *b) {
   for (auto &g : b->step_graphs) cudaGraphExecDestroy(g.exec);
   cudaStreamDestroy(b->stream);
   if (b->tx_stream) { cudaStreamDestroy(b->tx_stream); cudaEventDestroy(b->ev_txfork); cudaEventDestroy(b->ev_txjoin); }
+  if (b->rx.side2_stream) { cudaStreamDestroy(b->rx.side2_stream); cudaEventDestroy(b->rx.ev_join2); }
   if (b->rx.side_stream) { cudaStreamDestroy(b->rx.side_stream); cudaEventDestroy(b->rx.ev_fork); cudaEventDestroy(b->rx.ev_join); }
   delete b;
 }
@@ -923,7 +929,7 @@ RADE_EXPORT const char *rade_b200_profile_kernel_name(int k) {
   static const char *names[K_COUNT] = {"core_encoder_kernel", "ofdm_mod_kernel", "eoo_kernel", "channel_stream_kernel",
                                        "link_push_kernel", "link_pop_kernel", "rx_bpf_kernel", "rx_detect_kernel",
                                        "rx_track_kernel", "rx_demod_kernel", "rx_finish_kernel", "core_decoder_kernel",
-                                       "tx_bpf_clip_kernel"};
+                                       "tx_bpf_clip_kernel", "rx_refresh_kernel"};
   return (k >= 0 && k < K_COUNT) ? names[k] : "";
 }
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts) {
@@ -945,7 +951,8 @@ RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *coun
 
 // debug/test hook: DSP tables as built on the host (no device needed) — lets the CPU test-suite compare them with
 // the oracle's.  which: 0 Winv, 1 Wfwd, 2 p, 3 pend, 4 p_w, 5 Pmat, 6 eq_rot, 7 bpf_exp, 8 eoo_base (complex64);
-// 16 bpf_h, 17 fcoarse, 18 {pilot_gain, bpf_bw, bpf_centre, bpf_alpha} (float32).  Returns element count.
+// 16 bpf_h, 17 fcoarse, 18 {pilot_gain, bpf_bw, bpf_centre, bpf_alpha, residual of the coarse-grid basis}, 19 coarse-grid basis
+// [80][16], 20 its expansion coefficients [21][12] (float32; layouts: AcqTables in rade_common.h).  Returns element count.
 RADE_EXPORT int rade_b200_debug_tables(int which, float *out, int cap_floats) {
   DspTablesHost T; dsp_tables_host(T);
   const std::vector<std::complex<float>> *cv = nullptr; std::vector<float> fv;
@@ -954,7 +961,8 @@ RADE_EXPORT int rade_b200_debug_tables(int which, float *out, int cap_floats) {
     case 4: cv = &T.p_w; break; case 5: cv = &T.Pmat; break; case 6: cv = &T.eq_rot; break; case 7: cv = &T.bpf_exp; break;
     case 8: cv = &T.eoo_base; break;
     case 16: fv = T.bpf_h; break; case 17: fv = T.fcoarse; break;
-    case 18: fv = {(float)T.pilot_gain, T.bpf_bw, T.bpf_centre, T.bpf_alpha}; break;
+    case 18: fv = {(float)T.pilot_gain, T.bpf_bw, T.bpf_centre, T.bpf_alpha, (float)T.srch_residual}; break;
+    case 19: fv = T.srch_basis; break; case 20: fv = T.srch_expand; break;
     default: return -1;
   }
   if (cv) {

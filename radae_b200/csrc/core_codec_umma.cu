@@ -154,21 +154,24 @@ __device__ __forceinline__ float2 fma2_rn(float wx, float wy, float x, float ax,
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rw), "l"(rx), "l"(ra));
   return *reinterpret_cast<float2 *>(&rd);
 }
-template <int RS, bool FMA> __device__ __forceinline__ void mac4(float (&acc)[RS][4], const float4 w, const float (&x)[RS]) {
+template <int RS, bool FMA> __device__ __forceinline__ void mac4(float (&acc)[RS][4], const float4 w, const float (&x)[RS], float one) {
 #pragma unroll
   for (int r = 0; r < RS; r++) {
     if constexpr (FMA) {
       const float2 a0 = fma2_rn(w.x, w.y, x[r], acc[r][0], acc[r][1]), a1 = fma2_rn(w.z, w.w, x[r], acc[r][2], acc[r][3]);
       acc[r][0] = a0.x; acc[r][1] = a0.y; acc[r][2] = a1.x; acc[r][3] = a1.y;
     } else {
+      // acc + round(w x): the rounded product goes through a packed fused multiply-add as p * one + acc — exact and packed.
+      // `one` is 1.0f from a kernel parameter, so ptxas cannot contract it with the multiply (it fuses mul.rn.f32x2 + add.rn.f32x2
+      // and even mul + fma(p, 1.0f, acc) into one FFMA2, which rounds once instead of twice)
       const float2 p0 = prod2_rn(w.x, w.y, x[r]), p1 = prod2_rn(w.z, w.w, x[r]);
-      acc[r][0] = __fadd_rn(acc[r][0], p0.x); acc[r][1] = __fadd_rn(acc[r][1], p0.y);
-      acc[r][2] = __fadd_rn(acc[r][2], p1.x); acc[r][3] = __fadd_rn(acc[r][3], p1.y);
+      const float2 a0 = fma2_rn(p0.x, p0.y, one, acc[r][0], acc[r][1]), a1 = fma2_rn(p1.x, p1.y, one, acc[r][2], acc[r][3]);
+      acc[r][0] = a0.x; acc[r][1] = a0.y; acc[r][2] = a1.x; acc[r][3] = a1.y;
     }
   }
 }
 template <int NOUTP, int RS, bool FMA = false, typename CX>
-__device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[RS][4], const float *x0, int ldx, int K, int grp, bool act) {
+__device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[RS][4], const float *x0, int ldx, int K, int grp, bool act, float one) {
   for (int r0 = 0; r0 < K;) {
     if (cx.left == 0) cx.next_stage();
     const int n = min(K - r0, cx.left / (NOUTP * 4));
@@ -182,16 +185,16 @@ __device__ __forceinline__ void dense_seg(CX &cx, float (&acc)[RS][4], const flo
         float x[RS];
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].x;
-        mac4<RS, FMA>(acc, W4[(j + 0) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 0) * (NOUTP / 4)], x, one);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].y;
-        mac4<RS, FMA>(acc, W4[(j + 1) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 1) * (NOUTP / 4)], x, one);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].z;
-        mac4<RS, FMA>(acc, W4[(j + 2) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 2) * (NOUTP / 4)], x, one);
 #pragma unroll
         for (int r = 0; r < RS; r++) x[r] = xv[r].w;
-        mac4<RS, FMA>(acc, W4[(j + 3) * (NOUTP / 4)], x);
+        mac4<RS, FMA>(acc, W4[(j + 3) * (NOUTP / 4)], x, one);
       }
     }
     cx.consumed(n * NOUTP * 4);
@@ -356,7 +359,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) a[r][i] = 0.f;
       const bool act = grp < 64 / 4;
-      dense_seg<64, RSF>(cx, a, sm.fin[sl], FIN_LD, ENC_IN, grp, act);
+      dense_seg<64, RSF>(cx, a, sm.fin[sl], FIN_LD, ENC_IN, grp, act, W.one);
       if (act) {
         uint8_t *cb = sm.cb[t % NCB];
 #pragma unroll
@@ -382,8 +385,8 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
       float zacc[RSF][4];
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) zacc[r][i] = 0.f;
-      if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on);
-      else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on);
+      if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on, W.one);
+      else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.d1f[sl], SEG_LD, 64, grp, f_on, W.one);
       nb_sync(NB_F, NF * 32);                    // everybody is done with d1f and fin of this step
       if (t + 1 < T) { stage_input(t + 1); nb_sync(NB_F, NF * 32); dense1(t + 1); }
       else skip_seg<64>(cx, ENC_IN);
@@ -392,8 +395,8 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
         const int slot = nseg % NSEG;
         mbar_wait(&sm.seg_full[slot], (nseg / NSEG) & 1);
         if (ft == 0) TR(4096 + (t * 16 + j) * 2);
-        if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on);
-        else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on);
+        if (W.float_fma) dense_seg<RADE_LATENT, RSF, true>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on, W.one);
+        else dense_seg<RADE_LATENT, RSF>(cx, zacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? ENC_CONV : ENC_GRU, grp, f_on, W.one);
         __syncwarp();
         if (ft == 0) TR(4096 + (t * 16 + j) * 2 + 1);
         if (lane == 0) mbar_arrive(&sm.seg_empty[slot]);
@@ -664,7 +667,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
       float a[RSF][4];
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) a[r][i] = 0.f;
-      dense_seg<96, RSF>(cx, a, sm.zin[sl], ZIN_LD, DEC_IN, grp, f_on);
+      dense_seg<96, RSF>(cx, a, sm.zin[sl], ZIN_LD, DEC_IN, grp, f_on, W.one);
       if (f_on) {
         uint8_t *cb = sm.cb[t % NCB];
 #pragma unroll
@@ -690,8 +693,8 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
       float oacc[RSF][4];
 #pragma unroll
       for (int r = 0; r < RSF; r++) for (int i = 0; i < 4; i++) oacc[r][i] = 0.f;
-      if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on);
-      else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on);
+      if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on, W.one);
+      else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.d1f[sl], SEG_LD, 96, grp, f_on, W.one);
       nb_sync(NB_F, NF * 32);
       if (t + 1 < T) { stage_input(t + 1); nb_sync(NB_F, NF * 32); dense1(t + 1); }
       else skip_seg<96>(cx, DEC_IN);
@@ -700,8 +703,8 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
         const int slot = nseg % NSEG;
         mbar_wait(&sm.seg_full[slot], (nseg / NSEG) & 1);
         if (ft == 0) TR(4096 + (t * 16 + j) * 2);
-        if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on);
-        else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on);
+        if (W.float_fma) dense_seg<DEC_OUTP, RSF, true>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on, W.one);
+        else dense_seg<DEC_OUTP, RSF>(cx, oacc, sm.seg[slot][sl], SEG_LD, (j & 1) ? DEC_CONV : DEC_GRU, grp, f_on, W.one);
         __syncwarp();
         if (ft == 0) TR(4096 + (t * 16 + j) * 2 + 1);
         if (lane == 0) mbar_arrive(&sm.seg_empty[slot]);

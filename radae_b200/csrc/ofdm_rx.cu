@@ -25,6 +25,8 @@
 namespace {
 
 enum { ST_SEARCH = 0, ST_CANDIDATE = 1, ST_SYNC = 2 };
+// sqrt(-ln(Pacq_error / 5)) of radae/dsp.py:229, :300 for Pacq_error = 1e-4, 1e-5, as float64 evaluates them
+constexpr double K_ACQ_1E4 = 3.2893431387452243, K_ACQ_1E5 = 3.622480279781289;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
@@ -34,10 +36,14 @@ __device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
   acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
   acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
 }
-// Coarse-grid correlations for two sample windows x0, x1 against the pilot p shifted to the grid
-// frequencies +-2.5k Hz, k = 6*kg .. 6*kg+5:  D(+-f_k) = A_k +- j B_k with A_k = sum_n y[n] cos(w_k n), B_k = sum_n y[n] sin(w_k n),
-// y[n] = conj(x[n]) p[n]  (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; p_w = exp(j w n) p there).
-// One (cos, sin) pair serves the +f and -f grid points: 4 FMAs per tap per pair instead of 8.
+// Coarse-grid correlations D(+-f_k) = sum_n y[n] exp(+-j w_k n), y[n] = conj(x[n]) p[n], f_k = 2.5 k Hz, k = 0..20
+// (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; the reference multiplies by p_w = exp(j w n) p).
+// Only |D| is ever used, so the window may be centred: with n = 80 + m and n = 79 - m folded onto m = 0..79,
+//   A_k = sum_m (y[80+m] + y[79-m]) cos(w_k (m + 1/2)),  B_k = sum_m (y[80+m] - y[79-m]) sin(w_k (m + 1/2)),  |D(+-f_k)| = |A_k +- j B_k|.
+// The 21 cosine rows and the 20 sine rows are each spanned by RADE_SRANK = 6 basis vectors to 1e-9 (AcqTables, tables.cpp): a
+// window is first projected on the 12 basis vectors (12 complex accumulators instead of 41), then expanded to the 40 grid points.
+// Per window and timing offset: 80 x (6 + 12) packed FMAs + 21 x 12 for the expansion, against 160 x 56 for the direct sums —
+// at the same distance from the exact (float64) correlations as the direct float32 sums (tests/test_oracle_dsp.py).
 // Blackwell packed fp32: one FFMA2 does two independent IEEE FMAs on a register pair (SASS FFMA2 .F32x2)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
@@ -46,31 +52,51 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2 *>(&rd);
 }
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
-__device__ __forceinline__ void corr6(float2 (&A0)[6], float2 (&B0)[6], float2 (&A1)[6], float2 (&B1)[6], const float2 *x0,
-                                      const float2 *x1, const float4 *ps4, const float2 (*cs)[RADE_CSK], int kg) {
+// y = conj(x) p with two packed FMAs; pp = (p.x, p.y, p.y, -p.x)
+__device__ __forceinline__ float2 conj_mul_p(float2 x, float4 pp) {
+  return ffma2(splat(x.x), make_float2(pp.x, pp.y), ffma2(splat(x.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
+}
+struct Proj { float2 c[RADE_SRANK], s[RADE_SRANK]; };         // projections on the cosine / sine basis
+__device__ __forceinline__ void proj_zero(Proj &P) {
 #pragma unroll
-  for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
-#pragma unroll 2
-  for (int n = 0; n < RADE_M; n++) {
-    const float4 pp = ps4[n];                      // (p.x, p.y, p.y, -p.x): y = conj(x) p with two packed FMAs
-    const float2 a = x0[n], c = x1[n];
-    const float2 y0 = ffma2(splat(a.x), make_float2(pp.x, pp.y), ffma2(splat(a.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
-    const float2 y1 = ffma2(splat(c.x), make_float2(pp.x, pp.y), ffma2(splat(c.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
-    const float4 *t = reinterpret_cast<const float4 *>(&cs[n][kg * 6]);
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-      const float4 q = t[j];                       // (cos_k, sin_k, cos_k+1, sin_k+1)
-      A0[2 * j] = ffma2(y0, splat(q.x), A0[2 * j]);         B0[2 * j] = ffma2(y0, splat(q.y), B0[2 * j]);
-      A0[2 * j + 1] = ffma2(y0, splat(q.z), A0[2 * j + 1]); B0[2 * j + 1] = ffma2(y0, splat(q.w), B0[2 * j + 1]);
-      A1[2 * j] = ffma2(y1, splat(q.x), A1[2 * j]);         B1[2 * j] = ffma2(y1, splat(q.y), B1[2 * j]);
-      A1[2 * j + 1] = ffma2(y1, splat(q.z), A1[2 * j + 1]); B1[2 * j + 1] = ffma2(y1, splat(q.w), B1[2 * j + 1]);
-    }
+  for (int r = 0; r < RADE_SRANK; r++) P.c[r] = P.s[r] = make_float2(0.f, 0.f);
+}
+// one folded tap pair of one window: ya = y[80 + m], yb = y[79 - m]
+template <bool COS, bool SIN>
+__device__ __forceinline__ void proj_tap(Proj &P, float2 ya, float2 yb, const float4 *bm /* basis[m] */) {
+  if (COS) {
+    const float2 e = ffma2(yb, splat(1.f), ya);                 // ya + yb as one packed op
+    const float4 q0 = bm[0], q1 = bm[1];
+    P.c[0] = ffma2(e, splat(q0.x), P.c[0]); P.c[1] = ffma2(e, splat(q0.y), P.c[1]); P.c[2] = ffma2(e, splat(q0.z), P.c[2]);
+    P.c[3] = ffma2(e, splat(q0.w), P.c[3]); P.c[4] = ffma2(e, splat(q1.x), P.c[4]); P.c[5] = ffma2(e, splat(q1.y), P.c[5]);
+  }
+  if (SIN) {
+    const float2 o = ffma2(yb, splat(-1.f), ya);                // ya - yb
+    const float4 q2 = bm[2], q3 = bm[3];
+    P.s[0] = ffma2(o, splat(q2.x), P.s[0]); P.s[1] = ffma2(o, splat(q2.y), P.s[1]); P.s[2] = ffma2(o, splat(q2.z), P.s[2]);
+    P.s[3] = ffma2(o, splat(q2.w), P.s[3]); P.s[4] = ffma2(o, splat(q3.x), P.s[4]); P.s[5] = ffma2(o, splat(q3.y), P.s[5]);
   }
 }
+// A_k / B_k from the projections; ek = expand[k]
+__device__ __forceinline__ float2 expand_cos(const Proj &P, const float4 *ek) {
+  const float4 e0 = ek[0], e1 = ek[1];
+  float2 a = make_float2(P.c[0].x * e0.x, P.c[0].y * e0.x);
+  a = ffma2(P.c[1], splat(e0.y), a); a = ffma2(P.c[2], splat(e0.z), a); a = ffma2(P.c[3], splat(e0.w), a);
+  a = ffma2(P.c[4], splat(e1.x), a); a = ffma2(P.c[5], splat(e1.y), a);
+  return a;
+}
+__device__ __forceinline__ float2 expand_sin(const Proj &P, const float4 *ek) {
+  const float4 e1 = ek[1], e2 = ek[2];
+  float2 b = make_float2(P.s[0].x * e1.z, P.s[0].y * e1.z);
+  b = ffma2(P.s[1], splat(e1.w), b); b = ffma2(P.s[2], splat(e2.x), b); b = ffma2(P.s[3], splat(e2.y), b);
+  b = ffma2(P.s[4], splat(e2.z), b); b = ffma2(P.s[5], splat(e2.w), b);
+  return b;
+}
+__device__ __forceinline__ float mag2(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
 // |D(+f_k)|, |D(-f_k)| from A, B
 __device__ __forceinline__ void mags_pm(float2 A, float2 B, float &mp, float &mm) {
-  mp = hypotf(A.x - B.y, A.y + B.x);
-  mm = hypotf(A.x + B.y, A.y - B.x);
+  mp = mag2(A.x - B.y, A.y + B.x);
+  mm = mag2(A.x + B.y, A.y - B.x);
 }
 __device__ __forceinline__ int ring_idx(int head, int i) { int k = head + i; return k >= RADE_RXBUF ? k - RADE_RXBUF : k; }
 
@@ -91,6 +117,18 @@ __device__ float block_sum(float v, float *scratch) {
   __syncthreads();
   return scratch[0];
 }
+
+// The tables every lane reads at the same index live in constant memory: they reach the FP32 pipe through the uniform datapath
+// (ULDC / constant operands) and leave the shared-memory return path (128 B/clk per SM, which a broadcast LDS.128 occupies for
+// four cycles like any other) to the per-lane sample reads.  Measured on rx_track: the row refresh was bound by exactly those
+// broadcast loads (14.3k cycles per stream with the tables in shared memory).
+struct AcqConst {
+  float4 ps4[RADE_M];              // = AcqTables::ps4
+  float4 basis[RADE_M / 2][4];     // = AcqTables::basis
+  float4 expand[21][3];            // = AcqTables::expand
+};
+__constant__ AcqConst c_acq;
+
 
 // ================================================================= band-pass filter + ring append
 // 101-tap real FIR on complex samples.  Each thread produces four consecutive outputs from a sliding register window
@@ -164,22 +202,21 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
     c.ring_head = nh;                      // logical sample 0 of rx_buf now lives at ring[nh]
     c.detect_key = 0ull;
     c.candidate = 0; c.endofover = 0; c.valid_output = 0; c.uw_fail = 0; c.ran_sync = 0; c.ret = 0;
-    if (c.state != ST_SYNC) search_list[atomicAdd(&counters[0], 1)] = s;         // work list of rx_detect / rx_finish
-    else track_list[atomicAdd(&counters[2], 1)] = s;                              // work list of rx_track
+    c.tracking = c.state == ST_SYNC;
+    if (!c.tracking) search_list[atomicAdd(&counters[0], 1)] = s;                  // work list of rx_detect / rx_finish
+    else track_list[atomicAdd(&counters[2], 1)] = s;                              // work list of rx_refresh / rx_track
   }
 }
 
 // ================================================================= coarse pilot search (search / candidate streams)
-// work item = 32 timing offsets x 40 frequency offsets x 2 pilot positions, 160-tap complex correlations; 128-thread CTAs
-// (80 registers) fit next to a resident rx_track CTA, so the search branch runs concurrently with the tracking branch
-constexpr int DET_TB = 32, DET_THREADS = 4 * DET_TB;
+// work item = 64 timing offsets x 40 frequency offsets x 2 pilot positions.  One thread per timing offset: both windows are
+// projected on the 12 basis vectors in one pass over the 80 folded taps (48 packed accumulators), then expanded to the grid.
+// The tables are in constant memory; 64-thread CTAs with 3.6 KB of shared memory: many are resident per SM, next to rx_track.
+constexpr int DET_TB = 64, DET_THREADS = DET_TB;
 struct DetectSmem {
-  AcqTables tab;                   // one TMA bulk copy per CTA
   float2 r1[DET_TB + RADE_M];
   float2 r2[DET_TB + RADE_M];
-  float part[2][4][DET_TB];
   unsigned long long best[DET_THREADS / 32];
-  uint64_t tab_bar;
 };
 
 __global__ void __launch_bounds__(DET_THREADS)
@@ -191,13 +228,6 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
   const int tid = threadIdx.x;
   const int n_items = counters[0] * (RADE_NMF / DET_TB);
   if ((int)blockIdx.x >= n_items) return;         // steady state: (almost) nobody is searching
-  if (tid == 0) {
-    mbar_init(&sm.tab_bar, 1); mbar_fence_init();
-    mbar_expect_tx(&sm.tab_bar, (uint32_t)sizeof(AcqTables));
-    bulk_g2s(&sm.tab, T.acq_tab, (uint32_t)sizeof(AcqTables), &sm.tab_bar);
-  }
-  __syncthreads();
-  mbar_wait(&sm.tab_bar, 0);
   // persistent CTAs pull (stream, 64-offset block) items off a device-side counter
   for (;;) {
     __syncthreads();
@@ -214,38 +244,41 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       sm.r2[i] = rg[ring_idx(head, t0 + RADE_NMF + i)];
     }
     __syncthreads();
-    const int tl = tid & (DET_TB - 1), fg = tid / DET_TB;  // fg = k group: k = 6 fg .. 6 fg + 5
-    float2 A0[6], B0[6], A1[6], B1[6];
-    corr6(A0, B0, A1, B1, &sm.r1[tl], &sm.r2[tl], sm.tab.ps4, sm.tab.cs, fg);
+    Proj P1, P2;
+    proj_zero(P1); proj_zero(P2);
+    const float2 *x1 = &sm.r1[tid], *x2 = &sm.r2[tid];
+#pragma unroll 2
+    for (int m = 0; m < RADE_M / 2; m++) {
+      const float4 pa = c_acq.ps4[RADE_M / 2 + m], pb = c_acq.ps4[RADE_M / 2 - 1 - m];
+      proj_tap<true, true>(P1, conj_mul_p(x1[RADE_M / 2 + m], pa), conj_mul_p(x1[RADE_M / 2 - 1 - m], pb), c_acq.basis[m]);
+      proj_tap<true, true>(P2, conj_mul_p(x2[RADE_M / 2 + m], pa), conj_mul_p(x2[RADE_M / 2 - 1 - m], pb), c_acq.basis[m]);
+    }
     float s1 = 0.f, s2 = 0.f, best = -1.f; int bestf = RADE_NFCOARSE;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      const int k = fg * 6 + j;
-      if (k > 20) continue;
+#pragma unroll 3
+    for (int k = 0; k <= 20; k++) {
+      const float4 *ek = c_acq.expand[k];
       float p1, m1, p2, m2;
-      mags_pm(A0[j], B0[j], p1, m1); mags_pm(A1[j], B1[j], p2, m2);
-      if (k < 20) {                                   // +2.5k Hz -> grid index 20 + k
-        s1 += p1; s2 += p2;
-        const float d = p1 + p2; const int fi = 20 + k;
-        if (d > best || (d == best && fi < bestf)) { best = d; bestf = fi; }
-      }
+      mags_pm(expand_cos(P1, ek), expand_sin(P1, ek), p1, m1);
+      mags_pm(expand_cos(P2, ek), expand_sin(P2, ek), p2, m2);
       if (k > 0) {                                    // -2.5k Hz -> grid index 20 - k
         s1 += m1; s2 += m2;
         const float d = m1 + m2; const int fi = 20 - k;
         if (d > best || (d == best && fi < bestf)) { best = d; bestf = fi; }
       }
+      if (k < 20) {                                   // +2.5k Hz -> grid index 20 + k
+        s1 += p1; s2 += p2;
+        const float d = p1 + p2; const int fi = 20 + k;
+        if (d > best || (d == best && fi < bestf)) { best = d; bestf = fi; }
+      }
     }
-    sm.part[0][fg][tl] = s1; sm.part[1][fg][tl] = s2;
+    rowsum[((size_t)s * 2 + 0) * RADE_NMF + t0 + tid] = s1;
+    rowsum[((size_t)s * 2 + 1) * RADE_NMF + t0 + tid] = s2;
     // arg-max with "first (t, f) wins": larger key = larger value, then smaller flat index
-    unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (0xFFFFFFFFu - (unsigned)((t0 + tl) * RADE_NFCOARSE + bestf));
+    unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (0xFFFFFFFFu - (unsigned)((t0 + tid) * RADE_NFCOARSE + bestf));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
     if ((tid & 31) == 0) sm.best[tid >> 5] = key;
     __syncthreads();
-    if (tid < 2 * DET_TB) {
-      const int half = tid / DET_TB, t = tid & (DET_TB - 1);
-      rowsum[((size_t)s * 2 + half) * RADE_NMF + t0 + t] = ((sm.part[half][0][t] + sm.part[half][1][t]) + sm.part[half][2][t]) + sm.part[half][3][t];
-    }
     if (tid == 0) {
       unsigned long long k = sm.best[0];
       for (int i = 1; i < DET_THREADS / 32; i++) k = sm.best[i] > k ? sm.best[i] : k;
@@ -265,8 +298,21 @@ constexpr int REF_NFP = 24;                       // frequencies per pass = 6 DM
 constexpr int REF_VLD = 165;                      // vtab row: tap n lives at n + (n >> 5); 165 = 5 mod 8 spreads f over the banks
 constexpr int REF_RLEN = REF_NT + RADE_M + 8;     // widened window (+ over-read of the last k-step)
 constexpr int REF_THREADS = 128;                  // four warps
+constexpr int REF_NK = 9;                         // Taylor terms of exp(-j dw n'), |dw n'| <= 0.0625: truncation 6e-15
+struct MomentsSmem {                              // refine_moments (tracking)
+  double2 q[RADE_M];                              // conj(p[n]) exp(-j w0 (n - 79.5)), w0 = the tracked frequency
+  double2 part[4][32][REF_NK];                    // moments of (window, quarter of the taps)
+  double2 ph0[2];                                 // exp(-j w0 (79.5 + 960 pos))
+  double2 ra[REF_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
+  double2 pad_;
+  double2 rb[REF_RLEN];                           // rx[t_lo + Nmf ...]
+  float2 d1[REF_NFP][REF_NT];
+  float2 d2[REF_NFP][REF_NT];
+  float red_mag[4]; int red_ord[4];
+  float best_mag; int best_t; int best_found; double best_f;
+};
 struct RefineSmem {
-  double2 vtab[REF_NFP][REF_VLD];                 // conj(p[n]) exp(-j w_f n)
+  double2 vtab[REF_NFP][REF_VLD];                 // refine_dmma: conj(p[n]) exp(-j w_f n)
   double2 ramp[REF_NFP];                          // exp(-j w_f Nmf)
   double2 ra[REF_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
   double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
@@ -286,7 +332,7 @@ __device__ __forceinline__ int arange_len(double start, double stop, double step
 // otherwise warp = (pilot position, half of the n-tiles) with a single t tile.
 template <bool WIDE_T, typename Load>
 __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Load load, int t_lo, int nt,
-                            double f_start, double f_stop, double f_step, int g, int bar) {
+                            double f_start, double f_stop, double f_step, int g, int bar, long long *stamps = nullptr) {
   constexpr int NQ = WIDE_T ? 6 : 3;              // n-tiles per warp
   const int nf_all = arange_len(f_start, f_stop, f_step);
   const double delta = (f_start + f_step) - f_start;
@@ -300,6 +346,7 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
   for (int c0 = 0; c0 < nf_all; c0 += REF_NFP) {
     const int nf = min(REF_NFP, nf_all - c0);
     group_sync(bar, REF_THREADS);                 // previous pass done with vtab / d1 / d2
+    if (stamps && g == 0) stamps[0] = clock64();
     // steering vectors for this pass: thread = (f, 32-tap segment), one sincos pair + 31 rotations (|error| ~ 1e-15)
     for (int task = g; task < REF_NFP * 5; task += REF_THREADS) {
       const int fi = task / 5, seg = task % 5;
@@ -320,6 +367,7 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
       }
     }
     group_sync(bar, REF_THREADS);
+    if (stamps && g == 0) stamps[1] = clock64();
     {
       const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
       const int half = wr >> 1, mt = WIDE_T ? (wr & 1) : 0, q0 = WIDE_T ? 0 : 3 * (wr & 1);
@@ -357,6 +405,7 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
       }
     }
     group_sync(bar, REF_THREADS);
+    if (stamps && g == 0) stamps[2] = clock64();
     float bm = -1.f; int bo = 0x7fffffff;
     for (int q = g; q < nf * nt; q += REF_THREADS) {
       const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
@@ -384,6 +433,110 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
   group_sync(bar, REF_THREADS);
 }
 
+// The same search for the tracking case — 16 timing offsets, f in arange(f0 - 1, f0 + 1, 0.1) — without a steering vector per
+// frequency.  With n' = n - 79.5 and f = f0 + d:  exp(-j w_f n) = exp(-j w_f 79.5) exp(-j w0 n') exp(-j dw n'), and |dw n'| <= 0.0625 rad,
+// so exp(-j dw n') = sum_k (-j 80 dw)^k (n'/80)^k / k! to 6e-15 with k <= 8.  Per window: nine complex128 moments
+//   M_k = sum_n rx[t + n] q[n] (n'/80)^k / k!,   q[n] = conj(p[n]) exp(-j w0 n'),
+// then every frequency is a Horner evaluation in u = -j 80 dw and one phase rotation.  FP64 work per stream: 32 windows x 160 taps
+// x 22 FMA = 113k against 491k for the matrix form (20 steering vectors), and the 24 x 5 double sincos chains of the steering
+// table are gone (two sincos per thread, in parallel).  Results agree with the complex128 sums to ~1e-14 relative before the
+// rounding to csingle (radae/dsp.py:255-257 is reproduced from there on: d1, d2 rounded separately, then |csingle(d1 + d2)|).
+template <typename Load>
+__device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const double2 (*phd)[24], const double2 *pcd, Load load, int t_lo, int nt, double f0,
+                               int g, int bar, long long *stamps = nullptr) {
+  const double f_start = f0 - 1, f_stop = f0 + 1, f_step = 0.1;
+  const int nf_all = min(arange_len(f_start, f_stop, f_step), REF_NFP);
+  const double delta = (f_start + f_step) - f_start;
+  const double w0 = 2.0 * M_PI * f0 / RADE_FS;
+  if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
+  for (int i2 = g; i2 < REF_RLEN; i2 += REF_THREADS) {
+    const bool in = i2 < nt + RADE_M;
+    const float2 a = in ? load(t_lo + i2) : make_float2(0.f, 0.f), c = in ? load(t_lo + RADE_NMF + i2) : make_float2(0.f, 0.f);
+    sm.ra[i2] = make_double2((double)a.x, (double)a.y);
+    sm.rb[i2] = make_double2((double)c.x, (double)c.y);
+  }
+  {
+    // q[n] for n = g (and g + 128), the two stream-dependent phases by threads 32 and 33: at most two sincos per thread
+    double sn, cs;
+    sincos(w0 * ((double)g - 79.5), &sn, &cs);
+    sm.q[g] = dcmul(make_double2(cs, -sn), pcd[g]);
+    if (g < RADE_M - REF_THREADS + 2) {
+      const double arg = g < RADE_M - REF_THREADS ? (double)(g + REF_THREADS) - 79.5 : (g == RADE_M - REF_THREADS ? 79.5 : 79.5 + RADE_NMF);
+      sincos(w0 * arg, &sn, &cs);
+      if (g < RADE_M - REF_THREADS) sm.q[g + REF_THREADS] = dcmul(make_double2(cs, -sn), pcd[g + REF_THREADS]);
+      else sm.ph0[g - (RADE_M - REF_THREADS)] = make_double2(cs, -sn);
+    }
+  }
+  group_sync(bar, REF_THREADS);
+  if (stamps && g == 0) stamps[0] = clock64();
+  const int wdx = g & 31, qt = g >> 5;               // window = (pilot position, timing offset), quarter of the taps
+  const int pos = wdx >> 4, ti = wdx & 15;
+  {
+    double2 M[REF_NK];
+#pragma unroll
+    for (int k = 0; k < REF_NK; k++) M[k] = make_double2(0.0, 0.0);
+    const double2 *xr = (pos ? sm.rb : sm.ra) + ti;
+#pragma unroll 2
+    for (int n = qt * (RADE_M / 4); n < (qt + 1) * (RADE_M / 4); n++) {
+      const double2 xv = xr[n], qv = sm.q[n];
+      const double2 z = dcmul(xv, qv);
+      const double *b = bk[n];
+#pragma unroll
+      for (int k = 0; k < REF_NK; k++) { M[k].x = fma(z.x, b[k], M[k].x); M[k].y = fma(z.y, b[k], M[k].y); }
+    }
+#pragma unroll
+    for (int k = 0; k < REF_NK; k++) sm.part[qt][wdx][k] = M[k];
+  }
+  group_sync(bar, REF_THREADS);
+  if (stamps && g == 0) stamps[1] = clock64();
+  {
+    // thread = (window, frequencies qt, qt + 4, ...): add the four partial moments, Horner per frequency, phase, round to csingle
+    double2 M[REF_NK];
+#pragma unroll
+    for (int k = 0; k < REF_NK; k++) {
+      const double2 a = sm.part[0][wdx][k], b = sm.part[1][wdx][k], c = sm.part[2][wdx][k], d = sm.part[3][wdx][k];
+      M[k] = make_double2((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y));
+    }
+    const double2 ph0 = sm.ph0[pos];
+    if (ti < nt)
+      for (int fi = qt; fi < nf_all; fi += 4) {
+        const double f = f_start + (double)fi * delta;
+        const double al = 2.0 * M_PI * (f - f0) / RADE_FS * 80.0;          // u = -j al
+        double2 D = M[REF_NK - 1];
+#pragma unroll
+        for (int k = REF_NK - 2; k >= 0; k--) D = make_double2(fma(al, D.y, M[k].x), fma(-al, D.x, M[k].y));   // D (-j al) + M_k
+        const double2 e = dcmul(dcmul(D, ph0), phd[pos][fi]);
+        (pos ? sm.d2 : sm.d1)[fi][ti] = make_float2((float)e.x, (float)e.y);
+      }
+  }
+  group_sync(bar, REF_THREADS);
+  if (stamps && g == 0) stamps[2] = clock64();
+  float bm = -1.f; int bo = 0x7fffffff;
+  for (int q = g; q < nf_all * nt; q += REF_THREADS) {
+    const int fi = q / nt, t2 = q - fi * nt;         // ord = q: f outer loop, t inner loop
+    const float2 a = sm.d1[fi][t2], c = sm.d2[fi][t2];
+    const float m = hypotf(a.x + c.x, a.y + c.y);
+    if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
+    if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
+  }
+  if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
+  group_sync(bar, REF_THREADS);
+  if (g == 0) {
+    for (int q = 1; q < REF_THREADS / 32; q++)
+      if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
+    if (bm > 0.f) {                 // strict > against the initial Dtmax = 0 (radae/dsp.py:262)
+      sm.best_mag = bm; sm.best_found = 1;
+      sm.best_t = t_lo + bo % nt;
+      sm.best_f = f_start + (double)(bo / nt) * delta;
+    }
+  }
+  group_sync(bar, REF_THREADS);
+}
+
 // sigma_r = (mean|Dt1| + mean|Dt2|) / (2*sqrt(pi/2)) from the row sums, float32 like the reference's np.mean
 __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scratch) {
   float a = 0.f, b = 0.f;
@@ -394,224 +547,171 @@ __device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scr
   return (s1 + s2) / 2.0f;
 }
 
-// ================================================================= sync-state tracking: refine + check_pilots + slips
-// Persistent kernel: one CTA per SM walks the list of streams in sync (built by rx_bpf).  The constant tables (37 KB) are
-// bulk-copied into shared memory once per CTA; a producer warp prefetches the NEXT stream's sample ring (in logical
-// order), |Dt| row sums and control block with TMA bulk copies into the other half of a double buffer while the 16
-// consumer warps work on the current one:
-//   warps 0-11  check_pilots' refresh of 48 rows of the |Dt| row sums (fp32, packed FFMA2; even/odd tap split per lane pair)
-//   warps 12-15 refine: 16 timing x 20(21) frequency x 2 pilot positions in complex128 as a real GEMM on the FP64
-//               tensor cores (DMMA m8n8k4: 256 FMA per instruction instead of 32)
-// then sigma_r, the four complex128 spot correlations, slips and the sync-state part of the state machine.
-constexpr int TRK_REFRESH = 384, TRK_REFINE = REF_THREADS, TRK_CONSUMERS = TRK_REFRESH + TRK_REFINE, TRK_THREADS = TRK_CONSUMERS + 32;
-struct TrackStage {
-  alignas(128) float2 rx[RADE_RXBUF];             // rx_buf in LOGICAL order (two bulk copies around ring_head)
-  float rs[2 * RADE_NMF];                         // row sums
-  RxCtl ctl;
-};
-struct TrackSmem {
-  AcqTables tab;
-  TrackStage st[2];
-  RefineSmem ref;
-  float scratch[32];
-  double spot[4];
-  uint64_t full[2], empty[2], tab_bar;
-  int item[2];                     // stream handled from stage b (-1: no more work)
-};
-static_assert(sizeof(RxCtl) % 16 == 0 && sizeof(TrackStage) % 128 == 0, "bulk-copy alignment");
+// ================================================================= sync-state tracking: check_pilots row refresh | refine + spot correlations
+// Streams in sync (the list rx_bpf builds).  Two kernels with many small CTAs per SM instead of one persistent CTA per SM: every
+// phase of the per-stream work is a short dependent chain (FP64 latency, constant-bank latency), and with one warp per scheduler
+// nothing hid it — the persistent kernel spent 25k cycles per stream with every pipe under 30 % (profiles/r02_track_phases.txt).
+//   rx_refresh  CTA = one stream, 96 threads = (row, pilot position): 48 rows t_i = 20 i + rot of both |Dt| row-sum vectors
+//   rx_track    CTA = one stream, 128 threads: refine in complex128 (moments form) + the four spot correlations -> TrackTmp
+// The sync-state part of the state machine needs both results; it runs at the head of rx_demod (track_tail).
+struct TrackTmp { double best_f; double spot[4]; int best_found, best_t, pad[2]; };
 
-__global__ void __launch_bounds__(TRK_THREADS, 1)
-rx_track_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
-                int *__restrict__ uw_errors, const int *__restrict__ track_list, int *__restrict__ counters,
-                int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
+constexpr int RFR_STREAMS = 2, RFR_THREADS = RFR_STREAMS * RADE_NUPDATE;
+__global__ void __launch_bounds__(RFR_THREADS)
+rx_refresh_kernel(RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ rowsum,
+                  const int *__restrict__ track_list, const int *__restrict__ counters) {
+  __shared__ __align__(16) float2 rx[RFR_STREAMS][RADE_RXBUF];
+  const int tid = threadIdx.x, n_items = counters[2];
+  for (int it0 = blockIdx.x * RFR_STREAMS; it0 < n_items; it0 += gridDim.x * RFR_STREAMS) {
+    __syncthreads();
+    for (int q = 0; q < RFR_STREAMS; q++) {
+      if (it0 + q >= n_items) break;
+      const int s = track_list[it0 + q], head = ctl[s].ring_head;
+      const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+      for (int i = tid; i < RADE_RXBUF; i += RFR_THREADS) rx[q][i] = rg[ring_idx(head, i)];
+    }
+    __syncthreads();
+    // check_pilots row refresh (radae/dsp.py:288-295, deterministic schedule): rows t_i = 20 i + rot, both pilot positions,
+    // 40 grid frequencies.  thread = (stream of the pair, row i): both windows are projected on the 12 basis vectors in one pass
+    // (the table values are loaded once for the two), then expanded to the grid.
+    const int q = tid / RADE_NUPDATE, i = tid % RADE_NUPDATE;
+    if (it0 + q < n_items) {
+      const int s = track_list[it0 + q], rot = ctl[s].n_check % 20;
+      const float2 *x1 = rx[q] + rot + 20 * i, *x2 = x1 + RADE_NMF;
+      Proj P1, P2; proj_zero(P1); proj_zero(P2);
+#pragma unroll 2
+      for (int m = 0; m < RADE_M / 2; m++) {
+        const float4 pa = c_acq.ps4[RADE_M / 2 + m], pb = c_acq.ps4[RADE_M / 2 - 1 - m];
+        proj_tap<true, true>(P1, conj_mul_p(x1[RADE_M / 2 + m], pa), conj_mul_p(x1[RADE_M / 2 - 1 - m], pb), c_acq.basis[m]);
+        proj_tap<true, true>(P2, conj_mul_p(x2[RADE_M / 2 + m], pa), conj_mul_p(x2[RADE_M / 2 - 1 - m], pb), c_acq.basis[m]);
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 3
+      for (int k = 0; k <= 20; k++) {
+        const float4 *ek = c_acq.expand[k];
+        float p1, m1, p2, m2;
+        mags_pm(expand_cos(P1, ek), expand_sin(P1, ek), p1, m1);
+        mags_pm(expand_cos(P2, ek), expand_sin(P2, ek), p2, m2);
+        if (k > 0) { s1 += m1; s2 += m2; }              // grid index 20 - k
+        if (k < 20) { s1 += p1; s2 += p2; }             // grid index 20 + k
+      }
+      float *rs = rowsum + (size_t)s * 2 * RADE_NMF + 20 * i + rot;
+      rs[0] = s1; rs[RADE_NMF] = s2;
+    }
+  }
+}
+
+struct TrackSmem {
+  MomentsSmem ref;
+  double bk[RADE_M][10];                          // AcqTables::bk, staged once per CTA
+  double2 phd[2][24];
+  double2 pcd[RADE_M];
+  float2 pp[RADE_M], pend[RADE_M];                // pilot / end-of-over pilot (spot correlations)
+  double2 spot_e[32], spot_step;                  // exp(-j w lane), exp(-j 32 w): the same for the four spot correlations
+};
+__global__ void __launch_bounds__(REF_THREADS)
+rx_track_kernel(DspTables T, const RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, const int *__restrict__ track_list,
+                const int *__restrict__ counters, TrackTmp *__restrict__ tmp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TrackSmem &sm = *reinterpret_cast<TrackSmem *>(smem_raw);
-  const int tid = threadIdx.x;
-  const int n_items = counters[2];
+  const int tid = threadIdx.x, n_items = counters[2];
   if ((int)blockIdx.x >= n_items) return;
-  if (tid == 0) {
-    mbar_init(&sm.full[0], 1); mbar_init(&sm.full[1], 1); mbar_init(&sm.empty[0], 1); mbar_init(&sm.empty[1], 1);
-    mbar_init(&sm.tab_bar, 1);
-    mbar_fence_init();
+  {
+    const AcqTables &tab = *reinterpret_cast<const AcqTables *>(T.acq_tab);
+    for (int i = tid; i < RADE_M * 10; i += REF_THREADS) (&sm.bk[0][0])[i] = __ldg(&tab.bk[0][0] + i);
+    for (int i = tid; i < 2 * 24 * 2; i += REF_THREADS) reinterpret_cast<double *>(sm.phd)[i] = __ldg(reinterpret_cast<const double *>(tab.phd) + i);
+    for (int i = tid; i < RADE_M; i += REF_THREADS) {
+      sm.pcd[i] = make_double2(__ldg(&tab.pcd[i].x), __ldg(&tab.pcd[i].y));
+      const float4 p4 = __ldg(&tab.ps4[i]);
+      sm.pp[i] = make_float2(p4.x, p4.y); sm.pend[i] = __ldg(&tab.pend[i]);
+    }
   }
   __syncthreads();
-  if (tid >= TRK_CONSUMERS) {                     // ---- producer warp: TMA prefetch, one stream ahead
-    if (tid == TRK_CONSUMERS) {
-      mbar_expect_tx(&sm.tab_bar, (uint32_t)sizeof(AcqTables));
-      bulk_g2s(&sm.tab, T.acq_tab, (uint32_t)sizeof(AcqTables), &sm.tab_bar);
-      // streams are handed out dynamically (atomic counter): a CTA that starts late — its SM was still busy with another
-      // kernel of the frame pipeline — simply takes fewer of them
-      for (int k = 0;; k++) {
-        const int b = k & 1;
-        if (k >= 2) mbar_wait(&sm.empty[b], ((k >> 1) - 1) & 1);
-        const int it = atomicAdd(&counters[3], 1);
-        if (it >= n_items) { sm.item[b] = -1; mbar_arrive(&sm.full[b]); break; }
-        const int s = track_list[it];
-        sm.item[b] = s;
-        const int head = ctl[s].ring_head;        // even by construction (nin is 800 / 960 / 1120)
-        const float2 *rg = ring + (size_t)s * RADE_RXBUF;
-        TrackStage &st = sm.st[b];
-        mbar_expect_tx(&sm.full[b], (uint32_t)(sizeof(float2) * RADE_RXBUF + sizeof(float) * 2 * RADE_NMF + sizeof(RxCtl)));
-        bulk_g2s(st.rx, rg + head, (uint32_t)(sizeof(float2) * (RADE_RXBUF - head)), &sm.full[b]);
-        if (head) bulk_g2s(st.rx + (RADE_RXBUF - head), rg, (uint32_t)(sizeof(float2) * head), &sm.full[b]);
-        bulk_g2s(st.rs, rowsum + (size_t)s * 2 * RADE_NMF, (uint32_t)(sizeof(float) * 2 * RADE_NMF), &sm.full[b]);
-        bulk_g2s(&st.ctl, ctl + s, (uint32_t)sizeof(RxCtl), &sm.full[b]);
-      }
-    }
-    return;
-  }
-  mbar_wait(&sm.tab_bar, 0);
-  for (int k = 0;; k++) {
-    const int b = k & 1;
-    mbar_wait(&sm.full[b], (k >> 1) & 1);
-    const int s = sm.item[b];
-    if (s < 0) break;
-    TrackStage &st = sm.st[b];
-    const int tmax0 = st.ctl.tmax; const double fmax0 = st.ctl.fmax;
-    const int rot = st.ctl.n_check % 20;
-    if (tid < TRK_REFRESH) {
-      // ---- check_pilots row refresh (radae/dsp.py:288-295, deterministic schedule): rows t_i = 20 i + rot, both pilot
-      // positions, 40 grid frequencies.  lane = (row i, k group kg, tap parity ks): conflict-free shared-memory reads
-      const int ks = tid & 1, kg = (tid >> 1) & 3, i = tid >> 3;
-      const float2 *x0 = st.rx + rot + 20 * i, *x1 = x0 + RADE_NMF;
-      float2 A0[6], B0[6], A1[6], B1[6];
-#pragma unroll
-      for (int j = 0; j < 6; j++) { A0[j] = B0[j] = A1[j] = B1[j] = make_float2(0.f, 0.f); }
-      // software pipeline: the six shared-memory loads of tap n+2 are issued before the 28 packed FMAs of tap n
-      const float4 *csr = reinterpret_cast<const float4 *>(&sm.tab.cs[0][kg * 6]);       // row stride RADE_CSK/2 float4
-      float4 pp = sm.tab.ps4[ks], q0 = csr[ks * (RADE_CSK / 2)], q1 = csr[ks * (RADE_CSK / 2) + 1], q2 = csr[ks * (RADE_CSK / 2) + 2];
-      float2 a = x0[ks], c = x1[ks];
-#pragma unroll 2
-      for (int n = ks; n < RADE_M; n += 2) {
-        const int nn = (n + 2 < RADE_M) ? n + 2 : n;
-        const float4 ppn = sm.tab.ps4[nn], q0n = csr[nn * (RADE_CSK / 2)], q1n = csr[nn * (RADE_CSK / 2) + 1], q2n = csr[nn * (RADE_CSK / 2) + 2];
-        const float2 an = x0[nn], cn = x1[nn];
-        const float2 y0 = ffma2(splat(a.x), make_float2(pp.x, pp.y), ffma2(splat(a.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
-        const float2 y1 = ffma2(splat(c.x), make_float2(pp.x, pp.y), ffma2(splat(c.y), make_float2(pp.z, pp.w), make_float2(0.f, 0.f)));
-        const float4 qq[3] = {q0, q1, q2};
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const float4 q = qq[j];
-          A0[2 * j] = ffma2(y0, splat(q.x), A0[2 * j]);         B0[2 * j] = ffma2(y0, splat(q.y), B0[2 * j]);
-          A0[2 * j + 1] = ffma2(y0, splat(q.z), A0[2 * j + 1]); B0[2 * j + 1] = ffma2(y0, splat(q.w), B0[2 * j + 1]);
-          A1[2 * j] = ffma2(y1, splat(q.x), A1[2 * j]);         B1[2 * j] = ffma2(y1, splat(q.y), B1[2 * j]);
-          A1[2 * j + 1] = ffma2(y1, splat(q.z), A1[2 * j + 1]); B1[2 * j + 1] = ffma2(y1, splat(q.w), B1[2 * j + 1]);
-        }
-        pp = ppn; q0 = q0n; q1 = q1n; q2 = q2n; a = an; c = cn;
-      }
-      // the even-tap lane finishes k = 6 kg + {0,1,2}, the odd-tap lane k = 6 kg + {3,4,5}: swap the other three partials
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        float2 mine[4], send[4];
-        mine[0] = ks ? A0[j + 3] : A0[j]; send[0] = ks ? A0[j] : A0[j + 3];
-        mine[1] = ks ? B0[j + 3] : B0[j]; send[1] = ks ? B0[j] : B0[j + 3];
-        mine[2] = ks ? A1[j + 3] : A1[j]; send[2] = ks ? A1[j] : A1[j + 3];
-        mine[3] = ks ? B1[j + 3] : B1[j]; send[3] = ks ? B1[j] : B1[j + 3];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          mine[q].x += __shfl_xor_sync(0xffffffffu, send[q].x, 1);
-          mine[q].y += __shfl_xor_sync(0xffffffffu, send[q].y, 1);
-        }
-        const int kk = kg * 6 + ks * 3 + j;
-        if (kk <= 20) {
-          float p0, m0, p1, m1;
-          mags_pm(mine[0], mine[1], p0, m0); mags_pm(mine[2], mine[3], p1, m1);
-          if (kk < 20) { s0 += p0; s1 += p1; }
-          if (kk > 0) { s0 += m0; s1 += m1; }
-        }
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-      if ((tid & 7) == 0) {
-        const int r = 20 * i + rot;
-        st.rs[r] = s0; st.rs[RADE_NMF + r] = s1;
-        float *rs = rowsum + (size_t)s * 2 * RADE_NMF;
-        rs[r] = s0; rs[RADE_NMF + r] = s1;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // st.rs is overwritten by a bulk copy two streams later
-      }
-    } else {
-      // ---- refine (radae_rxe.py:202-205, radae/dsp.py:233-270): t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, .1)
-      const int t_lo = max(0, tmax0 - 8);
-      const float2 *rxl = st.rx;
-      refine_dmma<true>(sm.ref, sm.tab.pcd, [rxl](int i) { return rxl[i]; }, t_lo, tmax0 + 8 - t_lo, fmax0 - 1, fmax0 + 1, 0.1,
-                        tid - TRK_REFRESH, 1);
-    }
-    if (tid >= TRK_REFRESH) {
-      // spot correlations in complex128 (radae/dsp.py:305-314) by the refine warps, which finish before the row refresh does:
-      // refine warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]| at the refined timing / smoothed frequency
-      const int wp = (tid - TRK_REFRESH) >> 5, lane = tid & 31;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int s = track_list[it];
+    const int head = ctl[s].ring_head, tmax0 = ctl[s].tmax; const double fmax0 = ctl[s].fmax;
+    const float2 *rg = ring + (size_t)s * RADE_RXBUF;
+    auto load = [rg, head](int i) { return __ldg(rg + ring_idx(head, i)); };
+    // ---- refine (radae_rxe.py:202-205, radae/dsp.py:233-270): t in [max(0,tmax-8), tmax+8), f in arange(fmax-1, fmax+1, .1)
+    const int t_lo = max(0, tmax0 - 8);
+    refine_moments(sm.ref, sm.bk, sm.phd, sm.pcd, load, t_lo, tmax0 + 8 - t_lo, fmax0, tid, 1);
+    // ---- spot correlations in complex128 (radae/dsp.py:305-314): warp k -> |sum conj(w_vec*rx[o_k + n]) * q_k[n]| at the
+    // refined timing / smoothed frequency
+    {
+      const int wp = tid >> 5, lane = tid & 31;
       const int tm = sm.ref.best_found ? sm.ref.best_t : tmax0;
       const double fm = 0.9 * fmax0 + 0.1 * (sm.ref.best_found ? sm.ref.best_f : fmax0);
       const int o = tm + (wp == 0 ? 0 : wp == 2 ? RADE_M + RADE_NCP : RADE_NMF);
       const double w = 2.0 * M_PI * fm / RADE_FS;
-      double sn, cs, s32, c32; sincos(w * (double)lane, &sn, &cs); sincos(w * 32.0, &s32, &c32);
-      double2 e = make_double2(cs, -sn); const double2 step = make_double2(c32, -s32);
+      float2 xv[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) xv[j] = load(o + lane + 32 * j);
+      if (tid <= 32) {                               // 33 sincos instead of 256
+        double sn, cs; sincos(w * (double)tid, &sn, &cs);
+        if (tid < 32) sm.spot_e[tid] = make_double2(cs, -sn); else sm.spot_step = make_double2(cs, -sn);
+      }
+      group_sync(1, REF_THREADS);
+      double2 e = sm.spot_e[lane]; const double2 step = sm.spot_step;
       double ax = 0.0, ay = 0.0;
 #pragma unroll
-      for (int n = lane; n < RADE_M; n += 32) {
-        const float2 xv = st.rx[o + n];
-        const float2 qf = (wp < 2) ? make_float2(sm.tab.ps4[n].x, sm.tab.ps4[n].y) : sm.tab.pend[n];
-        const double2 v = dcmul(e, make_double2((double)xv.x, (double)xv.y));                       // w_vec * rx
+      for (int j = 0; j < 5; j++) {
+        const int n = lane + 32 * j;
+        const float2 qf = (wp < 2) ? sm.pp[n] : sm.pend[n];
+        const double2 v = dcmul(e, make_double2((double)xv[j].x, (double)xv[j].y));                 // w_vec * rx
         const double2 r2 = dcmul(make_double2(v.x, -v.y), make_double2((double)qf.x, (double)qf.y));
         ax += r2.x; ay += r2.y;
         e = dcmul(e, step);
       }
 #pragma unroll
       for (int q = 16; q > 0; q >>= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, q); ay += __shfl_xor_sync(0xffffffffu, ay, q); }
-      if (lane == 0) sm.spot[wp] = hypot(ax, ay);
+      if (lane == 0) tmp[s].spot[wp] = hypot(ax, ay);
+      if (tid == 0) { tmp[s].best_found = sm.ref.best_found; tmp[s].best_t = sm.ref.best_t; tmp[s].best_f = sm.ref.best_f; }
     }
-    group_sync(3, TRK_CONSUMERS);
-    int tmax = sm.ref.best_found ? sm.ref.best_t : tmax0;
-    const double fhat = sm.ref.best_found ? sm.ref.best_f : fmax0;
-    const double fmax = 0.9 * fmax0 + 0.1 * fhat;
-    // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (radae/dsp.py:297-300): per-warp partial
-    // sums now, thread 0 adds the 16 + 16 partials
-    {
-      float a = 0.f, c = 0.f;
-      for (int q = tid; q < RADE_NMF; q += TRK_CONSUMERS) { a += st.rs[q]; c += st.rs[RADE_NMF + q]; }
-      a = warp_sum(a); c = warp_sum(c);
-      if ((tid & 31) == 0) { sm.scratch[tid >> 5] = a; sm.scratch[16 + (tid >> 5)] = c; }
-    }
-    group_sync(3, TRK_CONSUMERS);
-    if (tid == 0) {
-      float sa = 0.f, sb = 0.f;
-      for (int q = 0; q < TRK_CONSUMERS / 32; q++) { sa += sm.scratch[q]; sb += sm.scratch[16 + q]; }
-      const float kf = 1.2533141373155001f;
-      const float sigma_r = ((sa / (float)(RADE_NMF * RADE_NFCOARSE)) / kf + (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / kf) / 2.0f;
-      RxCtl &c = ctl[s];
-      const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-4 / 5.0));
-      const double Dthresh_eoo = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
-      const double D = sm.spot[0] + sm.spot[1], De = sm.spot[2] + sm.spot[3];
-      const int valid = D > Dthresh, endofover = De > Dthresh_eoo;
-      c.Dthresh = (float)Dthresh; c.Dtmax12 = (float)D; c.Dtmax12_eoo = (float)De;
-      // timing slips (radae_rxe.py:208-218): the adjusted tmax is used for this call's extraction too
-      int nin = RADE_NMF;
-      if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
-      if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
-      c.tmax = tmax; c.fmax = fmax; c.n_check = st.ctl.n_check + 1;
-      const int synced_count = st.ctl.synced_count + 1;
-      c.synced_count = synced_count;
-      int uw_fail = 0;
-      if (synced_count % RADE_SYNCED_ONE_SEC == 0) {
-        if (uw_errors[s] > RADE_UW_THRESH) uw_fail = 1;
-        uw_errors[s] = 0;
-      }
-      const int valid_output = !endofover;
-      c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = valid_output; c.ran_sync = 1;
-      // sync-state branch of the state machine (radae_rxe.py:276-296); search / candidate streams: rx_finish_kernel
-      int next = ST_SYNC, vc = st.ctl.valid_count;
-      if (valid) vc = RADE_NMF_UNSYNC;
-      else { vc -= 1; if (vc == 0) next = ST_SEARCH; }
-      if (endofover || uw_fail) next = ST_SEARCH;
-      if (next == ST_SEARCH) nin = RADE_NMF;
-      c.valid_count = vc; c.state = next; c.nin = nin;
-      const int ret = valid_output | (endofover << 1);
-      c.ret = ret; ret_out[s] = ret; dec_active[s] = (unsigned char)valid_output; nin_out[s] = nin;
-    }
-    group_sync(3, TRK_CONSUMERS);
-    if (tid == 0) mbar_arrive(&sm.empty[b]);
+    group_sync(1, REF_THREADS);                     // best_* and spot_e are rewritten during the next item
   }
+}
+
+// Sync-state part of the state machine (radae_rxe.py:208-218, :276-296) and check_pilots' decisions (radae/dsp.py:297-320) for a
+// stream that was tracked this call: called by every thread of the stream's rx_demod CTA before the demodulation proper.
+__device__ void track_tail(RxCtl &c, const TrackTmp &tt, const float *__restrict__ rs, int *__restrict__ uw_errors, int s,
+                           int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out, float *scratch) {
+  // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums
+  const float sigma_r = sigma_r_from_rowsums(rs, scratch);
+  if (threadIdx.x == 0) {
+    const int tmax0 = c.tmax; const double fmax0 = c.fmax;
+    int tmax = tt.best_found ? tt.best_t : tmax0;
+    const double fhat = tt.best_found ? tt.best_f : fmax0;
+    const double fmax = 0.9 * fmax0 + 0.1 * fhat;
+    const double Dthresh = (double)(2.f * sigma_r) * K_ACQ_1E4;
+    const double Dthresh_eoo = (double)(2.f * sigma_r) * K_ACQ_1E5;
+    const double D = tt.spot[0] + tt.spot[1], De = tt.spot[2] + tt.spot[3];
+    const int valid = D > Dthresh, endofover = De > Dthresh_eoo;
+    c.Dthresh = (float)Dthresh; c.Dtmax12 = (float)D; c.Dtmax12_eoo = (float)De;
+    // timing slips (radae_rxe.py:208-218): the adjusted tmax is used for this call's extraction too
+    int nin = RADE_NMF;
+    if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
+    if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
+    c.tmax = tmax; c.fmax = fmax; c.n_check = c.n_check + 1;
+    const int synced_count = c.synced_count + 1;
+    c.synced_count = synced_count;
+    int uw_fail = 0;
+    if (synced_count % RADE_SYNCED_ONE_SEC == 0) {
+      if (uw_errors[s] > RADE_UW_THRESH) uw_fail = 1;
+      uw_errors[s] = 0;
+    }
+    const int valid_output = !endofover;
+    c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = valid_output; c.ran_sync = 1;
+    // sync-state branch of the state machine (radae_rxe.py:276-296); search / candidate streams: rx_finish_kernel
+    int next = ST_SYNC, vc = c.valid_count;
+    if (valid) vc = RADE_NMF_UNSYNC;
+    else { vc -= 1; if (vc == 0) next = ST_SEARCH; }
+    if (endofover || uw_fail) next = ST_SEARCH;
+    if (next == ST_SEARCH) nin = RADE_NMF;
+    c.valid_count = vc; c.state = next; c.nin = nin;
+    const int ret = valid_output | (endofover << 1);
+    c.ret = ret; ret_out[s] = ret; dec_active[s] = (unsigned char)valid_output; nin_out[s] = nin;
+  }
+  __syncthreads();
 }
 
 // ================================================================= frequency correction + OFDM demod + pilot EQ
@@ -626,12 +726,15 @@ struct DemodSmem {
 
 __global__ void __launch_bounds__(192)
 rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__ ring, float *__restrict__ z_hat,
-                float *__restrict__ eoo_out, const unsigned char *__restrict__ active) {
+                float *__restrict__ eoo_out, const unsigned char *__restrict__ active, const TrackTmp *__restrict__ tmp,
+                const float *__restrict__ rowsum, int *__restrict__ uw_errors, int *__restrict__ ret_out,
+                unsigned char *__restrict__ dec_active, int *__restrict__ nin_out) {
   __shared__ DemodSmem sm;
   const int s = blockIdx.x, tid = threadIdx.x;
   if (active && !active[s]) return;
   RxCtl &c = ctl[s];
-  if (!c.ran_sync) return;
+  if (!c.tracking) return;                        // in sync when this call began (flag written by rx_bpf with the track list)
+  track_tail(c, tmp[s], rowsum + (size_t)s * 2 * RADE_NMF, uw_errors, s, ret_out, dec_active, nin_out, sm.scratch);
   const int head = c.ring_head, tmax = c.tmax, endofover = c.endofover;
   const float2 *rg = ring + (size_t)s * RADE_RXBUF;
   const double w = 2.0 * M_PI * c.fmax / RADE_FS;
@@ -658,8 +761,15 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   if (tid < (RADE_NS + 2) * RADE_NC) {              // 180 DFT outputs, 160-point each
     const int r = tid / RADE_NC, cc = tid % RADE_NC;
     float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 4
-    for (int k = 0; k < RADE_M; k++) cmac(acc, sm.xs[r][k], T.Wfwd[k * RADE_NC + cc]);
+    const float2 *wf = T.Wfwd + cc;
+#pragma unroll 1
+    for (int k0 = 0; k0 < RADE_M; k0 += 16) {      // 16 twiddles in flight per thread (read-only path), sums in tap order
+      float2 w[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) w[j] = __ldg(wf + (k0 + j) * RADE_NC);
+#pragma unroll
+      for (int j = 0; j < 16; j++) cmac(acc, sm.xs[r][k0 + j], w[j]);
+    }
     sm.sym[r][cc] = acc;
   }
   __syncthreads();
@@ -769,7 +879,7 @@ rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       int tmax = 0; double fmax = 0.0;
       if (val > 0.f) { tmax = (int)(idx / RADE_NFCOARSE); fmax = (double)T.fcoarse[idx % RADE_NFCOARSE]; }
       c.tmax = tmax; c.fmax = fmax;
-      const double Dthresh = (double)(2.f * sigma_r) * sqrt(-log(1e-5 / 5.0));
+      const double Dthresh = (double)(2.f * sigma_r) * K_ACQ_1E5;
       c.Dthresh = (float)Dthresh; c.Dtmax12 = val;
       const int candidate = ((double)val > Dthresh) ? 1 : 0;
       c.candidate = candidate;
@@ -845,6 +955,11 @@ int rx_dsp_init_device() {
     float h[RADE_BPF_NTAP + 3] = {0.f};
     for (int i = 0; i < RADE_BPF_NTAP; i++) h[i] = th.bpf_h[i];
     CUDA_CHECK(cudaMemcpyToSymbol(c_bpf_h, h, sizeof(h)));
+    static AcqConst ac;
+    for (int n = 0; n < RADE_M; n++) { const float px = th.p[n].real(), py = th.p[n].imag(); ac.ps4[n] = make_float4(px, py, py, -px); }
+    memcpy(ac.basis, th.srch_basis.data(), sizeof(ac.basis));
+    memcpy(ac.expand, th.srch_expand.data(), sizeof(ac.expand));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_acq, &ac, sizeof(ac)));
   }
   CUDA_CHECK(cudaFuncSetAttribute(rx_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DetectSmem)));
   CUDA_CHECK(cudaFuncSetAttribute(rx_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrackSmem)));
@@ -869,19 +984,31 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   rx_bpf_kernel<<<S, BPF_THREADS, 0, stream>>>(T, B.ctl, B.ring, B.bpf_mem, rx_in, active, bpf_en, B.search_list, B.track_list, cnt, ls);
   prof->end(K_RX_BPF);
   if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_fork, stream)); CUDA_CHECK(cudaStreamWaitEvent(ss, B.ev_fork, 0)); }
+  // sync branch: the row refresh (fp32) and the refine + spot correlations (fp64) are independent -> two streams, joined before
+  // rx_demod, whose head holds the state machine that needs both
+  const int trk_grid = S < n_sm * 8 ? S : n_sm * 8;
+  const bool fork2 = fork && B.side2_stream;
+  cudaStream_t s2 = fork2 ? B.side2_stream : stream;
+  if (fork2) CUDA_CHECK(cudaStreamWaitEvent(s2, B.ev_fork, 0));
   prof->begin(K_RX_TRACK);
-  rx_track_kernel<<<S < n_sm ? S : n_sm, TRK_THREADS, sizeof(TrackSmem), stream>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.track_list,
-                                                                               cnt, ret_out, B.dec_active, B.nin);
-  prof->end(K_RX_TRACK); prof->begin(K_RX_DETECT);
+  rx_track_kernel<<<S < n_sm * 4 ? S : n_sm * 4, REF_THREADS, sizeof(TrackSmem), s2>>>(T, B.ctl, B.ring, B.track_list, cnt, (TrackTmp *)B.track_tmp);
+  prof->end(K_RX_TRACK);
+  if (fork2) CUDA_CHECK(cudaEventRecord(B.ev_join2, s2));
+  prof->begin(K_RX_REFRESH);
+  rx_refresh_kernel<<<(trk_grid + RFR_STREAMS - 1) / RFR_STREAMS, RFR_THREADS, 0, stream>>>(B.ctl, B.ring, B.rowsum, B.track_list, cnt);
+  prof->end(K_RX_REFRESH);
+  if (fork2) CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join2, 0));
+  prof->begin(K_RX_DETECT);
   int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 4) det_grid = n_sm * 4;
   rx_detect_kernel<<<det_grid, DET_THREADS, sizeof(DetectSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
   prof->end(K_RX_DETECT); prof->begin(K_RX_DEMOD);
-  rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active);
+  rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active, (const TrackTmp *)B.track_tmp, B.rowsum, B.uw_errors,
+                                         ret_out, B.dec_active, B.nin);
   prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
   rx_finish_kernel<<<S < 2 * n_sm ? S : 2 * n_sm, 256, sizeof(FinishSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
       reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_list, cnt, cnt_next, S);
   prof->end(K_RX_FINISH);
   if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_join, ss)); CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join, 0)); }
   CUDA_CHECK(cudaGetLastError());
-  return 5;
+  return 6;
 }

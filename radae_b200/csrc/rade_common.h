@@ -110,6 +110,7 @@ struct CoreWeightsDev {
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
   CodecStreamDev enc_stream, dec_stream;
   UmmaCodecDev enc_umma, dec_umma;
+  float one;               // 1.0f as a RUN-TIME value: acc = fma(round(w x), one, acc) is an exact packed add that ptxas cannot contract with the multiply
   int float_fma;           // MEASUREMENT ONLY (RADE_B200_DEBUG_FLOAT_FMA=1): wide float layers with fused multiply-add — not bit-exact, 9 % faster encoder
   long long *trace;        // debug: clock64() stamps of CTA 0's warp roles (rade_b200_debug_trace_*), nullptr in production
   int enc_z_tanh;          // bottleneck 1 (model05): tanh on the latents, src/rade_enc.c:107-113; 0 for bottleneck 3
@@ -145,8 +146,20 @@ struct DspTables {
 };
 
 // constant block the acquisition kernels keep resident in shared memory (rx_detect / rx_track), filled by one bulk copy
+#define RADE_SRANK 6                           // rank of the coarse-grid basis (each of the cos and the sin family), residual < 1e-8
 struct __align__(128) AcqTables {
-  float2 cs[RADE_M][RADE_CSK];   // (cos, sin) of the symmetric coarse grid
+  // Coarse grid in a low-rank basis.  The 40 grid frequencies are +-2.5 k Hz, k = 0..20, over a 160-sample window: time-bandwidth
+  // product 2, so cos(w_k (m + 1/2)) and sin(w_k (m + 1/2)), m = 0..79 (the window folded about its centre), are spanned to
+  // 1e-9 by six vectors each (singular values fall by ~100x per index).  basis[m] = {bc[m][0..3]}, {bc[m][4..5], 0, 0},
+  // {bs[m][0..3]}, {bs[m][4..5], 0, 0};  expand[k] = {ac[k][0..3]}, {ac[k][4..5], as[k][0..1]}, {as[k][2..5]} with
+  // cos(w_k (m + 1/2)) = sum_r ac[k][r] bc[m][r], sin(...) = sum_r as[k][r] bs[m][r]   (tables.cpp, one-sided Jacobi SVD)
+  float4 basis[RADE_M / 2][4];
+  float4 expand[21][3];
+  // fine search around the tracked frequency (refine_moments in ofdm_rx.cu): bk[n][k] = ((n - 79.5) / 80)^k / k!, k = 0..8, and
+  // phd[pos][i] = exp(-j 2 pi (-1 + 0.1 i) / Fs * (79.5 + 960 pos)), the part of the centre / next-frame phase that does not
+  // depend on the stream
+  double bk[RADE_M][10];
+  double2 phd[2][24];
   float4 ps4[RADE_M];            // (p.x, p.y, p.y, -p.x): conj(x)*p = x.x*(.x,.y) + x.y*(.z,.w) with two packed FMAs
   double2 pcd[RADE_M];           // conj(p) widened to complex128 (refine steering vectors)
   float2 pend[RADE_M];           // end-of-over pilot symbol
@@ -161,7 +174,7 @@ struct __align__(16) RxCtl {
   int state, nin, tmax, tmax_candidate;
   int valid_count, synced_count, n_check, bpf_first;
   int ring_head, candidate, endofover, valid_output;
-  int uw_fail, ret, ran_sync, pad1;
+  int uw_fail, ret, ran_sync, tracking;       // tracking: in sync when the current call began (rx_bpf)
 };
 
 // state of the optional TX band-pass filter (radae_tx(txbpf_en=True)); all zero == a new complex_bpf object

@@ -41,6 +41,8 @@ extern "C" const unsigned char rade_b200_default_weights_end[];
 #include <complex>
 struct DspTablesHost {
   std::vector<float> w, bpf_h, fcoarse;
+  std::vector<float> srch_basis, srch_expand;      // AcqTables::basis / ::expand (coarse grid in its low-rank basis)
+  double srch_residual;                            // max |cos / sin - expansion| over the grid, checked at start-up
   std::vector<std::complex<float>> Winv, Wfwd, P, Pend, p, pend, p_w, cs_tab, Pmat, eq_rot, bpf_exp, eoo_base;
   double pilot_gain;
   float bpf_bw, bpf_centre, bpf_alpha;
@@ -61,12 +63,14 @@ struct RxBuffers {
   unsigned char *dec_active;  // [S] valid_output of the last call
   int *nin;                // [S]
   int *search_list;        // [S] streams that need the coarse search this call (built by rx_bpf)
-  int *track_list;         // [S] streams in sync this call (built by rx_bpf) -> persistent rx_track CTAs
+  int *track_list;         // [S] streams in sync this call (built by rx_bpf) -> rx_refresh / rx_track
+  void *track_tmp;         // [S] TrackTmp (ofdm_rx.cu): refine + spot-correlation results handed from rx_track to rx_demod
   int *counters;           // [2][4] ping-pong by call parity: {search entries, search work-item counter, track entries, -};
                            //        rx_finish of call k zeroes the set call k+1 will use
   int parity;              // host-side: which counter set the next call uses
   cudaStream_t side_stream;   // the search branch (rx_detect -> rx_finish) runs here, concurrently with rx_track -> rx_demod
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t side2_stream;  // rx_track (fp64 refine) runs here, concurrently with rx_refresh (fp32) on the main stream
+  cudaEvent_t ev_fork, ev_join, ev_join2;
 };
 
 int ofdm_mod_launch(const DspTables &T, const float *z, float2 *tx, int S, cudaStream_t stream);
@@ -90,7 +94,7 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
 
 // ---- optional per-kernel timing with CUDA events on the context's stream (rade_b200_profile_*)
 enum KernelId { K_CORE_ENC = 0, K_OFDM_MOD, K_EOO, K_CHANNEL, K_LINK_PUSH, K_LINK_POP, K_RX_BPF, K_RX_DETECT, K_RX_TRACK,
-                K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_TX_BPF, K_COUNT };
+                K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_TX_BPF, K_RX_REFRESH, K_COUNT };
 struct Profiler {
   bool on = false;
   cudaStream_t stream = nullptr;

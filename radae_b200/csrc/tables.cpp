@@ -6,7 +6,10 @@
 //   complex_bpf.__init__     radae/dsp.py:40-61 with the float32 arguments radae_rxe.py:104-109 passes
 // Checked against oracle/dsp.py (itself pinned against the reference) by tests/test_tables.py through
 // rade_b200_debug_tables().
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 #include <complex>
 #include <vector>
 #include "rade_common.h"
@@ -72,6 +75,63 @@ void dsp_tables_host(DspTablesHost &T) {
       double a = 2 * M_PI * (2.5 * k) / RADE_FS * n;
       T.cs_tab[n * RADE_CSK + k] = cf((float)std::cos(a), (float)std::sin(a));
     }
+  // Low-rank basis of the coarse grid (AcqTables in rade_common.h): one-sided (Hestenes) Jacobi SVD, in double, of
+  //   C[k][m] = cos(w_k (m + 1/2)), S[k][m] = sin(w_k (m + 1/2)),  k = 0..20, m = 0..79, w_k = 2 pi 2.5 k / Fs.
+  // Rows are rotated pairwise until orthogonal; then row i = sigma_i v_i^T and C = U^T rows.  The RADE_SRANK strongest rows are
+  // the basis, U sigma the expansion coefficients.  The one-sided form keeps the small singular values accurate (the sixth is
+  // 6e-8 of the first; the eigenvalues of C C^T would lose it).
+  {
+    const int NK = 21, NM = RADE_M / 2, R = RADE_SRANK;
+    T.srch_basis.assign(NM * 16, 0.f); T.srch_expand.assign(NK * 12, 0.f); T.srch_residual = 0.0;
+    for (int fam = 0; fam < 2; fam++) {
+      std::vector<double> A(NK * NM), A0, U(NK * NK, 0.0);
+      for (int k = 0; k < NK; k++)
+        for (int m = 0; m < NM; m++) {
+          const double a = 2 * M_PI * (2.5 * k) / RADE_FS * (m + 0.5);
+          A[k * NM + m] = fam ? std::sin(a) : std::cos(a);
+        }
+      A0 = A;
+      for (int k = 0; k < NK; k++) U[k * NK + k] = 1.0;
+      for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0;
+        for (int i = 0; i < NK; i++)
+          for (int j = i + 1; j < NK; j++) {
+            double al = 0, be = 0, ga = 0;
+            for (int m = 0; m < NM; m++) { al += A[i * NM + m] * A[i * NM + m]; be += A[j * NM + m] * A[j * NM + m]; ga += A[i * NM + m] * A[j * NM + m]; }
+            if (std::fabs(ga) <= 1e-300 || std::fabs(ga) <= 1e-17 * std::sqrt(al * be)) continue;
+            off = std::max(off, std::fabs(ga) / std::sqrt(al * be + 1e-300));
+            const double zeta = (be - al) / (2 * ga);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1 + zeta * zeta));
+            const double c = 1 / std::sqrt(1 + t * t), sn = c * t;
+            for (int m = 0; m < NM; m++) { const double x = A[i * NM + m], y = A[j * NM + m]; A[i * NM + m] = c * x - sn * y; A[j * NM + m] = sn * x + c * y; }
+            for (int m = 0; m < NK; m++) { const double x = U[i * NK + m], y = U[j * NK + m]; U[i * NK + m] = c * x - sn * y; U[j * NK + m] = sn * x + c * y; }
+          }
+        if (off < 1e-15) break;
+      }
+      // A0 = U^T A: A0[k][m] = sum_i U[i][k] A[i][m].  Strongest rows first.
+      std::vector<std::pair<double, int>> sv;
+      for (int i = 0; i < NK; i++) { double n2 = 0; for (int m = 0; m < NM; m++) n2 += A[i * NM + m] * A[i * NM + m]; sv.push_back({std::sqrt(n2), i}); }
+      std::sort(sv.begin(), sv.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+      std::vector<double> B(NM * R), E(NK * R);
+      for (int r = 0; r < R; r++) {
+        const int i = sv[r].second; const double sg = sv[r].first;
+        const double scale = std::sqrt(sg);                      // split sigma evenly between basis and coefficients
+        for (int m = 0; m < NM; m++) B[m * R + r] = A[i * NM + m] / sg * scale;
+        for (int k = 0; k < NK; k++) E[k * R + r] = U[i * NK + k] * sg / scale;
+      }
+      // what the kernels will use is the float32 rounding of both tables: measure the residual of exactly that
+      for (int k = 0; k < NK; k++)
+        for (int m = 0; m < NM; m++) {
+          double acc = 0;
+          for (int r = 0; r < R; r++) acc += (double)(float)E[k * R + r] * (double)(float)B[m * R + r];
+          T.srch_residual = std::max(T.srch_residual, std::fabs(acc - A0[k * NM + m]));
+        }
+      for (int m = 0; m < NM; m++)
+        for (int r = 0; r < R; r++) T.srch_basis[m * 16 + fam * 8 + r] = (float)B[m * R + r];
+      for (int k = 0; k < NK; k++)
+        for (int r = 0; r < R; r++) T.srch_expand[k * 12 + fam * 6 + r] = (float)E[k * R + r];
+    }
+  }
   // LS projectors: Pmat[c] = inv(A^T A) A^T, A = [[1, e^{-j w_{m-1} a}], [1, e^{-j w_m a}], [1, e^{-j w_{m+1} a}]]
   const double a = 0.0025 * RADE_FS;
   T.Pmat.resize(NC * 6); T.eq_rot.resize(NC);
@@ -139,12 +199,24 @@ int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> 
     std::vector<unsigned char> blob(sizeof(AcqTables), 0);
     AcqTables *A = reinterpret_cast<AcqTables *>(blob.data());
     for (int n = 0; n < RADE_M; n++) {
-      for (int k = 0; k < RADE_CSK; k++) A->cs[n][k] = f2(T.cs_tab[n * RADE_CSK + k]);
       const float px = T.p[n].real(), py = T.p[n].imag();
       A->ps4[n] = make_float4(px, py, py, -px);
       A->pcd[n] = make_double2((double)px, -(double)py);
       A->pend[n] = f2(T.pend[n]);
     }
+    for (int n = 0; n < RADE_M; n++) {
+      const double sc = (n - 79.5) / 80.0;
+      double v = 1.0;
+      for (int k = 0; k < 10; k++) { A->bk[n][k] = k < 9 ? v : 0.0; v = v * sc / (k + 1); }
+    }
+    for (int pos = 0; pos < 2; pos++)
+      for (int i = 0; i < 24; i++) {
+        const double a = 2 * M_PI * (-1.0 + 0.1 * i) / RADE_FS * (79.5 + RADE_NMF * pos);
+        A->phd[pos][i] = make_double2(std::cos(a), -std::sin(a));
+      }
+    memcpy(A->basis, T.srch_basis.data(), sizeof(A->basis));
+    memcpy(A->expand, T.srch_expand.data(), sizeof(A->expand));
+    if (T.srch_residual > 2e-7) { fprintf(stderr, "libradae_b200: coarse-grid basis residual %.3g\n", T.srch_residual); return -1; }
     if (!(D->acq_tab = (const unsigned char *)up(blob.data(), blob.size()))) return -1;
   }
   D->pilot_gain = (float)T.pilot_gain;

@@ -73,8 +73,42 @@ def test_dsp_tables_match_oracle(lib):
     assert np.array_equal(cget(7, 1152), f.phase_vec_exp[:1152])     # receive filter reads [0,1120), TX filter up to the EOO frame
     h = np.zeros(101, np.float32); lib.rade_b200_debug_tables(16, h.ctypes.data, 101)
     assert np.max(np.abs(h - f.h)) < 1e-8
-    k = np.zeros(4, np.float32); lib.rade_b200_debug_tables(18, k.ctypes.data, 4)
+    k = np.zeros(5, np.float32); assert lib.rade_b200_debug_tables(18, k.ctypes.data, 5) == 5
     assert k[1] == c.bpf_bw and k[2] == c.bpf_centre and k[3] == f.alpha and abs(k[0] - c.pilot_gain) < 1e-5
+
+
+def test_coarse_grid_basis_spans_the_reference_grid(lib, golden):
+    """rx_detect / rx_track evaluate the 40-point coarse frequency grid (radae/dsp.py:163-173, :204-205) in a rank-6 + 6 basis of
+    the folded window.  (1) the float32 tables reproduce cos / sin of every grid point to 2e-7; (2) on a recorded signal the
+    float32 low-rank evaluation is as close to the exact (float64) |Dt| as the reference's own float32 matrix product"""
+    from oracle import dsp as od
+    k = np.zeros(5, np.float32); assert lib.rade_b200_debug_tables(18, k.ctypes.data, 5) == 5
+    basis = np.zeros(80 * 16, np.float32); assert lib.rade_b200_debug_tables(19, basis.ctypes.data, basis.size) == basis.size
+    expand = np.zeros(21 * 12, np.float32); assert lib.rade_b200_debug_tables(20, expand.ctypes.data, expand.size) == expand.size
+    basis = basis.reshape(80, 16); expand = expand.reshape(21, 12)
+    bc, bs = basis[:, 0:6], basis[:, 8:14]
+    ac, as_ = expand[:, 0:6], expand[:, 6:12]
+    assert not basis[:, 6:8].any() and not basis[:, 14:16].any()
+    m = np.arange(80) + 0.5
+    w = 2 * np.pi * 2.5 * np.arange(21) / od.FS
+    res = max(np.abs(ac.astype(np.float64) @ bc.astype(np.float64).T - np.cos(np.outer(w, m))).max(),
+              np.abs(as_.astype(np.float64) @ bs.astype(np.float64).T - np.sin(np.outer(w, m))).max())
+    assert res < 2e-7 and abs(res - k[4]) < 1e-8, (res, k[4])
+    # a received window: |Dt1| over 960 timing offsets x 40 frequencies, three ways
+    c = od.consts()
+    rx = golden("rx_mpp_3dB")["rx_in"][5000:5000 + od.RXBUF].astype(np.complex64)
+    n = np.arange(od.M)
+    Y32 = (np.conj(rx[np.arange(960)[:, None] + n[None, :]]) * c.p.astype(np.complex64)[None, :]).astype(np.complex64)
+    E = np.exp(2j * np.pi * np.outer(n, np.arange(-50, 50, 2.5)) / od.FS)           # the grid of radae/dsp.py:163-165
+    truth = np.abs(Y32.astype(np.complex128) @ E)
+    direct = np.abs(Y32 @ E.astype(np.complex64)).astype(np.float32)
+    ye = (Y32[:, 80:] + Y32[:, 79::-1]).astype(np.complex64); yo = (Y32[:, 80:] - Y32[:, 79::-1]).astype(np.complex64)
+    A = ((ye @ bc).astype(np.complex64) @ ac.T).astype(np.complex64); B = ((yo @ bs).astype(np.complex64) @ as_.T).astype(np.complex64)
+    low = np.zeros((960, 40), np.float32)
+    low[:, 20:40] = np.abs(A + 1j * B)[:, 0:20]; low[:, 19::-1] = np.abs(A - 1j * B)[:, 1:21]
+    e_direct = np.sqrt(np.mean((direct - truth) ** 2)) / truth.mean(); e_low = np.sqrt(np.mean((low - truth) ** 2)) / truth.mean()
+    assert e_low < 5e-7 and e_low < 1.5 * e_direct, (e_low, e_direct)
+    assert np.unravel_index(low.argmax(), low.shape) == np.unravel_index(truth.argmax(), truth.shape)
 
 
 def test_product_fails_loudly_without_a_gpu(lib):

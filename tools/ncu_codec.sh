@@ -17,3 +17,8 @@ for r in rows[2:]:
         if any(w in k for w in ["time_duration.sum","wavefronts","pipe_tensor","issue_active.avg.pct","bank_conflicts","warps_active.avg.pct","dram__bytes_read.sum","dram__bytes_write.sum","xbar2l1tex_read_bytes.sum","smsp__inst_executed.sum","warp_issue_stalled","sm__cycles_elapsed.max","shared_op","lsu_mem_shared"]):
             if d[k] not in ("","0","n/a"): print("  %-90s %s"%(k,d[k]))
 PY
+# per-instruction sampling (stall reasons) of the encoder kernel, SASS view
+ncu -i gpurun_out/${tag}_codec_umma.ncu-rep --page source --csv --print-source sass --kernel-name regex:core_encoder_umma_kernel > gpurun_out/${tag}_enc_source.csv 2>/dev/null
+ncu -i gpurun_out/${tag}_codec_umma.ncu-rep --page source --csv --print-source sass --kernel-name regex:core_decoder_umma_kernel > gpurun_out/${tag}_dec_source.csv 2>/dev/null
+rm -f gpurun_out/${tag}_codec_umma.ncu-rep
+ls -la gpurun_out/ | tail -5
