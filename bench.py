@@ -463,7 +463,9 @@ def run_gpu(args):
     try:                                                  # DRAM bytes per launch from the committed ncu --set full capture
         import glob
         for fn in sorted(glob.glob(os.path.join(REPO, "profiles", "r*_traffic.json"))):
-            traffic = json.load(open(fn))["bytes_per_launch"].get(dom, traffic)
+            bpl = json.load(open(fn))["bytes_per_launch"]
+            umma_codec = os.environ.get("RADE_B200_CODEC", "umma") != "mma"
+            traffic = bpl.get(dom.replace("_kernel", "_umma_kernel") if umma_codec else dom, bpl.get(dom, traffic))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
@@ -504,9 +506,9 @@ def run_gpu(args):
             feat_err = {"error": repr(e)}
 
     # what binds, next to the HBM fraction: pipe utilisations of the dominant kernels from the committed ncu --set full captures
-    # (profiles/r02_pipe_util.json; captured with the same command line, not in this run)
+    # (profiles/r03_pipe_util.json; captured with the same command line, not in this run)
     try:
-        pu = json.load(open(os.path.join(REPO, "profiles", "r02_pipe_util.json")))
+        pu = json.load(open(os.path.join(REPO, "profiles", "r03_pipe_util.json")))
         roofline["pipes"] = {k: v for k, v in pu.items() if k in kernels or k == "source"}
     except Exception:
         pass
@@ -621,7 +623,7 @@ def run_e2e(b, S, feats_host, codec_only, K, world, dist, torch, n_ctx=1, weight
         fused = {"value": S * world * F_PER_STEP * K / dtf, "unit": "frames/s", "h2d_bytes_per_step": int(S * 432 * 4), "d2h_bytes_per_step": int(S * (432 * 4 + 4)),
                  "steps": K, "host_threads": 1, "valid_output_fraction": float(vf.mean() / K),
                  "timing": "host wall clock around ONE rade_b200_loopback_run call for K modem frames per stream: every frame S x 432 features up from pinned host memory, "
-                           "S x 432 features + S return codes back (double-buffered copy streams next to the kernels); the modem samples stay on the device; max over ranks"}
+                           "S x 432 features + S return codes back (double-buffered copy streams next to the kernels); the modem samples stay on the device; no L2 flush between frames (the device-timed `value` flushes before every step); max over ranks"}
     run(0, 14 if not codec_only else 2)                               # warm-up incl. acquisition
     if not codec_only:
         c["valid"][:] = 0

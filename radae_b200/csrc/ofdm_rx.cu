@@ -15,9 +15,13 @@
 // ever reads back from its two 960x40 complex grids = 614 KB/stream), a 128-byte control block.
 // Kernels (one launch each per rade_rx call; every stream branches on its own state):
 //   rx_bpf (all streams; builds the search list and the track list)
-//     -> rx_track (persistent, streams in sync: refine on the FP64 tensor cores + row refresh + sync-state machine) -> rx_demod
+//     -> rx_refresh (streams in sync: 48-row refresh of the |Dt| row sums, fp32)   | two streams,
+//     -> rx_track   (streams in sync: refine in complex128 + spot correlations)    | concurrently
+//     -> rx_demod   (sync-state machine at its head, then frequency correction, DFT, pilot EQ)
 //     -> rx_detect (persistent over the search list: coarse grid search) -> rx_finish (search / candidate state machine)
-//   the second branch runs on a side stream concurrently with the first; both join before the core decoder.
+//   the search branch runs on a side stream concurrently with the sync branch; both join before the core decoder.
+// The two search kernels evaluate the coarse grid in a low-rank basis (proj_tap / expand_*), the refine as moments of the
+// window (refine_moments); rx_finish keeps the matrix form on the FP64 tensor cores (refine_dmma) for the +-10 Hz first fix.
 #include "rade_common.h"
 #include "rade_host.h"
 #include "tma.cuh"
@@ -129,6 +133,22 @@ struct AcqConst {
 };
 __constant__ AcqConst c_acq;
 
+
+// three block-wide sums at once (one pass of barriers), results valid in every thread; scratch: >= 96 floats
+__device__ void block_sum3(float &a, float &b, float &c, float *scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  __syncthreads();
+  if (lane == 0) { scratch[w] = a; scratch[32 + w] = b; scratch[64 + w] = c; }
+  __syncthreads();
+  if (w < 3) {
+    float t = (lane < nw) ? scratch[32 * w + lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32 * w] = t;
+  }
+  __syncthreads();
+  a = scratch[0]; b = scratch[32]; c = scratch[64];
+}
 
 // ================================================================= band-pass filter + ring append
 // 101-tap real FIR on complex samples.  Each thread produces four consecutive outputs from a sliding register window
@@ -332,7 +352,7 @@ __device__ __forceinline__ int arange_len(double start, double stop, double step
 // otherwise warp = (pilot position, half of the n-tiles) with a single t tile.
 template <bool WIDE_T, typename Load>
 __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Load load, int t_lo, int nt,
-                            double f_start, double f_stop, double f_step, int g, int bar, long long *stamps = nullptr) {
+                            double f_start, double f_stop, double f_step, int g, int bar) {
   constexpr int NQ = WIDE_T ? 6 : 3;              // n-tiles per warp
   const int nf_all = arange_len(f_start, f_stop, f_step);
   const double delta = (f_start + f_step) - f_start;
@@ -346,7 +366,6 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
   for (int c0 = 0; c0 < nf_all; c0 += REF_NFP) {
     const int nf = min(REF_NFP, nf_all - c0);
     group_sync(bar, REF_THREADS);                 // previous pass done with vtab / d1 / d2
-    if (stamps && g == 0) stamps[0] = clock64();
     // steering vectors for this pass: thread = (f, 32-tap segment), one sincos pair + 31 rotations (|error| ~ 1e-15)
     for (int task = g; task < REF_NFP * 5; task += REF_THREADS) {
       const int fi = task / 5, seg = task % 5;
@@ -367,7 +386,6 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
       }
     }
     group_sync(bar, REF_THREADS);
-    if (stamps && g == 0) stamps[1] = clock64();
     {
       const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
       const int half = wr >> 1, mt = WIDE_T ? (wr & 1) : 0, q0 = WIDE_T ? 0 : 3 * (wr & 1);
@@ -405,7 +423,6 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
       }
     }
     group_sync(bar, REF_THREADS);
-    if (stamps && g == 0) stamps[2] = clock64();
     float bm = -1.f; int bo = 0x7fffffff;
     for (int q = g; q < nf * nt; q += REF_THREADS) {
       const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
@@ -443,7 +460,7 @@ __device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Loa
 // rounding to csingle (radae/dsp.py:255-257 is reproduced from there on: d1, d2 rounded separately, then |csingle(d1 + d2)|).
 template <typename Load>
 __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const double2 (*phd)[24], const double2 *pcd, Load load, int t_lo, int nt, double f0,
-                               int g, int bar, long long *stamps = nullptr) {
+                               int g, int bar) {
   const double f_start = f0 - 1, f_stop = f0 + 1, f_step = 0.1;
   const int nf_all = min(arange_len(f_start, f_stop, f_step), REF_NFP);
   const double delta = (f_start + f_step) - f_start;
@@ -468,7 +485,6 @@ __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const do
     }
   }
   group_sync(bar, REF_THREADS);
-  if (stamps && g == 0) stamps[0] = clock64();
   const int wdx = g & 31, qt = g >> 5;               // window = (pilot position, timing offset), quarter of the taps
   const int pos = wdx >> 4, ti = wdx & 15;
   {
@@ -488,7 +504,6 @@ __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const do
     for (int k = 0; k < REF_NK; k++) sm.part[qt][wdx][k] = M[k];
   }
   group_sync(bar, REF_THREADS);
-  if (stamps && g == 0) stamps[1] = clock64();
   {
     // thread = (window, frequencies qt, qt + 4, ...): add the four partial moments, Horner per frequency, phase, round to csingle
     double2 M[REF_NK];
@@ -510,7 +525,6 @@ __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const do
       }
   }
   group_sync(bar, REF_THREADS);
-  if (stamps && g == 0) stamps[2] = clock64();
   float bm = -1.f; int bo = 0x7fffffff;
   for (int q = g; q < nf_all * nt; q += REF_THREADS) {
     const int fi = q / nt, t2 = q - fi * nt;         // ord = q: f outer loop, t inner loop
@@ -538,12 +552,12 @@ __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const do
 }
 
 // sigma_r = (mean|Dt1| + mean|Dt2|) / (2*sqrt(pi/2)) from the row sums, float32 like the reference's np.mean
-__device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scratch) {
-  float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < RADE_NMF; i += blockDim.x) { a += rs[i]; b += rs[RADE_NMF + i]; }
-  const float sa = block_sum(a, scratch), sb = block_sum(b, scratch);
+__device__ float sigma_r_from_rowsums(const float *rs /* [2][960] */, float *scratch /* >= 96 floats */) {
+  float a = 0.f, b = 0.f, z = 0.f;
+  for (int i = threadIdx.x; i < RADE_NMF; i += blockDim.x) { a += __ldg(rs + i); b += __ldg(rs + RADE_NMF + i); }
+  block_sum3(a, b, z, scratch);
   const float k = 1.2533141373155001f;              // (pi/2)**0.5 as float32
-  const float s1 = (sa / (float)(RADE_NMF * RADE_NFCOARSE)) / k, s2 = (sb / (float)(RADE_NMF * RADE_NFCOARSE)) / k;
+  const float s1 = (a / (float)(RADE_NMF * RADE_NFCOARSE)) / k, s2 = (b / (float)(RADE_NMF * RADE_NFCOARSE)) / k;
   return (s1 + s2) / 2.0f;
 }
 
@@ -720,7 +734,8 @@ struct DemodSmem {
   float2 sym[RADE_NS + 2][RADE_NC];
   float2 pil[2][RADE_NC];
   float2 rotc[RADE_NC];
-  float scratch[32];
+  double2 e1[32], e32[6], estep[RADE_NS + 2];     // exp(-j w l), exp(-j w 32 h), exp(-j w 192 r): 45 double sincos per stream instead of 320
+  float scratch[96];
   float mag;
 };
 
@@ -740,24 +755,34 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   const double w = 2.0 * M_PI * c.fmax / RADE_FS;
   const double2 P0 = make_double2(c.rx_phase_re, c.rx_phase_im);
   // rx_phase_vec[n] = rx_phase * exp(-j w (n+1)) (closed form of the recursion radae_rxe.py:227-231), stored csingle;
-  // keep only the M samples of each symbol after Ncp + time_offset = 16.  Thread t owns sample k = t of every symbol
-  // (t < 160): one complex128 sincos, then one rotation by exp(-j w 192) per symbol.
+  // keep only the M samples of each symbol after Ncp + time_offset = 16.  The phasors are products of three table entries:
+  // n + 1 = 32 h + l + 192 r.  Double sincos is a long dependent chain on this part; 46 threads do one each instead of 160 doing two.
+  double2 phase_next = make_double2(0.0, 0.0);
+  if (tid < 32 + 6 + RADE_NS + 2 + 1) {
+    const double arg = tid < 32 ? (double)tid : tid < 38 ? 32.0 * (tid - 32) : tid < 38 + RADE_NS + 2 ? (double)RADE_SYM * (tid - 38) : (double)RADE_NEOO;
+    double sn, cs; sincos(w * arg, &sn, &cs);
+    const double2 e = make_double2(cs, -sn);
+    if (tid < 32) sm.e1[tid] = e; else if (tid < 38) sm.e32[tid - 32] = e; else if (tid < 38 + RADE_NS + 2) sm.estep[tid - 38] = e;
+    else phase_next = dcmul(P0, e);
+  }
+  float2 xin[RADE_NS + 2];
+  const int n0 = RADE_NCP + RADE_TIME_OFFSET + tid;
   if (tid < RADE_M) {
-    const int n0 = RADE_NCP + RADE_TIME_OFFSET + tid;
-    double sn, cs, ss, cc; sincos(w * (double)(n0 + 1), &sn, &cs); sincos(w * (double)RADE_SYM, &ss, &cc);
-    double2 v = dcmul(P0, make_double2(cs, -sn)); const double2 step = make_double2(cc, -ss);
+#pragma unroll
+    for (int r = 0; r < RADE_NS + 2; r++) xin[r] = __ldg(rg + ring_idx(head, tmax - RADE_NCP + n0 + r * RADE_SYM));
+  }
+  __syncthreads();                                // everybody has read rx_phase
+  if (tid == 32 + 6 + RADE_NS + 2) { c.rx_phase_re = phase_next.x; c.rx_phase_im = phase_next.y; }
+  if (tid < RADE_M) {
+    const int a = n0 + 1;
+    const double2 v0 = dcmul(P0, dcmul(sm.e32[a >> 5], sm.e1[a & 31]));
 #pragma unroll
     for (int r = 0; r < RADE_NS + 2; r++) {
-      sm.xs[r][tid] = cmul(rg[ring_idx(head, tmax - RADE_NCP + n0 + r * RADE_SYM)], make_float2((float)v.x, (float)v.y));
-      v = dcmul(v, step);
+      const double2 v = dcmul(v0, sm.estep[r]);
+      sm.xs[r][tid] = cmul(xin[r], make_float2((float)v.x, (float)v.y));
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    double sn, cs; sincos(w * (double)RADE_NEOO, &sn, &cs);
-    const double2 v = dcmul(P0, make_double2(cs, -sn));
-    c.rx_phase_re = v.x; c.rx_phase_im = v.y;
-  }
   if (tid < (RADE_NS + 2) * RADE_NC) {              // 180 DFT outputs, 160-point each
     const int r = tid / RADE_NC, cc = tid % RADE_NC;
     float2 acc = make_float2(0.f, 0.f);
@@ -800,18 +825,21 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
       s2 = im * im;
     }
     if (tid < 2 * RADE_NC) { const float2 pl = sm.pil[tid / RADE_NC][tid % RADE_NC]; pw = pl.x * pl.x + pl.y * pl.y; }
-    const float S1 = block_sum(s1, sm.scratch), S2 = block_sum(s2, sm.scratch), PW = block_sum(pw, sm.scratch);
+    block_sum3(s1, s2, pw, sm.scratch);
+    const float S1 = s1, S2 = s2, PW = pw;
     if (tid == 0) {
-      double snr = (double)S1 / (2.0 * ((double)S2 + 1e-12)) - 1.0;
-      if (snr <= 0.0) snr = 0.1;
-      const double snrdB = (10.0 * log10(snr) - 2.513) / 0.8070;
-      const double Rs = (double)RADE_FS / RADE_M;
-      const double snr3k = snrdB + 10.0 * log10(Rs * RADE_NC / 3000.0) + 10.0 * log10((double)(RADE_M + RADE_NCP) / RADE_M);
-      c.snr_est = 0.9 * c.snr_est + 0.1 * snr3k;
       float mag = sqrtf(PW / (float)(2 * RADE_NC)) + 1e-6f;
       sm.mag = mag * T.p0_abs / T.pilot_gain;
     }
     __syncthreads();
+    if (tid == 160) {                               // a thread with nothing to do in the equaliser: the float64 log10 is a long chain
+      double snr = (double)S1 / (2.0 * ((double)S2 + 1e-12)) - 1.0;
+      if (snr <= 0.0) snr = 0.1;
+      const double snrdB = (10.0 * log10(snr) - 2.513) / 0.8070;
+      // + 10 log10(Rs Nc / 3000) + 10 log10((M + Ncp) / M), Rs = Fs / M (dsp.py:452-455), as float64 evaluates them
+      const double snr3k = snrdB + -3.010299956639812 + 0.7918124604762482;
+      c.snr_est = 0.9 * c.snr_est + 0.1 * snr3k;
+    }
     // phase-only EQ with the channel linearly interpolated between the two pilot rows, then demap (dsp.py:466-474, :507-512)
     if (tid < RADE_NS * RADE_NC) {
       const int r = 1 + tid / RADE_NC, cc = tid % RADE_NC;
@@ -822,7 +850,7 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
       const float2 rotv = (m > 0.f) ? make_float2(ch.x / m, -ch.y / m) : make_float2(1.f, 0.f);
       const float2 v = cmul(sm.sym[r][cc], rotv);
       float *z = z_hat + (size_t)s * RADE_NZMF * RADE_LATENT;
-      z[2 * tid] = v.x / sm.mag; z[2 * tid + 1] = v.y / sm.mag;
+      reinterpret_cast<float2 *>(z)[tid] = make_float2(v.x / sm.mag, v.y / sm.mag);
     }
   } else {
     // end of over: common phase from P, E, E (dsp.py:513-524); rows 2..4 carry 90 data symbols
@@ -848,7 +876,7 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
 // CTAs stride over the search list; inactive streams only get their outputs filled in.
 struct FinishSmem {
   RefineSmem ref;
-  float scratch[32];
+  float scratch[96];
   int do_refine;
 };
 
@@ -999,7 +1027,7 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   prof->end(K_RX_REFRESH);
   if (fork2) CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join2, 0));
   prof->begin(K_RX_DETECT);
-  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 4) det_grid = n_sm * 4;
+  int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 12) det_grid = n_sm * 12;      // 64-thread CTAs, 81 registers: 12 per SM
   rx_detect_kernel<<<det_grid, DET_THREADS, sizeof(DetectSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
   prof->end(K_RX_DETECT); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active, (const TrackTmp *)B.track_tmp, B.rowsum, B.uw_errors,
