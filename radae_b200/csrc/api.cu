@@ -18,7 +18,7 @@ struct rade_batch {
   cudaStream_t tx_stream; cudaEvent_t ev_txfork, ev_txjoin; int pipelined;
   // rade_b200_loopback_step_dev replays the whole step (9 kernels on up to 3 streams) as ONE CUDA graph launch; two
   // instances because the receiver's work-list counters ping-pong between calls
-  struct StepGraph { const void *key[5]; cudaGraphExec_t exec; };
+  struct StepGraph { const void *key[5]; cudaGraphExec_t exec; int n_kernels; };
   std::vector<StepGraph> step_graphs;
   long long launches;
   Profiler prof;
@@ -611,26 +611,27 @@ RADE_EXPORT int rade_b200_loopback_step_dev(rade_batch *b, const float *d_featur
   if (!graphs || b->prof.on) return loopback_step_body(b, d_features_next, d_features_out, d_ret, d_eoo_out);
   // one instantiated graph per (caller pointers, pipeline mode, counter parity): callers cycle through a few buffers
   const void *key[5] = {d_features_next, d_features_out, d_ret, d_eoo_out, (const void *)(size_t)(2 * b->pipelined + b->rx.parity + 1)};
-  cudaGraphExec_t exec = nullptr;
-  for (auto &g : b->step_graphs) if (memcmp(g.key, key, sizeof(key)) == 0) { exec = g.exec; break; }
+  cudaGraphExec_t exec = nullptr; int n_kernels = 0;
+  for (auto &g : b->step_graphs) if (memcmp(g.key, key, sizeof(key)) == 0) { exec = g.exec; n_kernels = g.n_kernels; break; }
   if (!exec) {
     if (b->step_graphs.size() >= 64) { for (auto &g : b->step_graphs) cudaGraphExecDestroy(g.exec); b->step_graphs.clear(); }
     cudaGraph_t g = nullptr;
     CUDA_CHECK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
     const long long launches0 = b->launches;
     const int rc = loopback_step_body(b, d_features_next, d_features_out, d_ret, d_eoo_out);  // toggles the parity once
+    n_kernels = (int)(b->launches - launches0);             // kernels inside the graph: counted per replay below
     b->launches = launches0;
     cudaError_t e = cudaStreamEndCapture(b->stream, &g);
     if (rc < 0 || e != cudaSuccess || !g) { fprintf(stderr, "libradae_b200: graph capture of the loop-back step failed (%s)\n", cudaGetErrorString(e)); return -1; }
     CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
     cudaGraphDestroy(g);
-    rade_batch::StepGraph sg; memcpy(sg.key, key, sizeof(key)); sg.exec = exec;
+    rade_batch::StepGraph sg; memcpy(sg.key, key, sizeof(key)); sg.exec = exec; sg.n_kernels = n_kernels;
     b->step_graphs.push_back(sg);
   } else {
     b->rx.parity ^= 1;
   }
   CUDA_CHECK(cudaGraphLaunch(exec, b->stream));
-  b->launches += 8;
+  b->launches += n_kernels;
   return 0;
 }
 // The whole loop-back pipeline (features -> core encoder -> OFDM modulator -> HF channel -> receiver -> core decoder -> features)

@@ -45,8 +45,10 @@ constexpr int NE = 8;                        // epilogue warps
 constexpr int SEG_LD = 100;                  // float row strides (16-byte aligned, bank-spreading)
 constexpr int FIN_LD = 92;
 constexpr int ZIN_LD = 84;
-constexpr int NSEG = 4;                      // depth of the float segment ring E -> F
-constexpr int I8_NST = 3, F32_NST = 2;
+constexpr int F32_NST = 2;                   // stages of the float weight ring
+// Per tile width NS (streams per CTA): stages of the int8 weight ring and depth of the float segment ring E -> F.  The 16-stream
+// tile has twice the activations, state and segments in shared memory and pays for them with shallower rings.
+template <int NS> struct RingCfg { static constexpr int I8_NST = NS > 8 ? 2 : 3, NSEG = NS > 8 ? 2 : 4, RSF = NS > 8 ? 2 : 1; };
 
 // named barriers (0 = __syncthreads)
 enum { NB_F = 1, NB_MAIN = 2, NB_E = 3, NB_R0 = 8 /* .. 11: z/r warp pairs */ };
@@ -260,25 +262,25 @@ template <int NS, bool ENC, int N> struct IssueAll<NS, ENC, N, N> {
 // ================================================================= encoder
 template <int NS> struct EncCfg {
   static constexpr int NC = NS / 2;                                // accumulator columns per epilogue thread
-  static constexpr int RSF = 1;                                    // streams per float thread (x 4 outputs)
+  static constexpr int RSF = RingCfg<NS>::RSF, I8_NST = RingCfg<NS>::I8_NST, NSEG = RingCfg<NS>::NSEG;   // RSF: streams per float thread (x 4 outputs)
   static constexpr int NFT = (NS / RSF) * (RADE_LATENT / 4);       // float threads: (stream pair, group of 4 outputs)
   static constexpr int NF = (NFT + 31) / 32;
   static constexpr int KB = ENC_CAT;                               // concat bytes per stream
   static constexpr int CB_BYTES = (NS / 8) * KB * 8;
   static constexpr int NCB = 4;                                    // concat buffers: t, t-1, t-2 and the one dense1(t+1) is written to
-  static constexpr int THREADS = (NE + 1 + NF + 2) * 32;
+  static constexpr int THREADS = (NE + NF + 2) * 32;                // float + epilogue warps, one producer warp (two lanes), one issuer warp
   static constexpr int TMEM_COLS = (10 * NS <= 128) ? 128 : 256;   // GRU slots 2 x 4 blocks, conv slots 2 x 1 block
 };
 template <int NS> struct EncSmemU {
-  RingSmem<I8_NST, UMMA_I8_STAGE_BYTES> i8;
+  RingSmem<RingCfg<NS>::I8_NST, UMMA_I8_STAGE_BYTES> i8;
   RingSmem<F32_NST, UMMA_F32_STAGE_BYTES> f32;
   alignas(128) uint8_t cb[EncCfg<NS>::NCB][EncCfg<NS>::CB_BYTES];
   alignas(16) float hs[NS][5 * ENC_GRU];
-  alignas(16) float seg[NSEG][NS][SEG_LD];
+  alignas(16) float seg[RingCfg<NS>::NSEG][NS][SEG_LD];
   alignas(16) float d1f[NS][SEG_LD];                               // dense1 output (float) = concat segment 0
   alignas(16) float fin[NS][FIN_LD];
   alignas(16) float rx[NS][ENC_GRU];                               // reset gates handed from the r lanes to the z / n lanes
-  alignas(8) uint64_t acc_full[10], act_ready[10], seg_full[NSEG], seg_empty[NSEG], d1_ready[2];   // d1_ready ping-pongs by step: the float warps run one step ahead
+  alignas(8) uint64_t acc_full[10], act_ready[10], seg_full[RingCfg<NS>::NSEG], seg_empty[RingCfg<NS>::NSEG], d1_ready[2];   // d1_ready ping-pongs by step: the float warps run one step ahead
   ChunkDesc i8_chunks[UMMA_MAX_I8_CHUNKS], f32_chunks[UMMA_MAX_F32_CHUNKS];
   uint32_t tmem_base;
   int any_active;
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(EncCfg<NS>::THREADS, 1)
 core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamState *__restrict__ state, const float *__restrict__ in, int in_mode,
                          float *__restrict__ z_out, const uint8_t *__restrict__ active, int S, int T) {
   typedef EncCfg<NS> C;
+  constexpr int NSEG = C::NSEG, I8_NST = C::I8_NST;
   constexpr int NC = C::NC, RSF = C::RSF, NSP = NS / RSF, NF = C::NF, KB = C::KB, NCB = C::NCB;
   constexpr int N_MAIN = (NE + 1 + NF) * 32;                       // epilogue + issuer + float threads
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -324,12 +327,12 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
   const uint32_t tmem = sm.tmem_base;
   long long *const trace = W.trace;
 
-  // ---------------------------------------------------------------- producers (last two warps)
-  if (warp == NF + NE || warp == NF + NE + 1) {
-    if (lane == 0) {
-      if (warp == NF + NE) produce(&sm.i8, U.i8_stream, sm.i8_chunks, 0, U.n_i8_chunks, T, W.trace);
-      else produce(&sm.f32, U.f32_stream, sm.f32_chunks, U.n_f32_prologue, U.n_f32_chunks, T, nullptr);
-    }
+  // ---------------------------------------------------------------- producers: lanes 0 and 1 of one warp, each walking its own ring
+  // (independent thread scheduling keeps the two blocking loops apart; a thread block of 512 instead of 544 threads also lifts the
+  // register cap from 96 to 128 per thread — the allocation unit is four warps — which removed the decoder's spills)
+  if (warp == NF + NE) {
+    if (lane == 0) produce(&sm.i8, U.i8_stream, sm.i8_chunks, 0, U.n_i8_chunks, T, W.trace);
+    else if (lane == 1) produce(&sm.f32, U.f32_stream, sm.f32_chunks, U.n_f32_prologue, U.n_f32_chunks, T, nullptr);
     return;
   }
 
@@ -419,7 +422,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
   }
 
   // ---------------------------------------------------------------- issuer warp
-  if (warp == NF + NE + 2) {
+  if (warp == NF + NE + 1) {
     nb_sync(NB_MAIN, N_MAIN);
     if (elect_one()) {                           // ONE thread runs the whole issue program (no reconvergence points inside)
       typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
@@ -578,25 +581,25 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
 // hidden states live in their own ping-pong buffers (hq), like the concat buffers in the B-operand layout.
 template <int NS> struct DecCfg {
   static constexpr int NC = NS / 2;
-  static constexpr int RSF = 1;                                    // streams per float thread (x 4 outputs)
+  static constexpr int RSF = RingCfg<NS>::RSF, I8_NST = RingCfg<NS>::I8_NST, NSEG = RingCfg<NS>::NSEG;
   static constexpr int NFT = (NS / RSF) * (DEC_OUTP / 4);
   static constexpr int NF = (NFT + 31) / 32;
   static constexpr int KB = DEC_CAT, KH = 5 * DEC_GRU;
   static constexpr int CB_BYTES = (NS / 8) * KB * 8, HQ_BYTES = (NS / 8) * KH * 8;
   static constexpr int NCB = 3;                                    // t, t-1 and the one dense1(t+1) is written to
-  static constexpr int THREADS = (NE + 1 + NF + 2) * 32;
+  static constexpr int THREADS = (NE + NF + 2) * 32;                // float + epilogue warps, one producer warp (two lanes), one issuer warp
   static constexpr int TMEM_COLS = (16 * NS <= 128) ? 128 : 256;   // GRU slots 2 x 6 blocks, GLU 2 x 1, conv 2 x 1
 };
 template <int NS> struct DecSmemU {
-  RingSmem<I8_NST, UMMA_I8_STAGE_BYTES> i8;
+  RingSmem<RingCfg<NS>::I8_NST, UMMA_I8_STAGE_BYTES> i8;
   RingSmem<F32_NST, UMMA_F32_STAGE_BYTES> f32;
   alignas(128) uint8_t cb[DecCfg<NS>::NCB][DecCfg<NS>::CB_BYTES];
   alignas(128) uint8_t hq[2][DecCfg<NS>::HQ_BYTES];
   alignas(16) float hs[NS][5 * DEC_GRU];
-  alignas(16) float seg[NSEG][NS][SEG_LD];
+  alignas(16) float seg[RingCfg<NS>::NSEG][NS][SEG_LD];
   alignas(16) float d1f[NS][SEG_LD];
   alignas(16) float zin[NS][ZIN_LD];
-  alignas(8) uint64_t acc_full[15], act_ready[15], seg_full[NSEG], seg_empty[NSEG], d1_ready[2];   // d1_ready ping-pongs by step: the float warps run one step ahead
+  alignas(8) uint64_t acc_full[15], act_ready[15], seg_full[RingCfg<NS>::NSEG], seg_empty[RingCfg<NS>::NSEG], d1_ready[2];   // d1_ready ping-pongs by step: the float warps run one step ahead
   ChunkDesc i8_chunks[UMMA_MAX_I8_CHUNKS], f32_chunks[UMMA_MAX_F32_CHUNKS];
   uint32_t tmem_base;
   int any_active;
@@ -610,6 +613,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
                          float *__restrict__ out, int out_mode, int *__restrict__ uw_count,
                          const uint8_t *__restrict__ active, int S, int T) {
   typedef DecCfg<NS> C;
+  constexpr int NSEG = C::NSEG, I8_NST = C::I8_NST;
   constexpr int NC = C::NC, RSF = C::RSF, NSP = NS / RSF, NF = C::NF, KB = C::KB, KH = C::KH, NCB = C::NCB;
   constexpr int N_MAIN = (NE + 1 + NF) * 32, NGRP = DEC_OUTP / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -644,11 +648,12 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
   const uint32_t tmem = sm.tmem_base;
   long long *const trace = W.trace;
 
-  if (warp == NF + NE || warp == NF + NE + 1) {  // ---- producers
-    if (lane == 0) {
-      if (warp == NF + NE) produce(&sm.i8, U.i8_stream, sm.i8_chunks, 0, U.n_i8_chunks, T, W.trace);
-      else produce(&sm.f32, U.f32_stream, sm.f32_chunks, U.n_f32_prologue, U.n_f32_chunks, T, nullptr);
-    }
+  // ---------------------------------------------------------------- producers: lanes 0 and 1 of one warp, each walking its own ring
+  // (independent thread scheduling keeps the two blocking loops apart; a thread block of 512 instead of 544 threads also lifts the
+  // register cap from 96 to 128 per thread — the allocation unit is four warps — which removed the decoder's spills)
+  if (warp == NF + NE) {
+    if (lane == 0) produce(&sm.i8, U.i8_stream, sm.i8_chunks, 0, U.n_i8_chunks, T, W.trace);
+    else if (lane == 1) produce(&sm.f32, U.f32_stream, sm.f32_chunks, U.n_f32_prologue, U.n_f32_chunks, T, nullptr);
     return;
   }
 
@@ -737,7 +742,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
     return;
   }
 
-  if (warp == NF + NE + 2) {                     // ---- issuer
+  if (warp == NF + NE + 1) {                     // ---- issuer
     nb_sync(NB_MAIN, N_MAIN);
     if (elect_one()) {
       typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
@@ -909,24 +914,36 @@ static int umma_grid(int S, int NS, int n_sm) {
   return g < 1 ? 1 : g;
 }
 static int g_n_sm = 148;
+// tile width: 16 streams per CTA once 8-stream tiles no longer fit one wave over the SMs (RADE_B200_CODEC_NS = 8 | 16 overrides)
+static int umma_tile(int S, int n_sm) {
+  static const int forced = getenv("RADE_B200_CODEC_NS") ? atoi(getenv("RADE_B200_CODEC_NS")) : 0;
+  if (forced == 8 || forced == 16) return forced;
+  return S > 8 * n_sm ? 16 : 8;
+}
 int core_codec_umma_init_device() {
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev);
   CUDA_CHECK(cudaFuncSetAttribute(core_encoder_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmemU<8>)));
   CUDA_CHECK(cudaFuncSetAttribute(core_decoder_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmemU<8>)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_encoder_umma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncSmemU<16>)));
+  CUDA_CHECK(cudaFuncSetAttribute(core_decoder_umma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmemU<16>)));
   return 0;
 }
 int core_encoder_umma_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                              const uint8_t *active, int S, int T, cudaStream_t stream) {
-  const int grid = umma_grid(S, 8, g_n_sm);
-  core_encoder_umma_kernel<8><<<grid, EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, state, in, in_mode, z, active, S, T);
+  if (umma_tile(S, g_n_sm) == 16)
+    core_encoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm), EncCfg<16>::THREADS, sizeof(EncSmemU<16>), stream>>>(W, state, in, in_mode, z, active, S, T);
+  else
+    core_encoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm), EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 int core_decoder_umma_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
                              int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
-  const int grid = umma_grid(S, 8, g_n_sm);
-  core_decoder_umma_kernel<8><<<grid, DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+  if (umma_tile(S, g_n_sm) == 16)
+    core_decoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm), DecCfg<16>::THREADS, sizeof(DecSmemU<16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+  else
+    core_decoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm), DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

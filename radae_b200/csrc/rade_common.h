@@ -77,7 +77,7 @@ struct CodecStreamDev { const unsigned char *stream; const ChunkDesc *chunks; in
 // The host compiles, next to the weight streams, the per-step MMA PROGRAM the issuer thread walks: one UmmaOp per int8 matrix.
 #define UMMA_I8_STAGE_BYTES 40960              // ring stage of the int8 weight stream: one cp.async.bulk each (the TMA unit of an SM
                                                // completes ~1 bulk copy per 440 cycles whatever its size: few, large copies)
-#define UMMA_F32_STAGE_BYTES 22528             // ring stage of the float weight stream (rows of dense1 / zdense / output)
+#define UMMA_F32_STAGE_BYTES 20480             // ring stage of the float weight stream (rows of dense1 / zdense / output)
 #define UMMA_MAX_RECS 120
 #define UMMA_MAX_I8_CHUNKS 48
 #define UMMA_MAX_F32_CHUNKS 24
