@@ -148,6 +148,10 @@ RADE_EXPORT int rade_b200_profile_enable(rade_batch *b, int enable);
 RADE_EXPORT int rade_b200_profile_n_kernels(void);
 RADE_EXPORT const char *rade_b200_profile_kernel_name(int k);
 RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *counts);
+/* timeline of the kernels of the steps issued between _begin and _read: event pairs on the launching streams, nothing serialised;
+ * records {kernel id (rade_b200_profile_kernel_name), start, end} in ms since _begin; returns the number of records */
+RADE_EXPORT int rade_b200_timeline_begin(rade_batch *b);
+RADE_EXPORT int rade_b200_timeline_read(rade_batch *b, int *kernel, float *start_ms, float *end_ms, int cap);
 
 /* --- host-side sample link in front of rade_b200_rx: a ring of 4 modem-frame slots [S][960] in pinned host
  * memory that producers fill, per-stream sample rings on the device that the receiver consumes; queued frames go up with the

@@ -79,6 +79,8 @@ SIGNATURES = {
     "rade_b200_duplex_run": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P]),
     # test hook
     "rade_b200_debug_tables": (_I, [_I, _P, _I]),
+    "rade_b200_timeline_begin": (_I, [_P]),
+    "rade_b200_timeline_read": (_I, [_P, _P, _P, _P, _I]),
     "rade_b200_debug_codec_stream": (C.c_longlong, [_I, _I, _P, C.c_longlong, _P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "rade_b200_debug_codec_program": (_I, [_I, _P, _I]),
     "rade_b200_debug_check_weights": (_I, [_P, C.c_size_t]),

@@ -154,6 +154,7 @@ RADE_EXPORT rade_batch *rade_b200_open(int n_streams, int device, int flags, con
   if (core_weights_upload((const unsigned char *)weights, weights_len, &b->weights) < 0) { delete b; return nullptr; }
   b->weights.dev.trace = nullptr;
   b->weights.dev.one = 1.0f;
+  b->weights.dev.full_tiles = 0;
   b->weights.dev.float_fma = 0;            // measurement switch only (tools/gpu_fma_ab.sh sets it through RADE_B200_DEBUG_FLOAT_FMA): never on in the product
   if (getenv("RADE_B200_DEBUG_FLOAT_FMA") && atoi(getenv("RADE_B200_DEBUG_FLOAT_FMA")) == 1) b->weights.dev.float_fma = 1;
   b->weights.dev.enc_z_tanh = (flags & RADE_B200_BOTTLENECK_1) ? 1 : 0;      // src/rade_enc.c:107-113
@@ -246,6 +247,7 @@ RADE_EXPORT int rade_b200_pipeline_enable(rade_batch *b, int enable) {
   }
   if (rade_b200_synchronize(b) < 0) return -1;
   b->pipelined = enable ? 1 : 0;
+  b->weights.dev.full_tiles = b->pipelined;      // kernels of the other side of the pipeline run beside the codec
   return 0;
 }
 RADE_EXPORT int rade_b200_pipeline_fork(rade_batch *b) {
@@ -568,12 +570,12 @@ RADE_EXPORT int rade_b200_tx_channel_link_dev(rade_batch *b, const float *d_feat
   }
   const rade_b200_channel_cfg &c = b->chan_cfg;
   const float sigma = sqrtf((float)RADE_FS / (powf(10.f, c.EbNodB / 10.f) * 2000.f));
-  b->prof.begin(K_CORE_ENC);
+  b->prof.begin(K_CORE_ENC, tx_side(b));
   if (core_encoder_launch(b->weights.dev, b->enc_state, d_features_in, 1, b->z_tx, nullptr, b->S, RADE_NZMF, tx_side(b)) < 0) return -1;
-  b->prof.end(K_CORE_ENC); b->prof.begin(K_CHANNEL);
+  b->prof.end(K_CORE_ENC, tx_side(b)); b->prof.begin(K_CHANNEL, tx_side(b));
   if (channel_stream_launch(b->tables, b->z_tx, nullptr, nullptr, b->chan_state, b->S, sigma, c.freq_offset_hz, c.freq_offset_spread_hz,
                             c.doppler_spread_hz, c.delay_samples, c.gain, c.seed, b->link_ring, b->link_wr, b->link_rd, b->link_overflow, tx_side(b)) < 0) return -1;
-  b->prof.end(K_CHANNEL);
+  b->prof.end(K_CHANNEL, tx_side(b));
   b->launches += 2;
   return 0;
 }
@@ -948,6 +950,37 @@ RADE_EXPORT int rade_b200_profile_read(rade_batch *b, float *total_ms, int *coun
     total_ms[k] = tot; counts[k] = n;
   }
   return K_COUNT;
+}
+
+// ---- timeline of one or more steps: like the profiler above, but the event pairs are recorded on whichever stream launches the
+// kernel and nothing is serialised, so the offsets show what really overlaps.  rade_b200_timeline_begin marks the origin;
+// rade_b200_timeline_read synchronises and returns up to cap records {kernel id, start ms, end ms} (ms since the origin).
+RADE_EXPORT int rade_b200_timeline_begin(rade_batch *b) {
+  cudaSetDevice(b->device);
+  for (int k = 0; k < K_COUNT; k++) { for (cudaEvent_t e : b->prof.ev[k]) cudaEventDestroy(e); b->prof.ev[k].clear(); }
+  if (!b->prof.t0) CUDA_CHECK(cudaEventCreate(&b->prof.t0));
+  CUDA_CHECK(cudaEventRecord(b->prof.t0, b->stream));
+  b->prof.on = false; b->prof.timeline = true;
+  return 0;
+}
+RADE_EXPORT int rade_b200_timeline_read(rade_batch *b, int *kernel, float *start_ms, float *end_ms, int cap) {
+  cudaSetDevice(b->device);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  b->prof.timeline = false;
+  int n = 0;
+  for (int k = 0; k < K_COUNT; k++) {
+    auto &v = b->prof.ev[k];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+      if (n < cap) {
+        kernel[n] = k;
+        cudaEventElapsedTime(&start_ms[n], b->prof.t0, v[i]); cudaEventElapsedTime(&end_ms[n], b->prof.t0, v[i + 1]);
+        n++;
+      }
+    }
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+  }
+  return n;
 }
 
 // debug/test hook: DSP tables as built on the host (no device needed) — lets the CPU test-suite compare them with

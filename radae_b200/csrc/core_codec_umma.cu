@@ -907,8 +907,12 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
 
 // ----------------------------------------------------------------- host side
 // tiles: at most NS streams each, and a whole number of waves over the SMs when there are more tiles than SMs
-static int umma_grid(int S, int NS, int n_sm) {
+// full_tiles: fewer tiles than SMs are NOT spread over all SMs — the free SMs go to the kernels that run beside the codec in the
+// frame pipeline (a resident codec CTA owns its SM).  1024 streams: 128 CTAs + 20 free SMs, step 0.304 -> 0.297 ms; the codec kernel
+// alone is 2 % slower that way (96.7 vs 94.4 us), so a stand-alone call keeps the uneven tiles.
+static int umma_grid(int S, int NS, int n_sm, int full_tiles) {
   int g = (S + NS - 1) / NS;
+  if (g < n_sm && full_tiles) return g < 1 ? 1 : g;
   if (g < n_sm) g = S < n_sm ? S : n_sm;                          // fewer, smaller tiles than SMs: one CTA per SM
   else g = ((g + n_sm - 1) / n_sm) * n_sm;
   return g < 1 ? 1 : g;
@@ -932,18 +936,18 @@ int core_codec_umma_init_device() {
 int core_encoder_umma_launch(const CoreWeightsDev &W, EncStreamState *state, const float *in, int in_mode, float *z,
                              const uint8_t *active, int S, int T, cudaStream_t stream) {
   if (umma_tile(S, g_n_sm) == 16)
-    core_encoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm), EncCfg<16>::THREADS, sizeof(EncSmemU<16>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm, W.full_tiles), EncCfg<16>::THREADS, sizeof(EncSmemU<16>), stream>>>(W, state, in, in_mode, z, active, S, T);
   else
-    core_encoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm), EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, state, in, in_mode, z, active, S, T);
+    core_encoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm, W.full_tiles), EncCfg<8>::THREADS, sizeof(EncSmemU<8>), stream>>>(W, state, in, in_mode, z, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 int core_decoder_umma_launch(const CoreWeightsDev &W, DecStreamState *state, const float *z, float *out, int out_mode,
                              int *uw_count, const uint8_t *active, int S, int T, cudaStream_t stream) {
   if (umma_tile(S, g_n_sm) == 16)
-    core_decoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm), DecCfg<16>::THREADS, sizeof(DecSmemU<16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_umma_kernel<16><<<umma_grid(S, 16, g_n_sm, W.full_tiles), DecCfg<16>::THREADS, sizeof(DecSmemU<16>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   else
-    core_decoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm), DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
+    core_decoder_umma_kernel<8><<<umma_grid(S, 8, g_n_sm, W.full_tiles), DecCfg<8>::THREADS, sizeof(DecSmemU<8>), stream>>>(W, state, z, out, out_mode, uw_count, active, S, T);
   CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -21,7 +21,7 @@
 //     -> rx_detect (persistent over the search list: coarse grid search) -> rx_finish (search / candidate state machine)
 //   the search branch runs on a side stream concurrently with the sync branch; both join before the core decoder.
 // The two search kernels evaluate the coarse grid in a low-rank basis (proj_tap / expand_*), the refine as moments of the
-// window (refine_moments); rx_finish keeps the matrix form on the FP64 tensor cores (refine_dmma) for the +-10 Hz first fix.
+// window (refine_moments); rx_finish uses the same moments form with 18 terms for the +-10 Hz first fix (refine_first_fix).
 #include "rade_common.h"
 #include "rade_host.h"
 #include "tma.cuh"
@@ -191,19 +191,21 @@ rx_bpf_kernel(DspTables T, RxCtl *__restrict__ ctl, float2 *__restrict__ ring, f
       const float4 *Xv = reinterpret_cast<const float4 *>(X + i0 + off);
       float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       float4 w0 = Xv[0], w1 = Xv[1];              // samples k..k+1, k+2..k+3
+      // real tap x complex sample = one packed FMA on the (re, im) pair (SASS FFMA2): half the FP32-pipe time of two scalar
+      // FMAs, the same two IEEE operations
 #pragma unroll
       for (int k = 0; k < RADE_BPF_NTAP + 1; k += 2) {
         const float4 w2 = Xv[k / 2 + 2];          // samples k+4, k+5
-        const float h0 = c_bpf_h[k], h1 = c_bpf_h[k + 1];        // h[101] = 0 pads the odd tap count
-        acc[0].x = fmaf(h0, w0.x, acc[0].x); acc[0].y = fmaf(h0, w0.y, acc[0].y);
-        acc[1].x = fmaf(h0, w0.z, acc[1].x); acc[1].y = fmaf(h0, w0.w, acc[1].y);
-        acc[2].x = fmaf(h0, w1.x, acc[2].x); acc[2].y = fmaf(h0, w1.y, acc[2].y);
-        acc[3].x = fmaf(h0, w1.z, acc[3].x); acc[3].y = fmaf(h0, w1.w, acc[3].y);
+        const float2 h0 = splat(c_bpf_h[k]), h1 = splat(c_bpf_h[k + 1]);        // h[101] = 0 pads the odd tap count
+        acc[0] = ffma2(h0, make_float2(w0.x, w0.y), acc[0]);
+        acc[1] = ffma2(h0, make_float2(w0.z, w0.w), acc[1]);
+        acc[2] = ffma2(h0, make_float2(w1.x, w1.y), acc[2]);
+        acc[3] = ffma2(h0, make_float2(w1.z, w1.w), acc[3]);
         if (k + 1 < RADE_BPF_NTAP) {
-          acc[0].x = fmaf(h1, w0.z, acc[0].x); acc[0].y = fmaf(h1, w0.w, acc[0].y);
-          acc[1].x = fmaf(h1, w1.x, acc[1].x); acc[1].y = fmaf(h1, w1.y, acc[1].y);
-          acc[2].x = fmaf(h1, w1.z, acc[2].x); acc[2].y = fmaf(h1, w1.w, acc[2].y);
-          acc[3].x = fmaf(h1, w2.x, acc[3].x); acc[3].y = fmaf(h1, w2.y, acc[3].y);
+          acc[0] = ffma2(h1, make_float2(w0.z, w0.w), acc[0]);
+          acc[1] = ffma2(h1, make_float2(w1.x, w1.y), acc[1]);
+          acc[2] = ffma2(h1, make_float2(w1.z, w1.w), acc[2]);
+          acc[3] = ffma2(h1, make_float2(w2.x, w2.y), acc[3]);
         }
         w0 = w1; w1 = w2;
       }
@@ -314,8 +316,7 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
 // (DMMA m8n8k4, 256 FMA per instruction): A = Toeplitz view of the widened samples [8 t][(n, re/im)], B = [(n, re/im)]
 // [(f, re/im)] formed on the fly from the steering table vtab; 24 frequencies (6 n-tiles) per pass.
 constexpr int REF_NT = 16;                        // max timing offsets
-constexpr int REF_NFP = 24;                       // frequencies per pass = 6 DMMA n-tiles of 4 complex columns
-constexpr int REF_VLD = 165;                      // vtab row: tap n lives at n + (n >> 5); 165 = 5 mod 8 spreads f over the banks
+constexpr int REF_NFP = 24;                       // room for the 20 or 21 frequencies of arange(f0 - 1, f0 + 1, 0.1)
 constexpr int REF_RLEN = REF_NT + RADE_M + 8;     // widened window (+ over-read of the last k-step)
 constexpr int REF_THREADS = 128;                  // four warps
 constexpr int REF_NK = 9;                         // Taylor terms of exp(-j dw n'), |dw n'| <= 0.0625: truncation 6e-15
@@ -331,126 +332,10 @@ struct MomentsSmem {                              // refine_moments (tracking)
   float red_mag[4]; int red_ord[4];
   float best_mag; int best_t; int best_found; double best_f;
 };
-struct RefineSmem {
-  double2 vtab[REF_NFP][REF_VLD];                 // refine_dmma: conj(p[n]) exp(-j w_f n)
-  double2 ramp[REF_NFP];                          // exp(-j w_f Nmf)
-  double2 ra[REF_RLEN];                           // rx[t_lo ...] widened once (np.dot up-casts csingle to complex128)
-  double2 pad_;                                   // shifts rb by one entry: ra/rb reads of one warp hit different banks
-  double2 rb[REF_RLEN];                           // rx[t_lo + Nmf ...]
-  float2 d1[REF_NFP][REF_NT];
-  float2 d2[REF_NFP][REF_NT];
-  float red_mag[4]; int red_ord[4];
-  float best_mag; int best_t; int best_found; double best_f;
-};
-
 // values of np.arange(start, stop, step) for float64: v[i] = start + i*((start+step)-start), len = ceil((stop-start)/step)
 __device__ __forceinline__ int arange_len(double start, double stop, double step) { return (int)ceil((stop - start) / step); }
 
-// Searches t in [t_lo, t_lo+nt) x f in arange(f_start, f_stop, f_step); result in sm.best_* (best_found == 0: nothing beat 0).
-// Executed by REF_THREADS threads (g = index within the group) that synchronise on named barrier `bar`.
-// load(i) returns rx_buf[i] (logical index).  WIDE_T: nt > 8 -> warp = (pilot position, 8-row t tile) x 6 n-tiles;
-// otherwise warp = (pilot position, half of the n-tiles) with a single t tile.
-template <bool WIDE_T, typename Load>
-__device__ void refine_dmma(RefineSmem &sm, const double2 *__restrict__ pcd, Load load, int t_lo, int nt,
-                            double f_start, double f_stop, double f_step, int g, int bar) {
-  constexpr int NQ = WIDE_T ? 6 : 3;              // n-tiles per warp
-  const int nf_all = arange_len(f_start, f_stop, f_step);
-  const double delta = (f_start + f_step) - f_start;
-  if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
-  for (int i2 = g; i2 < REF_RLEN; i2 += REF_THREADS) {
-    const bool in = i2 < nt + RADE_M;
-    const float2 a = in ? load(t_lo + i2) : make_float2(0.f, 0.f), c = in ? load(t_lo + RADE_NMF + i2) : make_float2(0.f, 0.f);
-    sm.ra[i2] = make_double2((double)a.x, (double)a.y);
-    sm.rb[i2] = make_double2((double)c.x, (double)c.y);
-  }
-  for (int c0 = 0; c0 < nf_all; c0 += REF_NFP) {
-    const int nf = min(REF_NFP, nf_all - c0);
-    group_sync(bar, REF_THREADS);                 // previous pass done with vtab / d1 / d2
-    // steering vectors for this pass: thread = (f, 32-tap segment), one sincos pair + 31 rotations (|error| ~ 1e-15)
-    for (int task = g; task < REF_NFP * 5; task += REF_THREADS) {
-      const int fi = task / 5, seg = task % 5;
-      double2 *row = sm.vtab[fi] + 33 * seg;
-      if (fi < nf) {
-        const double f = f_start + (double)(c0 + fi) * delta;
-        const double w = 2.0 * M_PI * f / RADE_FS;
-        double sn, cs, s1, c1; sincos(w * (double)(32 * seg), &sn, &cs); sincos(w, &s1, &c1);
-        double2 e = make_double2(cs, -sn); const double2 step = make_double2(c1, -s1);
-#pragma unroll 4
-        for (int q = 0; q < 32; q++) { row[q] = dcmul(e, pcd[32 * seg + q]); e = dcmul(e, step); }
-        if (seg == 0) {             // pilots of the NEXT frame: extra phase ramp exp(-j w Nmf)
-          sincos(w * (double)RADE_NMF, &sn, &cs);
-          sm.ramp[fi] = make_double2(cs, -sn);
-        }
-      } else {
-        for (int q = 0; q < 32; q++) row[q] = make_double2(0.0, 0.0);
-      }
-    }
-    group_sync(bar, REF_THREADS);
-    {
-      const int wr = g >> 5, lane = g & 31, gq = lane >> 2, c = lane & 3;
-      const int half = wr >> 1, mt = WIDE_T ? (wr & 1) : 0, q0 = WIDE_T ? 0 : 3 * (wr & 1);
-      const double *ap = reinterpret_cast<const double *>((half ? sm.rb : sm.ra) + mt * 8 + gq + (c >> 1)) + (c & 1);
-      const int reim = gq & 1, comp = c & 1;
-      const unsigned flip = (reim == 0 && comp == 1) ? 0x80000000u : 0u;      // B = [vr; -vi] for Re columns, [vi; vr] for Im
-      const double *bp[NQ];
-#pragma unroll
-      for (int q = 0; q < NQ; q++) bp[q] = reinterpret_cast<const double *>(sm.vtab[(q0 + q) * 4 + (gq >> 1)] + (c >> 1)) + (comp ^ reim);
-      double acc[NQ][2];
-#pragma unroll
-      for (int q = 0; q < NQ; q++) acc[q][0] = acc[q][1] = 0.0;
-#pragma unroll 1
-      for (int blk = 0; blk < 5; blk++) {
-#pragma unroll 4
-        for (int kk = 0; kk < 16; kk++) {
-          const double av = ap[4 * (16 * blk + kk)];
-#pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            double bv = bp[q][2 * (33 * blk + 2 * kk)];
-            bv = __hiloint2double(__double2hiint(bv) ^ flip, __double2loint(bv));
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                         : "+d"(acc[q][0]), "+d"(acc[q][1]) : "d"(av), "d"(bv));
-          }
-        }
-      }
-      const int ti = mt * 8 + gq;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const int fi = (q0 + q) * 4 + c;
-        if (fi < nf && ti < nt) {
-          if (half) { const double2 e = dcmul(make_double2(acc[q][0], acc[q][1]), sm.ramp[fi]); sm.d2[fi][ti] = make_float2((float)e.x, (float)e.y); }
-          else sm.d1[fi][ti] = make_float2((float)acc[q][0], (float)acc[q][1]);
-        }
-      }
-    }
-    group_sync(bar, REF_THREADS);
-    float bm = -1.f; int bo = 0x7fffffff;
-    for (int q = g; q < nf * nt; q += REF_THREADS) {
-      const int fi = q / nt, ti = q % nt;            // ord = q: f outer loop, t inner loop
-      const float2 a = sm.d1[fi][ti], c = sm.d2[fi][ti];
-      const float m = hypotf(a.x + c.x, a.y + c.y);
-      if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
-      if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
-    }
-    if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
-    group_sync(bar, REF_THREADS);
-    if (g == 0) {
-      for (int q = 1; q < REF_THREADS / 32; q++)
-        if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
-      if (bm > sm.best_mag) {       // strict >: passes are visited in increasing f, the initial Dtmax is 0 (radae/dsp.py:262)
-        sm.best_mag = bm; sm.best_found = 1;
-        sm.best_t = t_lo + bo % nt;
-        sm.best_f = f_start + (double)(c0 + bo / nt) * delta;
-      }
-    }
-  }
-  group_sync(bar, REF_THREADS);
-}
-
-// The same search for the tracking case — 16 timing offsets, f in arange(f0 - 1, f0 + 1, 0.1) — without a steering vector per
+// acquisition.refine for the tracking case — 16 timing offsets, f in arange(f0 - 1, f0 + 1, 0.1) — without a steering vector per
 // frequency.  With n' = n - 79.5 and f = f0 + d:  exp(-j w_f n) = exp(-j w_f 79.5) exp(-j w0 n') exp(-j dw n'), and |dw n'| <= 0.0625 rad,
 // so exp(-j dw n') = sum_k (-j 80 dw)^k (n'/80)^k / k! to 6e-15 with k <= 8.  Per window: nine complex128 moments
 //   M_k = sum_n rx[t + n] q[n] (n'/80)^k / k!,   q[n] = conj(p[n]) exp(-j w0 n'),
@@ -523,6 +408,105 @@ __device__ void refine_moments(MomentsSmem &sm, const double (*bk)[10], const do
         const double2 e = dcmul(dcmul(D, ph0), phd[pos][fi]);
         (pos ? sm.d2 : sm.d1)[fi][ti] = make_float2((float)e.x, (float)e.y);
       }
+  }
+  group_sync(bar, REF_THREADS);
+  float bm = -1.f; int bo = 0x7fffffff;
+  for (int q = g; q < nf_all * nt; q += REF_THREADS) {
+    const int fi = q / nt, t2 = q - fi * nt;         // ord = q: f outer loop, t inner loop
+    const float2 a = sm.d1[fi][t2], c = sm.d2[fi][t2];
+    const float m = hypotf(a.x + c.x, a.y + c.y);
+    if (m > bm || (m == bm && q < bo)) { bm = m; bo = q; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, bm, o); const int o2 = __shfl_xor_sync(0xffffffffu, bo, o);
+    if (m2 > bm || (m2 == bm && o2 < bo)) { bm = m2; bo = o2; }
+  }
+  if ((g & 31) == 0) { sm.red_mag[g >> 5] = bm; sm.red_ord[g >> 5] = bo; }
+  group_sync(bar, REF_THREADS);
+  if (g == 0) {
+    for (int q = 1; q < REF_THREADS / 32; q++)
+      if (sm.red_mag[q] > bm || (sm.red_mag[q] == bm && sm.red_ord[q] < bo)) { bm = sm.red_mag[q]; bo = sm.red_ord[q]; }
+    if (bm > 0.f) {                 // strict > against the initial Dtmax = 0 (radae/dsp.py:262)
+      sm.best_mag = bm; sm.best_found = 1;
+      sm.best_t = t_lo + bo % nt;
+      sm.best_f = f_start + (double)(bo / nt) * delta;
+    }
+  }
+  group_sync(bar, REF_THREADS);
+}
+
+// acquisition.refine for the first fix after acquisition (radae_rxe.py:267-273): t in [max(0, tmax - 1), tmax + 2),
+// f in arange(f0 - 10, f0 + 10, 0.25) — the same moments form with |80 dw| <= 0.63, i.e. 18 Taylor terms (truncation 4e-20).
+// Only six windows, so the layout is by task instead of by window: (1) q[n], the power table (n'/80)^k / k! and the two
+// stream-dependent phases, (2) z[w][n] = rx q, (3) one thread per (window, k) moment, (4) Horner + phase per (frequency, window),
+// (5) arg-max.  About 8 k cycles per stream instead of four passes of steering table + FP64 tensor-core GEMM (~45 k): the search
+// branch (rx_detect -> rx_finish) used to end after rx_demod and held the core decoder back (tools/step_timeline.py).
+constexpr int FF_NK = 18, FF_NF = 80, FF_NT = 3, FF_NW = 2 * FF_NT;
+struct FirstFixSmem {
+  double bk[RADE_M][FF_NK];
+  double2 z[FF_NW][RADE_M];
+  double2 q[RADE_M];
+  double2 M[FF_NW][FF_NK];
+  double2 ph0[2];
+  float2 d1[FF_NF][FF_NT], d2[FF_NF][FF_NT];
+  float red_mag[4]; int red_ord[4];
+  float best_mag; int best_t; int best_found; double best_f;
+};
+template <typename Load>
+__device__ void refine_first_fix(FirstFixSmem &sm, const AcqTables &tab, Load load, int t_lo, int nt, double f0, int g, int bar) {
+  const double f_start = f0 - 10, f_stop = f0 + 10, f_step = 0.25;
+  const int nf_all = min(arange_len(f_start, f_stop, f_step), FF_NF);
+  const double delta = (f_start + f_step) - f_start;
+  const double w0 = 2.0 * M_PI * f0 / RADE_FS;
+  const int nw = 2 * nt;
+  if (g == 0) { sm.best_mag = 0.f; sm.best_found = 0; sm.best_t = 0; sm.best_f = 0.0; }
+  {
+    double sn, cs;
+    sincos(w0 * ((double)g - 79.5), &sn, &cs);
+    sm.q[g] = dcmul(make_double2(cs, -sn), make_double2(__ldg(&tab.pcd[g].x), __ldg(&tab.pcd[g].y)));
+    if (g < RADE_M - REF_THREADS + 2) {
+      const double arg = g < RADE_M - REF_THREADS ? (double)(g + REF_THREADS) - 79.5 : (g == RADE_M - REF_THREADS ? 79.5 : 79.5 + RADE_NMF);
+      sincos(w0 * arg, &sn, &cs);
+      if (g < RADE_M - REF_THREADS) sm.q[g + REF_THREADS] = dcmul(make_double2(cs, -sn), make_double2(__ldg(&tab.pcd[g + REF_THREADS].x), __ldg(&tab.pcd[g + REF_THREADS].y)));
+      else sm.ph0[g - (RADE_M - REF_THREADS)] = make_double2(cs, -sn);
+    }
+    for (int n = g; n < RADE_M; n += REF_THREADS) {
+      const double sc = ((double)n - 79.5) / 80.0;
+      double v = 1.0;
+#pragma unroll
+      for (int k = 0; k < FF_NK; k++) { sm.bk[n][k] = v; v = v * sc / (double)(k + 1); }
+    }
+  }
+  group_sync(bar, REF_THREADS);
+  for (int i = g; i < nw * RADE_M; i += REF_THREADS) {
+    const int w = i / RADE_M, n = i - w * RADE_M, pos = w / nt, ti = w - pos * nt;
+    const float2 x = load(t_lo + ti + pos * RADE_NMF + n);
+    sm.z[w][n] = dcmul(make_double2((double)x.x, (double)x.y), sm.q[n]);
+  }
+  group_sync(bar, REF_THREADS);
+  if (g < nw * FF_NK) {
+    const int w = g / FF_NK, k = g - w * FF_NK;
+    double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+#pragma unroll 4
+    for (int n = 0; n < RADE_M; n += 2) {
+      const double2 z0 = sm.z[w][n], z1 = sm.z[w][n + 1];
+      const double b0 = sm.bk[n][k], b1 = sm.bk[n + 1][k];
+      ax = fma(z0.x, b0, ax); ay = fma(z0.y, b0, ay); bx = fma(z1.x, b1, bx); by = fma(z1.y, b1, by);
+    }
+    sm.M[w][k] = make_double2(ax + bx, ay + by);
+  }
+  group_sync(bar, REF_THREADS);
+  for (int i = g; i < nf_all * nw; i += REF_THREADS) {
+    const int fi = i / nw, w = i - fi * nw, pos = w / nt, ti = w - pos * nt;
+    const double f = f_start + (double)fi * delta;
+    const double al = 2.0 * M_PI * (f - f0) / RADE_FS * 80.0;              // u = -j al
+    double2 D = sm.M[w][FF_NK - 1];
+#pragma unroll
+    for (int k = FF_NK - 2; k >= 0; k--) D = make_double2(fma(al, D.y, sm.M[w][k].x), fma(-al, D.x, sm.M[w][k].y));
+    const double2 pd = make_double2(__ldg(&tab.phd10[pos][fi].x), __ldg(&tab.phd10[pos][fi].y));
+    const double2 e = dcmul(dcmul(D, sm.ph0[pos]), pd);
+    (pos ? sm.d2 : sm.d1)[fi][ti] = make_float2((float)e.x, (float)e.y);
   }
   group_sync(bar, REF_THREADS);
   float bm = -1.f; int bo = 0x7fffffff;
@@ -687,12 +671,12 @@ rx_track_kernel(DspTables T, const RxCtl *__restrict__ ctl, const float2 *__rest
 
 // Sync-state part of the state machine (radae_rxe.py:208-218, :276-296) and check_pilots' decisions (radae/dsp.py:297-320) for a
 // stream that was tracked this call: called by every thread of the stream's rx_demod CTA before the demodulation proper.
-__device__ void track_tail(RxCtl &c, const TrackTmp &tt, const float *__restrict__ rs, int *__restrict__ uw_errors, int s,
+__device__ void track_tail(RxCtl &c, const RxCtl &ci, const TrackTmp &tt, const float *__restrict__ rs, int *__restrict__ uw_errors, int s,
                            int *__restrict__ ret_out, unsigned char *__restrict__ dec_active, int *__restrict__ nin_out, float *scratch) {
-  // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums
+  // sigma_r = (mean|Dt1| + mean|Dt2|) / (2 sqrt(pi/2)) from the refreshed row sums (its barriers also order the staging of ci / tt)
   const float sigma_r = sigma_r_from_rowsums(rs, scratch);
   if (threadIdx.x == 0) {
-    const int tmax0 = c.tmax; const double fmax0 = c.fmax;
+    const int tmax0 = ci.tmax; const double fmax0 = ci.fmax;
     int tmax = tt.best_found ? tt.best_t : tmax0;
     const double fhat = tt.best_found ? tt.best_f : fmax0;
     const double fmax = 0.9 * fmax0 + 0.1 * fhat;
@@ -705,8 +689,8 @@ __device__ void track_tail(RxCtl &c, const TrackTmp &tt, const float *__restrict
     int nin = RADE_NMF;
     if (tmax >= RADE_NMF - RADE_M) { nin = RADE_NMF + RADE_M; tmax -= RADE_M; }
     if (tmax < RADE_M) { nin = RADE_NMF - RADE_M; tmax += RADE_M; }
-    c.tmax = tmax; c.fmax = fmax; c.n_check = c.n_check + 1;
-    const int synced_count = c.synced_count + 1;
+    c.tmax = tmax; c.fmax = fmax; c.n_check = ci.n_check + 1;
+    const int synced_count = ci.synced_count + 1;
     c.synced_count = synced_count;
     int uw_fail = 0;
     if (synced_count % RADE_SYNCED_ONE_SEC == 0) {
@@ -716,7 +700,7 @@ __device__ void track_tail(RxCtl &c, const TrackTmp &tt, const float *__restrict
     const int valid_output = !endofover;
     c.uw_fail = uw_fail; c.candidate = valid; c.endofover = endofover; c.valid_output = valid_output; c.ran_sync = 1;
     // sync-state branch of the state machine (radae_rxe.py:276-296); search / candidate streams: rx_finish_kernel
-    int next = ST_SYNC, vc = c.valid_count;
+    int next = ST_SYNC, vc = ci.valid_count;
     if (valid) vc = RADE_NMF_UNSYNC;
     else { vc -= 1; if (vc == 0) next = ST_SEARCH; }
     if (endofover || uw_fail) next = ST_SEARCH;
@@ -732,8 +716,10 @@ __device__ void track_tail(RxCtl &c, const TrackTmp &tt, const float *__restrict
 struct DemodSmem {
   float2 xs[RADE_NS + 2][RADE_M];
   float2 sym[RADE_NS + 2][RADE_NC];
+  float2 dft_part[4][RADE_NS + 2][RADE_NC];
   float2 pil[2][RADE_NC];
   float2 rotc[RADE_NC];
+  RxCtl ctl_in; TrackTmp tt;                        // the stream's control block / refine results as they were at kernel entry
   double2 e1[32], e32[6], estep[RADE_NS + 2];     // exp(-j w l), exp(-j w 32 h), exp(-j w 192 r): 45 double sincos per stream instead of 320
   float scratch[96];
   float mag;
@@ -749,7 +735,11 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
   if (active && !active[s]) return;
   RxCtl &c = ctl[s];
   if (!c.tracking) return;                        // in sync when this call began (flag written by rx_bpf with the track list)
-  track_tail(c, tmp[s], rowsum + (size_t)s * 2 * RADE_NMF, uw_errors, s, ret_out, dec_active, nin_out, sm.scratch);
+  // one coalesced read of the control block and the refine results: the state machine is a single thread's chain of dependent
+  // decisions and should not wait on global memory for every field
+  if (tid < (int)(sizeof(RxCtl) / 4)) reinterpret_cast<uint32_t *>(&sm.ctl_in)[tid] = reinterpret_cast<const uint32_t *>(&c)[tid];
+  else if (tid >= 64 && tid < 64 + (int)(sizeof(TrackTmp) / 4)) reinterpret_cast<uint32_t *>(&sm.tt)[tid - 64] = reinterpret_cast<const uint32_t *>(tmp + s)[tid - 64];
+  track_tail(c, sm.ctl_in, sm.tt, rowsum + (size_t)s * 2 * RADE_NMF, uw_errors, s, ret_out, dec_active, nin_out, sm.scratch);
   const int head = c.ring_head, tmax = c.tmax, endofover = c.endofover;
   const float2 *rg = ring + (size_t)s * RADE_RXBUF;
   const double w = 2.0 * M_PI * c.fmax / RADE_FS;
@@ -783,19 +773,38 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
     }
   }
   __syncthreads();
-  if (tid < (RADE_NS + 2) * RADE_NC) {              // 180 DFT outputs, 160-point each
-    const int r = tid / RADE_NC, cc = tid % RADE_NC;
-    float2 acc = make_float2(0.f, 0.f);
+  // DFT: 6 symbols x 30 carriers, 160 taps each.  thread = (carrier, quarter of the taps) on warps 0-3: one twiddle load serves the
+  // six symbols, every complex MAC is two packed FMAs, the four partial sums meet in shared memory (added in tap order).
+  if (tid < 128 && (tid & 31) < RADE_NC) {
+    const int cc = tid & 31, kq = tid >> 5;
+    float2 acc[RADE_NS + 2];
+#pragma unroll
+    for (int r = 0; r < RADE_NS + 2; r++) acc[r] = make_float2(0.f, 0.f);
     const float2 *wf = T.Wfwd + cc;
 #pragma unroll 1
-    for (int k0 = 0; k0 < RADE_M; k0 += 16) {      // 16 twiddles in flight per thread (read-only path), sums in tap order
-      float2 w[16];
+    for (int k0 = kq * (RADE_M / 4); k0 < (kq + 1) * (RADE_M / 4); k0 += 8) {
+      float2 w[8];
 #pragma unroll
-      for (int j = 0; j < 16; j++) w[j] = __ldg(wf + (k0 + j) * RADE_NC);
+      for (int j = 0; j < 8; j++) w[j] = __ldg(wf + (k0 + j) * RADE_NC);
 #pragma unroll
-      for (int j = 0; j < 16; j++) cmac(acc, sm.xs[r][k0 + j], w[j]);
+      for (int j = 0; j < 8; j++) {
+        const float2 ws = make_float2(-w[j].y, w[j].x);
+#pragma unroll
+        for (int r = 0; r < RADE_NS + 2; r++) {
+          const float2 x = sm.xs[r][k0 + j];
+          acc[r] = ffma2(splat(x.x), w[j], acc[r]);
+          acc[r] = ffma2(splat(x.y), ws, acc[r]);
+        }
+      }
     }
-    sm.sym[r][cc] = acc;
+#pragma unroll
+    for (int r = 0; r < RADE_NS + 2; r++) sm.dft_part[kq][r][cc] = acc[r];
+  }
+  __syncthreads();
+  if (tid < (RADE_NS + 2) * RADE_NC) {
+    const int r = tid / RADE_NC, cc = tid % RADE_NC;
+    const float2 a = sm.dft_part[0][r][cc], b = sm.dft_part[1][r][cc], c2 = sm.dft_part[2][r][cc], d = sm.dft_part[3][r][cc];
+    sm.sym[r][cc] = make_float2(((a.x + b.x) + c2.x) + d.x, ((a.y + b.y) + c2.y) + d.y);
   }
   __syncthreads();
   if (!endofover) {
@@ -875,7 +884,7 @@ rx_demod_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict__
 // Streams that entered this call in search / candidate state (the sync-state branch lives at the end of rx_track_kernel).
 // CTAs stride over the search list; inactive streams only get their outputs filled in.
 struct FinishSmem {
-  RefineSmem ref;
+  FirstFixSmem ref;
   float scratch[96];
   int do_refine;
 };
@@ -935,8 +944,8 @@ rx_finish_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
       const int t_lo = max(0, tm - 1);
       if (tid < REF_THREADS) {
         const float2 *rg = ring + (size_t)s * RADE_RXBUF; const int head = c.ring_head;
-        refine_dmma<false>(sm.ref, reinterpret_cast<const AcqTables *>(T.acq_tab)->pcd, [rg, head](int i) { return rg[ring_idx(head, i)]; },
-                           t_lo, tm + 2 - t_lo, fm - 10, fm + 10, 0.25, tid, 1);
+        refine_first_fix(sm.ref, *reinterpret_cast<const AcqTables *>(T.acq_tab), [rg, head](int i) { return __ldg(rg + ring_idx(head, i)); },
+                         t_lo, tm + 2 - t_lo, fm, tid, 1);
       }
       __syncthreads();
       if (tid == 0) {
@@ -1018,24 +1027,24 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
   const bool fork2 = fork && B.side2_stream;
   cudaStream_t s2 = fork2 ? B.side2_stream : stream;
   if (fork2) CUDA_CHECK(cudaStreamWaitEvent(s2, B.ev_fork, 0));
-  prof->begin(K_RX_TRACK);
+  prof->begin(K_RX_TRACK, s2);
   rx_track_kernel<<<S < n_sm * 4 ? S : n_sm * 4, REF_THREADS, sizeof(TrackSmem), s2>>>(T, B.ctl, B.ring, B.track_list, cnt, (TrackTmp *)B.track_tmp);
-  prof->end(K_RX_TRACK);
+  prof->end(K_RX_TRACK, s2);
   if (fork2) CUDA_CHECK(cudaEventRecord(B.ev_join2, s2));
   prof->begin(K_RX_REFRESH);
   rx_refresh_kernel<<<(trk_grid + RFR_STREAMS - 1) / RFR_STREAMS, RFR_THREADS, 0, stream>>>(B.ctl, B.ring, B.rowsum, B.track_list, cnt);
   prof->end(K_RX_REFRESH);
   if (fork2) CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join2, 0));
-  prof->begin(K_RX_DETECT);
+  prof->begin(K_RX_DETECT, ss);
   int det_grid = S * (RADE_NMF / DET_TB); if (det_grid > n_sm * 12) det_grid = n_sm * 12;      // 64-thread CTAs, 81 registers: 12 per SM
   rx_detect_kernel<<<det_grid, DET_THREADS, sizeof(DetectSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.search_list, cnt);
-  prof->end(K_RX_DETECT); prof->begin(K_RX_DEMOD);
+  prof->end(K_RX_DETECT, ss); prof->begin(K_RX_DEMOD);
   rx_demod_kernel<<<S, 192, 0, stream>>>(T, B.ctl, B.ring, B.z_hat, B.eoo, active, (const TrackTmp *)B.track_tmp, B.rowsum, B.uw_errors,
                                          ret_out, B.dec_active, B.nin);
-  prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH);
+  prof->end(K_RX_DEMOD); prof->begin(K_RX_FINISH, ss);
   rx_finish_kernel<<<S < 2 * n_sm ? S : 2 * n_sm, 256, sizeof(FinishSmem), ss>>>(T, B.ctl, B.ring, B.rowsum, B.uw_errors, B.dec_state,
       reset_dec_on_sync, ret_out, B.dec_active, B.nin, active, B.search_list, cnt, cnt_next, S);
-  prof->end(K_RX_FINISH);
+  prof->end(K_RX_FINISH, ss);
   if (fork) { CUDA_CHECK(cudaEventRecord(B.ev_join, ss)); CUDA_CHECK(cudaStreamWaitEvent(stream, B.ev_join, 0)); }
   CUDA_CHECK(cudaGetLastError());
   return 6;

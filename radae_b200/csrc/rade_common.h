@@ -110,6 +110,7 @@ struct CoreWeightsDev {
   I8LayerDev dec_gru_in[5], dec_gru_rec[5], dec_glu[5], dec_conv[5];
   CodecStreamDev enc_stream, dec_stream;
   UmmaCodecDev enc_umma, dec_umma;
+  int full_tiles;          // host-side hint for the launchers: keep full tiles and leave SMs free when other kernels run beside the codec
   float one;               // 1.0f as a RUN-TIME value: acc = fma(round(w x), one, acc) is an exact packed add that ptxas cannot contract with the multiply
   int float_fma;           // MEASUREMENT ONLY (RADE_B200_DEBUG_FLOAT_FMA=1): wide float layers with fused multiply-add — not bit-exact, 9 % faster encoder
   long long *trace;        // debug: clock64() stamps of CTA 0's warp roles (rade_b200_debug_trace_*), nullptr in production
@@ -160,6 +161,7 @@ struct __align__(128) AcqTables {
   // depend on the stream
   double bk[RADE_M][10];
   double2 phd[2][24];
+  double2 phd10[2][80];          // first fix: exp(-j 2 pi (-10 + 0.25 i) / Fs * (79.5 + 960 pos))
   float4 ps4[RADE_M];            // (p.x, p.y, p.y, -p.x): conj(x)*p = x.x*(.x,.y) + x.y*(.z,.w) with two packed FMAs
   double2 pcd[RADE_M];           // conj(p) widened to complex128 (refine steering vectors)
   float2 pend[RADE_M];           // end-of-over pilot symbol

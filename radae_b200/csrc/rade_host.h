@@ -96,12 +96,14 @@ int rx_dsp_launch(const DspTables &T, RxBuffers &B, const float2 *rx_in, const u
 enum KernelId { K_CORE_ENC = 0, K_OFDM_MOD, K_EOO, K_CHANNEL, K_LINK_PUSH, K_LINK_POP, K_RX_BPF, K_RX_DETECT, K_RX_TRACK,
                 K_RX_DEMOD, K_RX_FINISH, K_CORE_DEC, K_TX_BPF, K_RX_REFRESH, K_COUNT };
 struct Profiler {
-  bool on = false;
+  bool on = false;                            // serialising mode: everything on the main stream, one event pair per launch
+  bool timeline = false;                      // timeline mode: event pairs on the LAUNCHING stream, nothing is serialised (rade_b200_timeline_*)
   cudaStream_t stream = nullptr;
+  cudaEvent_t t0 = nullptr;                   // timeline origin
   std::vector<cudaEvent_t> ev[K_COUNT];       // start,end pairs
-  void begin(int k) { if (on) rec(k); }
-  void end(int k) { if (on) rec(k); }
-  void rec(int k) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); ev[k].push_back(e); }
+  void begin(int k, cudaStream_t s = nullptr) { if (on || timeline) rec(k, s ? s : stream); }
+  void end(int k, cudaStream_t s = nullptr) { if (on || timeline) rec(k, s ? s : stream); }
+  void rec(int k, cudaStream_t s) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev[k].push_back(e); }
 };
 
 int core_codec_init_device();

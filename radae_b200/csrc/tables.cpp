@@ -214,6 +214,11 @@ int dsp_tables_upload(const DspTablesHost &T, DspTables *D, std::vector<void *> 
         const double a = 2 * M_PI * (-1.0 + 0.1 * i) / RADE_FS * (79.5 + RADE_NMF * pos);
         A->phd[pos][i] = make_double2(std::cos(a), -std::sin(a));
       }
+    for (int pos = 0; pos < 2; pos++)
+      for (int i = 0; i < 80; i++) {
+        const double a = 2 * M_PI * (-10.0 + 0.25 * i) / RADE_FS * (79.5 + RADE_NMF * pos);
+        A->phd10[pos][i] = make_double2(std::cos(a), -std::sin(a));
+      }
     memcpy(A->basis, T.srch_basis.data(), sizeof(A->basis));
     memcpy(A->expand, T.srch_expand.data(), sizeof(A->expand));
     if (T.srch_residual > 2e-7) { fprintf(stderr, "libradae_b200: coarse-grid basis residual %.3g\n", T.srch_residual); return -1; }

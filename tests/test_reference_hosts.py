@@ -33,7 +33,7 @@ def test_reference_hosts_compile_and_link_unchanged(tmp_path):
 
 
 def test_stand_in_hosts_compile(tmp_path):
-    for name in ("radae_tx", "radae_rx"):
+    for name in ("radae_tx", "radae_rx", "multi_loopback"):
         src = os.path.join(HOSTS, name + ".c")
         exe = os.path.join(str(tmp_path), name)
         from radae_b200.build import build
