@@ -58,10 +58,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor: K-major, no swizzle, LBO (K-adjacent core matrices) = 128 B, SBO (8-row groups) as given
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t sbo_bytes) {
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | (uint64_t)(128 >> 4) << 16 | (uint64_t)(sbo_bytes >> 4) << 32 | (uint64_t)1 << 46;
-}
+// (shared-memory matrix descriptors — K-major, no swizzle, LBO = 128 B — are assembled by the issuer: desc_lo / desc_hi below)
 template <int N> __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
   // instruction descriptor: D = s32, A = B = s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
   constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);

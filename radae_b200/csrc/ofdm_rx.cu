@@ -35,11 +35,6 @@ constexpr double K_ACQ_1E4 = 3.2893431387452243, K_ACQ_1E5 = 3.622480279781289;
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 __device__ __forceinline__ double2 dcmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-// acc += a*b with four FMAs (the compiler otherwise emits FMUL+FFMA+FADD per component pair)
-__device__ __forceinline__ void cmac(float2 &acc, float2 a, float2 b) {
-  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
-  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
-}
 // Coarse-grid correlations D(+-f_k) = sum_n y[n] exp(+-j w_k n), y[n] = conj(x[n]) p[n], f_k = 2.5 k Hz, k = 0..20
 // (acquisition.detect_pilots / check_pilots, radae/dsp.py:204-205, :291-295; the reference multiplies by p_w = exp(j w n) p).
 // Only |D| is ever used, so the window may be centred: with n = 80 + m and n = 79 - m folded onto m = 0..79,
@@ -108,18 +103,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-// block-wide sum, result valid in every thread; scratch: >= 32 floats of shared memory
-__device__ float block_sum(float v, float *scratch) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[w] = v;
-  __syncthreads();
-  float t = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.f;
-  if (w == 0) { t = warp_sum(t); if (lane == 0) scratch[0] = t; }
-  __syncthreads();
-  return scratch[0];
 }
 
 // The tables every lane reads at the same index live in constant memory: they reach the FP32 pipe through the uniform datapath
