@@ -51,7 +51,7 @@ constexpr int F32_NST = 2;                   // stages of the float weight ring
 template <int NS> struct RingCfg { static constexpr int I8_NST = NS > 8 ? 2 : 3, NSEG = NS > 8 ? 2 : 4, RSF = NS > 8 ? 2 : 1; };
 
 // named barriers (0 = __syncthreads)
-enum { NB_F = 1, NB_MAIN = 2, NB_E = 3, NB_R0 = 8 /* .. 11: z/r warp pairs */ };
+enum { NB_F = 1, NB_MAIN = 2, NB_E = 3, NB_Z = 4, NB_START = 5, NB_R0 = 8 /* .. 11: z/r warp pairs */ };
 __device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -376,7 +376,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
       nb_sync(NB_F, NF * 32);
       if (ft == 0) mbar_arrive(&sm.d1_ready[t & 1]);
     };
-    nb_sync(NB_MAIN, N_MAIN);                    // state loaded, concat buffers initialised
+    nb_sync(NB_Z, NE * 32 + NF * 32);            // concat buffers zeroed; the state load of the epilogue warps runs beside dense1(0)
     stage_input(0);
     nb_sync(NB_F, NF * 32);
     dense1(0);
@@ -420,7 +420,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
 
   // ---------------------------------------------------------------- issuer warp
   if (warp == NF + NE + 1) {
-    nb_sync(NB_MAIN, N_MAIN);
+    nb_sync(NB_START, (NE + 1) * 32);            // state loaded by the epilogue warps
     if (elect_one()) {                           // ONE thread runs the whole issue program (no reconvergence points inside)
       typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
       IssueCtx<Ring> c;
@@ -453,18 +453,41 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
   // concat buffers: zero, then steps t-1 (cb[NCB-1]) and t-2 (cb[NCB-2]) from the per-stream row-major state
   for (int i = et; i < NCB * C::CB_BYTES / 4; i += NET) reinterpret_cast<uint32_t *>(sm.cb[0])[i] = 0u;
   nb_sync(NB_E, NET);
-  for (int r = 0; r < NS; r++) {
-    const bool ok = r < ns;
-    const EncStreamState *st = state + (s0 + (ok ? r : 0));
-    for (int i = et; i < 5 * ENC_GRU; i += NET) sm.hs[r][i] = ok ? st->h[i] : 0.f;
-    if (ok)
-      for (int i = et; i < KB / 4; i += NET) {
-        *reinterpret_cast<uint32_t *>(sm.cb[NCB - 1] + b_off<KB>(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat1)[i];
-        *reinterpret_cast<uint32_t *>(sm.cb[NCB - 2] + b_off<KB>(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat2)[i];
+  nb_arrive(NB_Z, NE * 32 + NF * 32);            // the float warps may start dense1(0)
+  // all streams' state in ONE pass: the loads of a thread (one per stream and array slice) are issued back to back, so the tile
+  // pays one global-memory latency instead of one per stream (the per-stream loop cost ~8 k cycles before the first MMA)
+  {
+    constexpr int HN = 5 * ENC_GRU, CN = KB / 4;
+    float hv[(NS * HN + NET - 1) / NET];
+#pragma unroll
+    for (int q = 0; q < (NS * HN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / HN, i = idx - r * HN;
+      hv[q] = (idx < NS * HN && r < ns) ? state[s0 + r].h[i] : 0.f;
+    }
+    uint32_t c1[(NS * CN + NET - 1) / NET], c2[(NS * CN + NET - 1) / NET];
+#pragma unroll
+    for (int q = 0; q < (NS * CN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / CN, i = idx - r * CN;
+      const bool ok = idx < NS * CN && r < ns;
+      c1[q] = ok ? reinterpret_cast<const uint32_t *>(state[s0 + r].cat1)[i] : 0u;
+      c2[q] = ok ? reinterpret_cast<const uint32_t *>(state[s0 + r].cat2)[i] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < (NS * HN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / HN, i = idx - r * HN;
+      if (idx < NS * HN) sm.hs[r][i] = hv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < (NS * CN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / CN, i = idx - r * CN;
+      if (idx < NS * CN && r < ns) {
+        *reinterpret_cast<uint32_t *>(sm.cb[NCB - 1] + b_off<KB>(r, 4 * i)) = c1[q];
+        *reinterpret_cast<uint32_t *>(sm.cb[NCB - 2] + b_off<KB>(r, 4 * i)) = c2[q];
       }
+    }
   }
   fence_async_smem();
-  nb_sync(NB_MAIN, N_MAIN);
+  nb_sync(NB_START, (NE + 1) * 32);               // with the issuer: state and concat buffers are in place
 
   int nseg = 0;
   for (int t = 0; t < T; t++) {
@@ -686,7 +709,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
       nb_sync(NB_F, NF * 32);
       if (ft == 0) mbar_arrive(&sm.d1_ready[t & 1]);
     };
-    nb_sync(NB_MAIN, N_MAIN);
+    nb_sync(NB_Z, NE * 32 + NF * 32);            // concat buffers zeroed (see the encoder)
     stage_input(0);
     nb_sync(NB_F, NF * 32);
     dense1(0);
@@ -740,7 +763,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
   }
 
   if (warp == NF + NE + 1) {                     // ---- issuer
-    nb_sync(NB_MAIN, N_MAIN);
+    nb_sync(NB_START, (NE + 1) * 32);
     if (elect_one()) {
       typedef RingCursor<I8_NST, UMMA_I8_STAGE_BYTES> Ring;
       IssueCtx<Ring> c;
@@ -769,20 +792,34 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
   constexpr int NET = NE * 32;
   for (int i = et; i < (NCB * C::CB_BYTES + 2 * C::HQ_BYTES) / 4; i += NET) reinterpret_cast<uint32_t *>(sm.cb[0])[i] = 0u;
   nb_sync(NB_E, NET);
-  for (int r = 0; r < NS; r++) {
-    const bool ok = r < ns;
-    const DecStreamState *st = state + (s0 + (ok ? r : 0));
-    for (int i = et; i < 5 * DEC_GRU; i += NET) {
-      const float h = ok ? st->h[i] : 0.f;
-      sm.hs[r][i] = h;
-      sm.hq[0][b_off<KH>(r, i)] = (uint8_t)quant8(h);
+  nb_arrive(NB_Z, NE * 32 + NF * 32);
+  {                                              // all streams' state in one pass (see the encoder)
+    constexpr int HN = 5 * DEC_GRU, CN = KB / 4;
+    float hv[(NS * HN + NET - 1) / NET];
+#pragma unroll
+    for (int q = 0; q < (NS * HN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / HN, i = idx - r * HN;
+      hv[q] = (idx < NS * HN && r < ns) ? state[s0 + r].h[i] : 0.f;
     }
-    if (ok)
-      for (int i = et; i < KB / 4; i += NET)
-        *reinterpret_cast<uint32_t *>(sm.cb[NCB - 1] + b_off<KB>(r, 4 * i)) = reinterpret_cast<const uint32_t *>(st->cat1)[i];
+    uint32_t c1[(NS * CN + NET - 1) / NET];
+#pragma unroll
+    for (int q = 0; q < (NS * CN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / CN, i = idx - r * CN;
+      c1[q] = (idx < NS * CN && r < ns) ? reinterpret_cast<const uint32_t *>(state[s0 + r].cat1)[i] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < (NS * HN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / HN, i = idx - r * HN;
+      if (idx < NS * HN) { sm.hs[r][i] = hv[q]; sm.hq[0][b_off<KH>(r, i)] = (uint8_t)quant8(hv[q]); }
+    }
+#pragma unroll
+    for (int q = 0; q < (NS * CN + NET - 1) / NET; q++) {
+      const int idx = et + q * NET, r = idx / CN, i = idx - r * CN;
+      if (idx < NS * CN && r < ns) *reinterpret_cast<uint32_t *>(sm.cb[NCB - 1] + b_off<KB>(r, 4 * i)) = c1[q];
+    }
   }
   fence_async_smem();
-  nb_sync(NB_MAIN, N_MAIN);
+  nb_sync(NB_START, (NE + 1) * 32);               // with the issuer: state and concat buffers are in place
 
   int nseg = 0;
   const int u = q * 32 + lane;                   // output feature / hidden unit of this thread (valid for u < 96)
