@@ -299,6 +299,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
   const int ns = s1 - s0;
   const UmmaCodecDev &U = W.enc_umma;
 
+  if (tid == 0 && W.trace && blockIdx.x == 0) W.trace[8000] = clock64();
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
   if (tid < ns && (!active || active[s0 + tid])) sm.any_active = 1;
@@ -323,6 +324,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   long long *const trace = W.trace;
+  if (tid == 0) TR(8001);
 
   // ---------------------------------------------------------------- producers: lanes 0 and 1 of one warp, each walking its own ring
   // (independent thread scheduling keeps the two blocking loops apart; a thread block of 512 instead of 544 threads also lifts the
@@ -583,6 +585,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
     }
   }
   nb_sync(NB_MAIN, N_MAIN);                      // every MMA has been consumed, the float warps are done with the segments
+  if (et == 0) TR(8002);
   if (warp == NF) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(C::TMEM_COLS) : "memory");
   const int last = (T + NCB - 1) % NCB, last2 = (T + NCB - 2) % NCB;
   for (int r = 0; r < ns; r++) {
@@ -594,6 +597,7 @@ core_encoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, EncStreamStat
       reinterpret_cast<uint32_t *>(st->cat2)[i] = *reinterpret_cast<const uint32_t *>(sm.cb[last2] + b_off<KB>(r, 4 * i));
     }
   }
+  if (et == 0) TR(8003);
 }
 
 // ================================================================= decoder
@@ -643,6 +647,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
   const int ns = s1 - s0;
   const UmmaCodecDev &U = W.dec_umma;
 
+  if (tid == 0 && W.trace && blockIdx.x == 0) W.trace[8000] = clock64();
   if (tid == 0) sm.any_active = 0;
   __syncthreads();
   if (tid < ns && (!active || active[s0 + tid])) sm.any_active = 1;
@@ -667,6 +672,7 @@ core_decoder_umma_kernel(const __grid_constant__ CoreWeightsDev W, DecStreamStat
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
   long long *const trace = W.trace;
+  if (tid == 0) TR(8001);
 
   // ---------------------------------------------------------------- producers: lanes 0 and 1 of one warp, each walking its own ring
   // (independent thread scheduling keeps the two blocking loops apart; a thread block of 512 instead of 544 threads also lifts the

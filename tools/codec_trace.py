@@ -32,6 +32,7 @@ n_recs = lib.rade_b200_debug_codec_program(w, None, 0)
 recs = np.zeros((n_recs, 13), np.int32); lib.rade_b200_debug_codec_program(w, recs.ctypes.data, n_recs)
 nlayers = 10 if which == "enc" else 15
 print(f"{which} S={S}: total span {int(tr[2048:8192].max() - t0)} cycles, {n_recs} records per step")
+print("  kernel entry %d, set-up done %d, all roles done %d, state stored %d (same origin)" % tuple(rel(tr[8000 + i]) for i in range(4)))
 for t in range(T):
     print(f"--- step {t}")
     for i in range(n_recs):
