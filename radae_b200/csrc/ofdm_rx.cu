@@ -295,12 +295,11 @@ rx_detect_kernel(DspTables T, RxCtl *__restrict__ ctl, const float2 *__restrict_
 // ================================================================= fine timing / frequency refinement (shared by track & finish)
 // acquisition.refine (radae/dsp.py:233-270): argmax over (f outer, t inner) of |Dt1 + Dt2|, strict >, with
 //   Dt1[t,f] = sum_n rx[t+n] conj(p[n]) exp(-j w_f n),  Dt2 = same at t + Nmf times exp(-j w_f Nmf),
-// computed in complex128 and rounded to csingle like the reference.  Here: a real GEMM on the FP64 tensor cores
-// (DMMA m8n8k4, 256 FMA per instruction): A = Toeplitz view of the widened samples [8 t][(n, re/im)], B = [(n, re/im)]
-// [(f, re/im)] formed on the fly from the steering table vtab; 24 frequencies (6 n-tiles) per pass.
+// computed in complex128 and rounded to csingle like the reference.  Here: moments of the window in complex128 (refine_moments
+// for the tracking search, refine_first_fix for the first fix after acquisition) instead of one steering vector per frequency.
 constexpr int REF_NT = 16;                        // max timing offsets
 constexpr int REF_NFP = 24;                       // room for the 20 or 21 frequencies of arange(f0 - 1, f0 + 1, 0.1)
-constexpr int REF_RLEN = REF_NT + RADE_M + 8;     // widened window (+ over-read of the last k-step)
+constexpr int REF_RLEN = REF_NT + RADE_M + 8;     // widened window
 constexpr int REF_THREADS = 128;                  // four warps
 constexpr int REF_NK = 9;                         // Taylor terms of exp(-j dw n'), |dw n'| <= 0.0625: truncation 6e-15
 struct MomentsSmem {                              // refine_moments (tracking)
