@@ -1,5 +1,6 @@
 """CPU tests: the numpy DSP oracle against golden vectors produced by the Python reference
 (radae_txe.radae_tx, radae_rxe.radae_rx, radae.complex_bpf — see tools/make_golden.py)."""
+import math
 import numpy as np
 import pytest
 from oracle import dsp as od
@@ -110,3 +111,35 @@ def test_channel_oracle_vs_reference_forward(golden):
         ref = g[f"{name}_rx"]
         err = np.sqrt(np.mean(np.abs(rx - ref) ** 2) / np.mean(np.abs(ref) ** 2))
         assert err < 2e-6, (name, err)          # float32 phase accumulation (torch.cumsum) vs the closed form
+
+
+@pytest.mark.parametrize("span, step, nk", [(1.0, 0.1, 9), (10.0, 0.25, 18)])
+def test_refine_moments_form_equals_direct_complex128(golden, span, step, nk):
+    """rx_track / rx_finish evaluate acquisition.refine (radae/dsp.py:233-270) as Taylor moments of the window about the tracked
+    frequency (refine_moments: 9 terms for +-1 Hz; refine_first_fix: 18 terms for +-10 Hz) instead of one complex128 steering
+    vector per frequency.  The formulation, restated in numpy float64, must agree with the reference's direct sums far below
+    the csingle rounding the reference applies afterwards — for every (t, f) of the search, on a recorded signal."""
+    c = od.consts()
+    rx = golden("rx_mpp_3dB")["rx_in"][5000:5000 + od.RXBUF].astype(np.complex64).astype(np.complex128)
+    p = c.p.astype(np.complex128)
+    n = np.arange(od.M); nc = n - 79.5
+    f0, tmax = -11.3, 400
+    fgrid = np.arange(f0 - span, f0 + span, step)
+    w0 = 2 * np.pi * f0 / od.FS
+    q = np.conj(p) * np.exp(-1j * w0 * nc)
+    bk = np.array([(nc / 80.0) ** k / math.factorial(k) for k in range(nk)])            # [nk][160]
+    worst = 0.0
+    for t in range(tmax - 8, tmax + 8):
+        for pos in (0, 1):
+            x = rx[t + pos * od.NMF: t + pos * od.NMF + od.M]
+            Mk = bk @ (x * q)                                                            # the moments
+            for f in fgrid:
+                w = 2 * np.pi * f / od.FS
+                direct = np.dot(x, np.exp(-1j * w * n) * np.conj(p)) * (np.exp(-1j * w * od.NMF) if pos else 1.0)
+                al = 2 * np.pi * (f - f0) / od.FS * 80.0
+                D = 0j
+                for k in range(nk - 1, -1, -1):
+                    D = D * (-1j * al) + Mk[k]
+                mom = D * np.exp(-1j * w * (79.5 + od.NMF * pos))
+                worst = max(worst, abs(mom - direct) / (np.abs(x).sum() * np.abs(p).max()))
+    assert worst < 2e-15, worst
